@@ -27,6 +27,8 @@ def rel_err(a, b):
     """max |a-b| / max(|b|, tiny): normwise relative error used by all parity tests."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
+    if a.size == 0 and b.size == 0:
+        return 0.0
     return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30))
 
 
