@@ -1,0 +1,354 @@
+// K5: the numpy tail of VecFakeEnv.step_wait (cmrl/models/fake_env.py:97-142,186-215) as HBM-bound
+// device kernels: member draw + Gaussian noise (Philox), bucketing of envs by drawn member, input
+// gather, head + sampling + scatter, MOPO penalty, and the episode bookkeeping / reset tail that
+// writes SB3-layout buffers.
+#include "common.cuh"
+
+namespace cmrl {
+
+constexpr int RT = 256;
+
+static inline int blocks_for(long long n, int threads = RT) {
+    long long b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+__device__ __forceinline__ float u32_to_unit_open(uint32_t x) {  // (0,1]
+    return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float* n0, float* n1) {
+    float u = u32_to_unit_open(a), v = u32_to_unit_open(b);
+    float r = sqrtf(-2.0f * logf(u));
+    float s, c;
+    sincospif(2.0f * v, &s, &c);
+    *n0 = r * c;
+    *n1 = r * s;
+}
+
+// one thread per env: block 0 of the counter space draws the member, blocks 1.. draw 4 normals each
+__global__ void draw_member_noise_kernel(unsigned long long seed, unsigned long long stream_id, int N,
+                                         const uint8_t* __restrict__ elite, int n_elite, int D,
+                                         uint8_t* __restrict__ member_idx, float* __restrict__ noise) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t s_lo = (uint32_t)stream_id, s_hi = (uint32_t)(stream_id >> 32);
+    uint4 r = philox4x32_10(make_uint4((uint32_t)n, 0u, s_lo, s_hi), key);
+    if (member_idx) member_idx[n] = elite[(uint32_t)(((unsigned long long)r.x * (unsigned long long)n_elite) >> 32)];
+    if (noise) {
+        for (int d0 = 0; d0 < D; d0 += 4) {
+            uint4 q = philox4x32_10(make_uint4((uint32_t)n, 1u + (uint32_t)(d0 >> 2), s_lo, s_hi), key);
+            float z[4];
+            box_muller(q.x, q.y, &z[0], &z[1]);
+            box_muller(q.z, q.w, &z[2], &z[3]);
+            for (int j = 0; j < 4 && d0 + j < D; ++j) noise[(long long)n * D + d0 + j] = z[j];
+        }
+    }
+}
+
+__global__ void draw_uniform_index_kernel(unsigned long long seed, unsigned long long stream_id, int N,
+                                          unsigned int upper, int* __restrict__ out) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    uint4 r = philox4x32_10(make_uint4((uint32_t)n, 0x7fffffffu, (uint32_t)stream_id, (uint32_t)(stream_id >> 32)), key);
+    out[n] = (int)(((unsigned long long)r.x * (unsigned long long)upper) >> 32);
+}
+
+// ------------------------------------------------------------------------------------------- bucketing
+constexpr int MAX_E = 256;
+
+__global__ void bucket_hist_kernel(const uint8_t* __restrict__ idx, int N, int E, int* __restrict__ counts) {
+    __shared__ int h[MAX_E];
+    for (int i = threadIdx.x; i < E; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        int e = idx[n];
+        if (e < E) atomicAdd(&h[e], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < E; i += blockDim.x)
+        if (h[i]) atomicAdd(&counts[i], h[i]);
+}
+
+// each block owns a contiguous chunk of envs; reserves per-member ranges with one global atomic per member
+__global__ void bucket_scatter_kernel(const uint8_t* __restrict__ idx, int N, int E, const int* __restrict__ counts,
+                                      int* __restrict__ cursor, int* __restrict__ perm, int* __restrict__ offsets,
+                                      int chunk) {
+    __shared__ int h[MAX_E];     // local counts, then local cursors
+    __shared__ int base[MAX_E];  // global start of this block's range per member
+    for (int i = threadIdx.x; i < E; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const int n0 = blockIdx.x * chunk, n1 = min(N, n0 + chunk);
+    for (int n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
+        int e = idx[n];
+        if (e < E) atomicAdd(&h[e], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int e = 0; e < E; ++e) {
+            int start = run;
+            run += counts[e];
+            if (blockIdx.x == 0) offsets[e] = start;
+            base[e] = start + (h[e] ? atomicAdd(&cursor[e], h[e]) : 0);
+            h[e] = 0;
+        }
+        if (blockIdx.x == 0) offsets[E] = run;
+    }
+    __syncthreads();
+    for (int n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
+        int e = idx[n];
+        if (e < E) perm[base[e] + atomicAdd(&h[e], 1)] = n;
+    }
+}
+
+__global__ void gather_inputs_kernel(const float* __restrict__ obs, const float* __restrict__ act,
+                                     const int* __restrict__ perm, int N, int O, int A, float* __restrict__ x) {
+    const int in = O + A;
+    const long long total = (long long)N * in;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % in);
+        long long r = i / in;
+        long long env = perm ? perm[r] : r;
+        x[i] = c < O ? obs[env * O + c] : act[env * A + (c - O)];
+    }
+}
+
+__global__ void sample_scatter_kernel(const float* __restrict__ raw, int layout, const int* __restrict__ perm, int N,
+                                      int D, const float* __restrict__ obs, int obs_ld, const float* __restrict__ mn,
+                                      const float* __restrict__ mx, int bounds_n, const float* __restrict__ noise,
+                                      float* __restrict__ pred) {
+    const long long total = (long long)N * D;
+    const bool gaussian = mn != nullptr;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int d = (int)(i % D);
+        long long r = i / D;
+        long long env = perm ? perm[r] : r;
+        float m, lvraw = 0.0f;
+        if (layout == CMRL_HEAD_PLAIN) {
+            const float* row = raw + r * (gaussian ? 2 * D : D);
+            m = row[d];
+            if (gaussian) lvraw = row[D + d];
+        } else {
+            const float* row = raw + ((long long)d * N + r) * (gaussian ? 2 : 1);
+            m = row[0];
+            if (gaussian) lvraw = row[1];
+        }
+        if (obs) m += obs[env * obs_ld + d];
+        float out = m;
+        if (gaussian && noise) {
+            int bi = bounds_n == 1 ? 0 : d;
+            float lv = soft_clamp_logvar(lvraw, mn[bi], mx[bi]);
+            out = m + sqrtf(expf(lv)) * noise[env * D + d];
+        }
+        pred[env * D + d] = out;
+    }
+}
+
+__global__ void select_sample_kernel(const float* __restrict__ mean, const float* __restrict__ logvar,
+                                     const uint8_t* __restrict__ idx, int E, int N, int D,
+                                     const float* __restrict__ noise, float* __restrict__ pred) {
+    const long long total = (long long)N * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long n = i / D;
+        long long src = (long long)idx[n] * N * D + i;
+        float out = mean[src];
+        if (noise && logvar) out += sqrtf(expf(logvar[src])) * noise[i];
+        pred[i] = out;
+    }
+}
+
+// one thread per env (O is small): mean over members, then max member distance
+__global__ void mopo_penalty_kernel(const float* __restrict__ mean, int E, int N, int O, float* __restrict__ penalty) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float best = 0.0f;
+    // two passes over [E,O] per env; avg recomputed per member to keep registers O-independent
+    for (int e = 0; e < E; ++e) {
+        float d2 = 0.0f;
+        for (int o = 0; o < O; ++o) {
+            float avg = 0.0f;
+            for (int k = 0; k < E; ++k) avg += mean[((long long)k * N + n) * O + o];
+            avg /= (float)E;
+            float diff = mean[((long long)e * N + n) * O + o] - avg;
+            d2 = fmaf(diff, diff, d2);
+        }
+        best = fmaxf(best, sqrtf(d2));
+    }
+    penalty[n] = best;
+}
+
+// TPE = threads per env (1 for small O, 32 for wide observations)
+template <int TPE>
+__global__ void env_step_tail_kernel(const float* __restrict__ next_obs, const float* __restrict__ reward,
+                                     const float* __restrict__ terminal, const uint8_t* __restrict__ terminal_u8,
+                                     const float* __restrict__ penalty, float penalty_coeff, int* __restrict__ env_len,
+                                     int max_steps, const float* __restrict__ reset_obs,
+                                     const int* __restrict__ reset_index, int N, int O, float* __restrict__ obs_out,
+                                     float* __restrict__ reward_out, uint8_t* __restrict__ done_out,
+                                     uint8_t* __restrict__ trunc_out, float* __restrict__ terminal_obs,
+                                     int* __restrict__ n_done) {
+    const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = gt / TPE;
+    const int sub = (int)(gt % TPE);
+    bool done = false;
+    if (n < N) {
+        int len = env_len[n] + 1;
+        bool trunc = len >= max_steps;
+        bool term = (terminal && terminal[n] != 0.0f) || (terminal_u8 && terminal_u8[n] != 0);
+        done = term || trunc;
+        if (TPE > 1) __syncwarp();
+        if (sub == 0) {
+            float r = reward[n];
+            if (penalty) r -= penalty[n] * penalty_coeff;
+            reward_out[n] = r;
+            done_out[n] = done ? 1 : 0;
+            trunc_out[n] = trunc ? 1 : 0;
+            env_len[n] = done ? 0 : len;
+        }
+        const long long rs = reset_index ? (long long)reset_index[n] : n;
+        for (int o = sub; o < O; o += TPE) {
+            float v = next_obs[n * O + o];
+            if (terminal_obs) terminal_obs[n * O + o] = v;
+            obs_out[n * O + o] = (done && reset_obs) ? reset_obs[rs * O + o] : v;
+        }
+    }
+    if (n_done) {
+        unsigned ballot = __ballot_sync(0xffffffffu, done && sub == 0);
+        if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_done, __popc(ballot));
+    }
+}
+
+}  // namespace cmrl
+
+using namespace cmrl;
+
+extern "C" int cmrl_draw_member_noise(unsigned long long seed, unsigned long long stream_id, int N,
+                                      const uint8_t* elite, int n_elite, int D, uint8_t* member_idx, float* noise,
+                                      void* stream) {
+    CMRL_REQUIRE(N >= 0 && D >= 0, "draw_member_noise: bad dims");
+    CMRL_REQUIRE(!member_idx || (elite && n_elite >= 1), "draw_member_noise: elite list required");
+    if (N == 0) return 0;
+    draw_member_noise_kernel<<<blocks_for(N), RT, 0, (cudaStream_t)stream>>>(seed, stream_id, N, elite, n_elite, D,
+                                                                           member_idx, noise);
+    CMRL_CHECK_LAUNCH("draw_member_noise");
+    return 0;
+}
+
+extern "C" int cmrl_draw_uniform_index(unsigned long long seed, unsigned long long stream_id, int N, int upper,
+                                       int* out, void* stream) {
+    CMRL_REQUIRE(out && upper >= 1 && N >= 0, "draw_uniform_index: bad arguments");
+    if (N == 0) return 0;
+    draw_uniform_index_kernel<<<blocks_for(N), RT, 0, (cudaStream_t)stream>>>(seed, stream_id, N, (unsigned)upper, out);
+    CMRL_CHECK_LAUNCH("draw_uniform_index");
+    return 0;
+}
+
+extern "C" int cmrl_member_bucket(const uint8_t* member_idx, int N, int E, int* perm, int* offsets, int* counters,
+                                  void* stream) {
+    CMRL_REQUIRE(member_idx && perm && offsets && counters, "member_bucket: null pointer");
+    CMRL_REQUIRE(E >= 1 && E <= MAX_E, "member_bucket: E must be in [1,%d]", MAX_E);
+    cudaStream_t st = (cudaStream_t)stream;
+    CMRL_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * 2 * (E + 1), st));
+    if (N == 0) {
+        CMRL_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int) * (E + 1), st));
+        return 0;
+    }
+    int nb = blocks_for(N, RT * 8);
+    if (nb > 4 * num_sms()) nb = 4 * num_sms();
+    bucket_hist_kernel<<<nb, RT, 0, st>>>(member_idx, N, E, counters);
+    CMRL_CHECK_LAUNCH("member_bucket.hist");
+    int chunk = (N + nb - 1) / nb;
+    bucket_scatter_kernel<<<nb, RT, 0, st>>>(member_idx, N, E, counters, counters + (E + 1), perm, offsets, chunk);
+    CMRL_CHECK_LAUNCH("member_bucket.scatter");
+    return 0;
+}
+
+extern "C" int cmrl_gather_inputs(const float* obs, const float* act, const int* perm, int N, int O, int A,
+                                  float* x_sorted, void* stream) {
+    CMRL_REQUIRE(obs && x_sorted && (act || A == 0), "gather_inputs: null pointer");
+    long long total = (long long)N * (O + A);
+    if (total == 0) return 0;
+    int nb = blocks_for(total);
+    if (nb > 16 * num_sms()) nb = 16 * num_sms();
+    gather_inputs_kernel<<<nb, RT, 0, (cudaStream_t)stream>>>(obs, act, perm, N, O, A, x_sorted);
+    CMRL_CHECK_LAUNCH("gather_inputs");
+    return 0;
+}
+
+extern "C" int cmrl_sample_scatter(const float* raw_sorted, int layout, const int* perm, int N, int D, const float* obs,
+                                   int obs_ld, const float* min_logvar, const float* max_logvar, int bounds_n,
+                                   const float* noise, float* pred, void* stream) {
+    CMRL_REQUIRE(raw_sorted && pred, "sample_scatter: null pointer");
+    CMRL_REQUIRE(layout == CMRL_HEAD_PLAIN || layout == CMRL_HEAD_PARALLEL, "sample_scatter: bad layout");
+    CMRL_REQUIRE((min_logvar == nullptr) == (max_logvar == nullptr), "sample_scatter: need both bounds or none");
+    CMRL_REQUIRE(!min_logvar || bounds_n == 1 || bounds_n == D, "sample_scatter: bounds must have 1 or D entries");
+    long long total = (long long)N * D;
+    if (total == 0) return 0;
+    int nb = blocks_for(total);
+    if (nb > 16 * num_sms()) nb = 16 * num_sms();
+    sample_scatter_kernel<<<nb, RT, 0, (cudaStream_t)stream>>>(raw_sorted, layout, perm, N, D, obs, obs_ld, min_logvar,
+                                                             max_logvar, bounds_n, noise, pred);
+    CMRL_CHECK_LAUNCH("sample_scatter");
+    return 0;
+}
+
+extern "C" int cmrl_select_sample(const float* mean, const float* logvar, const uint8_t* member_idx, int E, int N,
+                                  int D, const float* noise, float* pred, void* stream) {
+    CMRL_REQUIRE(mean && member_idx && pred, "select_sample: null pointer");
+    long long total = (long long)N * D;
+    if (total == 0) return 0;
+    int nb = blocks_for(total);
+    if (nb > 16 * num_sms()) nb = 16 * num_sms();
+    select_sample_kernel<<<nb, RT, 0, (cudaStream_t)stream>>>(mean, logvar, member_idx, E, N, D, noise, pred);
+    CMRL_CHECK_LAUNCH("select_sample");
+    return 0;
+}
+
+extern "C" int cmrl_mopo_penalty(const float* mean, int E, int N, int O, float* penalty, void* stream) {
+    CMRL_REQUIRE(mean && penalty, "mopo_penalty: null pointer");
+    if (N == 0) return 0;
+    mopo_penalty_kernel<<<blocks_for(N), RT, 0, (cudaStream_t)stream>>>(mean, E, N, O, penalty);
+    CMRL_CHECK_LAUNCH("mopo_penalty");
+    return 0;
+}
+
+extern "C" int cmrl_env_step_tail(const float* next_obs, const float* reward, const float* terminal,
+                                  const uint8_t* terminal_u8, const float* penalty, float penalty_coeff, int* env_len,
+                                  int max_episode_steps, const float* reset_obs, const int* reset_index, int N, int O,
+                                  float* obs_out, float* reward_out, uint8_t* done, uint8_t* truncated,
+                                  float* terminal_obs, int* n_done, void* stream) {
+    CMRL_REQUIRE(next_obs && reward && env_len && obs_out && reward_out && done && truncated,
+                 "env_step_tail: null pointer");
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (O <= 16) {
+        env_step_tail_kernel<1><<<blocks_for(N), RT, 0, st>>>(next_obs, reward, terminal, terminal_u8, penalty,
+                                                              penalty_coeff, env_len, max_episode_steps, reset_obs,
+                                                              reset_index, N, O, obs_out, reward_out, done, truncated,
+                                                              terminal_obs, n_done);
+    } else {
+        env_step_tail_kernel<32><<<blocks_for((long long)N * 32), RT, 0, st>>>(
+            next_obs, reward, terminal, terminal_u8, penalty, penalty_coeff, env_len, max_episode_steps, reset_obs,
+            reset_index, N, O, obs_out, reward_out, done, truncated, terminal_obs, n_done);
+    }
+    CMRL_CHECK_LAUNCH("env_step_tail");
+    return 0;
+}

@@ -1,0 +1,422 @@
+"""BaseDynamics / PlainEnsembleDynamics / ConstraintBasedDynamics with the reference's public interface
+(cmrl/models/dynamics/base_dynamics.py:22-221, plain_dynamics.py:18-142, constraint_based_dynamics.py:22-183);
+the arithmetic runs on libcmrl_b200 kernels:
+
+* `train`    -- per batch: K1 forward (saving pre-activations), K3 NLL forward + backward, K2 backward, K1
+                backward writing straight into the flat gradient arena, one fused L2-Adam launch
+                (no autograd graph, no per-parameter optimiser loop).
+* `evaluate` -- K1/K2 forward on un-replicated rows + K3 MSE; `evaluate_member_mse` reduces on device to
+                the [E] vector elite selection needs.
+* `query`    -- all-member forward on un-replicated rows (the reference repeats the input E times).
+
+Deliberate differences from the reference: a learned termination mech trains on `batch_done`
+(the reference raises KeyError 'batch_terminal').
+"""
+import abc
+import collections
+import copy
+import itertools
+import pathlib
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .mlp import EnsembleMLP
+from .optim import FusedAdamL2
+from .reward_mech import BaseRewardMech
+from .termination_mech import BaseTerminationMech
+from .transition import BaseTransition
+from .transition_iterator import BootstrapIterator, TransitionIterator
+from .types import InteractionBatch
+from .util import to_tensor
+
+
+def split_dict(old_dict: Dict, need_keys: List[str]):
+    return dict([(key, old_dict[key]) for key in need_keys])
+
+
+class BaseDynamics:
+    _MECH_TO_VARIABLE = {
+        "transition": "batch_next_obs",
+        "reward_mech": "batch_reward",
+        "termination_mech": "batch_terminal",
+    }
+    _VARIABLE_TO_MECH = dict([(value, key) for key, value in _MECH_TO_VARIABLE.items()])
+
+    def __init__(
+        self,
+        transition: BaseTransition,
+        learned_reward: bool = True,
+        reward_mech: Optional[BaseRewardMech] = None,
+        learned_termination: bool = False,
+        termination_mech: Optional[BaseTerminationMech] = None,
+        optim_lr: float = 1e-4,
+        weight_decay: float = 1e-5,
+        optim_eps: float = 1e-8,
+        logger=None,
+    ):
+        super(BaseDynamics, self).__init__()
+        self.transition = transition
+        self.learned_reward = learned_reward
+        self.reward_mech = reward_mech
+        self.learned_termination = learned_termination
+        self.termination_mech = termination_mech
+
+        self.optim_lr = optim_lr
+        self.weight_decay = weight_decay
+        self.optim_eps = optim_eps
+        self.logger = logger
+
+        self.device = self.transition.device
+        self.ensemble_num = self.transition.ensemble_num
+
+        self.learn_mech = ["transition"]
+        self.transition_optimizer = self._make_optimizer(self.transition)
+        if self.learned_reward:
+            self.reward_mech_optimizer = self._make_optimizer(self.reward_mech)
+            self.learn_mech.append("reward_mech")
+        if self.learned_termination:
+            self.termination_mech_optimizer = self._make_optimizer(self.termination_mech)
+            self.learn_mech.append("termination_mech")
+
+        self.total_epoch = {}
+        for mech in self.learn_mech:
+            self.total_epoch[mech] = 0
+
+        # data-parallel training (optional): torch.distributed process group + this rank's row slice
+        self.dp_group = None
+
+    def _make_optimizer(self, model):
+        return FusedAdamL2(model, lr=self.optim_lr, weight_decay=self.weight_decay, eps=self.optim_eps)
+
+    @abc.abstractmethod
+    def learn(self, replay_buffer, **kwargs):
+        pass
+
+    # ------------------------------------------------------------------ "single batch data" helpers
+    def get_3d_tensor(self, data: Union[np.ndarray, torch.Tensor], is_ensemble: bool):
+        """[E,B,D] device tensor.  Non-ensemble data is broadcast over members as a stride-0 view instead of
+        the reference's physical `repeat([E,1,1])` (base_dynamics.py:90-100)."""
+        if isinstance(data, np.ndarray):
+            data = torch.from_numpy(data)
+        if data.dtype != torch.float32:
+            data = data.to(torch.float32)
+        if is_ensemble:
+            if data.ndim == 2:  # reward or terminal
+                data = data.unsqueeze(data.ndim)
+            return data.to(self.device)
+        if data.ndim == 1:  # reward or terminal
+            data = data.unsqueeze(data.ndim)
+        return data.to(self.device).unsqueeze(0).expand(self.ensemble_num, -1, -1)
+
+    def _batch_variable(self, batch: InteractionBatch, variable: str):
+        if variable == "batch_terminal":  # reference quirk 1: InteractionBatch calls it batch_done
+            return batch.batch_done
+        return getattr(batch, variable)
+
+    def get_mech_loss(self, batch: InteractionBatch, mech: str = "transition", loss_type: str = "default",
+                      is_ensemble: bool = False):  # fmt: skip
+        model = getattr(self, mech)
+        model_in = {
+            "batch_obs": self.get_3d_tensor(batch.batch_obs, is_ensemble=is_ensemble),
+            "batch_action": self.get_3d_tensor(batch.batch_action, is_ensemble=is_ensemble),
+        }
+        if loss_type == "default":
+            loss_type = "mse" if model.deterministic else "nll"
+        target = self.get_3d_tensor(self._batch_variable(batch, self._MECH_TO_VARIABLE[mech]), is_ensemble=is_ensemble)
+        get_loss = getattr(model, "get_{}_loss".format(loss_type))
+        return get_loss(model_in, target)
+
+    # ------------------------------------------------------------------ "replay buffer" helper
+    def dataset_split(self, replay_buffer, validation_ratio: float = 0.2, batch_size: int = 256,
+                      shuffle_each_epoch: bool = True, bootstrap_permutes: bool = False,
+                      ) -> Tuple[TransitionIterator, Optional[TransitionIterator]]:  # fmt: skip
+        size = replay_buffer.buffer_size if replay_buffer.full else replay_buffer.pos
+        data = InteractionBatch(
+            replay_buffer.observations[:size, 0].astype(np.float32),
+            replay_buffer.actions[:size, 0],
+            replay_buffer.next_observations[:size, 0].astype(np.float32),
+            replay_buffer.rewards[:size, 0],
+            replay_buffer.dones[:size, 0],
+        )
+        val_size = int(len(data) * validation_ratio)
+        train_size = len(data) - val_size
+        train_iter = BootstrapIterator(data[:train_size], batch_size, self.ensemble_num,
+                                       shuffle_each_epoch=shuffle_each_epoch, permute_indices=bootstrap_permutes)  # fmt: skip
+        val_iter = None
+        if val_size > 0:
+            val_iter = TransitionIterator(data[train_size:], batch_size, shuffle_each_epoch=False)
+        return train_iter, val_iter
+
+    # ------------------------------------------------------------------ "dataset" helpers
+    def evaluate(self, dataset: TransitionIterator, mech: str = "transition"):
+        """Hold-out MSE, un-reduced: [E, N_val, D] on the CPU like base_dynamics.py:159-171."""
+        assert not isinstance(dataset, BootstrapIterator)
+        batch_loss_list = []
+        with torch.no_grad():
+            for batch in dataset:
+                batch_loss_list.append(self.get_mech_loss(batch, mech=mech, loss_type="mse", is_ensemble=False))
+        return torch.cat(batch_loss_list, dim=batch_loss_list[0].ndim - 2).cpu()
+
+    def evaluate_member_mse(self, dataset: TransitionIterator, mech: str = "transition", chunk: int = 65536):
+        """`evaluate(...).mean(dim=(1, 2))` -> [E] without materialising the [E,N,D] loss: the whole hold-out
+        set goes through the forward kernels in large chunks and K3 reduces per member on the device (fp64)."""
+        assert not isinstance(dataset, BootstrapIterator)
+        model = getattr(self, mech)
+        data = dataset.transitions
+        target_np = self._batch_variable(data, self._MECH_TO_VARIABLE[mech])
+        sums = torch.zeros(self.ensemble_num, device=self.device, dtype=torch.float64)
+        n, d = len(data), 1
+        with torch.no_grad():
+            for s in range(0, n, chunk):
+                sl = slice(s, min(n, s + chunk))
+                obs = self.get_3d_tensor(data.batch_obs[sl], is_ensemble=False)
+                act = self.get_3d_tensor(data.batch_action[sl], is_ensemble=False)
+                target = self.get_3d_tensor(target_np[sl], is_ensemble=False)
+                mean, _ = model.forward(obs, act)
+                d = mean.shape[-1]
+                ops.mse_member_sums(mean, target, sums)
+        return (sums / float(n * d)).to(torch.float32).cpu()
+
+    def train_step(self, mech: str, obs: torch.Tensor, act: torch.Tensor, target: torch.Tensor,
+                   want_loss: bool = True, grad_rows: Optional[int] = None):  # fmt: skip
+        """One optimiser step on an ensemble batch (obs/act/target: [E,B,*] device tensors), equivalent to
+        `loss = get_nll_loss(...); zero_grad(); loss.mean().backward(); step()` (base_dynamics.py:181-186).
+        Returns the un-reduced loss [E,B,D] (None if not wanted).  grad_rows: global rows per member when the
+        batch is one shard of a data-parallel step."""
+        model = getattr(self, mech)
+        optim = getattr(self, "{}_optimizer".format(mech))
+        if model.deterministic or any(p.requires_grad for p in model._bounds() if p is not None):
+            # uncommon configurations go through the autograd nodes (same kernels)
+            loss = (model.get_mse_loss if model.deterministic else model.get_nll_loss)(
+                {"batch_obs": obs, "batch_action": act}, target)  # fmt: skip
+            optim.zero_grad()
+            loss.mean().backward()
+            self._sync_grads(model)
+            optim.step()
+            return loss.detach()
+        E, B = obs.shape[0], obs.shape[1]
+        flat, flat_grad = model.flat_parameters()
+        params = model._stack_params()
+        L = model.num_layers
+        kind = model._act_kind
+        mask = model._kernel_mask()
+        mask_str = ops.mask_strides(mask, model._parallel_num(), E, B) if mask is not None else (0, 0, 0)
+        obs_c, act_c = obs.contiguous(), act.contiguous()
+        x = ops.gather_inputs(obs_c.view(E * B, -1), act_c.view(E * B, -1), None).view(E, B, -1)
+        hs, zs, h = [x], [], x
+        for i in range(L):
+            h, z = ops.ens_linear_fwd(h, params[2 * i], params[2 * i + 1], kind, mask if i == 0 else None, mask_str,
+                                      want_z=True)  # fmt: skip
+            hs.append(h)
+            zs.append(z)
+        raw = ops.ens_linear_fwd(h, params[2 * L], params[2 * L + 1], ops.ACT_IDENTITY)
+        mn, mx = model._bounds()
+        D = model._head_dim
+        mean, logvar = ops.gaussian_head_fwd(raw, model._head_layout, E, B, D, obs_c if model._residual() else None,
+                                             mn, mx)  # fmt: skip
+        loss = ops.nll_loss_fwd(mean, logvar, target, model._nll_reg()) if want_loss else None
+        rows = B if grad_rows is None else grad_rows
+        g_mean, g_logvar = ops.nll_loss_bwd(mean, logvar, target, g_scalar=1.0 / float(E * rows * D))
+        dz = ops.gaussian_head_bwd(raw, model._head_layout, E, B, D, mn, mx, g_mean, g_logvar)
+        for i in range(L, -1, -1):
+            w, b = params[2 * i], params[2 * i + 1]
+            h_in = hs[i]
+            if i == 0 and h_in.dim() < w.dim():
+                h_in = h_in.expand(tuple(w.shape[:-2]) + tuple(h_in.shape[-2:]))
+            ops.ens_linear_bwd_dw(h_in, dz, w.shape, mask if i == 0 else None, mask_str, dw=w.grad, db=b.grad)
+            if i > 0:
+                dz = ops.ens_linear_bwd_dx(dz, w, zs[i - 1], kind)
+        self._sync_grads(model)
+        optim.step()
+        return loss
+
+    def _sync_grads(self, model):
+        """Data-parallel gradient exchange: one NCCL all-reduce (sum) over the flat gradient arena."""
+        if self.dp_group is not None:
+            import torch.distributed as dist
+
+            _, flat_grad = model.flat_parameters()
+            dist.all_reduce(flat_grad[: model._n_trainable], op=dist.ReduceOp.SUM, group=self.dp_group)
+
+    def train(self, dataset: TransitionIterator, mech: str = "transition"):
+        """One pass over the bootstrap iterator; returns the un-reduced train loss [E, N_train, D] on the CPU
+        like base_dynamics.py:173-188."""
+        assert isinstance(dataset, BootstrapIterator)
+        variable = self._MECH_TO_VARIABLE[mech]
+        batch_loss_list = []
+        for batch in dataset:
+            obs = self.get_3d_tensor(batch.batch_obs, is_ensemble=True)
+            act = self.get_3d_tensor(batch.batch_action, is_ensemble=True)
+            target = self.get_3d_tensor(self._batch_variable(batch, variable), is_ensemble=True)
+            batch_loss_list.append(self.train_step(mech, obs, act, target))
+        return torch.cat(batch_loss_list, dim=batch_loss_list[0].ndim - 2).detach().cpu()
+
+    def query(self, obs, action, return_as_np=True):
+        """All-member prediction: variable -> {"mean", "logvar"} as [E,B,D] (base_dynamics.py:190-204)."""
+        result = collections.defaultdict(dict)
+        obs = self.get_3d_tensor(obs, is_ensemble=False)
+        action = self.get_3d_tensor(action, is_ensemble=False)
+        for mech in self.learn_mech:
+            with torch.no_grad():
+                mean, logvar = getattr(self, "{}".format(mech)).forward(obs, action)
+            variable = self.get_variable_by_mech(mech)
+            if return_as_np:
+                result[variable]["mean"] = mean.cpu().numpy()
+                result[variable]["logvar"] = logvar.cpu().numpy()
+            else:
+                result[variable]["mean"] = mean.cpu()
+                result[variable]["logvar"] = logvar.cpu()
+        return result
+
+    # ------------------------------------------------------------------ other helpers
+    def save(self, save_dir: Union[str, pathlib.Path]):
+        for mech in self.learn_mech:
+            getattr(self, mech).save(save_dir=save_dir)
+
+    def load(self, load_dir: Union[str, pathlib.Path], load_device: Optional[str] = None):
+        for mech in self.learn_mech:
+            getattr(self, mech).load(load_dir=load_dir, load_device=load_device)
+
+    def get_variable_by_mech(self, mech: str) -> str:
+        assert mech in self._MECH_TO_VARIABLE
+        return self._MECH_TO_VARIABLE[mech]
+
+    def get_mach_by_variable(self, variable: str) -> str:
+        assert variable in self._VARIABLE_TO_MECH
+        return self._VARIABLE_TO_MECH[variable]
+
+
+class PlainEnsembleDynamics(BaseDynamics):
+    def __init__(
+        self,
+        transition: BaseTransition,
+        learned_reward: bool = True,
+        reward_mech: Optional[BaseRewardMech] = None,
+        learned_termination: bool = False,
+        termination_mech: Optional[BaseTerminationMech] = None,
+        # trainer
+        optim_lr: float = 1e-4,
+        weight_decay: float = 1e-5,
+        optim_eps: float = 1e-8,
+        logger=None,
+    ):
+        super(PlainEnsembleDynamics, self).__init__(
+            transition=transition, learned_reward=learned_reward, reward_mech=reward_mech,
+            learned_termination=learned_termination, termination_mech=termination_mech, optim_lr=optim_lr,
+            weight_decay=weight_decay, optim_eps=optim_eps, logger=logger,
+        )  # fmt: skip
+
+    def _before_mech(self, mech: str):
+        pass
+
+    def _val_loss(self, val_dataset, mech):
+        """[E] hold-out MSE = evaluate(...).mean(dim=(1,2)) (plain_dynamics.py:74,82), reduced on the device."""
+        return self.evaluate_member_mse(val_dataset, mech=mech)
+
+    def learn(
+        self,
+        # data
+        replay_buffer,
+        # dataset split
+        validation_ratio: float = 0.2,
+        batch_size: int = 256,
+        shuffle_each_epoch: bool = True,
+        bootstrap_permutes: bool = False,
+        # model learning
+        longest_epoch: int = -1,
+        improvement_threshold: float = 0.1,
+        patience: int = 5,
+        work_dir: Optional[Union[str, pathlib.Path]] = None,
+        # other
+        **kwargs
+    ):
+        """Early-stopped training of every learned mechanism, then elite selection by best hold-out MSE
+        (plain_dynamics.py:44-111)."""
+        train_dataset, val_dataset = self.dataset_split(replay_buffer, validation_ratio, batch_size,
+                                                        shuffle_each_epoch, bootstrap_permutes)  # fmt: skip
+        for mech in self.learn_mech:
+            self._before_mech(mech)
+            best_weights: Optional[Dict] = None
+            epoch_iter = range(longest_epoch) if (longest_epoch is not None and longest_epoch > 0) else itertools.count()
+            epochs_since_update = 0
+
+            best_val_loss = self._val_loss(val_dataset, mech)
+
+            for epoch in epoch_iter:
+                train_loss = self.train(train_dataset, mech=mech)
+                val_loss = self._val_loss(val_dataset, mech)
+
+                maybe_best_weights = self.maybe_get_best_weights(best_val_loss, val_loss, mech, improvement_threshold)
+                if maybe_best_weights:
+                    best_val_loss = torch.minimum(best_val_loss, val_loss)
+                    best_weights = maybe_best_weights
+                    epochs_since_update = 0
+                else:
+                    epochs_since_update += 1
+
+                self.total_epoch[mech] += 1
+                if self.logger is not None:
+                    self.logger.record("{}/epoch".format(mech), epoch)
+                    self.logger.record("{}/train_dataset_size".format(mech), train_dataset.num_stored)
+                    self.logger.record("{}/val_dataset_size".format(mech), val_dataset.num_stored)
+                    self.logger.record("{}/train_loss".format(mech), train_loss.mean().item())
+                    self.logger.record("{}/val_loss".format(mech), val_loss.mean().item())
+                    self.logger.record("{}/best_val_loss".format(mech), best_val_loss.mean().item())
+                    self.logger.dump(self.total_epoch[mech])
+
+                if patience and epochs_since_update >= patience:
+                    break
+
+            self.maybe_set_best_weights_and_elite(best_weights, best_val_loss, mech=mech)
+        if work_dir is not None:
+            self.save(work_dir)
+
+    def maybe_get_best_weights(self, best_val_loss: torch.Tensor, val_loss: torch.Tensor, mech: str = "transition",
+                               threshold: float = 0.01):  # fmt: skip
+        """Snapshot of the WHOLE state_dict as soon as any member improved by more than `threshold`
+        (plain_dynamics.py:113-127, quirk 7)."""
+        improvement = (best_val_loss - val_loss) / torch.abs(best_val_loss)
+        if (improvement > threshold).any().item():
+            return copy.deepcopy(getattr(self, mech).state_dict())
+        return None
+
+    def maybe_set_best_weights_and_elite(self, best_weights: Optional[Dict], best_val_loss: torch.Tensor,
+                                         mech: str = "transition"):  # fmt: skip
+        model = getattr(self, mech)
+        assert isinstance(model, EnsembleMLP)
+        if best_weights is not None:
+            model.load_state_dict(best_weights)
+        sorted_indices = np.argsort(best_val_loss.tolist())
+        model.set_elite_members(sorted_indices[: model.elite_num])
+
+
+class ConstraintBasedDynamics(PlainEnsembleDynamics):
+    """PlainEnsembleDynamics whose masked mechanisms get an oracle causal mask before training
+    (constraint_based_dynamics.py:22-183; its CMI-test network is commented out in the reference)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        for mech in self.learn_mech:
+            if hasattr(getattr(self, mech), "input_mask"):
+                setattr(self, "{}_oracle_mask".format(mech), None)
+                setattr(self, "{}_history_mask".format(mech),
+                        torch.ones(getattr(self, mech).input_mask.shape).to(self.device))  # fmt: skip
+
+    def set_oracle_mask(self, mech: str, mask):
+        assert hasattr(self, "{}_oracle_mask".format(mech))
+        setattr(self, "{}_oracle_mask".format(mech), to_tensor(mask))
+
+    def _before_mech(self, mech: str):
+        if hasattr(self, "{}_oracle_mask".format(mech)):
+            getattr(self, mech).set_input_mask(getattr(self, "{}_oracle_mask".format(mech)))
+
+    def learn(self, replay_buffer, validation_ratio: float = 0.2, batch_size: int = 256,
+              shuffle_each_epoch: bool = True, bootstrap_permutes: bool = False, longest_epoch: Optional[int] = None,
+              improvement_threshold: float = 0.1, patience: int = 5,
+              work_dir: Optional[Union[str, pathlib.Path]] = None, **kwargs):  # fmt: skip
+        super().learn(replay_buffer, validation_ratio, batch_size, shuffle_each_epoch, bootstrap_permutes,
+                      longest_epoch, improvement_threshold, patience, None, **kwargs)  # fmt: skip
+        self.save(work_dir)  # the reference saves unconditionally here (constraint_based_dynamics.py:152)

@@ -1,0 +1,392 @@
+"""VecFakeEnv with the reference's interface (cmrl/models/fake_env.py:23-230): a Stable-Baselines3 VecEnv whose
+transitions come from the learned ensemble dynamics.  Observations, episode lengths and the model stay resident on
+the GPU; one `step_wait` is a fixed sequence of libcmrl_b200 launches:
+
+    member draw (+ Gaussian noise) -> bucket envs by member -> gather inputs -> K1 layers on the SELECTED member's
+    rows only -> head + sampling + scatter -> (reward / termination mechs likewise) -> step tail
+
+The reference evaluates all E members for every env and then indexes one (fake_env.py:195-215); evaluating only the
+drawn member gives identical outputs (rows are independent) at 1/E of the FLOPs.  With `penalty_coeff != 0` the MOPO
+penalty needs every member's mean, so the transition takes the all-member path.
+
+Extra (non-reference) attributes, all optional:
+    rng_mode     "numpy"  (default): member choice and noise drawn by `self.generator` in the reference's order --
+                           bit-exact member choice / done flags against the reference for the same seed;
+                 "device": Philox draws on the GPU (statistically equivalent, no host RNG work).
+    infos_mode   "dicts"  (default): one fresh dict per env like the reference;
+                 "shared": envs that are neither done nor truncated share one read-only dict (O(#done) host work).
+"""
+from typing import Any, Dict, List, Optional, Type
+
+import numpy as np
+import torch
+
+from . import ops
+
+try:  # the real SB3 base class when it is installed; an interface-compatible stand-in otherwise
+    from stable_baselines3.common.vec_env.base_vec_env import VecEnv
+except Exception:  # pragma: no cover - SB3 is absent in the build image
+
+    class VecEnv:  # type: ignore
+        def __init__(self, num_envs, observation_space, action_space):
+            self.num_envs = num_envs
+            self.observation_space = observation_space
+            self.action_space = action_space
+
+        def step(self, actions):
+            self.step_async(actions)
+            return self.step_wait()
+
+
+_MECHS = ("transition", "reward_mech", "termination_mech")
+
+
+class VecFakeEnv(VecEnv):
+    def __init__(self, num_envs: int, observation_space, action_space):
+        super(VecFakeEnv, self).__init__(num_envs=num_envs, observation_space=observation_space, action_space=action_space)
+        self.has_set_up = False
+
+        self.penalty_coeff = None
+        self.deterministic = None
+        self.max_episode_steps = None
+
+        self.dynamics = None
+        self.reward_fn = None
+        self.termination_fn = None
+        self.learned_reward = None
+        self.learned_termination = None
+        self.get_init_obs_fn = None
+        self.replay_buffer = None
+        self.generator = np.random.default_rng()
+        self.device = None
+        self.logger = None
+
+        self._current_batch_obs = None
+        self._current_batch_action = None
+        self._reset_by_buffer = True
+
+        # B200-side knobs and state
+        self.rng_mode = "numpy"
+        self.infos_mode = "dicts"
+        self.init_obs_pool_size = None  # device rng_mode + get_init_obs_fn: size of the pre-drawn reset pool
+        self._device_seed = 0
+        self._draw_counter = 0
+        self._obs_dev = None
+        self._env_len_dev = None
+        self._pool_dev = None
+        self._pool_rows = 0
+        self._bufs = None
+
+    # ------------------------------------------------------------------ set-up (fake_env.py:60-92)
+    def set_up(self, dynamics, reward_fn=None, termination_fn=None, get_init_obs_fn=None, real_replay_buffer=None,
+               penalty_coeff: float = 0.0, deterministic=False, max_episode_steps=1000, logger=None):  # fmt: skip
+        self.dynamics = dynamics
+        self.penalty_coeff = penalty_coeff
+        self.deterministic = deterministic
+        self.max_episode_steps = max_episode_steps
+
+        self.reward_fn = reward_fn
+        self.termination_fn = termination_fn
+        assert self.dynamics.learned_reward or reward_fn
+        assert self.dynamics.learned_termination or termination_fn
+        self.learned_reward = self.dynamics.learned_reward
+        self.learned_termination = self.dynamics.learned_termination
+        self.get_init_obs_fn = get_init_obs_fn
+        self.replay_buffer = real_replay_buffer
+        self.logger = logger
+
+        assert self.get_init_obs_fn or self.replay_buffer
+        self._reset_by_buffer = self.replay_buffer is not None
+
+        self.device = dynamics.device
+        self.has_set_up = True
+        self._alloc()
+
+    def _alloc(self):
+        N, dev = self.num_envs, self.device
+        tr = self.dynamics.transition
+        O, A = tr.obs_size, tr.action_size
+        b = {}
+        b["act"] = torch.empty((N, A), device=dev, dtype=torch.float32)
+        b["act_pin"] = torch.empty((N, A), dtype=torch.float32).pin_memory()
+        b["next_obs"] = torch.empty((N, O), device=dev, dtype=torch.float32)
+        b["reward"] = torch.empty((N, 1), device=dev, dtype=torch.float32)
+        b["terminal"] = torch.empty((N, 1), device=dev, dtype=torch.float32)
+        b["reward_out"] = torch.empty(N, device=dev, dtype=torch.float32)
+        b["done"] = torch.empty(N, device=dev, dtype=torch.uint8)
+        b["trunc"] = torch.empty(N, device=dev, dtype=torch.uint8)
+        b["term_obs"] = torch.empty((N, O), device=dev, dtype=torch.float32)
+        b["n_done"] = torch.zeros(1, device=dev, dtype=torch.int32)
+        b["perm"] = torch.empty(N, device=dev, dtype=torch.int32)
+        E = self.dynamics.ensemble_num
+        b["offsets"] = torch.empty(E + 1, device=dev, dtype=torch.int32)
+        b["counters"] = torch.empty(2 * (E + 1), device=dev, dtype=torch.int32)
+        # pinned host mirrors for the per-step device->host read of the SB3 return values
+        b["h_obs"] = torch.empty((N, O), dtype=torch.float32).pin_memory()
+        b["h_term_obs"] = torch.empty((N, O), dtype=torch.float32).pin_memory()
+        b["h_reward"] = torch.empty(N, dtype=torch.float32).pin_memory()
+        b["h_done"] = torch.empty(N, dtype=torch.uint8).pin_memory()
+        b["h_trunc"] = torch.empty(N, dtype=torch.uint8).pin_memory()
+        self._bufs = b
+        self._obs_dev = torch.zeros((N, O), device=dev, dtype=torch.float32)
+        self._env_len_dev = torch.zeros(N, device=dev, dtype=torch.int32)
+        self._elite_cache = {}
+
+    @property
+    def _envs_length(self):
+        if self._env_len_dev is None:
+            return np.zeros(self.num_envs, dtype=int)
+        return self._env_len_dev.cpu().numpy().astype(int)
+
+    @_envs_length.setter
+    def _envs_length(self, value):
+        if self._env_len_dev is not None:
+            self._env_len_dev.copy_(torch.as_tensor(np.asarray(value), dtype=torch.int32))
+
+    # ------------------------------------------------------------------ stepping (fake_env.py:94-142)
+    def step_async(self, actions: np.ndarray) -> None:
+        self._current_batch_action = actions
+
+    def _elite_u8(self, mech):
+        model = getattr(self.dynamics, mech)
+        key = tuple(int(e) for e in model.elite_members)
+        cached = self._elite_cache.get(mech)
+        if cached is None or cached[0] != key:
+            cached = (key, torch.tensor(key, dtype=torch.uint8, device=self.device))
+            self._elite_cache[mech] = cached
+        return cached[1]
+
+    def _draw(self, mech, D):
+        """Member index [N] (uint8, device) and N(0,1) noise [N,D] (device) for one mechanism, consuming
+        `self.generator` exactly like get_dynamics_predict (fake_env.py:205-214) in numpy mode."""
+        N = self.num_envs
+        model = getattr(self.dynamics, mech)
+        if self.rng_mode == "numpy":
+            idx = model.get_random_index(N, self.generator)
+            idx_dev = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.uint8)).to(self.device, non_blocking=True)
+            noise_dev = None
+            if not self.deterministic:
+                noise = self.generator.normal(size=(N, D)).astype(np.float32)
+                noise_dev = torch.from_numpy(noise).to(self.device, non_blocking=True)
+            return idx_dev, noise_dev
+        if self.rng_mode == "device":
+            self._draw_counter += 1
+            return ops.draw_member_noise(self._device_seed, self._draw_counter, N, self._elite_u8(mech), D,
+                                         want_noise=not self.deterministic)  # fmt: skip
+        raise ValueError("rng_mode must be 'numpy' or 'device'")
+
+    def _predict(self, mech, obs, act, all_member_out=None):
+        """next value of `mech`'s variable for every env: [N,D] device tensor."""
+        model = getattr(self.dynamics, mech)
+        N, D = self.num_envs, model._head_dim
+        idx, noise = self._draw(mech, D)
+        mask = model._kernel_mask()
+        per_sample_mask = mask is not None and (mask.dim() == 4 or (mask.dim() == 3 and mask.shape[1] != model.ensemble_num))
+        if all_member_out is not None or per_sample_mask:
+            with torch.no_grad():
+                mean, logvar = model.forward(obs.unsqueeze(0), act.unsqueeze(0))
+            if all_member_out is not None:
+                all_member_out["mean"] = mean
+            return ops.select_sample(mean, logvar, idx, noise)
+        return self.predict_selected(model, obs, act, idx, noise)
+
+    def predict_selected(self, model, obs, act, idx, noise):
+        """Selected-member evaluation: bucket envs by drawn member, run the MLP on each member's rows only."""
+        b = self._bufs
+        N, D, E = obs.shape[0], model._head_dim, model.ensemble_num
+        perm, offsets = ops.member_bucket(idx, E, b["perm"], b["offsets"], b["counters"])
+        h = ops.gather_inputs(obs, act, perm)
+        params = model._stack_params()
+        L = model.num_layers
+        mask = model._kernel_mask()
+        mask_str = ops.mask_strides(mask, model._parallel_num(), E, N) if mask is not None else (0, 0, 0)
+        for i in range(L):
+            h = ops.ens_linear_fwd(h, params[2 * i], params[2 * i + 1], model._act_kind, mask if i == 0 else None,
+                                   mask_str, row_offsets=offsets)  # fmt: skip
+        raw = ops.ens_linear_fwd(h, params[2 * L], params[2 * L + 1], ops.ACT_IDENTITY, row_offsets=offsets)
+        mn, mx = model._bounds()
+        return ops.sample_scatter(raw, model._head_layout, perm, N, D, obs if model._residual() else None, mn, mx, noise)
+
+    def step_wait(self):
+        assert self.has_set_up, "fake-env has not set up"
+        assert len(self._current_batch_action.shape) == 2  # batch, action_dim
+        b = self._bufs
+        N = self.num_envs
+        obs = self._obs_dev
+        b["act_pin"].copy_(torch.from_numpy(np.ascontiguousarray(self._current_batch_action, dtype=np.float32)))
+        act = b["act"]
+        act.copy_(b["act_pin"], non_blocking=True)
+
+        need_all = self.penalty_coeff != 0
+        all_out = {} if need_all else None
+        next_obs = self._predict("transition", obs, act, all_out)
+        host_obs = host_next = None
+        if self.learned_reward:
+            reward = self._predict("reward_mech", obs, act)
+        else:
+            host_next, host_obs = next_obs.cpu().numpy(), self._current_batch_obs
+            r = np.asarray(self.reward_fn(host_next, host_obs, self._current_batch_action), dtype=np.float32)
+            reward = torch.from_numpy(r.reshape(N, 1)).to(self.device)
+        terminal_f = terminal_u8 = None
+        if self.learned_termination:
+            terminal_f = self._predict("termination_mech", obs, act)
+        else:
+            if host_next is None:
+                host_next, host_obs = next_obs.cpu().numpy(), self._current_batch_obs
+            t = np.asarray(self.termination_fn(host_next, host_obs, self._current_batch_action))
+            terminal_u8 = torch.from_numpy(np.ascontiguousarray(t.reshape(N) != 0, dtype=np.uint8)).to(self.device)
+
+        penalty = None
+        if need_all:
+            penalty = ops.mopo_penalty(all_out["mean"])
+            if self.logger is not None:
+                self.logger.record_mean("rollout/penalty", penalty.mean().item())
+
+        device_reset = self.rng_mode == "device"
+        reset_rows = reset_index = None
+        if device_reset:
+            reset_rows, reset_index = self._device_reset_source()
+        ops.env_step_tail(next_obs, reward, terminal_f, terminal_u8, penalty, self.penalty_coeff, self._env_len_dev,
+                          self.max_episode_steps, reset_rows, reset_index, obs, b["reward_out"], b["done"], b["trunc"],
+                          b["term_obs"], None)  # fmt: skip
+
+        # ---- device -> host: the SB3 return values ------------------------------------------------------
+        b["h_term_obs"].copy_(b["term_obs"], non_blocking=True)
+        b["h_reward"].copy_(b["reward_out"], non_blocking=True)
+        b["h_done"].copy_(b["done"], non_blocking=True)
+        b["h_trunc"].copy_(b["trunc"], non_blocking=True)
+        if device_reset:
+            b["h_obs"].copy_(obs, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        batch_done = b["h_done"].numpy().astype(bool)
+        batch_truncate = b["h_trunc"].numpy().astype(bool)
+        batch_next_obs = b["h_term_obs"].numpy()
+        batch_reward = b["h_reward"].numpy()
+        done_idx = np.nonzero(batch_done)[0]
+        if device_reset:
+            self._current_batch_obs = b["h_obs"].numpy().copy()
+        else:
+            # host reset in the reference's order (ascending env index; fake_env.py:131-135,171-181)
+            self._current_batch_obs = batch_next_obs.copy()
+            if done_idx.size:
+                rows = self._host_reset_rows(done_idx.size)
+                self._current_batch_obs[done_idx] = rows
+                di = torch.from_numpy(done_idx).to(self.device)
+                obs.index_copy_(0, di, torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)).to(self.device))
+
+        infos = self._make_infos(batch_truncate, done_idx, batch_next_obs)
+        return self._current_batch_obs.copy(), batch_reward.copy(), batch_done.copy(), infos
+
+    def _make_infos(self, batch_truncate, done_idx, batch_next_obs):
+        N = self.num_envs
+        if self.infos_mode == "shared":
+            shared = {"TimeLimit.truncated": np.False_}
+            infos = [shared] * N
+            for i in np.nonzero(batch_truncate)[0]:
+                infos[i] = {"TimeLimit.truncated": np.True_}
+            for i in done_idx:
+                infos[i] = {"TimeLimit.truncated": batch_truncate[i], "terminal_observation": batch_next_obs[i].copy()}
+            return infos
+        infos = [{"TimeLimit.truncated": t} for t in batch_truncate]
+        for i in done_idx:
+            infos[i]["terminal_observation"] = batch_next_obs[i].copy()
+        return infos
+
+    # ------------------------------------------------------------------ resets (fake_env.py:144-181)
+    def _upper_bound(self):
+        return self.replay_buffer.buffer_size if self.replay_buffer.full else self.replay_buffer.pos
+
+    def _host_reset_rows(self, n):
+        """n reset observations in the reference's draw order: one global `np.random.randint` per done env
+        (buffer resets), or `get_init_obs_fn` (one batched call of size n instead of n calls of size 1)."""
+        if self._reset_by_buffer:
+            upper_bound = self._upper_bound()
+            inds = np.array([np.random.randint(0, upper_bound) for _ in range(n)], dtype=np.int64)
+            return self.replay_buffer.observations[inds, 0]
+        assert self.get_init_obs_fn is not None
+        return np.asarray(self.get_init_obs_fn(n)).reshape(n, -1)
+
+    def _device_reset_source(self):
+        """(rows [R,O] device, reset_index [N] device) for the fused tail in device rng_mode."""
+        N = self.num_envs
+        if self._reset_by_buffer:
+            ub = self._upper_bound()
+            if self._pool_dev is None or self._pool_rows != ub:
+                rows = np.ascontiguousarray(self.replay_buffer.observations[:ub, 0], dtype=np.float32)
+                self._pool_dev, self._pool_rows = torch.from_numpy(rows).to(self.device), ub
+        else:
+            size = self.init_obs_pool_size or max(4096, N)
+            if self._pool_dev is None or self._pool_rows != size:
+                rows = np.ascontiguousarray(np.asarray(self.get_init_obs_fn(size)).reshape(size, -1), dtype=np.float32)
+                self._pool_dev, self._pool_rows = torch.from_numpy(rows).to(self.device), size
+        self._draw_counter += 1
+        idx = ops.draw_uniform_index(self._device_seed, self._draw_counter, N, self._pool_rows, self.device)
+        return self._pool_dev, idx
+
+    def reset(self, *, seed: Optional[int] = None, return_info: bool = False, options: Optional[dict] = None):
+        if self.has_set_up:
+            if self._reset_by_buffer:
+                upper_bound = self._upper_bound()
+                batch_inds = np.random.randint(0, upper_bound, size=self.num_envs)
+                self._current_batch_obs = self.replay_buffer.observations[batch_inds, 0]
+            else:
+                self._current_batch_obs = self.get_init_obs_fn(self.num_envs)
+            self._current_batch_obs = np.ascontiguousarray(self._current_batch_obs, dtype=np.float32)
+            self._obs_dev.copy_(torch.from_numpy(self._current_batch_obs))
+            self._env_len_dev.zero_()
+            return self._current_batch_obs.copy()
+
+    def seed(self, seed: Optional[int] = None):
+        self.generator = np.random.default_rng(seed=seed)
+        self._device_seed = 0 if seed is None else int(seed)
+        self._draw_counter = 0
+
+    def close(self) -> None:
+        pass
+
+    def env_is_wrapped(self, wrapper_class: Type, indices=None) -> List[bool]:
+        return [False for _ in range(self.num_envs)]
+
+    def single_reset(self, idx):
+        assert self.has_set_up, "fake-env has not set up"
+        self._env_len_dev[idx] = 0
+        row = np.asarray(self._host_reset_rows(1), dtype=np.float32).reshape(-1)
+        self._current_batch_obs[idx] = row
+        self._obs_dev[idx] = torch.from_numpy(row).to(self.device)
+
+    def render(self, mode="human"):
+        raise NotImplementedError
+
+    @staticmethod
+    def get_penalty(ensemble_batch_next_obs):
+        """MOPO max-disagreement penalty (fake_env.py:186-193) on the K5 kernel; accepts [E,N,O] numpy or tensor."""
+        t = torch.as_tensor(ensemble_batch_next_obs, dtype=torch.float32)
+        was_np = not isinstance(ensemble_batch_next_obs, torch.Tensor)
+        if not t.is_cuda:
+            t = t.cuda()
+        pen = ops.mopo_penalty(t)
+        return pen.cpu().numpy() if was_np else pen
+
+    def get_dynamics_predict(self, origin_predict: Dict, mech: str, deterministic: bool = False):
+        """Reference-compatible entry (fake_env.py:195-215): sample one elite member per env from a `query` result
+        ([E,N,D] numpy mean / logvar) with `self.generator`; the gather + sampling runs on the K5 kernel."""
+        variable = self.dynamics.get_variable_by_mech(mech)
+        ensemble_mean, ensemble_logvar = origin_predict[variable]["mean"], origin_predict[variable]["logvar"]
+        batch_size = ensemble_mean.shape[1]
+        random_index = getattr(self.dynamics, mech).get_random_index(batch_size, self.generator)
+        idx = torch.from_numpy(np.ascontiguousarray(random_index, dtype=np.uint8)).to(self.device)
+        mean = torch.as_tensor(ensemble_mean, dtype=torch.float32).to(self.device)
+        if deterministic:
+            return ops.select_sample(mean, None, idx, None).cpu().numpy()
+        noise = self.generator.normal(size=ensemble_mean.shape[1:]).astype(np.float32)
+        logvar = torch.as_tensor(ensemble_logvar, dtype=torch.float32).to(self.device)
+        return ops.select_sample(mean, logvar, idx, torch.from_numpy(noise).to(self.device)).cpu().numpy()
+
+    def env_method(self, method_name: str, *method_args, indices=None, **method_kwargs) -> List[Any]:
+        pass
+
+    def get_attr(self, attr_name: str, indices=None) -> List[Any]:
+        pass
+
+    def set_attr(self, attr_name: str, value: Any, indices=None) -> None:
+        pass

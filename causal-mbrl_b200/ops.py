@@ -1,0 +1,295 @@
+"""torch-facing wrappers over the C ABI: pointer/stride extraction and output allocation only.
+
+PyTorch is plumbing here (device memory, streams); every arithmetic op below is a kernel of
+libcmrl_b200.so launched on torch's current CUDA stream.
+"""
+import torch
+
+from . import _lib
+from ._lib import ACT_IDENTITY, ACT_RELU, ACT_SILU, HEAD_PARALLEL, HEAD_PLAIN  # noqa: F401
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.CmrlB200Error(
+            "%s must be a CUDA tensor: cmrl_b200 runs on sm_100a kernels only, there is no CPU path" % name
+        )
+    if t.dtype != dtype:
+        raise _lib.CmrlB200Error("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _rows_contig(x, name):
+    """x[..., B, C] with dense rows; leading dims may be broadcast (stride 0)."""
+    if x.stride(-1) != 1 or (x.shape[-2] > 1 and x.stride(-2) != x.shape[-1]):
+        x = x.contiguous()
+    return x
+
+
+def _lead_strides(x):
+    s_e = x.stride(-3) if x.dim() >= 3 and x.shape[-3] > 1 else 0
+    s_p = x.stride(-4) if x.dim() >= 4 and x.shape[-4] > 1 else 0
+    return s_p, s_e
+
+
+def mask_strides(mask, P, E, B):
+    """Resolve the four mask shapes of ExternalMaskTransition.mask_input
+    (external_mask_transition.py:116-139) to element strides (m_sp, m_se, m_sb)."""
+    in_size = mask.shape[-1]
+    if mask.dim() == 2:
+        return in_size, 0, 0
+    if mask.dim() == 3:
+        if mask.shape[1] == E:  # [P,E,in]  (ensemble reading wins when E == B, reference quirk 5)
+            return E * in_size, in_size, 0
+        if mask.shape[1] == B:  # [P,B,in]
+            return B * in_size, 0, in_size
+        raise RuntimeError("input mask shape %a does not match x shape %a" % (tuple(mask.shape), (P, E, B, in_size)))
+    if mask.dim() == 4:
+        assert tuple(mask.shape[:3]) == (P, E, B)
+        return E * B * in_size, B * in_size, in_size
+    raise AssertionError("input mask must have 2..4 dims")
+
+
+def ens_linear_fwd(x, w, b, act=ACT_IDENTITY, mask=None, mask_str=(0, 0, 0), want_z=False, row_offsets=None):
+    """y = act((x*mask) @ w + b).  w: [E,in,out] or [P,E,in,out]; x: [B,in] | [E,B,in] | [P,E,B,in]
+    (broadcast dims allowed).  Ragged mode: x [N,in] flat + int32 row_offsets [E+1] -> y [N,out] / [P,N,out]."""
+    _req(x, "x"), _req(w, "weight")
+    parallel = w.dim() == 4
+    P = w.shape[0] if parallel else 1
+    E, in_size, out_size = w.shape[-3], w.shape[-2], w.shape[-1]
+    w = w.contiguous()
+    if b is not None:
+        b = _req(b, "bias").contiguous()
+    x = _rows_contig(x, "x")
+    assert x.shape[-1] == in_size, "x last dim %d != in_size %d" % (x.shape[-1], in_size)
+    B = x.shape[-2]
+    if row_offsets is not None:
+        assert x.dim() == 2 or (parallel and x.dim() == 3 and x.shape[0] == P)
+        x_sp, x_se = (x.stride(0) if x.dim() == 3 else 0), 0
+        out_shape = (P, B, out_size) if parallel else (B, out_size)
+    else:
+        x_sp, x_se = _lead_strides(x)
+        out_shape = (P, E, B, out_size) if parallel else (E, B, out_size)
+    y = torch.empty(out_shape, device=x.device, dtype=torch.float32)
+    z = torch.empty_like(y) if want_z else None
+    if mask is not None:
+        mask = _req(mask, "mask").contiguous()
+    _lib.call(
+        "cmrl_ens_linear_fwd", x.data_ptr(), x_sp, x_se, w.data_ptr(), _ptr(b), y.data_ptr(), _ptr(z), P, E, B,
+        in_size, out_size, _ptr(mask), mask_str[0], mask_str[1], mask_str[2], _ptr(row_offsets), act, _stream(),
+    )  # fmt: skip
+    return (y, z) if want_z else y
+
+
+def ens_linear_bwd_dx(dz, w, z_prev, act_prev):
+    """dx = (dz @ w^T) * act'(z_prev); dz [(P,)E,B,out] dense."""
+    dz = _req(dz, "dz").contiguous()
+    w = w.contiguous()
+    parallel = w.dim() == 4
+    P = w.shape[0] if parallel else 1
+    E, in_size, out_size = w.shape[-3], w.shape[-2], w.shape[-1]
+    B = dz.shape[-2]
+    dx = torch.empty(dz.shape[:-1] + (in_size,), device=dz.device, dtype=torch.float32)
+    if z_prev is not None:
+        z_prev = z_prev.contiguous()
+    _lib.call(
+        "cmrl_ens_linear_bwd_dx", dz.data_ptr(), w.data_ptr(), _ptr(z_prev), dx.data_ptr(), P, E, B, in_size,
+        out_size, act_prev, _stream(),
+    )  # fmt: skip
+    return dx
+
+
+def ens_linear_bwd_dw(x, dz, w_shape, mask=None, mask_str=(0, 0, 0), dw=None, db=None, want_db=True, accumulate=False):
+    """dw = (x*mask)^T @ dz, db = sum_b dz, written into dw/db when given (flat-arena views)."""
+    dz = _req(dz, "dz").contiguous()
+    x = _rows_contig(_req(x, "x"), "x")
+    parallel = len(w_shape) == 4
+    P = w_shape[0] if parallel else 1
+    E, in_size, out_size = w_shape[-3], w_shape[-2], w_shape[-1]
+    B = dz.shape[-2]
+    x_sp, x_se = _lead_strides(x)
+    if dw is None:
+        dw = torch.empty(tuple(w_shape), device=dz.device, dtype=torch.float32)
+        accumulate = False
+    if db is None and want_db:
+        db = torch.empty(tuple(w_shape[:-2]) + (1, out_size), device=dz.device, dtype=torch.float32)
+    assert dw.is_contiguous() and (db is None or db.is_contiguous())
+    _lib.call(
+        "cmrl_ens_linear_bwd_dw", x.data_ptr(), x_sp, x_se, _ptr(mask), mask_str[0], mask_str[1], mask_str[2],
+        dz.data_ptr(), dw.data_ptr(), _ptr(db), P, E, B, in_size, out_size, 1 if accumulate else 0, _stream(),
+    )  # fmt: skip
+    return dw, db
+
+
+def gaussian_head_fwd(raw, layout, E, B, D, obs, min_logvar, max_logvar, deterministic=False):
+    raw = _req(raw, "raw").contiguous()
+    mean = torch.empty((E, B, D), device=raw.device, dtype=torch.float32)
+    logvar = None if deterministic else torch.empty_like(mean)
+    obs_se, obs_ld = 0, 0
+    if obs is not None:
+        obs = _rows_contig(_req(obs, "obs"), "obs")
+        obs_ld = obs.shape[-1]
+        obs_se = _lead_strides(obs)[1]
+    bounds_n = 0 if deterministic else min_logvar.numel()
+    _lib.call(
+        "cmrl_gaussian_head_fwd", raw.data_ptr(), layout, E, B, D, _ptr(obs), obs_se, obs_ld,
+        None if deterministic else min_logvar.data_ptr(), None if deterministic else max_logvar.data_ptr(), bounds_n,
+        mean.data_ptr(), _ptr(logvar), _stream(),
+    )  # fmt: skip
+    return mean, logvar
+
+
+def gaussian_head_bwd(raw, layout, E, B, D, min_logvar, max_logvar, g_mean, g_logvar, d_min=None, d_max=None):
+    raw = raw.contiguous()
+    d_raw = torch.empty_like(raw)
+    if g_mean is not None:
+        g_mean = g_mean.contiguous()
+    if g_logvar is not None:
+        g_logvar = g_logvar.contiguous()
+    bounds_n = 0 if min_logvar is None else min_logvar.numel()
+    _lib.call(
+        "cmrl_gaussian_head_bwd", raw.data_ptr(), layout, E, B, D, _ptr(min_logvar), _ptr(max_logvar), bounds_n,
+        _ptr(g_mean), _ptr(g_logvar), d_raw.data_ptr(), _ptr(d_min), _ptr(d_max), _stream(),
+    )  # fmt: skip
+    return d_raw
+
+
+def _target_stride(target, E):
+    """target [E,B,D] (or broadcast over members) -> (contiguous-rows tensor, member stride)."""
+    target = _req(target, "target")
+    if target.dim() == 3 and target.shape[0] == E and target.stride(0) != 0 and E > 1:
+        target = target.contiguous()
+        return target, target.stride(0)
+    if target.dim() == 3:  # broadcast over members
+        t0 = target[0].contiguous()
+        return t0, 0
+    return target.contiguous(), 0
+
+
+def nll_loss_fwd(mean, logvar, target, reg):
+    mean, logvar = mean.contiguous(), logvar.contiguous()
+    E = mean.shape[0]
+    n = mean[0].numel()
+    target, t_se = _target_stride(target, E)
+    loss = torch.empty_like(mean)
+    _lib.call("cmrl_nll_loss_fwd", mean.data_ptr(), logvar.data_ptr(), target.data_ptr(), t_se, E, n, float(reg),
+              loss.data_ptr(), _stream())  # fmt: skip
+    return loss
+
+
+def nll_loss_bwd(mean, logvar, target, g_loss=None, g_scalar=0.0):
+    mean, logvar = mean.contiguous(), logvar.contiguous()
+    E = mean.shape[0]
+    n = mean[0].numel()
+    target, t_se = _target_stride(target, E)
+    g_mean, g_logvar = torch.empty_like(mean), torch.empty_like(mean)
+    if g_loss is not None:
+        g_loss = g_loss.contiguous()
+    _lib.call("cmrl_nll_loss_bwd", mean.data_ptr(), logvar.data_ptr(), target.data_ptr(), t_se, E, n, _ptr(g_loss),
+              float(g_scalar), g_mean.data_ptr(), g_logvar.data_ptr(), _stream())  # fmt: skip
+    return g_mean, g_logvar
+
+
+def mse_loss_fwd(mean, target):
+    mean = mean.contiguous()
+    E = mean.shape[0]
+    n = mean[0].numel()
+    target, t_se = _target_stride(target, E)
+    loss = torch.empty_like(mean)
+    _lib.call("cmrl_mse_loss_fwd", mean.data_ptr(), target.data_ptr(), t_se, E, n, loss.data_ptr(), _stream())
+    return loss
+
+
+def mse_member_sums(mean, target, sums):
+    """sums (float64 [E], caller-zeroed) += per-member sum of squared errors."""
+    mean = mean.contiguous()
+    E = mean.shape[0]
+    n = mean[0].numel()
+    target, t_se = _target_stride(target, E)
+    assert sums.dtype == torch.float64 and sums.numel() == E
+    _lib.call("cmrl_mse_member_sums", mean.data_ptr(), target.data_ptr(), t_se, E, n, sums.data_ptr(), _stream())
+    return sums
+
+
+def adam_l2_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    n = param.numel()
+    assert param.is_contiguous() and grad.is_contiguous() and grad.numel() == n
+    _lib.call("cmrl_adam_l2_step", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
+              float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale), int(step),
+              _stream())  # fmt: skip
+
+
+# ----------------------------------------------------------------------------- rollout
+def draw_member_noise(seed, stream_id, N, elite_u8, D, want_noise=True, device=None):
+    device = elite_u8.device if device is None else device
+    idx = torch.empty(N, device=device, dtype=torch.uint8)
+    noise = torch.empty((N, D), device=device, dtype=torch.float32) if want_noise else None
+    _lib.call("cmrl_draw_member_noise", int(seed), int(stream_id), N, elite_u8.data_ptr(), elite_u8.numel(), D,
+              idx.data_ptr(), _ptr(noise), _stream())  # fmt: skip
+    return idx, noise
+
+
+def draw_uniform_index(seed, stream_id, N, upper, device):
+    out = torch.empty(N, device=device, dtype=torch.int32)
+    _lib.call("cmrl_draw_uniform_index", int(seed), int(stream_id), N, int(upper), out.data_ptr(), _stream())
+    return out
+
+
+def member_bucket(member_idx, E, perm=None, offsets=None, counters=None):
+    N = member_idx.numel()
+    dev = member_idx.device
+    perm = torch.empty(N, device=dev, dtype=torch.int32) if perm is None else perm
+    offsets = torch.empty(E + 1, device=dev, dtype=torch.int32) if offsets is None else offsets
+    counters = torch.empty(2 * (E + 1), device=dev, dtype=torch.int32) if counters is None else counters
+    _lib.call("cmrl_member_bucket", member_idx.data_ptr(), N, E, perm.data_ptr(), offsets.data_ptr(),
+              counters.data_ptr(), _stream())  # fmt: skip
+    return perm, offsets
+
+
+def gather_inputs(obs, act, perm):
+    N, O = obs.shape
+    A = act.shape[1]
+    x = torch.empty((N, O + A), device=obs.device, dtype=torch.float32)
+    _lib.call("cmrl_gather_inputs", obs.data_ptr(), act.data_ptr(), _ptr(perm), N, O, A, x.data_ptr(), _stream())
+    return x
+
+
+def sample_scatter(raw_sorted, layout, perm, N, D, obs, min_logvar, max_logvar, noise, out=None):
+    pred = torch.empty((N, D), device=raw_sorted.device, dtype=torch.float32) if out is None else out
+    bounds_n = 0 if min_logvar is None else min_logvar.numel()
+    _lib.call("cmrl_sample_scatter", raw_sorted.data_ptr(), layout, _ptr(perm), N, D, _ptr(obs),
+              0 if obs is None else obs.shape[-1], _ptr(min_logvar), _ptr(max_logvar), bounds_n, _ptr(noise),
+              pred.data_ptr(), _stream())  # fmt: skip
+    return pred
+
+
+def select_sample(mean, logvar, member_idx, noise):
+    E, N, D = mean.shape
+    pred = torch.empty((N, D), device=mean.device, dtype=torch.float32)
+    _lib.call("cmrl_select_sample", mean.data_ptr(), _ptr(logvar), member_idx.data_ptr(), E, N, D, _ptr(noise),
+              pred.data_ptr(), _stream())  # fmt: skip
+    return pred
+
+
+def mopo_penalty(mean):
+    E, N, O = mean.shape
+    pen = torch.empty(N, device=mean.device, dtype=torch.float32)
+    _lib.call("cmrl_mopo_penalty", mean.contiguous().data_ptr(), E, N, O, pen.data_ptr(), _stream())
+    return pen
+
+
+def env_step_tail(next_obs, reward, terminal_f, terminal_u8, penalty, penalty_coeff, env_len, max_episode_steps,
+                  reset_obs, reset_index, obs_out, reward_out, done, truncated, terminal_obs, n_done):  # fmt: skip
+    N, O = next_obs.shape
+    _lib.call("cmrl_env_step_tail", next_obs.data_ptr(), reward.data_ptr(), _ptr(terminal_f), _ptr(terminal_u8),
+              _ptr(penalty), float(penalty_coeff), env_len.data_ptr(), int(max_episode_steps), _ptr(reset_obs),
+              _ptr(reset_index), N, O, obs_out.data_ptr(), reward_out.data_ptr(), done.data_ptr(),
+              truncated.data_ptr(), _ptr(terminal_obs), _ptr(n_done), _stream())  # fmt: skip

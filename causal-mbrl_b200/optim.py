@@ -1,0 +1,54 @@
+"""FusedAdamL2: torch.optim.Adam semantics as configured at cmrl/models/dynamics/base_dynamics.py:58-63
+(L2-coupled weight decay, bias correction, eps outside the sqrt) as ONE kernel launch over a mechanism's flat
+parameter arena (`EnsembleMLP.flat_parameters`)."""
+import torch
+
+from . import ops
+
+
+class FusedAdamL2(torch.optim.Optimizer):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.model = model
+        params = list(model.parameters())
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._step = 0
+        self._exp_avg = None
+        self._exp_avg_sq = None
+
+    def _arena(self):
+        flat, flat_grad = self.model.flat_parameters()
+        n = self.model._n_trainable
+        if self._exp_avg is None or self._exp_avg.numel() != n or self._exp_avg.device != flat.device:
+            self._exp_avg = torch.zeros(n, device=flat.device, dtype=torch.float32)
+            self._exp_avg_sq = torch.zeros(n, device=flat.device, dtype=torch.float32)
+        return flat[:n], flat_grad[:n]
+
+    def zero_grad(self, set_to_none: bool = False):
+        """Zeroes the flat gradient buffer; parameter .grad stay views of it (never set to None)."""
+        _, flat_grad = self.model.flat_parameters()
+        flat_grad.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        loss = closure() if closure is not None else None
+        g = self.param_groups[0]
+        p, grad = self._arena()
+        self._step += 1
+        ops.adam_l2_step(p, grad, self._exp_avg, self._exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                         g["weight_decay"], self._step, grad_scale)  # fmt: skip
+        return loss
+
+    def state_dict(self):
+        return {
+            "step": self._step,
+            "exp_avg": None if self._exp_avg is None else self._exp_avg.clone(),
+            "exp_avg_sq": None if self._exp_avg_sq is None else self._exp_avg_sq.clone(),
+            "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
+        }
+
+    def load_state_dict(self, state):
+        self._step = state["step"]
+        self._exp_avg = None if state["exp_avg"] is None else state["exp_avg"].clone()
+        self._exp_avg_sq = None if state["exp_avg_sq"] is None else state["exp_avg_sq"].clone()
+        for g, s in zip(self.param_groups, state["param_groups"]):
+            g.update(s)

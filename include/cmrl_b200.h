@@ -1,0 +1,181 @@
+/*
+ * cmrl_b200.h -- C ABI of libcmrl_b200.so: the sm_100a kernels behind the cmrl
+ * ensemble-dynamics hot path (polixir/causal-mbrl, reference tree /root/reference).
+ *
+ * The reference has no FFI: its "operators" are torch/numpy calls inside Python
+ * classes.  Each entry point below names the reference call site it replaces
+ * (file:line relative to /root/reference).  The Python host mirror
+ * (causal-mbrl_b200/, importable as `cmrl_b200`) binds these with ctypes; see
+ * INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller unless the name ends in
+ *    `_host`.  The library never allocates, frees or retains caller memory.
+ *  - All tensors are dense row-major fp32 unless stated.  Group dims: P = parallel
+ *    sub-networks (ExternalMaskTransition: one per output dim), E = ensemble members.
+ *    A "net" is one (p,e) pair.  A stride of 0 broadcasts that dim.
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and
+ *    performs no host synchronisation.
+ *  - Return value: 0 ok; <0 invalid argument / unsupported shape; >0 a cudaError_t.
+ *    cmrl_last_error() returns a thread-local message for the last non-zero return.
+ *  - No CPU fallback exists: on a machine without an sm_100 device every compute entry
+ *    returns cudaErrorNoDevice / cudaErrorNoKernelImageForDevice.
+ */
+#ifndef CMRL_B200_H
+#define CMRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMRL_B200_ABI_VERSION 1
+
+enum cmrl_act { CMRL_ACT_IDENTITY = 0, CMRL_ACT_RELU = 1, CMRL_ACT_SILU = 2 };
+/* layout of the head's raw output (see cmrl_gaussian_head_fwd) */
+enum cmrl_head_layout { CMRL_HEAD_PLAIN = 0, CMRL_HEAD_PARALLEL = 1 };
+
+int cmrl_abi_version(void);
+const char* cmrl_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long cmrl_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  EnsembleLinearLayer.forward  (cmrl/models/layers.py:60-65)  and
+ *     ParallelEnsembleLinearLayer.forward (layers.py:106-111):  y = act(x.matmul(W) + b),
+ *     with the activation module of plain_transition.py:69-83 fused, and the input mask of
+ *     ExternalMaskTransition.mask_input (external_mask_transition.py:116-139) fused into the
+ *     A-operand load instead of materialising repeat(P) * mask (:149-150).
+ *
+ *  x    [P?,E?,B,in]   element strides x_sp / x_se between sub-nets / members (0 = shared)
+ *  w    [P,E,in,out]   b [P,E,1,out] or NULL
+ *  y    [P,E,B,out]    post-activation;  z: same shape, pre-activation, may be NULL
+ *  mask NULL, or 0/1 floats addressed mask[p*m_sp + e*m_se + b*m_sb + i]
+ *  row_offsets NULL, or int32 [E+1] (device): ragged mode -- member e owns rows
+ *       [row_offsets[e], row_offsets[e+1]) of a flat [B,in] x and [P,B,out] y (x_se ignored);
+ *       used by selected-member rollouts (VecFakeEnv.get_dynamics_predict, fake_env.py:195-215).
+ * ------------------------------------------------------------------------------------------ */
+int cmrl_ens_linear_fwd(const float* x, long long x_sp, long long x_se, const float* w, const float* b,
+                        float* y, float* z, int P, int E, int B, int in_size, int out_size,
+                        const float* mask, long long m_sp, long long m_se, long long m_sb,
+                        const int* row_offsets, int act, void* stream);
+
+/* Backward of K1 w.r.t. the input, fused with the previous layer's activation derivative
+ * (autograd of layers.py:61 + the activation; base_dynamics.py:185 `.backward()`):
+ *   dx[p,e,b,i] = (sum_o dz[p,e,b,o] * w[p,e,i,o]) * act'(z_prev[p,e,b,i])
+ * z_prev NULL or act_prev == IDENTITY -> plain dz.W^T. */
+int cmrl_ens_linear_bwd_dx(const float* dz, const float* w, const float* z_prev, float* dx, int P, int E,
+                           int B, int in_size, int out_size, int act_prev, void* stream);
+
+/* Backward of K1 w.r.t. weight and bias:
+ *   dw[p,e,i,o] = sum_b (x*mask)[p,e,b,i] * dz[p,e,b,o];   db[p,e,0,o] = sum_b dz[p,e,b,o]
+ * db may be NULL.  accumulate != 0 adds into dw/db instead of overwriting. */
+int cmrl_ens_linear_bwd_dw(const float* x, long long x_sp, long long x_se, const float* mask, long long m_sp,
+                           long long m_se, long long m_sb, const float* dz, float* dw, float* db, int P,
+                           int E, int B, int in_size, int out_size, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  Gaussian head: split, double soft-clamp, residual (and the ExternalMask transpose)
+ *     plain_transition.py:111-120, external_mask_transition.py:154-167, plain_reward_mech.py:86-92
+ *   PLAIN    raw [E,B,2D] (deterministic: [E,B,D]);  PARALLEL raw [D(=P),E,B,2] (det.: [D,E,B,1])
+ *   mean/logvar out [E,B,D];  lv = max - softplus(max - raw_lv); lv = min + softplus(lv - min)
+ *   (softplus beta=1, threshold=20);  min_logvar/max_logvar: [D] (bounds_n == D) or [1].
+ *   obs (for the residual): [E?,B,obs_ld] with member stride obs_se (0 = shared); NULL = no residual.
+ *   logvar == NULL -> deterministic head (mean only).
+ * ------------------------------------------------------------------------------------------ */
+int cmrl_gaussian_head_fwd(const float* raw, int layout, int E, int B, int D, const float* obs, long long obs_se,
+                           int obs_ld, const float* min_logvar, const float* max_logvar, int bounds_n,
+                           float* mean, float* logvar, void* stream);
+
+/* Backward of K2: given g_mean, g_logvar [E,B,D] (g_logvar may be NULL) writes d_raw in raw's layout and,
+ * when d_min/d_max are non-NULL, ACCUMULATES (atomicAdd) the gradients of the bounds into them. */
+int cmrl_gaussian_head_bwd(const float* raw, int layout, int E, int B, int D, const float* min_logvar,
+                           const float* max_logvar, int bounds_n, const float* g_mean, const float* g_logvar,
+                           float* d_raw, float* d_min, float* d_max, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  losses.  gaussian_nll (cmrl/models/util.py:14-37, reduce=False) + the constant of
+ *     EnsembleMLP.get_nll_loss (mlp.py:72-76):  loss = (mu-y)^2 * exp(-lv) + lv + reg
+ *     EnsembleMLP.get_mse_loss (mlp.py:68-70):  loss = (mu-y)^2
+ *     target: [E?,n_per_member] with member stride t_se (0 = same target for all members).
+ * ------------------------------------------------------------------------------------------ */
+int cmrl_nll_loss_fwd(const float* mean, const float* logvar, const float* target, long long t_se, int E,
+                      long long n_per_member, float reg, float* loss, void* stream);
+/* g_mean = g * 2 (mu-y) exp(-lv);  g_logvar = g * (1 - (mu-y)^2 exp(-lv)).  g_loss NULL -> g = g_scalar
+ * (the `.mean()` of base_dynamics.py:185 gives g_scalar = 1/(E*B*D)). */
+int cmrl_nll_loss_bwd(const float* mean, const float* logvar, const float* target, long long t_se, int E,
+                      long long n_per_member, const float* g_loss, float g_scalar, float* g_mean,
+                      float* g_logvar, void* stream);
+int cmrl_mse_loss_fwd(const float* mean, const float* target, long long t_se, int E, long long n_per_member,
+                      float* loss, void* stream);
+/* Hold-out MSE for elite selection (plain_dynamics.py:74,82 `evaluate(...).mean(dim=(1,2))`):
+ * sums[e] += sum_i (mean[e,i]-target[e,i])^2 in fp64 (caller zeroes `sums` [E] doubles, divides by n). */
+int cmrl_mse_member_sums(const float* mean, const float* target, long long t_se, int E, long long n_per_member,
+                         double* sums, void* stream);
+
+/* torch.optim.Adam as built at base_dynamics.py:58-63 (L2-coupled weight decay, bias correction,
+ * eps outside the sqrt), one launch over a flat parameter arena.  grad_scale multiplies the gradient
+ * first (data-parallel averaging). `step` is the 1-based step count after this update. */
+int cmrl_adam_l2_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, float grad_scale, int step,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  rollout step (VecFakeEnv.step_wait, cmrl/models/fake_env.py:97-142)
+ * ------------------------------------------------------------------------------------------ */
+/* Device RNG (throughput mode; the parity mode supplies numpy draws): Philox4x32-10 keyed by
+ * (seed, stream_id), counter = (env, draw).  member_idx[n] = elite[u32 * n_elite >> 32] (uint8),
+ * noise [N,D] ~ N(0,1) by Box-Muller.  Replaces Generator.choice + Generator.normal (fake_env.py:205-214,
+ * mlp.py:40-44).  noise may be NULL (deterministic rollouts). */
+int cmrl_draw_member_noise(unsigned long long seed, unsigned long long stream_id, int N, const uint8_t* elite,
+                           int n_elite, int D, uint8_t* member_idx, float* noise, void* stream);
+
+/* out[n] = uniform integer in [0, upper) (Philox): reset-row draw replacing np.random.randint at
+ * fake_env.py:154,177 in throughput mode. */
+int cmrl_draw_uniform_index(unsigned long long seed, unsigned long long stream_id, int N, int upper, int* out,
+                            void* stream);
+
+/* Counting sort of envs by drawn member: perm [N] lists env ids grouped by member, offsets [E+1].
+ * counters: int32 [2*(E+1)] scratch, zeroed by the call. */
+int cmrl_member_bucket(const uint8_t* member_idx, int N, int E, int* perm, int* offsets, int* counters,
+                       void* stream);
+
+/* x_sorted[r, :] = concat(obs[perm[r]], act[perm[r]])  (torch.concat at plain_transition.py:108 on the
+ * bucketed order).  perm NULL = identity. */
+int cmrl_gather_inputs(const float* obs, const float* act, const int* perm, int N, int O, int A, float* x_sorted,
+                       void* stream);
+
+/* get_dynamics_predict (fake_env.py:195-215) on bucketed rows: for sorted row r (env = perm[r]) apply the
+ * Gaussian head to raw_sorted (PLAIN [N,2D] or PARALLEL [D,N,2]; deterministic heads: [N,D] / [D,N,1] with
+ * min_logvar NULL), add the residual obs[env] when obs != NULL, and write
+ *   pred[env, d] = mean + sqrt(exp(logvar)) * noise[env, d]      (noise NULL -> mean). */
+int cmrl_sample_scatter(const float* raw_sorted, int layout, const int* perm, int N, int D, const float* obs,
+                        int obs_ld, const float* min_logvar, const float* max_logvar, int bounds_n,
+                        const float* noise, float* pred, void* stream);
+
+/* All-member variant: mean/logvar [E,N,D] from query (base_dynamics.py:190-204), member_idx [N]:
+ *   pred[n,d] = mean[idx[n],n,d] + sqrt(exp(logvar[idx[n],n,d])) * noise[n,d]. */
+int cmrl_select_sample(const float* mean, const float* logvar, const uint8_t* member_idx, int E, int N, int D,
+                       const float* noise, float* pred, void* stream);
+
+/* VecFakeEnv.get_penalty (fake_env.py:186-193): penalty[n] = max_e || mean[e,n,:] - avg_e mean[:,n,:] ||_2 */
+int cmrl_mopo_penalty(const float* mean, int E, int N, int O, float* penalty, void* stream);
+
+/* Step tail (fake_env.py:116-142), SB3 layout outputs:
+ *   reward_out = reward - penalty_coeff * penalty (penalty NULL -> no penalty)
+ *   env_len += 1; truncated = env_len >= max_episode_steps; done = (terminal != 0) | truncated
+ *   terminal_obs = next_obs (pre-reset copy, the infos["terminal_observation"] rows)
+ *   obs_out = done ? reset_obs[reset_index ? reset_index[n] : n] : next_obs;  env_len = done ? 0 : env_len
+ *   terminal: float [N] (learned mech sample, non-zero => done: reference quirk) or NULL;
+ *   terminal_u8: uint8 [N] flags from a termination_fn, or NULL.  n_done: int32 [1], incremented by #done. */
+int cmrl_env_step_tail(const float* next_obs, const float* reward, const float* terminal, const uint8_t* terminal_u8,
+                       const float* penalty, float penalty_coeff, int* env_len, int max_episode_steps,
+                       const float* reset_obs, const int* reset_index, int N, int O, float* obs_out,
+                       float* reward_out, uint8_t* done, uint8_t* truncated, float* terminal_obs, int* n_done,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMRL_B200_H */

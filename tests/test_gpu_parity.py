@@ -1,0 +1,472 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against
+ (a) golden outputs of the unmodified reference (tests/golden/*.npz) and
+ (b) the CPU oracle (oracle/cmrl_oracle.py) on seeded random inputs.
+Tolerances: fp32 tier 1e-5 relative (max|a-b| / max|b|) for outputs/losses; integer / flag outputs bit-exact."""
+import os
+import tempfile
+from unittest import mock
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, params_of, rel_err
+from oracle import cmrl_oracle as oc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # north_star: 1e-5 relative at fp32
+SILU = {"_target_": "torch.nn.SiLU"}
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def cm():
+    import cmrl_b200
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return cmrl_b200
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def load_sd(model, params):
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+
+
+def act_cfg(name):
+    return None if "relu" in name else SILU
+
+
+# ------------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("P,E,B,I,O_", [(1, 7, 128, 6, 200), (1, 7, 33, 200, 200), (1, 7, 1, 200, 10), (5, 7, 40, 6, 24), (3, 4, 257, 24, 2), (1, 1, 5, 3, 1)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_ens_linear_fwd_bwd_vs_oracle(cm, P, E, B, I, O_, act):
+    rng = np.random.default_rng(P * 1000 + B + act)
+    lead = (E,) if P == 1 else (P, E)
+    x = rng.normal(size=lead + (B, I)).astype(np.float32)
+    w = (rng.normal(size=lead + (I, O_)) / np.sqrt(I)).astype(np.float32)
+    b = rng.normal(size=lead + (1, O_)).astype(np.float32)
+    y, z = cm.ops.ens_linear_fwd(t(x), t(w), t(b), act, want_z=True)
+    z_ref = oc.ens_linear(x, w, b)
+    y_ref = oc.activation(z_ref, act)
+    assert rel_err(z.cpu().numpy(), z_ref) < TOL
+    assert rel_err(y.cpu().numpy(), y_ref) < TOL
+    dz = rng.normal(size=lead + (B, O_)).astype(np.float32)
+    zprev = rng.normal(size=lead + (B, I)).astype(np.float32)
+    dx = cm.ops.ens_linear_bwd_dx(t(dz), t(w), t(zprev), act)
+    dx_ref = np.matmul(dz, np.swapaxes(w, -1, -2)) * oc.activation_grad(zprev, act)
+    assert rel_err(dx.cpu().numpy(), dx_ref) < TOL
+    dw, db = cm.ops.ens_linear_bwd_dw(t(x), t(dz), w.shape)
+    assert rel_err(dw.cpu().numpy(), np.matmul(np.swapaxes(x, -1, -2), dz)) < TOL
+    assert rel_err(db.cpu().numpy(), dz.sum(-2, keepdims=True)) < TOL
+
+
+def test_ens_linear_shared_input_and_layer_modules(cm):
+    """reference unit tests test_layers.py:25-33,51-54 (output shapes) + broadcast input rows."""
+    lin = cm.EnsembleLinearLayer(5, 6, ensemble_num=4).to(DEV)
+    x = torch.rand(4, 128, 5, device=DEV)
+    assert lin(x).shape == (4, 128, 6)
+    assert rel_err(lin(x).detach().cpu().numpy(), (x.matmul(lin.weight) + lin.bias).detach().cpu().numpy()) < TOL
+    plin = cm.ParallelEnsembleLinearLayer(5, 6, parallel_num=3, ensemble_num=4).to(DEV)
+    xp = torch.rand(3, 4, 128, 5, device=DEV)
+    assert plin(xp).shape == (3, 4, 128, 6)
+    x1 = torch.rand(128, 5, device=DEV)
+    y = cm.ops.ens_linear_fwd(x1, lin.weight.detach(), lin.bias.detach())
+    assert torch.equal(y, cm.ops.ens_linear_fwd(x1.expand(4, 128, 5), lin.weight.detach(), lin.bias.detach()))
+    # autograd through the layer module
+    lin.zero_grad()
+    out = lin(x)
+    out.square().sum().backward()
+    ref = (x.matmul(lin.weight.detach().requires_grad_()) + lin.bias.detach())
+    w2 = lin.weight.detach().clone().requires_grad_()
+    b2 = lin.bias.detach().clone().requires_grad_()
+    (x.matmul(w2) + b2).square().sum().backward()
+    assert rel_err(lin.weight.grad.cpu().numpy(), w2.grad.cpu().numpy()) < TOL
+    assert rel_err(lin.bias.grad.cpu().numpy(), b2.grad.cpu().numpy()) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ forward vs golden
+@pytest.mark.parametrize("name", ["plain_c1_forward.npz", "plain_relu_forward.npz", "plain_noresidual_forward.npz"])
+def test_plain_transition_forward_golden(cm, name):
+    g = load_golden(name)
+    p = params_of(g)
+    E, B, O = g["obs"].shape
+    A = g["act"].shape[-1]
+    H = p["hidden_layers.0.0.weight"].shape[-1]
+    m = cm.PlainTransition(O, A, ensemble_num=E, hid_size=H, activation_fn_cfg=act_cfg(name), residual="noresidual" not in name, device=DEV)
+    load_sd(m, p)
+    with torch.no_grad():
+        mean, logvar = m.forward(t(g["obs"]), t(g["act"]))
+        model_in = {"batch_obs": t(g["obs"]), "batch_action": t(g["act"])}
+        nll = m.get_nll_loss(model_in, t(g["target"]))
+        mse = m.get_mse_loss(model_in, t(g["target"]))
+    assert mean.shape == logvar.shape == (E, B, O)
+    assert rel_err(mean.cpu().numpy(), g["mean"]) < TOL
+    assert rel_err(logvar.cpu().numpy(), g["logvar"]) < TOL
+    assert rel_err(nll.cpu().numpy(), g["nll"]) < 3e-5
+    assert rel_err(mse.cpu().numpy(), g["mse"]) < 3e-5
+    # shared-row (query) path == replicated path, bit for bit
+    if name == "plain_c1_forward.npz":
+        with torch.no_grad():
+            mean2, logvar2 = m.forward(t(g["obs"][:1]).expand(E, B, O), t(g["act"][:1]).expand(E, B, A))
+        assert torch.equal(mean, mean2) and torch.equal(logvar, logvar2)
+
+
+@pytest.mark.parametrize("name,cls", [("reward_forward.npz", "PlainRewardMech"), ("termination_forward.npz", "PlainTerminationMech")])
+def test_reward_termination_forward_golden(cm, name, cls):
+    g = load_golden(name)
+    p = params_of(g)
+    m = getattr(cm, cls)(5, 1, ensemble_num=7, hid_size=p["hidden_layers.0.0.weight"].shape[-1], activation_fn_cfg=SILU, device=DEV)
+    load_sd(m, p)
+    with torch.no_grad():
+        mean, logvar = m.forward(t(g["obs"]), t(g["act"]))
+        nll = m.get_nll_loss({"batch_obs": t(g["obs"]), "batch_action": t(g["act"])}, t(g["target"]))
+    assert mean.shape == (7, 50, 1)
+    assert rel_err(mean.cpu().numpy(), g["mean"]) < TOL and rel_err(logvar.cpu().numpy(), g["logvar"]) < TOL
+    assert rel_err(nll.cpu().numpy(), g["nll"]) < 3e-5
+
+
+@pytest.mark.parametrize("tag", ["2d", "3de", "3db", "4d", "wide"])
+def test_external_mask_forward_golden(cm, tag):
+    g = load_golden("extmask_%s_forward.npz" % tag)
+    p = params_of(g)
+    E, B, O = g["obs"].shape
+    A = g["act"].shape[-1]
+    m = cm.ExternalMaskTransition(O, A, ensemble_num=E, elite_num=min(5, E - 1), hid_size=p["hidden_layers.0.0.weight"].shape[-1], activation_fn_cfg=SILU, device=DEV)
+    load_sd(m, p)
+    m.set_input_mask(torch.from_numpy(g["input_mask"]))
+    with torch.no_grad():
+        mean, logvar = m.forward(t(g["obs"]), t(g["act"]))
+        nll = m.get_nll_loss({"batch_obs": t(g["obs"]), "batch_action": t(g["act"])}, t(g["target"]))
+    assert mean.shape == logvar.shape == (E, B, O)
+    assert rel_err(mean.cpu().numpy(), g["mean"]) < TOL and rel_err(logvar.cpu().numpy(), g["logvar"]) < TOL
+    assert rel_err(nll.cpu().numpy(), g["nll"]) < 3e-5
+
+
+def test_reference_invariants(cm):
+    """test_basic_ensemble.py:40-72 and test_external_mask_ensemble.py:42-93 re-used as black-box tests."""
+    torch.manual_seed(0)
+    obs = torch.rand(7, 128, 11, device=DEV)
+    act = torch.rand(7, 128, 3, device=DEV)
+    det = cm.PlainTransition(11, 3, device=DEV, deterministic=True)
+    mean, logvar = det.forward(obs, act)
+    assert mean.shape == (7, 128, 11) and logvar is None
+    for cls in (cm.PlainTransition, cm.ExternalMaskTransition):
+        a = cls(11, 3, device=DEV, hid_size=64)
+        mean, logvar = a.forward(obs, act)
+        assert mean.shape == logvar.shape == (7, 128, 11)
+        with tempfile.TemporaryDirectory() as d:
+            a.save(d)
+            b = cls(11, 3, device=DEV, hid_size=64)
+            mean_b, _ = b.forward(obs, act)
+            assert not (mean == mean_b).all()
+            b.load(d)
+            mean_b, logvar_b = b.forward(obs, act)
+            assert (mean == mean_b).all() and (logvar == logvar_b).all()  # bit-equal after save -> load
+            assert list(np.asarray(b.elite_members)) == list(np.asarray(a.elite_members))
+    em = cm.ExternalMaskTransition(11, 3, device=DEV, hid_size=64)
+    det_em = cm.ExternalMaskTransition(11, 3, device=DEV, hid_size=64, deterministic=True)
+    m1, lv1 = det_em.forward(obs, act)
+    assert m1.shape == (7, 128, 11) and lv1 is None
+    mask = torch.ones(11, 14)
+    em.set_input_mask(mask)
+    mean, _ = em.forward(obs, act)
+    mask2 = mask.clone()
+    mask2[0] = 0
+    em.set_input_mask(mask2)
+    new_mean, _ = em.forward(obs, act)
+    assert not (mean == new_mean).all()
+    assert (mean[..., 1:] == new_mean[..., 1:]).all()  # sub-network independence, mask orientation [out,in]
+    fe = cm.ForwardEulerTransition(cm.PlainTransition(11, 3, device=DEV, hid_size=32), repeat_times=3)
+    mean, logvar = fe.forward(obs, act)
+    assert mean.shape == logvar.shape == (7, 128, 11)
+
+
+# ------------------------------------------------------------------------------------------------ training
+def _build_for_train(cm, name, g):
+    p = params_of(g, "p0.")
+    H = p["hidden_layers.0.0.weight"].shape[-1]
+    if name.startswith("reward"):
+        m = cm.PlainRewardMech(5, 1, hid_size=H, activation_fn_cfg=SILU, device=DEV)
+    elif name.startswith("extmask"):
+        m = cm.ExternalMaskTransition(5, 1, hid_size=H, activation_fn_cfg=SILU, device=DEV)
+        m.set_input_mask(torch.from_numpy(g["input_mask"]))
+    else:
+        m = cm.PlainTransition(5, 1, hid_size=H, activation_fn_cfg=act_cfg(name), learn_logvar_bounds="learnbounds" in name, device=DEV)
+    load_sd(m, p)
+    return m
+
+
+@pytest.mark.parametrize("name", ["plain_train.npz", "plain_relu_train.npz", "reward_train.npz", "extmask_train.npz", "plain_learnbounds_train.npz"])
+@pytest.mark.parametrize("path", ["fused", "autograd"])
+def test_train_steps_golden(cm, name, path):
+    g = load_golden(name)
+    m = _build_for_train(cm, name, g)
+    mech = "reward_mech" if name.startswith("reward") else "transition"
+    tr = m if mech == "transition" else cm.PlainTransition(5, 1, hid_size=8, device=DEV)
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=mech == "reward_mech", reward_mech=m if mech == "reward_mech" else None)
+    optim = getattr(dyn, mech + "_optimizer")
+    steps = int(g["steps"])
+    for s in range(steps):
+        obs, act, target = t(g["obs%d" % s]), t(g["act%d" % s]), t(g["target%d" % s])
+        if path == "fused":
+            loss = dyn.train_step(mech, obs, act, target)
+        else:
+            loss = m.get_nll_loss({"batch_obs": obs, "batch_action": act}, target)
+            optim.zero_grad()
+            loss.mean().backward()
+            if s == 0:
+                for k, prm in m.named_parameters():
+                    if prm.requires_grad:
+                        assert rel_err(prm.grad.cpu().numpy(), g["g0." + k]) < 1e-4, k
+            optim.step()
+        assert rel_err(loss.detach().cpu().numpy(), g["loss%d" % s]) < 3e-5
+    ref = params_of(g, "p%d." % steps)
+    sd = m.state_dict()
+    for k in ref:
+        mine = sd[k].cpu().numpy()
+        if k.endswith("weight"):
+            assert rel_err(mine, ref[k]) < TOL, k
+        # the 3-step update itself (magnitude ~3e-4) must match
+        assert rel_err(mine - g["p0." + k], ref[k] - g["p0." + k]) < 2e-3 or np.array_equal(mine, ref[k]), k
+
+
+def test_learn_golden(cm):
+    """PlainEnsembleDynamics.learn end to end against the reference run (same seeded iterators):
+    elite indices bit-exact, final weights within 1e-4 (4 epochs of Adam steps)."""
+    g = load_golden("learn_small.npz")
+    tr = cm.PlainTransition(5, 1, hid_size=32, activation_fn_cfg=SILU, device=DEV)
+    rw = cm.PlainRewardMech(5, 1, hid_size=32, activation_fn_cfg=SILU, device=DEV)
+    load_sd(tr, params_of(g, "tr0."))
+    load_sd(rw, params_of(g, "rw0."))
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw, optim_lr=1e-3)
+    from oracle.refshim import DuckReplayBuffer
+
+    buf = DuckReplayBuffer(g["obs"], g["act"], g["next_obs"], g["rew"], g["done"])
+    seeds = iter(range(1000, 2000))
+    real_default_rng = np.random.default_rng
+
+    def seeded_default_rng(seed=None):
+        return real_default_rng(next(seeds) if seed is None else seed)
+
+    with mock.patch("numpy.random.default_rng", seeded_default_rng):
+        dyn.learn(buf, validation_ratio=0.2, batch_size=64, longest_epoch=4, improvement_threshold=0.01, patience=3)
+    assert dyn.total_epoch == {"transition": int(g["total_epoch_tr"]), "reward_mech": int(g["total_epoch_rw"])}
+    assert list(map(int, tr.elite_members)) == list(map(int, g["tr_elite"]))
+    assert list(map(int, rw.elite_members)) == list(map(int, g["rw_elite"]))
+    for pre, m in (("tr1.", tr), ("rw1.", rw)):
+        ref = params_of(g, pre)
+        sd = m.state_dict()
+        for k in ref:
+            if k.endswith("weight"):
+                assert rel_err(sd[k].cpu().numpy(), ref[k]) < 1e-4, k
+    _, val_it = dyn.dataset_split(buf, 0.2, 64)
+    assert rel_err(dyn.evaluate_member_mse(val_it, "transition").numpy(), g["tr_val_mse"]) < 1e-4
+    assert rel_err(dyn.evaluate(val_it, "transition").mean(dim=(1, 2)).numpy(), g["tr_val_mse"]) < 1e-4
+    assert rel_err(dyn.evaluate_member_mse(val_it, "reward_mech").numpy(), g["rw_val_mse"]) < 1e-4
+    with tempfile.TemporaryDirectory() as d:
+        dyn.save(d)
+        assert sorted(os.listdir(d)) == ["plain_reward_mech.pth", "plain_transition.pth"]
+        dyn.load(d)
+
+
+# ------------------------------------------------------------------------------------------------ VecFakeEnv
+def _build_env(cm, g, rng_mode="numpy"):
+    learned_term, penalty_coeff, deterministic, max_steps = g["cfg"]
+    learned_term, deterministic, max_steps = bool(learned_term), bool(deterministic), int(max_steps)
+    O, A, E, H, N = 5, 1, 7, 32, g["reset_obs"].shape[0]
+    if "input_mask" in g:
+        tr = cm.ExternalMaskTransition(O, A, hid_size=H, activation_fn_cfg=SILU, device=DEV)
+        tr.set_input_mask(torch.from_numpy(g["input_mask"]))
+    else:
+        tr = cm.PlainTransition(O, A, hid_size=H, activation_fn_cfg=SILU, device=DEV)
+    rw = cm.PlainRewardMech(O, A, hid_size=H, activation_fn_cfg=SILU, device=DEV)
+    tm = cm.PlainTerminationMech(O, A, hid_size=H, activation_fn_cfg=SILU, device=DEV) if learned_term else None
+    load_sd(tr, params_of(g, "tr."))
+    load_sd(rw, params_of(g, "rw."))
+    tr.set_elite_members(list(g["tr_elite"]))
+    rw.set_elite_members(list(g["rw_elite"]))
+    if learned_term:
+        load_sd(tm, params_of(g, "tm."))
+        tm.set_elite_members(list(g["tm_elite"]))
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw, learned_termination=learned_term, termination_mech=tm)
+    init_rng = np.random.default_rng(77)
+    env = cm.VecFakeEnv(N, None, None)
+    env.set_up(
+        dyn,
+        termination_fn=None if learned_term else (lambda next_obs, obs, act: np.abs(next_obs[:, 0:1]) > 1.5),
+        get_init_obs_fn=lambda n: init_rng.normal(size=(n, O)).astype(np.float32),
+        penalty_coeff=penalty_coeff,
+        deterministic=deterministic,
+        max_episode_steps=max_steps,
+    )
+    env.rng_mode = rng_mode
+    env.seed(11)
+    return env
+
+
+@pytest.mark.parametrize(
+    "name", ["fake_env_termfn.npz", "fake_env_truncate.npz", "fake_env_learned_term.npz", "fake_env_penalty.npz", "fake_env_deterministic.npz", "fake_env_extmask.npz"]
+)
+@pytest.mark.parametrize("infos_mode", ["dicts", "shared"])
+def test_fake_env_step_golden(cm, name, infos_mode):
+    """VecFakeEnv.step vs the reference run with the same seed: done / truncated flags (and hence member
+    choice) bit-exact, obs / reward within 1e-5."""
+    g = load_golden(name)
+    env = _build_env(cm, g)
+    env.infos_mode = infos_mode
+    obs0 = env.reset()
+    assert np.array_equal(obs0, g["reset_obs"])
+    N = obs0.shape[0]
+    for step in range(int(g["T"])):
+        obs, rew, done, infos = env.step(g["actions"][step])
+        assert obs.dtype == np.float32 and rew.dtype == np.float32 and done.dtype == bool
+        assert obs.shape == (N, 5) and rew.shape == (N,) and done.shape == (N,) and len(infos) == N
+        assert np.array_equal(done, g["done%d" % step])
+        assert np.array_equal(np.asarray([i["TimeLimit.truncated"] for i in infos]), g["trunc%d" % step])
+        assert rel_err(obs, g["obs%d" % step]) < TOL
+        assert rel_err(rew, g["rew%d" % step]) < TOL
+        for i, info in enumerate(infos):
+            assert ("terminal_observation" in info) == bool(done[i])
+            if done[i]:
+                assert rel_err(info["terminal_observation"], g["termobs%d" % step][i]) < TOL
+
+
+def test_selected_member_path_equals_all_member_path(cm):
+    """Evaluating only the drawn member (ragged K1) is bit-identical to query + gather (reference order)."""
+    g = load_golden("fake_env_extmask.npz")
+    env = _build_env(cm, g)
+    env.reset()
+    rng = np.random.default_rng(3)
+    N = env.num_envs
+    for mech, D in (("transition", 5), ("reward_mech", 1)):
+        model = getattr(env.dynamics, mech)
+        obs = env._obs_dev
+        act = t(rng.uniform(-1, 1, size=(N, 1)).astype(np.float32))
+        idx = t(rng.choice(np.asarray(model.elite_members), size=N).astype(np.uint8))
+        noise = t(rng.normal(size=(N, D)).astype(np.float32))
+        sel = env.predict_selected(model, obs, act, idx, noise)
+        with torch.no_grad():
+            mean, logvar = model.forward(obs.unsqueeze(0), act.unsqueeze(0))
+        allm = cm.ops.select_sample(mean, logvar, idx, noise)
+        assert torch.equal(sel, allm)
+        ref = oc.dynamics_predict(mean.cpu().numpy(), logvar.cpu().numpy(), idx.cpu().numpy().astype(np.int64), noise.cpu().numpy())
+        assert rel_err(sel.cpu().numpy(), ref) < TOL
+
+
+def test_query_and_get_dynamics_predict(cm):
+    g = load_golden("fake_env_termfn.npz")
+    env = _build_env(cm, g)
+    obs = g["reset_obs"]
+    act = g["actions"][0]
+    q = env.dynamics.query(torch.from_numpy(obs), torch.from_numpy(act))
+    assert set(q) == {"batch_next_obs", "batch_reward"}
+    tr = params_of(g, "tr.")
+    o3, a3 = np.repeat(obs[None], 7, 0), np.repeat(act[None], 7, 0)
+    mean, logvar = oc.plain_transition_forward(tr, o3, a3)
+    assert q["batch_next_obs"]["mean"].shape == (7, obs.shape[0], 5)
+    assert rel_err(q["batch_next_obs"]["mean"], mean) < TOL and rel_err(q["batch_next_obs"]["logvar"], logvar) < TOL
+    env.seed(5)
+    pred = env.get_dynamics_predict(q, "transition")
+    gen = np.random.default_rng(5)
+    idx = gen.choice(np.asarray(env.dynamics.transition.elite_members), size=obs.shape[0])
+    noise = gen.normal(size=(obs.shape[0], 5)).astype(np.float32)
+    assert rel_err(pred, oc.dynamics_predict(q["batch_next_obs"]["mean"], q["batch_next_obs"]["logvar"], idx, noise)) < TOL
+    pen = cm.VecFakeEnv.get_penalty(q["batch_next_obs"]["mean"])
+    assert rel_err(pen, oc.mopo_penalty(q["batch_next_obs"]["mean"])) < TOL
+
+
+def test_device_rng_mode_statistics(cm):
+    """Throughput mode: Philox member draw uniform over the elites, noise ~ N(0,1); env runs and resets."""
+    elite = torch.tensor([0, 2, 3, 5, 6], dtype=torch.uint8, device=DEV)
+    N = 1 << 20
+    idx, noise = cm.ops.draw_member_noise(123, 1, N, elite, 6)
+    counts = np.bincount(idx.cpu().numpy(), minlength=7)
+    assert counts[1] == 0 and counts[4] == 0
+    assert np.all(np.abs(counts[[0, 2, 3, 5, 6]] / N - 0.2) < 0.003)
+    z = noise.cpu().numpy().astype(np.float64)
+    assert abs(z.mean()) < 0.003 and abs(z.std() - 1) < 0.003
+    assert abs((z**3).mean()) < 0.01 and abs((z**4).mean() - 3) < 0.03
+    assert abs(np.corrcoef(z[:, 0], z[:, 1])[0, 1]) < 0.005
+    idx2, noise2 = cm.ops.draw_member_noise(123, 2, N, elite, 6)
+    assert not torch.equal(noise, noise2)
+    idx3, noise3 = cm.ops.draw_member_noise(123, 1, N, elite, 6)
+    assert torch.equal(noise, noise3) and torch.equal(idx, idx3)
+    u = cm.ops.draw_uniform_index(7, 3, N, 1000, DEV).cpu().numpy()
+    assert u.min() == 0 and u.max() == 999 and abs(u.mean() - 499.5) < 2
+
+    g = load_golden("fake_env_truncate.npz")
+    env = _build_env(cm, g, rng_mode="device")
+    env.reset()
+    lengths = np.zeros(env.num_envs, dtype=int)
+    for step in range(6):
+        obs, rew, done, infos = env.step(g["actions"][step % 4])
+        lengths += 1
+        trunc = np.asarray([i["TimeLimit.truncated"] for i in infos])
+        assert np.array_equal(trunc, lengths >= 3)
+        assert np.all(done[trunc])
+        lengths[done] = 0
+        assert np.array_equal(env._envs_length, lengths)
+        assert np.isfinite(obs).all() and np.isfinite(rew).all()
+
+
+def test_member_bucket_and_tail_edge_cases(cm):
+    rng = np.random.default_rng(0)
+    for N, E in ((1, 1), (5, 7), (1000, 7), (100003, 16)):
+        idx = rng.integers(0, E, size=N).astype(np.uint8)
+        perm, offsets = cm.ops.member_bucket(t(idx), E)
+        perm, offsets = perm.cpu().numpy(), offsets.cpu().numpy()
+        assert np.array_equal(offsets, np.concatenate([[0], np.cumsum(np.bincount(idx, minlength=E))]))
+        assert np.array_equal(np.sort(perm), np.arange(N))  # a permutation
+        assert np.all(np.diff(idx[perm]) >= 0)  # grouped by member
+    # empty member buckets (all envs choose member 3)
+    perm, offsets = cm.ops.member_bucket(t(np.full(64, 3, np.uint8)), 7)
+    assert offsets.cpu().tolist() == [0, 0, 0, 0, 64, 64, 64, 64]
+    # wide observations take the warp-per-env tail
+    N, O = 257, 40
+    nxt = rng.normal(size=(N, O)).astype(np.float32)
+    reset = rng.normal(size=(N, O)).astype(np.float32)
+    term = (rng.uniform(size=N) < 0.3).astype(np.float32) * 0.25
+    env_len = rng.integers(0, 5, size=N).astype(np.int32)
+    rew = rng.normal(size=N).astype(np.float32)
+    obs_out, rew_out = torch.empty(N, O, device=DEV), torch.empty(N, device=DEV)
+    done, trunc = torch.empty(N, dtype=torch.uint8, device=DEV), torch.empty(N, dtype=torch.uint8, device=DEV)
+    term_obs, n_done, len_dev = torch.empty(N, O, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV), t(env_len)
+    cm.ops.env_step_tail(t(nxt), t(rew), t(term), None, None, 0.0, len_dev, 4, t(reset), None, obs_out, rew_out, done, trunc, term_obs, n_done)
+    o_ref, r_ref, d_ref, t_ref, to_ref, l_ref = oc.env_step_tail(nxt, rew, term, env_len.astype(np.int64), 4, reset)
+    assert np.array_equal(done.cpu().numpy().astype(bool), d_ref) and np.array_equal(trunc.cpu().numpy().astype(bool), t_ref)
+    assert np.array_equal(obs_out.cpu().numpy(), o_ref) and np.array_equal(term_obs.cpu().numpy(), to_ref)
+    assert np.array_equal(len_dev.cpu().numpy(), l_ref) and int(n_done.item()) == int(d_ref.sum())
+
+
+def test_large_rollout_properties(cm):
+    """BASELINE-size property check (C2: 100k envs, ExternalMask 4x200): selected path == all-member path on a
+    random subset, and the step is deterministic for fixed draws."""
+    torch.manual_seed(0)
+    np.random.seed(0)
+    N = 100_000
+    tr = cm.ExternalMaskTransition(5, 1, activation_fn_cfg=SILU, device=DEV)
+    rng = np.random.default_rng(0)
+    mask = (rng.uniform(size=(5, 6)) < 0.5).astype(np.float32)
+    mask[np.arange(5), np.arange(5)] = 1
+    tr.set_input_mask(torch.from_numpy(mask))
+    rw = cm.PlainRewardMech(5, 1, activation_fn_cfg=SILU, device=DEV)
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw)
+    env = cm.VecFakeEnv(N, None, None)
+    env.set_up(dyn, termination_fn=lambda n, o, a: np.zeros((n.shape[0], 1), bool), get_init_obs_fn=lambda n: rng.normal(size=(n, 5)).astype(np.float32))
+    env.reset()
+    obs = env._obs_dev.clone()
+    act = t(rng.uniform(-1, 1, size=(N, 1)).astype(np.float32))
+    idx = t(rng.choice(np.asarray(tr.elite_members), size=N).astype(np.uint8))
+    noise = t(rng.normal(size=(N, 5)).astype(np.float32))
+    a = env.predict_selected(tr, obs, act, idx, noise)
+    b = env.predict_selected(tr, obs, act, idx, noise)
+    assert torch.equal(a, b)
+    sub = torch.arange(0, N, 97, device=DEV)
+    with torch.no_grad():
+        mean, logvar = tr.forward(obs[sub].unsqueeze(0), act[sub].unsqueeze(0))
+    ref = cm.ops.select_sample(mean, logvar, idx[sub].contiguous(), noise[sub].contiguous())
+    assert torch.equal(a[sub], ref)
