@@ -277,6 +277,33 @@ class VecFakeEnv(VecEnv):
         infos = self._make_infos(batch_truncate, done_idx, batch_next_obs)
         return self._current_batch_obs.copy(), batch_reward.copy(), batch_done.copy(), infos
 
+    def step_device(self, actions: torch.Tensor, termination=None):
+        """Device-resident step for rollout collectors that keep their buffers on the GPU: `actions` is a CUDA
+        tensor [N,A]; nothing is copied to the host and nothing synchronises.  Needs rng_mode == "device" and a
+        learned reward mech; termination is the learned mech, or `termination(next_obs, obs, actions)` -> CUDA
+        uint8/bool [N] tensor, or None (episodes end by truncation only).  Returns views of internal buffers
+        (next_obs_after_reset [N,O], reward [N], done u8 [N], truncated u8 [N], terminal_obs [N,O]) that are
+        overwritten by the next step (SB3 ReplayBuffer slabs copy them out on the device)."""
+        assert self.has_set_up, "fake-env has not set up"
+        assert self.rng_mode == "device" and self.learned_reward
+        b = self._bufs
+        obs = self._obs_dev
+        need_all = self.penalty_coeff != 0
+        all_out = {} if need_all else None
+        next_obs = self._predict("transition", obs, actions, all_out)
+        reward = self._predict("reward_mech", obs, actions)
+        terminal_f = terminal_u8 = None
+        if self.learned_termination:
+            terminal_f = self._predict("termination_mech", obs, actions)
+        elif termination is not None:
+            terminal_u8 = termination(next_obs, obs, actions).to(torch.uint8).contiguous()
+        penalty = ops.mopo_penalty(all_out["mean"]) if need_all else None
+        reset_rows, reset_index = self._device_reset_source()
+        ops.env_step_tail(next_obs, reward, terminal_f, terminal_u8, penalty, self.penalty_coeff, self._env_len_dev,
+                          self.max_episode_steps, reset_rows, reset_index, obs, b["reward_out"], b["done"], b["trunc"],
+                          b["term_obs"], None)  # fmt: skip
+        return obs, b["reward_out"], b["done"], b["trunc"], b["term_obs"]
+
     def _make_infos(self, batch_truncate, done_idx, batch_next_obs):
         N = self.num_envs
         if self.infos_mode == "shared":
