@@ -274,8 +274,36 @@ def dominant_kernel_roofline(cm, env, tr, act_dev, args, flush):
 
     pk, src = peaks()
     N = env.num_envs
-    if getattr(env, "precision", "fp32") == "f16" and hasattr(env, "time_dominant_kernel"):
-        return env.time_dominant_kernel(act_dev, flush, pk, src)
+    if getattr(env, "precision", "fp32") == "f16":
+        # tensor-core tier: the fused whole-MLP kernel of the transition mech (5 sub-nets x 4x200 + head per env)
+        idx, noise = cm.ops.draw_member_noise(1, 1, N, env._elite_u8("transition"), O)
+        obs = env._obs_dev
+        for _ in range(3):
+            env.predict_selected(tr, obs, act_dev, idx, noise)
+        reps = max(3, args.steps)
+        perm, offsets = cm.ops.member_bucket(idx, E)
+        mn, mx = tr._bounds()
+        pack = tr.packed_f16()
+        tot = 0.0
+        for r in range(reps):
+            flush.fill_(1.0)
+            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            cm.ops.mlp_rollout_f16(pack, O, E, obs, act_dev, perm, offsets, H, O, cm.ops.HEAD_PARALLEL, True,
+                                   cm.ops.ACT_SILU, True, mn, mx, noise)
+            c.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(c)
+        ms = tot / reps
+        flops = float(FLOP_SUBNET) * O * N
+        achieved = flops / (ms * 1e-3) / 1e12
+        return {
+            "dtype": "f16", "kernel": "mlp_rollout_f16_kernel (fused 4x200 MLP + head + sampling, 5 sub-nets, tcgen05 kind::f16)",
+            "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": src + " bf16 burst",
+            "flops_per_launch": flops, "ms_per_launch": ms,
+            "note": "algorithmic FLOPs = 243200 per (sub-net, env) x 5 sub-nets x N envs (drawn member only, padding not counted)",
+        }  # fmt: skip
     # fp32 tier: grouped SGEMM hidden layer on the bucketed rows of all P sub-nets
     idx, _ = cm.ops.draw_member_noise(1, 1, N, env._elite_u8("transition"), O, want_noise=False)
     perm, offsets = cm.ops.member_bucket(idx, E)

@@ -13,6 +13,8 @@ Extra (non-reference) attributes, all optional:
     rng_mode     "numpy"  (default): member choice and noise drawn by `self.generator` in the reference's order --
                            bit-exact member choice / done flags against the reference for the same seed;
                  "device": Philox draws on the GPU (statistically equivalent, no host RNG work).
+    precision    "fp32"   (default): CUDA-core FFMA kernels, 1e-5 relative parity with the reference;
+                 "f16":   the fused tcgen05 kernel (fp16 operands, fp32 accumulation), 1e-3 relative parity.
     infos_mode   "dicts"  (default): one fresh dict per env like the reference;
                  "shared": envs that are neither done nor truncated share one read-only dict (O(#done) host work).
 """
@@ -68,6 +70,7 @@ class VecFakeEnv(VecEnv):
         # B200-side knobs and state
         self.rng_mode = "numpy"
         self.infos_mode = "dicts"
+        self.precision = "fp32"  # "fp32": CUDA-core tier (1e-5 parity); "f16": tcgen05 tier (1e-3 parity)
         self.init_obs_pool_size = None  # device rng_mode + get_init_obs_fn: size of the pre-drawn reset pool
         self._device_seed = 0
         self._draw_counter = 0
@@ -195,6 +198,12 @@ class VecFakeEnv(VecEnv):
         b = self._bufs
         N, D, E = obs.shape[0], model._head_dim, model.ensemble_num
         perm, offsets = ops.member_bucket(idx, E, b["perm"], b["offsets"], b["counters"])
+        if self.precision == "f16":
+            mn, mx = model._bounds()
+            return ops.mlp_rollout_f16(model.packed_f16(), model._parallel_num(), E, obs, act, perm, offsets,
+                                       model.hid_size, D, model._head_layout, not model.deterministic, model._act_kind,
+                                       model._residual(), mn, mx, noise)  # fmt: skip
+        assert self.precision == "fp32", "precision must be 'fp32' or 'f16'"
         h = ops.gather_inputs(obs, act, perm)
         params = model._stack_params()
         L = model.num_layers

@@ -287,6 +287,27 @@ class EnsembleMLP(nn.Module):
             self._reg_cache = cached
         return cached[1]
 
+    # ------------------------------------------------------------------ private fp16 weight cache (tcgen05 tier)
+    def packed_f16(self):
+        """Padded fp16 copy of the weights in the layout cmrl_mlp_rollout_f16 stages by TMA; rebuilt whenever a
+        parameter (or the input mask) changed.  Private: never appears in state_dict / checkpoints."""
+        params = self._stack_params()
+        n_lin = len(params) - self._n_bound_params()
+        mask = self._kernel_mask()
+        key = tuple(p._version for p in params[:n_lin]) + tuple(p.data_ptr() for p in params[:n_lin]) + (
+            None if mask is None else (mask.data_ptr(), mask._version),)  # fmt: skip
+        cached = self._packed.get("f16")
+        if cached is None or cached[0] != key:
+            E = self.ensemble_num
+            if mask is not None and (mask.dim() == 4 or (mask.dim() == 3 and mask.shape[1] != E)):
+                raise ops._lib.CmrlB200Error("per-sample input masks cannot be folded into packed weights; use precision='fp32'")
+            mask_str = ops.mask_strides(mask, self._parallel_num(), E, -1) if mask is not None else (0, 0, 0)
+            with torch.no_grad():
+                pack = ops.pack_mlp_f16(params[0:n_lin:2], params[1:n_lin:2], mask, mask_str)
+            cached = (key, pack)
+            self._packed["f16"] = cached
+        return cached[1]
+
     # ------------------------------------------------------------------ flat parameter arena
     def _flatten_parameters(self):
         """Re-home every parameter as a view of one contiguous fp32 buffer (16-byte aligned slots).

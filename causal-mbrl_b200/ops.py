@@ -293,3 +293,57 @@ def env_step_tail(next_obs, reward, terminal_f, terminal_u8, penalty, penalty_co
               _ptr(penalty), float(penalty_coeff), env_len.data_ptr(), int(max_episode_steps), _ptr(reset_obs),
               _ptr(reset_index), N, O, obs_out.data_ptr(), reward_out.data_ptr(), done.data_ptr(),
               truncated.data_ptr(), _ptr(terminal_obs), _ptr(n_done), _stream())  # fmt: skip
+
+
+# ----------------------------------------------------------------------------- tensor-core tier (tcgen05, fp16)
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0)):
+    """Pack a mechanism's fp32 parameters into the private fp16 device layout of cmrl_mlp_rollout_f16.
+    weights/biases: per layer [(P,)E,in,out] / [(P,)E,1,out] (hidden layers, then the head).
+    Returns (blob half tensor [nets, blob_halfs], layer_off, layer_k, layer_n) -- never part of state_dict."""
+    w0 = weights[0]
+    parallel = w0.dim() == 4
+    P = w0.shape[0] if parallel else 1
+    E = w0.shape[-3]
+    layer_k, layer_n, layer_off, off = [], [], [], 0
+    for w in weights:
+        k_pad, n_pad = _round_up(w.shape[-2] + 1, 16), _round_up(w.shape[-1], 16)
+        layer_k.append(k_pad)
+        layer_n.append(n_pad)
+        layer_off.append(off)
+        off += k_pad * n_pad
+    # hidden outputs feed the next layer's K (incl. the bias slot): widen N of hidden layers to the next K
+    for i in range(len(weights) - 1):
+        layer_n[i] = layer_k[i + 1]
+    layer_off, off = [], 0
+    for k_pad, n_pad in zip(layer_k, layer_n):
+        layer_off.append(off)
+        off += k_pad * n_pad
+    blob = torch.zeros((P * E, off), device=w0.device, dtype=torch.float16)
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        w, b = w.detach().contiguous(), b.detach().contiguous()
+        m = mask if i == 0 else None
+        _lib.call("cmrl_pack_layer_f16", w.data_ptr(), b.data_ptr(), _ptr(m), mask_str[0], mask_str[1], P, E,
+                  w.shape[-2], w.shape[-1], layer_k[i], layer_n[i], blob.data_ptr() + 2 * layer_off[i], off, _stream())  # fmt: skip
+    return blob, layer_off, layer_k, layer_n
+
+
+def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, gaussian, act_kind, residual,
+                    min_logvar, max_logvar, noise, out=None):  # fmt: skip
+    import ctypes
+
+    blob, layer_off, layer_k, layer_n = pack
+    N, O = obs.shape
+    A = act.shape[1]
+    L = len(layer_k) - 1
+    arr = ctypes.c_int * (L + 1)
+    pred = torch.empty((N, head_dim), device=obs.device, dtype=torch.float32) if out is None else out
+    bounds_n = 0 if min_logvar is None else min_logvar.numel()
+    _lib.call("cmrl_mlp_rollout_f16", blob.data_ptr(), blob.shape[1], arr(*layer_off), arr(*layer_k), arr(*layer_n), L,
+              P, E, N, O, A, H, head_dim, layout, 1 if gaussian else 0, act_kind, obs.data_ptr(), act.data_ptr(),
+              perm.data_ptr(), offsets.data_ptr(), 1 if residual else 0, _ptr(min_logvar), _ptr(max_logvar), bounds_n,
+              _ptr(noise), pred.data_ptr(), _stream())  # fmt: skip
+    return pred

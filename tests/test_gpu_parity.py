@@ -470,3 +470,78 @@ def test_large_rollout_properties(cm):
         mean, logvar = tr.forward(obs[sub].unsqueeze(0), act[sub].unsqueeze(0))
     ref = cm.ops.select_sample(mean, logvar, idx[sub].contiguous(), noise[sub].contiguous())
     assert torch.equal(a[sub], ref)
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 tier
+TOL_TC = 1e-3  # north_star: 1e-3 relative at TF32 / 16-bit operands
+
+
+def _tc_case(cm, kind, N, H, seed):
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    O, A = 5, 1
+    if kind == "extmask":
+        m = cm.ExternalMaskTransition(O, A, hid_size=H, activation_fn_cfg=SILU, device=DEV)
+        mask = (rng.uniform(size=(O, O + A)) < 0.5).astype(np.float32)
+        mask[np.arange(O), np.arange(O)] = 1
+        m.set_input_mask(torch.from_numpy(mask))
+    elif kind == "plain":
+        m = cm.PlainTransition(O, A, hid_size=H, activation_fn_cfg=SILU, device=DEV)
+    elif kind == "plain_relu":
+        m = cm.PlainTransition(O, A, hid_size=H, device=DEV)
+    else:
+        m = cm.PlainRewardMech(O, A, hid_size=H, activation_fn_cfg=SILU, device=DEV)
+    with torch.no_grad():  # non-trivial biases / head so every term of the epilogue matters
+        for prm in m.parameters():
+            if prm.dim() >= 3 and prm.shape[-2] == 1:
+                prm.add_(torch.randn_like(prm) * 0.1)
+    dyn = cm.PlainEnsembleDynamics(m if kind != "reward" else cm.PlainTransition(O, A, hid_size=8, device=DEV),
+                                   learned_reward=kind == "reward", reward_mech=m if kind == "reward" else None)
+    env = cm.VecFakeEnv(N, None, None)
+    env.set_up(dyn, reward_fn=lambda n, o, a: np.zeros((n.shape[0], 1), np.float32), termination_fn=lambda n, o, a: np.zeros((n.shape[0], 1), bool),
+               get_init_obs_fn=lambda n: rng.normal(size=(n, O)).astype(np.float32))
+    env.reset()
+    obs = env._obs_dev
+    act = t(rng.uniform(-1, 1, size=(N, A)).astype(np.float32))
+    idx = t(rng.choice(np.asarray(m.elite_members), size=N).astype(np.uint8))
+    noise = t(rng.normal(size=(N, m._head_dim)).astype(np.float32))
+    return env, m, obs, act, idx, noise
+
+
+@pytest.mark.parametrize("kind,N,H", [("plain", 300, 200), ("extmask", 1000, 200), ("reward", 777, 200), ("plain_relu", 130, 64),
+                                      ("extmask", 5, 40), ("plain", 20000, 200)])
+def test_tcgen05_rollout_vs_fp32_tier(cm, kind, N, H):
+    """The fused tcgen05 kernel (fp16 operands, fp32 accumulate) against the fp32 tier on the same draws:
+    1e-3 relative on the predicted variable, and on the network's own contribution (pred - obs residual)."""
+    env, m, obs, act, idx, noise = _tc_case(cm, kind, N, H, seed=N)
+    env.precision = "fp32"
+    ref = env.predict_selected(m, obs, act, idx, noise)
+    env.precision = "f16"
+    out = env.predict_selected(m, obs, act, idx, noise)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < TOL_TC
+    # deterministic part only (no noise): isolates mean from logvar
+    env.precision = "fp32"
+    ref_m = env.predict_selected(m, obs, act, idx, None)
+    env.precision = "f16"
+    out_m = env.predict_selected(m, obs, act, idx, None)
+    assert rel_err(out_m.cpu().numpy(), ref_m.cpu().numpy()) < TOL_TC
+    if m._residual():
+        d_ref = (ref_m - obs).cpu().numpy()
+        d_out = (out_m - obs).cpu().numpy()
+        assert rel_err(d_out, d_ref) < 5e-3  # the head's own output (no residual to hide behind)
+    # repeatable
+    assert torch.equal(out, env.predict_selected(m, obs, act, idx, noise))
+
+
+def test_tcgen05_pack_refreshes_on_weight_change(cm):
+    env, m, obs, act, idx, noise = _tc_case(cm, "plain", 256, 200, seed=9)
+    env.precision = "f16"
+    a = env.predict_selected(m, obs, act, idx, noise)
+    with torch.no_grad():
+        m.mean_and_logvar.bias.add_(0.5)
+    b = env.predict_selected(m, obs, act, idx, noise)
+    assert not torch.equal(a, b)
+    assert "hidden_layers.0.0.weight" in m.state_dict() and all(v.dtype == torch.float32 for v in m.state_dict().values())
