@@ -242,7 +242,7 @@ def run_native(args):
 
     if rank == 0:
         cpu = None
-        if world == 1 or rank == 0:
+        if not args.no_cpu_baseline:
             v, ms, threads = time_port(args.ref_envs, 2, 1)
             cpu = {"value": v, "unit": "transitions/s", "cores": threads, "kind": "port",
                    "sample": "%d envs x 2 steps of the same C2 step on the torch-CPU port of the reference" % args.ref_envs}  # fmt: skip
@@ -370,7 +370,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--envs", type=int, default=100_000)
     ap.add_argument("--ref-envs", type=int, default=10_000)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "f16"])
+    ap.add_argument("--precision", default="f16", choices=["fp32", "f16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU port timing (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

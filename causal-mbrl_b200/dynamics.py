@@ -33,6 +33,14 @@ from .types import InteractionBatch
 from .util import to_tensor
 
 
+def dp_row_slice(num_rows: int, world_size: int, rank: int) -> slice:
+    """Rows of an ensemble batch owned by `rank` in data-parallel training: contiguous, remainder to the low
+    ranks, so ragged last batches are covered exactly once."""
+    base, rem = divmod(num_rows, world_size)
+    start = rank * base + min(rank, rem)
+    return slice(start, start + base + (1 if rank < rem else 0))
+
+
 def split_dict(old_dict: Dict, need_keys: List[str]):
     return dict([(key, old_dict[key]) for key in need_keys])
 
@@ -233,6 +241,16 @@ class BaseDynamics:
         optim.step()
         return loss
 
+    def enable_data_parallel(self, group=None):
+        """Shard every ensemble batch's rows over the ranks of `group` (default: the world group) in `train`;
+        gradients are summed with one all-reduce over the flat arena and the loss scale uses the global row count,
+        so every rank applies the identical Adam update."""
+        import torch.distributed as dist
+
+        self.dp_group = group if group is not None else dist.group.WORLD
+        self.dp_world = dist.get_world_size(self.dp_group)
+        self.dp_rank = dist.get_rank(self.dp_group)
+
     def _sync_grads(self, model):
         """Data-parallel gradient exchange: one NCCL all-reduce (sum) over the flat gradient arena."""
         if self.dp_group is not None:
@@ -251,7 +269,12 @@ class BaseDynamics:
             obs = self.get_3d_tensor(batch.batch_obs, is_ensemble=True)
             act = self.get_3d_tensor(batch.batch_action, is_ensemble=True)
             target = self.get_3d_tensor(self._batch_variable(batch, variable), is_ensemble=True)
-            batch_loss_list.append(self.train_step(mech, obs, act, target))
+            if self.dp_group is not None:
+                rows = obs.shape[1]
+                sl = dp_row_slice(rows, self.dp_world, self.dp_rank)
+                batch_loss_list.append(self.train_step(mech, obs[:, sl], act[:, sl], target[:, sl], grad_rows=rows))
+            else:
+                batch_loss_list.append(self.train_step(mech, obs, act, target))
         return torch.cat(batch_loss_list, dim=batch_loss_list[0].ndim - 2).detach().cpu()
 
     def query(self, obs, action, return_as_np=True):

@@ -1,0 +1,84 @@
+"""World-size-2 `gloo` tests (CPU) of the data-parallel host logic: row sharding, gradient all-reduce
+equivalence (sum of shard gradients with the global loss scale == full-batch gradient) and the bench reference arm
+under torchrun semantics (rank 0 alone prints)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_golden, params_of, rel_err
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from oracle import cmrl_oracle as oc
+    import cmrl_b200 as cm
+    from cmrl_b200.dynamics import dp_row_slice
+
+    g = load_golden("plain_train.npz")
+    p = params_of(g, "p0.")
+    obs, act, target = g["obs0"], g["act0"], g["target0"]
+    B = obs.shape[1]
+    sl = dp_row_slice(B, world, rank)
+    # local gradient of the shard, scaled by the GLOBAL element count (train_step's grad_rows)
+    _, grads = oc.plain_nll_backward(p, obs[:, sl], act[:, sl], target[:, sl])
+    local_rows = sl.stop - sl.start
+    flat = torch.cat([torch.from_numpy(grads[k] * np.float32(local_rows / B)).reshape(-1) for k in sorted(grads)])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    # a dynamics object picks up the group and shards consistently
+    dyn = cm.PlainEnsembleDynamics(cm.PlainTransition(5, 1, hid_size=8), learned_reward=False)
+    dyn.enable_data_parallel()
+    ok = dyn.dp_world == world and dyn.dp_rank == rank
+    if rank == 0:
+        _, full = oc.plain_nll_backward(p, obs, act, target)
+        ref = torch.cat([torch.from_numpy(full[k]).reshape(-1) for k in sorted(full)])
+        out.put((rel_err(flat.numpy(), ref.numpy()), ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_gradient_allreduce_matches_full_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and err < 1e-5
+
+
+def test_dp_row_slices_cover_ragged_batches():
+    from cmrl_b200.dynamics import dp_row_slice
+
+    for rows in (0, 1, 7, 256, 257):
+        for world in (1, 2, 4, 8):
+            covered = np.concatenate([np.arange(rows)[dp_row_slice(rows, world, r)] for r in range(world)])
+            assert np.array_equal(covered, np.arange(rows))
+            sizes = [dp_row_slice(rows, world, r).stop - dp_row_slice(rows, world, r).start for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_bench_reference_arm_prints_one_line_on_rank0_only():
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + os.getpid() % 200), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "0", "--ref-envs", "256"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["unit"] == "transitions/s" and rec["value"] > 0
+    assert rec["cpu_baseline"]["kind"] == "port" and rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["n_gpus"] == 2

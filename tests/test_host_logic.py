@@ -1,0 +1,212 @@
+"""CPU tests: host-side mirror of the reference interface, the C-ABI symbol table and (when the reference tree is
+mounted) drop-in equivalences against the unmodified reference classes.  No CUDA compute calls."""
+import ctypes
+import os
+import re
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden, params_of
+
+import cmrl_b200 as cm
+from oracle import refshim
+
+SILU = {"_target_": "torch.nn.SiLU"}
+
+
+def test_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "cmrl_b200.h")).read()
+    declared = set(re.findall(r"\b(cmrl_[a-z0-9_]+)\s*\(", header))
+    lib = cm._lib.load()
+    assert lib.cmrl_abi_version() == 1
+    for name in declared:
+        assert hasattr(lib, name), "libcmrl_b200.so does not export %s" % name
+    bound = set(cm._lib.PROTOTYPES) | {"cmrl_abi_version", "cmrl_last_error", "cmrl_launch_count"}
+    assert declared == bound, declared ^ bound
+    # argument validation happens before any CUDA call
+    rc = lib.cmrl_ens_linear_fwd(None, 0, 0, None, None, None, None, 1, 1, 1, 1, 1, None, 0, 0, 0, None, 0, None)
+    assert rc < 0 and b"null pointer" in lib.cmrl_last_error()
+
+
+def test_no_cpu_fallback():
+    m = cm.PlainTransition(5, 1, hid_size=8)
+    with pytest.raises(cm._lib.CmrlB200Error):
+        m.forward(torch.zeros(7, 3, 5), torch.zeros(7, 3, 1))
+    with pytest.raises(cm._lib.CmrlB200Error):
+        cm.EnsembleLinearLayer(3, 4, ensemble_num=2)(torch.zeros(2, 5, 3))
+
+
+def test_unsupported_activation_is_loud():
+    with pytest.raises(NotImplementedError):
+        cm.PlainTransition(5, 1, hid_size=8, activation_fn_cfg={"_target_": "torch.nn.Tanh"})
+
+
+@pytest.mark.parametrize("cls,kw,fname", [
+    ("PlainTransition", {}, "plain_transition.pth"),
+    ("ExternalMaskTransition", {}, "external_mask_transition.pth"),
+    ("PlainRewardMech", {}, "plain_reward_mech.pth"),
+    ("PlainTerminationMech", {}, "plain_termination_mech.pth"),
+])
+def test_state_dict_layout_and_checkpoint_roundtrip(cls, kw, fname):
+    m = getattr(cm, cls)(5, 1, hid_size=16, activation_fn_cfg=SILU, **kw)
+    sd = m.state_dict()
+    lead = (5, 7) if cls == "ExternalMaskTransition" else (7,)
+    head = 10 if cls == "PlainTransition" else 2
+    assert tuple(sd["hidden_layers.0.0.weight"].shape) == lead + (6, 16)
+    assert tuple(sd["hidden_layers.3.0.bias"].shape) == lead + (1, 16)
+    assert tuple(sd["mean_and_logvar.weight"].shape) == lead + (16, head)
+    bounds = {"PlainTransition": (1, 5), "ExternalMaskTransition": (5, 1, 1, 1)}.get(cls, (1,))
+    assert tuple(sd["min_logvar"].shape) == bounds and float(sd["min_logvar"].flatten()[0]) == -10.0
+    assert float(sd["max_logvar"].flatten()[0]) == 0.5 and not m.min_logvar.requires_grad
+    assert m.model_file_name == fname
+    with tempfile.TemporaryDirectory() as d:
+        m.save(d)
+        assert os.listdir(d) == [fname]
+        m2 = getattr(cm, cls)(5, 1, hid_size=16, activation_fn_cfg=SILU, **kw)
+        m2.load(d)
+        for k in sd:
+            assert torch.equal(sd[k], m2.state_dict()[k])
+        assert list(np.asarray(m2.elite_members)) == list(np.asarray(m.elite_members))
+        if cls == "ExternalMaskTransition":
+            assert torch.equal(m2.input_mask, m.input_mask) and "input_mask" in m.save_attr
+
+
+def test_elite_bookkeeping_and_random_index():
+    m = cm.PlainTransition(5, 1, hid_size=8)
+    assert len(m.elite_members) == 5
+    m.set_elite_members([0, 2, 3, 5, 6])
+    m.set_elite_members(list(range(7)))  # ignored when all members are passed (mlp.py:31-34)
+    assert m.elite_members == [0, 2, 3, 5, 6]
+    a = m.get_random_index(100, np.random.default_rng(3))
+    b = np.random.default_rng(3).choice([0, 2, 3, 5, 6], size=100)
+    assert np.array_equal(a, b)
+
+
+def test_interaction_batch():
+    """tests/test_types.py:9-47 of the reference."""
+    n = 12
+    b = cm.InteractionBatch(np.zeros((n, 3)), np.zeros((n, 2)), np.zeros((n, 3)), np.zeros(n), np.zeros(n, bool))
+    assert len(b) == n and len(b.as_tuple()) == 5
+    sub = b[[1, 4, 5]]
+    assert len(sub) == 3 and sub.batch_obs.shape == (3, 3)
+    r = b.add_new_batch_dim(4)
+    assert r.batch_obs.shape == (4, 3, 3) and r.batch_reward.shape == (4, 3) and r.batch_done.shape == (4, 3)
+    with pytest.raises(ValueError):
+        b.add_new_batch_dim(5)
+    assert b.attrs == ["batch_obs", "batch_action", "batch_next_obs", "batch_reward", "batch_done"]
+
+
+def _data(n, rng):
+    return cm.InteractionBatch(rng.normal(size=(n, 3)).astype(np.float32), rng.normal(size=(n, 1)).astype(np.float32),
+                               rng.normal(size=(n, 3)).astype(np.float32), rng.normal(size=n).astype(np.float32),
+                               np.zeros(n, bool))
+
+
+def test_iterators_shapes_and_coverage():
+    rng = np.random.default_rng(0)
+    data = _data(103, rng)
+    it = cm.TransitionIterator(data, 32, shuffle_each_epoch=True, rng=np.random.default_rng(1))
+    assert len(it) == 4
+    seen = np.concatenate([b.batch_reward for b in it])
+    assert np.array_equal(np.sort(seen), np.sort(data.batch_reward))  # a permutation, ragged last batch of 7
+    bt = cm.BootstrapIterator(data, 32, 7, shuffle_each_epoch=True, permute_indices=False, rng=np.random.default_rng(2))
+    batches = list(bt)
+    assert [b.batch_obs.shape for b in batches] == [(7, 32, 3)] * 3 + [(7, 7, 3)]
+    assert batches[0].batch_reward.shape == (7, 32) and batches[0].batch_done.dtype == bool
+    mi, order = bt.device_plan()
+    assert mi.shape == (7, 103) and np.array_equal(batches[1].batch_obs[3], data.batch_obs[mi[3, order[32:64]]])
+    bp = cm.BootstrapIterator(data, 32, 7, permute_indices=True, rng=np.random.default_rng(2))
+    assert all(np.array_equal(np.sort(row), np.arange(103)) for row in bp.member_indices)
+    bp.toggle_bootstrap()
+    assert next(iter(bp)).batch_obs.shape == (32, 3)
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted (GPU box)")
+def test_iterators_match_reference_bit_for_bit():
+    ref = refshim.load_reference()
+    rng = np.random.default_rng(0)
+    data = _data(257, rng)
+    rdata = ref.InteractionBatch(*data.as_tuple())
+    for permute in (False, True):
+        a = cm.BootstrapIterator(data, 64, 7, shuffle_each_epoch=True, permute_indices=permute, rng=np.random.default_rng(5))
+        b = ref.BootstrapIterator(rdata, 64, 7, shuffle_each_epoch=True, permute_indices=permute, rng=np.random.default_rng(5))
+        for _ in range(2):  # two epochs: the shuffle consumes the generator identically
+            for x, y in zip(a, b):
+                for u, v in zip(x.as_tuple(), y.as_tuple()):
+                    assert np.array_equal(u, v)
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("cls,kw", [("PlainTransition", {}), ("ExternalMaskTransition", {}), ("PlainRewardMech", {}),
+                                     ("PlainTransition", {"activation_fn_cfg": None, "deterministic": True})])
+def test_same_seed_gives_the_reference_initial_weights(cls, kw):
+    """Constructing with the same torch / numpy seeds reproduces the reference's init (truncated normal
+    resampling order, layers.py:8-28) and its random initial elites (mlp.py:27) exactly."""
+    ref = refshim.load_reference()
+    args = dict(hid_size=24, activation_fn_cfg=SILU)
+    args.update(kw)
+    torch.manual_seed(7)
+    np.random.seed(7)
+    a = getattr(cm, cls)(5, 1, **args)
+    torch.manual_seed(7)
+    np.random.seed(7)
+    b = getattr(ref, cls)(5, 1, **args)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert list(a.elite_members) == list(b.elite_members)
+
+
+def test_dynamics_host_logic_without_gpu():
+    tr = cm.PlainTransition(3, 1, hid_size=8)
+    rw = cm.PlainRewardMech(3, 1, hid_size=8)
+    tm = cm.PlainTerminationMech(3, 1, hid_size=8)
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw, learned_termination=True, termination_mech=tm)
+    assert dyn.learn_mech == ["transition", "reward_mech", "termination_mech"]
+    assert dyn.get_variable_by_mech("reward_mech") == "batch_reward" and dyn.get_mach_by_variable("batch_next_obs") == "transition"
+    assert dyn.total_epoch == {"transition": 0, "reward_mech": 0, "termination_mech": 0}
+    rng = np.random.default_rng(0)
+    n = 50
+    buf = refshim.DuckReplayBuffer(rng.normal(size=(n, 3)).astype(np.float32), rng.normal(size=(n, 1)).astype(np.float32),
+                                   rng.normal(size=(n, 3)).astype(np.float32), rng.normal(size=n).astype(np.float32), np.zeros(n, bool))
+    tr_it, val_it = dyn.dataset_split(buf, validation_ratio=0.2, batch_size=16)
+    assert tr_it.num_stored == 40 and val_it.num_stored == 10 and isinstance(tr_it, cm.BootstrapIterator)
+    assert np.array_equal(val_it.transitions.batch_obs, buf.observations[40:, 0])  # tail = validation, no shuffle
+    # elite selection and best-weight snapshot rules (plain_dynamics.py:113-142)
+    best = torch.tensor([1.0, 2.0, 0.5, 4.0, 3.0, 0.1, 9.0])
+    assert dyn.maybe_get_best_weights(best, best * 0.95, "transition", 0.1) is None
+    snap = dyn.maybe_get_best_weights(best, torch.where(torch.arange(7) == 3, best * 0.5, best), "transition", 0.1)
+    assert snap is not None and set(snap) == set(tr.state_dict())
+    dyn.maybe_set_best_weights_and_elite(None, best, "transition")
+    assert list(tr.elite_members) == [5, 2, 0, 1, 4]
+    t = dyn.get_3d_tensor(np.ones((4, 3), np.float32), is_ensemble=False)
+    assert tuple(t.shape) == (7, 4, 3) and t.stride(0) == 0  # broadcast view, never replicated
+    assert tuple(dyn.get_3d_tensor(np.ones((7, 4), np.float32), is_ensemble=True).shape) == (7, 4, 1)
+
+
+def test_fake_env_host_side_contract():
+    env = cm.VecFakeEnv(8, None, None)
+    assert env.num_envs == 8 and not env.has_set_up and env.reset() is None
+    with pytest.raises(AssertionError):
+        env.step_async(np.zeros((8, 1), np.float32))
+        env.step_wait()
+    infos = env._make_infos(np.array([False, True] + [False] * 6), np.array([1, 3]), np.arange(16, dtype=np.float32).reshape(8, 2))
+    assert [i["TimeLimit.truncated"] for i in infos] == [False, True] + [False] * 6
+    assert "terminal_observation" in infos[1] and "terminal_observation" in infos[3] and "terminal_observation" not in infos[0]
+    env.infos_mode = "shared"
+    infos2 = env._make_infos(np.array([False, True] + [False] * 6), np.array([1, 3]), np.arange(16, dtype=np.float32).reshape(8, 2))
+    assert [bool(i["TimeLimit.truncated"]) for i in infos2] == [False, True] + [False] * 6
+    assert np.array_equal(infos2[3]["terminal_observation"], [6.0, 7.0]) and infos2[0] is infos2[2]
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted (GPU box)")
+def test_batched_reset_draws_equal_reference_per_env_draws():
+    """One get_init_obs_fn(n) call == n calls of size 1 for generator-backed callbacks (DESIGN.md decision 3)."""
+    a, b = np.random.default_rng(3), np.random.default_rng(3)
+    x = a.normal(size=(5, 4)).astype(np.float32)
+    y = np.concatenate([b.normal(size=(1, 4)).astype(np.float32) for _ in range(5)])
+    assert np.array_equal(x, y)
