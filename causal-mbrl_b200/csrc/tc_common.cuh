@@ -1,0 +1,142 @@
+// Inline-PTX helpers shared by the tcgen05 kernels (mbarrier, TMA bulk copy, UMMA descriptors, TMEM access).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace cmrl {
+namespace tc {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int A_CHUNK_BYTES = TILE_M * 16;  // one 8-element K chunk for all 128 rows (core matrices of 8 rows x 16 B)
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t HEAD_TMEM_COL = 256;
+constexpr unsigned long long SPIN_LIMIT = 1ull << 27;  // ~ seconds; a broken pipeline traps instead of hanging the GPU
+
+struct RolloutP {
+    const __half* packed;      // [nets][blob]
+    long long blob_halfs;      // per-net blob size (halves)
+    int layer_off[8];          // offset (halves) of each layer's B blob inside a net blob
+    int layer_k[8];            // padded K per layer (multiple of 16)
+    int layer_n[8];            // padded N per layer (multiple of 16)
+    int num_layers;            // hidden layers L; layer index L is the head
+    int P, E, N, O, A, H;
+    int head_dim;              // D: outputs per env this mech predicts (O, or 1)
+    int layout;                // CMRL_HEAD_PLAIN / CMRL_HEAD_PARALLEL
+    int gaussian;              // 0 = deterministic head
+    int act;
+    const float* obs;          // [N,O] env order
+    const float* actn;         // [N,A]
+    const int* perm;           // [N] sorted row -> env
+    const int* offsets;        // [E+1]
+    int residual;
+    const float* min_logvar;
+    const float* max_logvar;
+    int bounds_n;
+    const float* noise;        // [N,D] env order or NULL
+    float* pred;               // [N,D] env order
+    uint32_t w_stage_bytes;    // max over layers of n*k*2
+    int a_chunks;              // K chunks (of 8) the A buffer holds
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    unsigned long long spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE ("interleave"): core matrix = 8 rows x 16 bytes
+// contiguous; LBO = byte step between the two K core matrices of one MMA, SBO = byte step between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;                // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, M x N
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    __syncwarp();
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float act_fast(float z, int act) {
+    if (act == CMRL_ACT_RELU) return fmaxf(z, 0.0f);
+    if (act == CMRL_ACT_SILU) return __fdividef(z, 1.0f + __expf(-z));
+    return z;
+}
+
+// two fp32 -> packed fp16x2 (a in the low half), round-to-nearest, saturating to +-65504 instead of inf
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+
+
+}  // namespace tc
+}  // namespace cmrl

@@ -331,6 +331,9 @@ def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0)):
     return blob, layer_off, layer_k, layer_n
 
 
+TC_VARIANT = 2  # 2: weight-stationary CTA pairs (default); 1: single-CTA streamed weights
+
+
 def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, gaussian, act_kind, residual,
                     min_logvar, max_logvar, noise, out=None):  # fmt: skip
     import ctypes
@@ -345,5 +348,5 @@ def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, ga
     _lib.call("cmrl_mlp_rollout_f16", blob.data_ptr(), blob.shape[1], arr(*layer_off), arr(*layer_k), arr(*layer_n), L,
               P, E, N, O, A, H, head_dim, layout, 1 if gaussian else 0, act_kind, obs.data_ptr(), act.data_ptr(),
               perm.data_ptr(), offsets.data_ptr(), 1 if residual else 0, _ptr(min_logvar), _ptr(max_logvar), bounds_n,
-              _ptr(noise), pred.data_ptr(), _stream())  # fmt: skip
+              _ptr(noise), pred.data_ptr(), TC_VARIANT, _stream())  # fmt: skip
     return pred

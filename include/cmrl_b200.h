@@ -190,12 +190,14 @@ int cmrl_pack_layer_f16(const float* w, const float* b, const float* mask, long 
  * PlainTransition / ExternalMaskTransition / PlainRewardMech / PlainTerminationMech forward): for every
  * bucketed env row (perm/offsets from cmrl_member_bucket) run the drawn member's whole MLP on tcgen05 tensor
  * cores with TMA-staged packed weights and write pred[env,:] = mean (+obs) + sqrt(exp(logvar)) * noise[env,:].
- * layer_*: arrays of num_layers+1 entries (hidden layers, then the head). */
+ * layer_*: arrays of num_layers+1 entries (hidden layers, then the head).
+ * variant: 2 = weight-stationary CTA pairs (cta_group::2, pipelined epilogue; hidden <= 207), 1 = single-CTA
+ * tiles with per-layer streamed weights (any hidden width whose stage fits shared memory). */
 int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, const int* layer_off_halfs, const int* layer_k,
                          const int* layer_n, int num_layers, int P, int E, int N, int O, int A, int H, int head_dim,
                          int layout, int gaussian, int act, const float* obs, const float* actn, const int* perm,
                          const int* offsets, int residual, const float* min_logvar, const float* max_logvar,
-                         int bounds_n, const float* noise, float* pred, void* stream);
+                         int bounds_n, const float* noise, float* pred, int variant, void* stream);
 
 #ifdef __cplusplus
 }

@@ -509,9 +509,17 @@ def _tc_case(cm, kind, N, H, seed):
     return env, m, obs, act, idx, noise
 
 
+@pytest.fixture(params=[2, 1], ids=["cta_pair", "single_cta"])
+def tc_variant(request, cm):
+    old = cm.ops.TC_VARIANT
+    cm.ops.TC_VARIANT = request.param
+    yield request.param
+    cm.ops.TC_VARIANT = old
+
+
 @pytest.mark.parametrize("kind,N,H", [("plain", 300, 200), ("extmask", 1000, 200), ("reward", 777, 200), ("plain_relu", 130, 64),
-                                      ("extmask", 5, 40), ("plain", 20000, 200)])
-def test_tcgen05_rollout_vs_fp32_tier(cm, kind, N, H):
+                                      ("extmask", 5, 40), ("plain", 20000, 200), ("extmask", 100000, 200)])
+def test_tcgen05_rollout_vs_fp32_tier(cm, tc_variant, kind, N, H):
     """The fused tcgen05 kernel (fp16 operands, fp32 accumulate) against the fp32 tier on the same draws:
     1e-3 relative on the predicted variable, and on the network's own contribution (pred - obs residual)."""
     env, m, obs, act, idx, noise = _tc_case(cm, kind, N, H, seed=N)
@@ -521,6 +529,7 @@ def test_tcgen05_rollout_vs_fp32_tier(cm, kind, N, H):
     out = env.predict_selected(m, obs, act, idx, noise)
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
+    print("tc variant %d %s N=%d H=%d rel_err %.2e" % (tc_variant, kind, N, H, rel_err(out.cpu().numpy(), ref.cpu().numpy())))
     assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < TOL_TC
     # deterministic part only (no noise): isolates mean from logvar
     env.precision = "fp32"
