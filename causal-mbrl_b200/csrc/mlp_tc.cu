@@ -288,6 +288,12 @@ int launch_rollout_v2(const RolloutP& p, cudaStream_t st);
 
 using namespace cmrl;
 
+static long long* g_dbg_buffer = nullptr;
+static int g_dbg_flags = 0;
+extern "C" void cmrl_debug_set_flags(int f) { g_dbg_flags = f; }
+// profiling hook (not part of the public header): device buffer [grid][16] of per-role cycle counters, or NULL
+extern "C" void cmrl_debug_set_buffer(void* buf) { g_dbg_buffer = (long long*)buf; }
+
 extern "C" int cmrl_pack_layer_f16(const float* w, const float* b, const float* mask, long long m_sp, long long m_se,
                                    int P, int E, int in_size, int out_size, int k_pad, int n_pad, void* dst_half,
                                    long long net_stride_halfs, void* stream) {
@@ -353,6 +359,8 @@ extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, co
     p.bounds_n = bounds_n;
     p.noise = noise;
     p.pred = pred;
+    p.dbg = g_dbg_buffer;
+    p.dbg_flags = g_dbg_flags;
     if (variant == 2) return tc::launch_rollout_v2(p, (cudaStream_t)stream);
     CMRL_REQUIRE(variant == 1, "mlp_rollout_f16: variant must be 1 (streamed weights) or 2 (weight-stationary CTA pairs)");
     size_t w_stage = 0;

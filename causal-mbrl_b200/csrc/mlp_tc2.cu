@@ -9,8 +9,9 @@
 //     still converting the remaining columns;
 //   * layer-0 operands (obs | act | 1) are gathered one tile ahead by two loader warps.
 //
-// Warp roles per CTA (256 threads): 0-3 epilogue (TMEM lanes = rows), 4 MMA issuer (leader CTA) + TMEM alloc,
-// 5 weight TMA producer, 6-7 layer-0 operand loaders.
+// Warp roles per CTA (640 threads): 0-15 epilogue (TMEM lane quarter = warp % 4; the four warps of a quarter interleave
+// the 16-column chunks so SFU / TMEM-load / shared-store latencies overlap), 16 MMA issuer (leader CTA) + TMEM alloc,
+// 17 weight TMA producer, 18-19 layer-0 operand loaders.
 #include <cooperative_groups.h>
 
 #include "tc_common.cuh"
@@ -18,7 +19,9 @@
 namespace cmrl {
 namespace tc {
 
-constexpr int V2_THREADS = 256;
+constexpr int V2_THREADS = 640;
+constexpr int V2_EPI_WARPS = 16;    // 4 per SM sub-partition (set s = warp / 4 takes the chunks c = s mod 4)
+constexpr int V2_WARP_MMA = 16, V2_WARP_W = 17, V2_WARP_X = 18;
 constexpr int V2_TILE = 256;        // rows per CTA pair
 constexpr int V2_GROUP_COLS = 64;   // epilogue -> MMA handoff granularity (columns of the next layer's K)
 constexpr uint32_t V2_D1_COL = 208; // second accumulator buffer (requires HP <= 208 for now)
@@ -55,13 +58,16 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at the same smem offset in CTA `rank` of the cluster (release at cluster scope)
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster.  Default (CTA-scope release) on purpose:
+// `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR per arrive (measured: 4x slower epilogue).  The data the
+// arrive publishes (A-operand chunks) is written and consumed inside the same CTA (by its own tensor unit, after a
+// fence.proxy.async); only the signal crosses the pair.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
     asm volatile(
         "{\n"
         ".reg .b32 ra;\n"
         "mapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
         "}\n" ::"r"(smem_u32(bar)),
         "r"(rank)
         : "memory");
@@ -74,7 +80,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(ok)
@@ -110,6 +116,38 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// activation on a packed fp16x2 pre-activation.  SiLU(z) = z*sigmoid(z) = 0.5z*(1 + tanh(0.5z)): one MUFU op
+// (tanh.approx.f16x2) per TWO elements instead of ex2 + rcp per element -- the epilogue is MUFU/issue bound.
+template <int ACT>
+__device__ __forceinline__ uint32_t act_h2(uint32_t z) {
+    if (ACT == CMRL_ACT_SILU) {
+        uint32_t hz, t, y;
+        asm("mul.f16x2 %0, %1, %2;" : "=r"(hz) : "r"(z), "r"(0x38003800u));  // 0.5 * z
+        asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(hz));
+        asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(y) : "r"(hz), "r"(t));      // hz * t + hz
+        return y;
+    } else if (ACT == CMRL_ACT_RELU) {
+        uint32_t y;
+        asm("max.f16x2 %0, %1, %2;" : "=r"(y) : "r"(z), "r"(0u));
+        return y;
+    }
+    return z;
+}
+
+// fp32 variant: MUFU.TANH (fp32) issues at the full SFU rate, MUFU.TANH.F16 measured at half of it on sm_100a
+template <int ACT>
+__device__ __forceinline__ uint32_t act_pack(float a, float b) {
+    if (ACT == CMRL_ACT_SILU) {
+        float ha = 0.5f * a, hb = 0.5f * b, ta, tb;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(ha));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(hb));
+        return pack_h2(fmaf(ha, ta, ha), fmaf(hb, tb, hb));
+    } else if (ACT == CMRL_ACT_RELU) {
+        return pack_h2(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
+    }
+    return pack_h2(a, b);
+}
+
 // item -> (p, e, first sorted row of the 256-row tile, rows in tile)
 __device__ __forceinline__ bool v2_decode(const RolloutP& p, int item, int tiles_total, const int* s_off, int& pp, int& e,
                                           int& row0, int& nrows) {
@@ -128,6 +166,7 @@ __device__ __forceinline__ bool v2_decode(const RolloutP& p, int item, int tiles
     return false;
 }
 
+template <int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
     mlp_rollout_f16_v2_kernel(const RolloutP p, const V2Smem sm) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -154,11 +193,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
             mbar_init(&bars[BAR_X_EMPTY + i], 1);
             mbar_init(&bars[BAR_D_FULL + i], 1);
         }
-        for (int g = 0; g < 4; ++g) mbar_init(&bars[BAR_A_READY + g], 8);
+        for (int g = 0; g < 4; ++g) mbar_init(&bars[BAR_A_READY + g], 2 * V2_EPI_WARPS);
         mbar_init(&bars[BAR_DH_FULL], 1);
         fence_barrier_init();
     }
-    if (warp == 4) {
+    if (warp == V2_WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -177,7 +216,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
     const int item_begin = (int)((long long)cid * n_items / n_clusters);
     const int item_end = (int)((long long)(cid + 1) * n_items / n_clusters);
 
-    if (warp == 5) {
+    if (warp == V2_WARP_W) {
         // ===================== weight producer: this CTA's half of every layer of the current net ==============
         if (lane == 0) {
             int cur_net = -1;
@@ -203,11 +242,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
                 cur_net = net;
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == V2_WARP_MMA) {
         // ===================== MMA issuer: one lane of the leader CTA ============================================
         if (rank == 0 && lane == 0) {
             int cur_net = -1;
             uint32_t n_w = 0, n_x = 0, n_epi = 0;
+            long long t_wx = 0, t_wa = 0, t_issue = 0, t_all0 = clock64(), tt;
             const uint32_t a_addr = smem_u32(a_buf);
             const uint32_t idesc_h = umma_idesc_f16(256, HP);
             const uint32_t idesc_head = umma_idesc_f16(256, NH);
@@ -229,9 +269,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
                     const uint32_t x_addr = smem_u32(smem + sm.x_off[xb]);
                     const uint32_t b_addr = smem_u32(smem + sm.w_off[0]);
                     const uint32_t b_sbo = (uint32_t)(K0 / 8) * 128;
+                    const uint64_t ad0 = umma_desc(x_addr, A_CHUNK_BYTES, 128), bd0 = umma_desc(b_addr, 128, b_sbo);
                     for (int ks = 0; ks < K0 / 16; ++ks)
-                        umma_f16_2cta(tmem_base, umma_desc(x_addr + ks * 2 * A_CHUNK_BYTES, A_CHUNK_BYTES, 128),
-                                      umma_desc(b_addr + ks * 256, 128, b_sbo), idesc_h, ks > 0);
+                        umma_f16_2cta(tmem_base, ad0 + (uint64_t)(ks * (2 * A_CHUNK_BYTES / 16)), bd0 + (uint64_t)(ks * (256 / 16)),
+                                      idesc_h, ks > 0);
                     umma_commit_2cta(&bars[BAR_X_EMPTY + xb]);
                     umma_commit_2cta(&bars[BAR_D_FULL + 0]);
                 }
@@ -242,24 +283,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
                     const uint32_t b_addr = smem_u32(smem + sm.w_off[l]);
                     const uint32_t b_sbo = (uint32_t)(HP / 8) * 128;
                     const uint32_t idesc = head ? idesc_head : idesc_h;
+                    const uint64_t ad0 = umma_desc(a_addr, A_CHUNK_BYTES, 128), bd0 = umma_desc(b_addr, 128, b_sbo);
                     for (int g = 0; g < n_groups; ++g) {
+                        if (p.dbg) tt = clock64();
                         mbar_wait_cluster(&bars[BAR_A_READY + g], n_epi & 1);
+                        if (p.dbg) {
+                            long long t = clock64();
+                            t_wa += t - tt;
+                            tt = t;
+                        }
                         tc_fence_after();
                         const int ks0 = g * (V2_GROUP_COLS / 16);
                         const int ks1 = min(HP / 16, ks0 + V2_GROUP_COLS / 16);
-                        for (int ks = ks0; ks < ks1; ++ks)
-                            umma_f16_2cta(d_tmem, umma_desc(a_addr + ks * 2 * A_CHUNK_BYTES, A_CHUNK_BYTES, 128),
-                                          umma_desc(b_addr + ks * 256, 128, b_sbo), idesc, ks > 0);
+                        for (int ks = ks0; ks < ks1; ++ks)  // start-address field advances in 16-byte units
+                            umma_f16_2cta(d_tmem, ad0 + (uint64_t)(ks * (2 * A_CHUNK_BYTES / 16)), bd0 + (uint64_t)(ks * (256 / 16)),
+                                          idesc, ks > 0);
+                        if (p.dbg) t_issue += clock64() - tt;
                     }
                     umma_commit_2cta(head ? &bars[BAR_DH_FULL] : &bars[BAR_D_FULL + (l & 1)]);
                     ++n_epi;
                 }
                 ++n_x;
             }
+            if (p.dbg) {
+                long long* d = p.dbg + (long long)blockIdx.x * 16;
+                d[0] = clock64() - t_all0;
+                d[1] = t_wx;
+                d[2] = t_wa;
+                d[3] = t_issue;
+                d[4] = item_end - item_begin;
+            }
         }
-    } else if (warp >= 6) {
+    } else if (warp >= V2_WARP_X) {
         // ===================== layer-0 operand loaders (64 threads, 2 rows each), one tile ahead =================
-        const int lt = threadIdx.x - 6 * 32;
+        const int lt = threadIdx.x - V2_WARP_X * 32;
         uint32_t n_x = 0;
         const int in = p.O + p.A;
         for (int item = item_begin; item < item_end; ++item, ++n_x) {
@@ -297,9 +354,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
         }
     } else {
         // ===================== epilogue warps: rows = TMEM lanes ==================================================
-        const int r = threadIdx.x;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        uint32_t n_full[2] = {0, 0}, n_h = 0;
+        // 16 warps = 4 per SM sub-partition.  Warp (quarter q, set s) converts the 16-column chunks c = 4g + s of TMEM
+        // lanes 32q..32q+31, so every 64-column handoff group g gets exactly one chunk from each set and is published
+        // (to the MMA issuer of the leader CTA) as soon as the four sets are through it.
+        const int quarter = warp & 3, cset = warp >> 2;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        uint32_t n_full0 = 0, n_full1 = 0, n_h = 0;
+        const int n_chunks = HP / 16;
+        uint8_t* a_row = a_buf + r * 16;
+        const bool timing = p.dbg != nullptr && threadIdx.x == 0;
+        long long t_wd = 0, t_loop = 0, t_head = 0, t0 = timing ? clock64() : 0, tt = 0;
         for (int item = item_begin; item < item_end; ++item) {
             int pp, e, row0, nrows;
             v2_decode(p, item, tiles_total, s_off, pp, e, row0, nrows);
@@ -308,44 +373,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
             const long long env = valid ? p.perm[row0 + grow] : 0;
             for (int l = 0; l < L; ++l) {
                 const int b = l & 1;
-                mbar_wait(&bars[BAR_D_FULL + b], n_full[b] & 1);
-                ++n_full[b];
+                if (timing) tt = clock64();
+                if (b) {
+                    mbar_wait(&bars[BAR_D_FULL + 1], n_full1 & 1);
+                    ++n_full1;
+                } else {
+                    mbar_wait(&bars[BAR_D_FULL + 0], n_full0 & 1);
+                    ++n_full0;
+                }
+                if (timing) {
+                    long long t = clock64();
+                    t_wd += t - tt;
+                    tt = t;
+                }
                 tc_fence_after();
                 const uint32_t d_addr = tmem_base + lane_base + (b ? V2_D1_COL : 0u);
-                const int n_chunks = HP / 16;
                 uint32_t ra[16], rb[16];
-                auto process = [&](int c, const uint32_t(&raw)[16]) {
-                    float v[16];
+                auto convert_store = [&](int c, const uint32_t(&raw)[16]) {
+                    uint32_t h[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        v[j] = act_fast(__uint_as_float(raw[j]), p.act);
-                        if (c * 16 + j == p.H) v[j] = 1.0f;
-                    }
-                    *reinterpret_cast<uint4*>(a_buf + (2 * c) * A_CHUNK_BYTES + r * 16) =
-                        make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                    *reinterpret_cast<uint4*>(a_buf + (2 * c + 1) * A_CHUNK_BYTES + r * 16) =
-                        make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
-                    if ((c & 3) == 3 || c == n_chunks - 1) {
-                        if (c == n_chunks - 1) tc_fence_before();  // all TMEM reads of this buffer are done
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_remote(&bars[BAR_A_READY + (c >> 2)], 0);
-                    }
+                    for (int j = 0; j < 8; ++j) h[j] = act_pack<ACT>(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+                    *reinterpret_cast<uint4*>(a_row + (2 * c) * A_CHUNK_BYTES) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(a_row + (2 * c + 1) * A_CHUNK_BYTES) = make_uint4(h[4], h[5], h[6], h[7]);
+                    if (c == (p.H >> 4))  // the ones column (fp16 1.0) that carries the next layer's bias
+                        *reinterpret_cast<uint16_t*>(a_row + (p.H >> 3) * A_CHUNK_BYTES + (p.H & 7) * 2) = 0x3C00;
+                };
+                auto publish = [&](int g) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(&bars[BAR_A_READY + g], 0);
                 };
                 __syncwarp();
-                tmem_ld16_issue(d_addr, ra);
-                for (int c = 0; c < n_chunks; c += 2) {
-                    tmem_ld_wait();
-                    if (c + 1 < n_chunks) tmem_ld16_issue(d_addr + (c + 1) * 16, rb);
-                    process(c, ra);
-                    if (c + 1 < n_chunks) {
+                int c = cset;
+                if (c < n_chunks) tmem_ld16_issue(d_addr + c * 16, ra);
+                for (int g = 0; g < n_groups; g += 2) {
+                    if (c < n_chunks) {
                         tmem_ld_wait();
-                        if (c + 2 < n_chunks) tmem_ld16_issue(d_addr + (c + 2) * 16, ra);
-                        process(c + 1, rb);
+                        if (c + 4 < n_chunks) tmem_ld16_issue(d_addr + (c + 4) * 16, rb);
+                        else tc_fence_before();
+                        convert_store(c, ra);
+                    }
+                    publish(g);
+                    c += 4;
+                    if (g + 1 < n_groups) {
+                        if (c < n_chunks) {
+                            tmem_ld_wait();
+                            if (c + 4 < n_chunks) tmem_ld16_issue(d_addr + (c + 4) * 16, ra);
+                            else tc_fence_before();
+                            convert_store(c, rb);
+                        }
+                        publish(g + 1);
+                        c += 4;
                     }
                 }
+                if (timing) t_loop += clock64() - tt;
             }
+            if (cset != 0) continue;  // the head epilogue (one row per lane) is done by the first warp set
             // ---- head -------------------------------------------------------------------------------------------
+            if (timing) tt = clock64();
             const int D = p.head_dim;
             float res0 = 0.0f, nz0 = 0.0f;
             if (p.layout == CMRL_HEAD_PARALLEL && valid) {  // prefetch before the wait
@@ -369,12 +454,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
                     p.pred[env * D + pp] = out;
                 }
             } else {
-                for (int c = 0; c < NH / 16; ++c) {
+                for (int cc = 0; cc < NH / 16; ++cc) {
                     float v[16];
-                    tmem_ld16(h_addr + c * 16, v);
+                    tmem_ld16(h_addr + cc * 16, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int col = c * 16 + j;
+                        const int col = cc * 16 + j;
                         if (valid && col < D) {
                             float m = v[j];
                             if (p.residual) m += p.obs[env * p.O + col];
@@ -383,12 +468,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
                     }
                 }
                 if (p.gaussian && p.noise) {
-                    for (int c = 0; c < NH / 16; ++c) {
+                    for (int cc = 0; cc < NH / 16; ++cc) {
                         float v[16];
-                        tmem_ld16(h_addr + c * 16, v);
+                        tmem_ld16(h_addr + cc * 16, v);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const int col = c * 16 + j;
+                            const int col = cc * 16 + j;
                             if (valid && col >= D && col < 2 * D) {
                                 const int d = col - D;
                                 const int bi = p.bounds_n == 1 ? 0 : d;
@@ -400,6 +485,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
                 }
             }
             tc_fence_before();
+            if (timing) t_head += clock64() - tt;
+        }
+        if (timing) {
+            long long* d = p.dbg + (long long)blockIdx.x * 16;
+            d[8] = clock64() - t0;
+            d[9] = t_wd;
+            d[10] = t_loop;
+            d[12] = t_head;
         }
     }
 
@@ -407,7 +500,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 4) {
+    if (warp == V2_WARP_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
@@ -436,14 +529,21 @@ int launch_rollout_v2(const RolloutP& p, cudaStream_t st) {
     CMRL_REQUIRE(sm.total <= 232448 - 1024, "mlp_rollout_f16 v2: needs %u B of shared memory", sm.total);
     static bool attr_set = false;
     if (!attr_set) {
-        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         attr_set = true;
     }
     int max_items = p.P * ((p.N + V2_TILE - 1) / V2_TILE + p.E);
     int clusters = num_sms() / 2;
     if (clusters > max_items) clusters = max_items;
     if (clusters < 1) clusters = 1;
-    mlp_rollout_f16_v2_kernel<<<clusters * 2, V2_THREADS, sm.total, st>>>(p, sm);
+    if (p.act == CMRL_ACT_SILU)
+        mlp_rollout_f16_v2_kernel<CMRL_ACT_SILU><<<clusters * 2, V2_THREADS, sm.total, st>>>(p, sm);
+    else if (p.act == CMRL_ACT_RELU)
+        mlp_rollout_f16_v2_kernel<CMRL_ACT_RELU><<<clusters * 2, V2_THREADS, sm.total, st>>>(p, sm);
+    else
+        mlp_rollout_f16_v2_kernel<CMRL_ACT_IDENTITY><<<clusters * 2, V2_THREADS, sm.total, st>>>(p, sm);
     CMRL_CHECK_LAUNCH("mlp_rollout_f16_v2");
     return 0;
 }

@@ -38,6 +38,8 @@ struct RolloutP {
     float* pred;               // [N,D] env order
     uint32_t w_stage_bytes;    // max over layers of n*k*2
     int a_chunks;              // K chunks (of 8) the A buffer holds
+    int dbg_flags;             // profiling experiments only (results invalid): 1 skip A stores, 2 skip TMEM loads, 4 skip activation
+    long long* dbg;            // optional [gridDim.x][16] cycle counters (profiling builds of the caller), else NULL
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
