@@ -201,32 +201,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_rollout_f16_kernel(const R
                     p.pred[(long long)env * D + pp] = out;
                 }
             } else {
-                // PLAIN: columns [0,D) mean, [D,2D) raw logvar.  Two passes over the <= 256 head columns.
+                // PLAIN: packed head columns are interleaved (2d = mean_d, 2d+1 = raw logvar_d; deterministic: d).
                 for (int c = 0; c < Nh / 16; ++c) {
                     float v[16];
                     tmem_ld16(tmem_base + lane_base + HEAD_TMEM_COL + c * 16, v);
+                    if (p.gaussian) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        int col = c * 16 + j;
-                        if (valid && col < D) {
-                            float m = v[j];
-                            if (p.residual) m += p.obs[(long long)env * p.O + col];
-                            p.pred[(long long)env * D + col] = m;  // mean first; noise term added below
+                        for (int j = 0; j < 16; j += 2) {
+                            const int d = (c * 16 + j) >> 1;
+                            if (valid && d < D) {
+                                float m = v[j];
+                                if (p.residual) m += p.obs[(long long)env * p.O + d];
+                                if (p.noise) {
+                                    const int bi = p.bounds_n == 1 ? 0 : d;
+                                    const float lv = soft_clamp_logvar(v[j + 1], p.min_logvar[bi], p.max_logvar[bi]);
+                                    m += sqrtf(expf(lv)) * p.noise[(long long)env * D + d];
+                                }
+                                p.pred[(long long)env * D + d] = m;
+                            }
                         }
-                    }
-                }
-                if (p.gaussian && p.noise) {
-                    for (int c = 0; c < Nh / 16; ++c) {
-                        float v[16];
-                        tmem_ld16(tmem_base + lane_base + HEAD_TMEM_COL + c * 16, v);
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            int col = c * 16 + j;
-                            if (valid && col >= D && col < 2 * D) {
-                                int d = col - D;
-                                int bi = p.bounds_n == 1 ? 0 : d;
-                                float lv = soft_clamp_logvar(v[j], p.min_logvar[bi], p.max_logvar[bi]);
-                                p.pred[(long long)env * D + d] += sqrtf(expf(lv)) * p.noise[(long long)env * D + d];
+                            const int d = c * 16 + j;
+                            if (valid && d < D) {
+                                float m = v[j];
+                                if (p.residual) m += p.obs[(long long)env * p.O + d];
+                                p.pred[(long long)env * D + d] = m;
                             }
                         }
                     }
@@ -249,7 +250,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_rollout_f16_kernel(const R
 //   half index = (n/8)*(k_pad*8) + (k/8)*64 + (n%8)*8 + (k%8)
 __global__ void pack_layer_f16_kernel(const float* __restrict__ w, const float* __restrict__ b,
                                       const float* __restrict__ mask, long long m_sp, long long m_se, int E, int in,
-                                      int out, int k_pad, int n_pad, __half* __restrict__ dst, long long net_stride) {
+                                      int out, int k_pad, int n_pad, int interleave_d, __half* __restrict__ dst,
+                                      long long net_stride) {
     const int g = blockIdx.y;
     const long long total = (long long)n_pad * k_pad;
     const float* wg = w + (long long)g * in * out;
@@ -265,11 +267,13 @@ __global__ void pack_layer_f16_kernel(const float* __restrict__ w, const float* 
         int n = ng * 8 + nn, k = kc * 8 + kk;
         float v = 0.0f;
         if (n < out) {
+            // Gaussian PLAIN heads are stored with (mean_d, logvar_d) in adjacent columns (2d, 2d+1)
+            const int src = interleave_d ? ((n & 1) ? interleave_d + (n >> 1) : (n >> 1)) : n;
             if (k < in) {
-                v = wg[(long long)k * out + n];
+                v = wg[(long long)k * out + src];
                 if (mg) v *= mg[k];
             } else if (k == in && b) {
-                v = b[(long long)g * out + n];
+                v = b[(long long)g * out + src];
             }
         }
         v = fminf(fmaxf(v, -65504.0f), 65504.0f);
@@ -283,6 +287,7 @@ __global__ void pack_layer_f16_kernel(const float* __restrict__ w, const float* 
 namespace cmrl {
 namespace tc {
 int launch_rollout_v2(const RolloutP& p, cudaStream_t st);
+int launch_rollout_v3(const RolloutP& p, cudaStream_t st);
 }
 }  // namespace cmrl
 
@@ -295,18 +300,19 @@ extern "C" void cmrl_debug_set_flags(int f) { g_dbg_flags = f; }
 extern "C" void cmrl_debug_set_buffer(void* buf) { g_dbg_buffer = (long long*)buf; }
 
 extern "C" int cmrl_pack_layer_f16(const float* w, const float* b, const float* mask, long long m_sp, long long m_se,
-                                   int P, int E, int in_size, int out_size, int k_pad, int n_pad, void* dst_half,
-                                   long long net_stride_halfs, void* stream) {
+                                   int P, int E, int in_size, int out_size, int k_pad, int n_pad, int interleave_d,
+                                   void* dst_half, long long net_stride_halfs, void* stream) {
     CMRL_REQUIRE(w && dst_half, "pack_layer_f16: null pointer");
     CMRL_REQUIRE(k_pad % 16 == 0 && n_pad % 16 == 0 && k_pad >= in_size + 1 && n_pad >= out_size,
                  "pack_layer_f16: k_pad must be a multiple of 16 >= in+1, n_pad a multiple of 16 >= out");
     CMRL_REQUIRE(P * E <= 65535, "pack_layer_f16: too many nets");
+    CMRL_REQUIRE(interleave_d == 0 || out_size == 2 * interleave_d, "pack_layer_f16: interleave_d must be out_size / 2");
     long long total = (long long)n_pad * k_pad;
     int bx = (int)((total + 255) / 256);
     if (bx > 1024) bx = 1024;
     dim3 grid(bx, P * E);
     tc::pack_layer_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, b, mask, m_sp, m_se, E, in_size, out_size, k_pad,
-                                                                    n_pad, (__half*)dst_half, net_stride_halfs);
+                                                                    n_pad, interleave_d, (__half*)dst_half, net_stride_halfs);
     CMRL_CHECK_LAUNCH("pack_layer_f16");
     return 0;
 }
@@ -361,8 +367,9 @@ extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, co
     p.pred = pred;
     p.dbg = g_dbg_buffer;
     p.dbg_flags = g_dbg_flags;
+    if (variant == 3) return tc::launch_rollout_v3(p, (cudaStream_t)stream);
     if (variant == 2) return tc::launch_rollout_v2(p, (cudaStream_t)stream);
-    CMRL_REQUIRE(variant == 1, "mlp_rollout_f16: variant must be 1 (streamed weights) or 2 (weight-stationary CTA pairs)");
+    CMRL_REQUIRE(variant == 1, "mlp_rollout_f16: variant must be 1 (streamed weights), 2 (weight-stationary CTA pairs) or 3 (pairs, two tiles in flight)");
     size_t w_stage = 0;
     int kmax = 0;
     for (int l = 0; l <= num_layers; ++l) {

@@ -454,31 +454,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
                     p.pred[env * D + pp] = out;
                 }
             } else {
-                for (int cc = 0; cc < NH / 16; ++cc) {
+                for (int cc = 0; cc < NH / 16; ++cc) {  // interleaved head columns: 2d = mean_d, 2d+1 = raw logvar_d
                     float v[16];
                     tmem_ld16(h_addr + cc * 16, v);
+                    if (p.gaussian) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int col = cc * 16 + j;
-                        if (valid && col < D) {
-                            float m = v[j];
-                            if (p.residual) m += p.obs[env * p.O + col];
-                            p.pred[env * D + col] = m;
+                        for (int j = 0; j < 16; j += 2) {
+                            const int d = (cc * 16 + j) >> 1;
+                            if (valid && d < D) {
+                                float m = v[j];
+                                if (p.residual) m += p.obs[env * p.O + d];
+                                if (p.noise) {
+                                    const int bi = p.bounds_n == 1 ? 0 : d;
+                                    const float lv = soft_clamp_logvar(v[j + 1], p.min_logvar[bi], p.max_logvar[bi]);
+                                    m += sqrtf(expf(lv)) * p.noise[env * D + d];
+                                }
+                                p.pred[env * D + d] = m;
+                            }
                         }
-                    }
-                }
-                if (p.gaussian && p.noise) {
-                    for (int cc = 0; cc < NH / 16; ++cc) {
-                        float v[16];
-                        tmem_ld16(h_addr + cc * 16, v);
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const int col = cc * 16 + j;
-                            if (valid && col >= D && col < 2 * D) {
-                                const int d = col - D;
-                                const int bi = p.bounds_n == 1 ? 0 : d;
-                                const float lv = soft_clamp_logvar(v[j], p.min_logvar[bi], p.max_logvar[bi]);
-                                p.pred[env * D + d] += sqrtf(expf(lv)) * p.noise[env * D + d];
+                            const int d = cc * 16 + j;
+                            if (valid && d < D) {
+                                float m = v[j];
+                                if (p.residual) m += p.obs[env * p.O + d];
+                                p.pred[env * D + d] = m;
                             }
                         }
                     }

@@ -1,0 +1,603 @@
+// Tensor-core tier, v3: weight-stationary CTA pairs with TWO row tiles in flight ("ping-pong").
+//
+// Measured on B200 (profiles/tools/*.cu): a 16-element SiLU epilogue chunk costs ~140 cycles per SM sub-partition
+// (SFU bound, tanh.approx = 8 cycles per warp instruction), a [256 x 208 x 16] cta_group::2 MMA 105 cycles, and the
+// two do not slow each other down.  A single tile per pair therefore leaves the tensor pipe idle while the epilogue
+// converts the layer and vice versa (dependency chain inside one tile).  Here each pair works on two independent
+// 128-row tiles (64 rows per CTA, tcgen05.mma cta_group::2 with M=128, which runs at the full rate: 53.8 cycles per
+// K step for N=208): while the 16 epilogue warps convert tile a's layer l, the tensor pipe runs tile b's layer l.
+//
+// Accumulator layout of M=128 / cta_group::2 (probed with profiles/tools/tmem_layout.cu): each CTA holds its 64 rows
+// as 128 TMEM lanes x N/2 columns -- lanes 0-63 = rows 0-63, columns [0, N/2); lanes 64-127 = rows 0-63, columns
+// [N/2, N).  So all four lane quarters take part in the epilogue.
+//
+// Warp roles per CTA (768 threads): 0-15 epilogue (quarter = warp % 4, set = warp / 4 takes the 8-column chunks
+// c = set mod 4), 16-19 head epilogue (Gaussian head, residual, sampling, scatter), 20/21 MMA issuers of tile slot
+// 0/1 (leader CTA; a [128 x 208 x 16] MMA lasts 54 cycles but costs ~100 cycles of single-thread issue work, so one
+// issuer per slot keeps the tensor pipe fed; warp 20 also owns the TMEM allocation), 22 weight TMA producer,
+// 23 layer-0 operand loader (two rows per lane).
+#include "tc_common.cuh"
+
+namespace cmrl {
+namespace tc {
+
+constexpr int V3_THREADS = 768;
+constexpr int V3_TILE = 128;    // rows per tile per CTA pair
+constexpr int V3_ROWS = 64;     // rows per tile per CTA
+constexpr int V3_CHUNK = V3_ROWS * 16;  // bytes of one 8-element K chunk of the A operand (64 rows)
+constexpr int V3_EPI_WARPS = 16, V3_HEAD_WARP0 = 16, V3_WARP_MMA = 20 /* and 21: one issuer per tile slot */, V3_WARP_W = 22, V3_WARP_X = 23;
+// TMEM columns: hidden-layer accumulators of tile slot 0 / 1 (N/2 <= 128 columns each), then the head accumulators
+__device__ __forceinline__ uint32_t v3_d_col(int s) { return (uint32_t)s * 128u; }
+__device__ __forceinline__ uint32_t v3_dh_col(int s) { return 256u + (uint32_t)s * 64u; }
+
+struct V3Smem {
+    uint32_t w_off[8];
+    uint32_t a_off[2];      // A operand per tile slot
+    uint32_t x_off[2][2];   // layer-0 operand [stage][slot]
+    uint32_t bar_off;
+    uint32_t total;
+};
+
+enum {
+    V3_W_FULL = 0,    // local (tx)
+    V3_W_READY = 1,   // leader, count 2
+    V3_W_EMPTY = 2,   // both (one commit per MMA issuer -> count 2)
+    V3_X_READY = 3,   // leader [stage*2+slot], count 2 (one loader warp per CTA)
+    V3_X_EMPTY = 7,   // both   [stage*2+slot] (commit)
+    V3_A_READY = 11,  // leader [slot], count 2 * 16 warps
+    V3_D_FULL = 13,   // both   [slot] (commit)
+    V3_DH_FULL = 15,  // both   [slot] (commit)
+    V3_DH_EMPTY = 17, // leader [slot], count 2 * 4 head warps
+    V3_BAR_COUNT = 19,
+};
+
+__device__ __forceinline__ uint32_t v3_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void v3_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void v3_arrive_leader(uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void v3_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// same, descriptors passed as (lo, hi) words: only the low word (start-address field) changes between K steps, so the
+// issue loop is two 32-bit adds per MMA (a single thread issues dependent instructions at ~1 per 4-6 cycles; a long
+// per-MMA address computation makes the ISSUE, not the tensor pipe, the bottleneck -- measured 173 cycles per MMA)
+__device__ __forceinline__ void v3_mma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Warp-uniform variants: executed by ALL lanes of the (converged) MMA warp with warp-uniform operands; one elected
+// lane issues.  Keeping the control flow uniform lets ptxas keep descriptors in uniform registers instead of emitting
+// an ELECT / R2UR.BROADCAST waterfall loop around every UTCHMMA.
+__device__ __forceinline__ void v3_mma_uni(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, p;\n"
+        ".reg .b64 da, db;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void v3_commit_uni(uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void v3_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void v3_ld8_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void v3_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void v3_sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void v3_sts16(uint32_t saddr, uint16_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
+}
+
+template <int ACT>
+__device__ __forceinline__ uint32_t v3_act_pack(float a, float b) {
+    if (ACT == CMRL_ACT_SILU) {  // z*sigmoid(z) = 0.5z*(1 + tanh(0.5z)): one SFU op per element
+        float ha = 0.5f * a, hb = 0.5f * b, ta, tb;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(ha));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(hb));
+        return pack_h2(fmaf(ha, ta, ha), fmaf(hb, tb, hb));
+    } else if (ACT == CMRL_ACT_RELU) {
+        return pack_h2(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
+    }
+    return pack_h2(a, b);
+}
+
+// The work list of a cluster is a contiguous range of 128-row tiles in (p, member, tile) order; consecutive tiles of
+// the same net are processed two at a time.  Every role walks the list with this iterator.
+struct V3Pair {
+    int net, pp, n;       // net index, sub-net index, tiles in this pair (1 or 2)
+    int row0[2], nrows[2];
+};
+__device__ __forceinline__ void v3_decode(const RolloutP& p, int item, int tiles_total, const int* s_off, int& pp, int& e, int& row0,
+                                          int& nrows) {
+    pp = item / tiles_total;
+    int t = item - pp * tiles_total;
+    row0 = 0;
+    nrows = 0;
+    for (e = 0; e < p.E; ++e) {
+        const int cnt = s_off[e + 1] - s_off[e];
+        const int nt = (cnt + V3_TILE - 1) / V3_TILE;
+        if (t < nt) {
+            row0 = s_off[e] + t * V3_TILE;
+            nrows = min(V3_TILE, cnt - t * V3_TILE);
+            return;
+        }
+        t -= nt;
+    }
+}
+__device__ __forceinline__ int v3_next_pair(const RolloutP& p, int item, int item_end, int tiles_total, const int* s_off, V3Pair& pr) {
+    int e;
+    v3_decode(p, item, tiles_total, s_off, pr.pp, e, pr.row0[0], pr.nrows[0]);
+    pr.net = pr.pp * p.E + e;
+    pr.n = 1;
+    if (item + 1 < item_end) {
+        int pp2, e2;
+        v3_decode(p, item + 1, tiles_total, s_off, pp2, e2, pr.row0[1], pr.nrows[1]);
+        if (pp2 == pr.pp && e2 == e) pr.n = 2;
+    }
+    return item + pr.n;
+}
+
+template <int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
+    mlp_rollout_f16_v3_kernel(const RolloutP p, const V3Smem sm) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ int s_off[65];
+    const int L = p.num_layers;
+    const int HP = p.layer_n[0];
+    const int K0 = p.layer_k[0];
+    const int NH = p.layer_n[L];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bar_off);
+    const uint32_t rank = v3_ctarank();
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i <= p.E; i += blockDim.x) s_off[i] = p.offsets[i];
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[V3_W_FULL], 1);
+        mbar_init(&bars[V3_W_READY], 2);
+        mbar_init(&bars[V3_W_EMPTY], 2);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&bars[V3_X_READY + i], 2);
+            mbar_init(&bars[V3_X_EMPTY + i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[V3_A_READY + i], 2 * V3_EPI_WARPS);
+            mbar_init(&bars[V3_D_FULL + i], 1);
+            mbar_init(&bars[V3_DH_FULL + i], 1);
+            mbar_init(&bars[V3_DH_EMPTY + i], 2 * 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == V3_WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    v3_cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    int tiles_total = 0;
+    for (int e = 0; e < p.E; ++e) tiles_total += (s_off[e + 1] - s_off[e] + V3_TILE - 1) / V3_TILE;
+    const int n_items = p.P * tiles_total;
+    const int n_clusters = gridDim.x / 2;
+    const int cid = blockIdx.x / 2;
+    const int item_begin = (int)((long long)cid * n_items / n_clusters);
+    const int item_end = (int)((long long)(cid + 1) * n_items / n_clusters);
+
+    if (warp == V3_WARP_W) {
+        // ===================== weight producer ===================================================================
+        if (lane == 0) {
+            int cur_net = -1;
+            uint32_t n_w = 0;
+            V3Pair pr;
+            for (int item = item_begin; item < item_end;) {
+                item = v3_next_pair(p, item, item_end, tiles_total, s_off, pr);
+                if (pr.net == cur_net) continue;
+                if (cur_net != -1) mbar_wait(&bars[V3_W_EMPTY], (n_w - 1) & 1);
+                const __half* blob = p.packed + (long long)pr.net * p.blob_halfs;
+                uint32_t total = 0;
+                for (int l = 0; l <= L; ++l) total += (uint32_t)(p.layer_n[l] / 2) * p.layer_k[l] * 2;
+                mbar_expect_tx(&bars[V3_W_FULL], total);
+                for (int l = 0; l <= L; ++l) {
+                    const uint32_t half_halfs = (uint32_t)(p.layer_n[l] / 2) * p.layer_k[l];
+                    tma_bulk_g2s(smem + sm.w_off[l], blob + p.layer_off[l] + (size_t)rank * half_halfs, half_halfs * 2,
+                                 &bars[V3_W_FULL]);
+                }
+                mbar_wait(&bars[V3_W_FULL], n_w & 1);
+                v3_arrive_leader(&bars[V3_W_READY]);
+                ++n_w;
+                cur_net = pr.net;
+            }
+        }
+    } else if (warp == V3_WARP_MMA || warp == V3_WARP_MMA + 1) {
+        // ===================== MMA issuers: warp 20 drives tile slot 0, warp 21 slot 1 ================================
+        // The whole warp walks the (warp-uniform) schedule; one elected lane issues.  tcgen05.commit only tracks the
+        // MMAs of the issuing thread, so the two slots are independent pipelines sharing the tensor pipe.
+        if (rank == 0) {
+            const int s = warp - V3_WARP_MMA;
+            int cur_net = -1;
+            uint32_t n_w = 0, n_pair = 0, n_a = 0, n_h = 0, n_x[2] = {0, 0};
+            const uint32_t idesc_h = umma_idesc_f16(V3_TILE, HP), idesc_head = umma_idesc_f16(V3_TILE, NH);
+            const uint32_t b_sbo0 = (uint32_t)(K0 / 8) * 128, b_sbo = (uint32_t)(HP / 8) * 128;
+            const uint64_t ad_a = umma_desc(smem_u32(smem + sm.a_off[s]), V3_CHUNK, 128);
+            const uint32_t a_hi = (uint32_t)(ad_a >> 32);
+            const bool timing = p.dbg != nullptr && lane == 0 && s == 0;
+            long long t_wa = 0, t_issue = 0, t_wx = 0, t_all = timing ? clock64() : 0, tt = 0;
+            V3Pair pr;
+            for (int item = item_begin; item < item_end; ++n_pair) {
+                item = v3_next_pair(p, item, item_end, tiles_total, s_off, pr);
+                if (pr.net != cur_net) {
+                    if (cur_net != -1) v3_commit_uni(&bars[V3_W_EMPTY]);
+                    mbar_wait(&bars[V3_W_READY], n_w & 1);
+                    ++n_w;
+                    cur_net = pr.net;
+                }
+                if (s >= pr.n) continue;
+                const int st = n_pair & 1;
+                // ---- layer 0 ------------------------------------------------------------------------------------------
+                {
+                    if (timing) tt = clock64();
+                    mbar_wait(&bars[V3_X_READY + st * 2 + s], n_x[st] & 1);
+                    if (timing) t_wx += clock64() - tt;
+                    ++n_x[st];
+                    tc_fence_after();
+                    const uint64_t ad0 = umma_desc(smem_u32(smem + sm.x_off[st][s]), V3_CHUNK, 128);
+                    const uint64_t bd0 = umma_desc(smem_u32(smem + sm.w_off[0]), 128, b_sbo0);
+                    uint32_t a_lo = (uint32_t)ad0, b_lo = (uint32_t)bd0;
+                    const uint32_t b_hi = (uint32_t)(bd0 >> 32);
+                    for (int ks = 0; ks < K0 / 16; ++ks, a_lo += 2 * V3_CHUNK / 16, b_lo += 16)
+                        v3_mma_uni(tmem_base + v3_d_col(s), a_lo, (uint32_t)(ad0 >> 32), b_lo, b_hi, idesc_h, ks > 0);
+                    v3_commit_uni(&bars[V3_X_EMPTY + st * 2 + s]);
+                    v3_commit_uni(&bars[V3_D_FULL + s]);
+                }
+                // ---- layers 1..L (L = head) ------------------------------------------------------------------------------
+                for (int l = 1; l <= L; ++l) {
+                    const bool head = (l == L);
+                    const uint64_t bd0 = umma_desc(smem_u32(smem + sm.w_off[l]), 128, b_sbo);
+                    if (timing) tt = clock64();
+                    mbar_wait(&bars[V3_A_READY + s], n_a & 1);
+                    ++n_a;
+                    if (head) {  // the head accumulator of this slot must have been drained by the head warps
+                        mbar_wait(&bars[V3_DH_EMPTY + s], (n_h & 1) ^ 1);
+                        ++n_h;
+                    }
+                    if (timing) {
+                        long long t = clock64();
+                        t_wa += t - tt;
+                        tt = t;
+                    }
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (head ? v3_dh_col(s) : v3_d_col(s));
+                    const uint32_t idesc = head ? idesc_head : idesc_h;
+                    uint32_t a_lo = (uint32_t)ad_a, b_lo = (uint32_t)bd0;
+                    const uint32_t b_hi = (uint32_t)(bd0 >> 32);
+                    const int nks = HP / 16;
+                    v3_mma_uni(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, 0u);
+                    for (int ks = 1; ks < nks; ++ks) {
+                        a_lo += 2 * V3_CHUNK / 16;
+                        b_lo += 16;
+                        v3_mma_uni(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+                    }
+                    v3_commit_uni(head ? &bars[V3_DH_FULL + s] : &bars[V3_D_FULL + s]);
+                    if (timing) t_issue += clock64() - tt;
+                }
+            }
+            if (timing) {
+                long long* d = p.dbg + (long long)blockIdx.x * 16;
+                d[0] = clock64() - t_all;
+                d[1] = t_wx;
+                d[2] = t_wa;
+                d[3] = t_issue;
+                d[4] = item_end - item_begin;
+            }
+        }
+    } else if (warp == V3_WARP_X) {
+        // ===================== layer-0 operand loader: two rows per lane, one pair ahead ===============================
+        const int in = p.O + p.A;
+        uint32_t n_pair = 0, n_x[4] = {0, 0, 0, 0};
+        V3Pair pr;
+        for (int item = item_begin; item < item_end; ++n_pair) {
+            item = v3_next_pair(p, item, item_end, tiles_total, s_off, pr);
+            const int st = n_pair & 1;
+            for (int s = 0; s < pr.n; ++s) {
+                mbar_wait(&bars[V3_X_EMPTY + st * 2 + s], (n_x[st * 2 + s] & 1) ^ 1);
+                ++n_x[st * 2 + s];
+                uint8_t* xbuf = smem + sm.x_off[st][s];
+#pragma unroll
+                for (int hr = 0; hr < 2; ++hr) {
+                    const int r = lane + hr * 32;
+                    const int grow = (int)rank * V3_ROWS + r;
+                    const bool valid = grow < pr.nrows[s];
+                    const long long env = valid ? p.perm[pr.row0[s] + grow] : 0;
+                    for (int c = 0; c < K0 / 8; ++c) {
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int k = c * 8 + j;
+                            float x = 0.0f;
+                            if (valid) {
+                                if (k < p.O) x = p.obs[env * p.O + k];
+                                else if (k < in) x = p.actn[env * p.A + (k - p.O)];
+                                else if (k == in) x = 1.0f;
+                            }
+                            v[j] = x;
+                        }
+                        *reinterpret_cast<uint4*>(xbuf + c * V3_CHUNK + r * 16) =
+                            make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) v3_arrive_leader(&bars[V3_X_READY + st * 2 + s]);
+            }
+        }
+    } else if (warp >= V3_HEAD_WARP0) {
+        // ===================== head warps: Gaussian head + residual + sampling + scatter ============================
+        // accumulator of the head (N_head columns, interleaved (mean_d, logvar_d)): lanes 0-63 hold columns
+        // [0, NH/2), lanes 64-127 columns [NH/2, NH) of rows 0-63
+        const int q = warp - V3_HEAD_WARP0;
+        const int row = (q & 1) * 32 + lane;
+        const int col_half = (q >> 1) * (NH / 2);
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int D = p.head_dim;
+        uint32_t n_h[2] = {0, 0};
+        V3Pair pr;
+        for (int item = item_begin; item < item_end;) {
+            item = v3_next_pair(p, item, item_end, tiles_total, s_off, pr);
+            for (int s = 0; s < pr.n; ++s) {
+                const int grow = (int)rank * V3_ROWS + row;
+                const bool valid = grow < pr.nrows[s];
+                const long long env = valid ? p.perm[pr.row0[s] + grow] : 0;
+                mbar_wait(&bars[V3_DH_FULL + s], n_h[s] & 1);
+                ++n_h[s];
+                tc_fence_after();
+                for (int c0 = 0; c0 < NH / 2; c0 += 8) {
+                    uint32_t raw[8];
+                    __syncwarp();
+                    v3_ld8_issue(tmem_base + lane_base + v3_dh_col(s) + c0, raw);
+                    v3_ld_wait();
+                    if (!valid) continue;
+                    if (p.layout == CMRL_HEAD_PARALLEL) {
+                        if (col_half + c0 == 0) {
+                            float out = __uint_as_float(raw[0]);
+                            if (p.residual) out += p.obs[env * p.O + pr.pp];
+                            if (p.gaussian && p.noise) {
+                                const int bi = p.bounds_n == 1 ? 0 : pr.pp;
+                                const float lv = soft_clamp_logvar(__uint_as_float(raw[1]), p.min_logvar[bi], p.max_logvar[bi]);
+                                out += sqrtf(expf(lv)) * p.noise[env * D + pr.pp];
+                            }
+                            p.pred[env * D + pr.pp] = out;
+                        }
+                    } else if (p.gaussian) {
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2) {
+                            const int d = (col_half + c0 + j) >> 1;
+                            if (d < D) {
+                                float m = __uint_as_float(raw[j]);
+                                if (p.residual) m += p.obs[env * p.O + d];
+                                if (p.noise) {
+                                    const int bi = p.bounds_n == 1 ? 0 : d;
+                                    const float lv = soft_clamp_logvar(__uint_as_float(raw[j + 1]), p.min_logvar[bi], p.max_logvar[bi]);
+                                    m += sqrtf(expf(lv)) * p.noise[env * D + d];
+                                }
+                                p.pred[env * D + d] = m;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int d = col_half + c0 + j;
+                            if (d < D) {
+                                float m = __uint_as_float(raw[j]);
+                                if (p.residual) m += p.obs[env * p.O + d];
+                                p.pred[env * D + d] = m;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) v3_arrive_leader(&bars[V3_DH_EMPTY + s]);
+            }
+        }
+    } else {
+        // ===================== epilogue warps ============================================================================
+        // quarter q: TMEM lanes 32q..32q+31 = rows 32(q&1).. of the tile, accumulator columns of half h = q>>1, i.e.
+        // hidden units [h*HP/2, (h+1)*HP/2).  Set s converts the 8-column chunks c = s, s+4, ... : one tcgen05.ld.x8,
+        // 8 activations, one 16-byte store = K chunk (h*HP/16 + c) of the next layer's A operand.  All of a warp's loads
+        // are issued before the single wait; the loop body is kept to ~4 instructions per element (the epilogue is
+        // issue / SFU bound: 16 SFU lanes per SM).
+        const int q = warp & 3, cset = warp >> 2;
+        const int row = (q & 1) * 32 + lane;
+        const int h = q >> 1;
+        const int n_chunks = HP / 16;                      // 8-column chunks per half
+        const int my_n = (n_chunks - cset + 3) >> 2;       // chunks of this warp: cset, cset+4, ...
+        const int kc0 = h * n_chunks + cset;               // K chunk of the first one
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cset * 8;
+        const uint32_t a_addr[2] = {smem_u32(smem + sm.a_off[0]) + (uint32_t)(kc0 * V3_CHUNK + row * 16),
+                                    smem_u32(smem + sm.a_off[1]) + (uint32_t)(kc0 * V3_CHUNK + row * 16)};
+        // does this thread own the ones column (fp16 1.0 at hidden unit H, the next layer's bias input)?
+        const int ones_chunk = p.H >> 3;
+        const int ones_rel = ones_chunk - kc0;
+        const bool owns_ones = ones_rel >= 0 && (ones_rel & 3) == 0 && (ones_rel >> 2) < my_n && ones_chunk < (h + 1) * n_chunks;
+        const uint32_t ones_off = (uint32_t)(ones_rel * V3_CHUNK + (p.H & 7) * 2);
+        uint32_t n_d0 = 0, n_d1 = 0;
+        const bool timing = p.dbg != nullptr && threadIdx.x == 0;
+        long long t_wd = 0, t_loop = 0, t_pub = 0, t0 = timing ? clock64() : 0, tt = 0;
+        V3Pair pr;
+        for (int item = item_begin; item < item_end;) {
+            item = v3_next_pair(p, item, item_end, tiles_total, s_off, pr);
+            for (int l = 0; l < L; ++l) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if (s >= pr.n) break;
+                    if (timing) tt = clock64();
+                    if (s == 0) {
+                        mbar_wait(&bars[V3_D_FULL + 0], n_d0 & 1);
+                        ++n_d0;
+                    } else {
+                        mbar_wait(&bars[V3_D_FULL + 1], n_d1 & 1);
+                        ++n_d1;
+                    }
+                    if (timing) {
+                        long long t = clock64();
+                        t_wd += t - tt;
+                        tt = t;
+                    }
+                    tc_fence_after();
+                    const uint32_t d_addr = t_addr + v3_d_col(s);
+                    uint32_t raw[4][8];
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i < my_n) v3_ld8_issue(d_addr + i * 32, raw[i]);
+                    v3_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (i < my_n) {
+                            uint32_t hh[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) hh[j] = v3_act_pack<ACT>(__uint_as_float(raw[i][2 * j]), __uint_as_float(raw[i][2 * j + 1]));
+                            v3_sts128(a_addr[s] + (uint32_t)(i * 4 * V3_CHUNK), hh[0], hh[1], hh[2], hh[3]);
+                        }
+                    }
+                    if (owns_ones) v3_sts16(a_addr[s] + ones_off, (uint16_t)0x3C00);
+                    if (timing) {
+                        long long t = clock64();
+                        t_loop += t - tt;
+                        tt = t;
+                    }
+                    tc_fence_before();
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) v3_arrive_leader(&bars[V3_A_READY + s]);
+                    if (timing) t_pub += clock64() - tt;
+                }
+            }
+        }
+        if (timing) {
+            long long* d = p.dbg + (long long)blockIdx.x * 16;
+            d[8] = clock64() - t0;
+            d[9] = t_wd;
+            d[10] = t_loop;
+            d[14] = t_pub;
+        }
+    }
+
+    // ---- teardown ----------------------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    v3_cluster_sync();
+    if (warp == V3_WARP_MMA) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+int launch_rollout_v3(const RolloutP& p, cudaStream_t st) {
+    const int L = p.num_layers;
+    const int HP = p.layer_n[0];
+    CMRL_REQUIRE(HP <= 256 && HP % 16 == 0, "mlp_rollout_f16 v3: padded hidden width must be <= 256");
+    CMRL_REQUIRE(p.layer_n[L] <= 128, "mlp_rollout_f16 v3: head wider than 128 columns");
+    V3Smem sm{};
+    uint32_t off = 0;
+    for (int l = 0; l <= L; ++l) {
+        sm.w_off[l] = off;
+        off += (uint32_t)(p.layer_n[l] / 2) * p.layer_k[l] * 2;
+        off = (off + 127) / 128 * 128;
+    }
+    for (int s = 0; s < 2; ++s) {
+        sm.a_off[s] = off;
+        off += (uint32_t)(HP / 8) * V3_CHUNK;
+    }
+    for (int stg = 0; stg < 2; ++stg)
+        for (int s = 0; s < 2; ++s) {
+            sm.x_off[stg][s] = off;
+            off += (uint32_t)(p.layer_k[0] / 8) * V3_CHUNK;
+        }
+    sm.bar_off = off;
+    off += V3_BAR_COUNT * 8;
+    sm.total = off;
+    CMRL_REQUIRE(sm.total <= 232448 - 1024, "mlp_rollout_f16 v3: hidden width %d needs %u B of shared memory (> 227 KB)", p.H, sm.total);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+        attr_set = true;
+    }
+    int max_items = p.P * ((p.N + V3_TILE - 1) / V3_TILE + p.E);
+    int clusters = num_sms() / 2;
+    if (clusters > (max_items + 1) / 2) clusters = (max_items + 1) / 2;
+    if (clusters < 1) clusters = 1;
+    if (p.act == CMRL_ACT_SILU)
+        mlp_rollout_f16_v3_kernel<CMRL_ACT_SILU><<<clusters * 2, V3_THREADS, sm.total, st>>>(p, sm);
+    else if (p.act == CMRL_ACT_RELU)
+        mlp_rollout_f16_v3_kernel<CMRL_ACT_RELU><<<clusters * 2, V3_THREADS, sm.total, st>>>(p, sm);
+    else
+        mlp_rollout_f16_v3_kernel<CMRL_ACT_IDENTITY><<<clusters * 2, V3_THREADS, sm.total, st>>>(p, sm);
+    CMRL_CHECK_LAUNCH("mlp_rollout_f16_v3");
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace cmrl

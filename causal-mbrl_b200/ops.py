@@ -300,7 +300,7 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0)):
+def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0), head_interleave_d=0):
     """Pack a mechanism's fp32 parameters into the private fp16 device layout of cmrl_mlp_rollout_f16.
     weights/biases: per layer [(P,)E,in,out] / [(P,)E,1,out] (hidden layers, then the head).
     Returns (blob half tensor [nets, blob_halfs], layer_off, layer_k, layer_n) -- never part of state_dict."""
@@ -326,12 +326,14 @@ def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0)):
     for i, (w, b) in enumerate(zip(weights, biases)):
         w, b = w.detach().contiguous(), b.detach().contiguous()
         m = mask if i == 0 else None
+        inter = head_interleave_d if i == len(weights) - 1 else 0
         _lib.call("cmrl_pack_layer_f16", w.data_ptr(), b.data_ptr(), _ptr(m), mask_str[0], mask_str[1], P, E,
-                  w.shape[-2], w.shape[-1], layer_k[i], layer_n[i], blob.data_ptr() + 2 * layer_off[i], off, _stream())  # fmt: skip
+                  w.shape[-2], w.shape[-1], layer_k[i], layer_n[i], inter, blob.data_ptr() + 2 * layer_off[i], off,
+                  _stream())  # fmt: skip
     return blob, layer_off, layer_k, layer_n
 
 
-TC_VARIANT = 2  # 2: weight-stationary CTA pairs (default); 1: single-CTA streamed weights
+TC_VARIANT = 3  # 3: CTA pairs, two tiles in flight (default); 2: CTA pairs, one tile; 1: single-CTA streamed weights
 
 
 def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, gaussian, act_kind, residual,

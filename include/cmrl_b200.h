@@ -181,9 +181,10 @@ int cmrl_env_step_tail(const float* next_obs, const float* reward, const float* 
 /* pack_weights: one layer of every net, fp32 state_dict tensors -> the private padded fp16 device layout
  * (UMMA K-major core-matrix order, bias folded in as K row `in_size`, optional 0/1 input mask
  * mask[p*m_sp + e*m_se + i] folded into the rows: exact per SURVEY Appendix B).  dst: half*, net g's layer
- * blob at dst + g*net_stride_halfs, n_pad*k_pad halves.  Never visible in state_dict. */
+ * blob at dst + g*net_stride_halfs, n_pad*k_pad halves.  interleave_d = D for the Gaussian PLAIN head layer
+ * (output columns re-ordered to 2d = mean_d, 2d+1 = logvar_d), 0 otherwise.  Never visible in state_dict. */
 int cmrl_pack_layer_f16(const float* w, const float* b, const float* mask, long long m_sp, long long m_se, int P,
-                        int E, int in_size, int out_size, int k_pad, int n_pad, void* dst_half,
+                        int E, int in_size, int out_size, int k_pad, int n_pad, int interleave_d, void* dst_half,
                         long long net_stride_halfs, void* stream);
 
 /* Fused selected-member rollout of ONE mechanism (VecFakeEnv.get_dynamics_predict, fake_env.py:195-215, over
@@ -191,8 +192,9 @@ int cmrl_pack_layer_f16(const float* w, const float* b, const float* mask, long 
  * bucketed env row (perm/offsets from cmrl_member_bucket) run the drawn member's whole MLP on tcgen05 tensor
  * cores with TMA-staged packed weights and write pred[env,:] = mean (+obs) + sqrt(exp(logvar)) * noise[env,:].
  * layer_*: arrays of num_layers+1 entries (hidden layers, then the head).
- * variant: 2 = weight-stationary CTA pairs (cta_group::2, pipelined epilogue; hidden <= 207), 1 = single-CTA
- * tiles with per-layer streamed weights (any hidden width whose stage fits shared memory). */
+ * variant: 3 = weight-stationary CTA pairs (cta_group::2, M=128) with two row tiles in flight (default),
+ * 2 = CTA pairs with one 256-row tile and a pipelined epilogue (hidden <= 207), 1 = single-CTA tiles with
+ * per-layer streamed weights. */
 int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, const int* layer_off_halfs, const int* layer_k,
                          const int* layer_n, int num_layers, int P, int E, int N, int O, int A, int H, int head_dim,
                          int layout, int gaussian, int act, const float* obs, const float* actn, const int* perm,

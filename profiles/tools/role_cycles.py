@@ -26,7 +26,7 @@ for flags in [0]:
   lib.cmrl_debug_set_buffer(None); lib.cmrl_debug_set_flags(0)
   d=dbg.cpu().numpy().reshape(148,16)
   lead=d[0::2]
-  print('=== dbg flags', flags, '(1 skip STS, 2 skip LDTM, 4 skip act)')
+  print('=== variant', cm.ops.TC_VARIANT, 'dbg flags', flags, '(1 skip A stores, 4 skip activation)')
   print('MMA thread (leader CTAs): total, wait_x, wait_a, issue, items  (mean over clusters)')
   print(lead[:,:5].mean(0).astype(int), ' per item:', (lead[:,:4].mean(0)/lead[:,4].mean()).astype(int))
   print('epilogue warp0: total, wait_d, loop, wait_h, head, ld_wait, publish')

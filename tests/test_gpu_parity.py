@@ -509,7 +509,7 @@ def _tc_case(cm, kind, N, H, seed):
     return env, m, obs, act, idx, noise
 
 
-@pytest.fixture(params=[2, 1], ids=["cta_pair", "single_cta"])
+@pytest.fixture(params=[3, 2, 1], ids=["pingpong", "cta_pair", "single_cta"])
 def tc_variant(request, cm):
     old = cm.ops.TC_VARIANT
     cm.ops.TC_VARIANT = request.param
