@@ -333,33 +333,75 @@ def dominant_kernel_roofline(cm, env, tr, act_dev, args, flush):
     }  # fmt: skip
 
 
-def time_train(cm, dyn, dev, args, world, barrier):
-    """BaseDynamics.train_step on resident ensemble batches: E x 256 rows, ExternalMask transition."""
+def time_train(cm, dyn_unused, dev, args, world, barrier):
+    """Second half of the metric: ensemble train member-samples/s.  C4-shaped: PlainTransition E=7 (4x200, SiLU, O=5,
+    A=1), bs 256 per member, fp32 tier, one device-resident epoch (on-device bootstrap gather + CUDA-graph replay of
+    the optimiser step) over a synthetic training set; replicas per GPU (gradient all-reduce is exercised by
+    `enable_data_parallel`, not timed here)."""
     import torch
     import torch.distributed as dist
 
-    B = 256
-    g = torch.Generator(device=dev)
-    g.manual_seed(0)
-    obs = torch.randn(E, B, O, device=dev, generator=g)
-    act = torch.rand(E, B, A, device=dev, generator=g) * 2 - 1
-    target = obs + 0.1 * torch.randn(E, B, O, device=dev, generator=g)
-    steps = max(20, args.steps)
-    for _ in range(5):
-        dyn.train_step("transition", obs, act, target, want_loss=False)
+    from oracle.refshim import DuckReplayBuffer
+
+    B, n_batches = 256, 200
+    N = int(B * n_batches / 0.8)
+    rng = np.random.default_rng(7)
+    obs = rng.normal(size=(N, O)).astype(np.float32)
+    act = rng.uniform(-1, 1, size=(N, A)).astype(np.float32)
+    M = (rng.normal(size=(O, O)) / np.sqrt(O)).astype(np.float32)
+    K = rng.normal(size=(A, O)).astype(np.float32)
+    nxt = (obs + 0.1 * np.tanh(obs @ M + act @ K) + 0.01 * rng.normal(size=(N, O))).astype(np.float32)
+    rew = (np.cos(obs[:, 0]) - 0.1 * (act**2).sum(-1)).astype(np.float32)
+    buf = DuckReplayBuffer(obs, act, nxt, rew, np.zeros(N, bool))
+    torch.manual_seed(1)
+    tr = cm.PlainTransition(O, A, ensemble_num=E, elite_num=ELITE, hid_size=H, activation_fn_cfg=SILU, device=dev)
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=False)
+    train_it, _ = dyn.dataset_split(buf, 0.2, B)
+    steps = len(train_it)
+    dyn.train_epoch_device(train_it, "transition")  # warm-up epoch: uploads the set, captures the graph
     barrier()
     a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(steps):
-        dyn.train_step("transition", obs, act, target, want_loss=False)
+    loss = dyn.train_epoch_device(train_it, "transition")
     c.record()
     barrier()
     t = torch.tensor([a.elapsed_time(c)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / steps
-    return {"metric": "ensemble_train_member_samples_per_sec", "value": E * B * world / (ms * 1e-3), "unit": "member-samples/s",
-            "ms_per_step": ms, "config": "ExternalMaskTransition P=5 E=7 4x200, bs 256 per member per GPU, fp32, replicas"}  # fmt: skip
+    out = {"metric": "ensemble_train_member_samples_per_sec", "value": E * B * world / (ms * 1e-3), "unit": "member-samples/s",
+           "ms_per_step": ms, "steps_per_epoch": steps, "epoch_mean_nll": loss,
+           "config": "C4-shaped: PlainTransition E=7 4x200 SiLU O=5 A=1, bs 256 per member per GPU, fp32 tier, "
+                     "device-resident epoch (on-device bootstrap gather + CUDA-graph replay), replicas"}  # fmt: skip
+    if not args.no_cpu_baseline and int(os.environ.get("RANK", "0")) == 0:
+        out["cpu_baseline"] = time_port_train(B)
+    return out
+
+
+def time_port_train(B, n_steps=30):
+    """The reference's training step (NLL + backward + torch.optim.Adam) on the host cores (torch-CPU port)."""
+    import torch
+
+    from oracle import cmrl_oracle as oc
+    from oracle import ref_port_torch as rp
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    rng = np.random.default_rng(0)
+    params = {k: torch.from_numpy(v).requires_grad_(not k.endswith("logvar"))
+              for k, v in oc.init_plain_params(rng, O + A, H, 2 * O, E, L, bounds_shape=(1, O)).items()}  # fmt: skip
+    optim = torch.optim.Adam([v for v in params.values() if v.requires_grad], lr=1e-4, weight_decay=1e-5, eps=1e-8)
+    obs = torch.randn(E, B, O)
+    act = torch.rand(E, B, A) * 2 - 1
+    tgt = obs + 0.1 * torch.randn(E, B, O)
+    for _ in range(3):
+        rp.train_batch(params, optim, obs.clone(), act, tgt, rp._act("silu"))
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        rp.train_batch(params, optim, obs.clone(), act, tgt, rp._act("silu"))
+    dt = (time.perf_counter() - t0) / n_steps
+    return {"value": E * B / dt, "unit": "member-samples/s", "cores": threads, "kind": "port",
+            "sample": "%d optimiser steps of bs %d x %d members on the torch-CPU port" % (n_steps, B, E)}  # fmt: skip
 
 
 def main():

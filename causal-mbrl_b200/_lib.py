@@ -31,6 +31,8 @@ PROTOTYPES = {
     "cmrl_mse_loss_fwd": [_P, _P, _LL, _I, _LL, _P, _P],
     "cmrl_mse_member_sums": [_P, _P, _LL, _I, _LL, _P, _P],
     "cmrl_adam_l2_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _I, _P],
+    "cmrl_adam_l2_step_dev": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _P, _P],
+    "cmrl_bootstrap_gather": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "cmrl_draw_member_noise": [_ULL, _ULL, _I, _P, _I, _I, _P, _P, _P],
     "cmrl_draw_uniform_index": [_ULL, _ULL, _I, _I, _P, _P],
     "cmrl_member_bucket": [_P, _I, _I, _P, _P, _P, _P],

@@ -156,9 +156,88 @@ __global__ void adam_l2_kernel(float* __restrict__ p, const float* __restrict__ 
     }
 }
 
+// Adam with the step counter in device memory (CUDA-graph replayable): t = *step_dev + 1; a trailing one-thread
+// kernel bumps the counter.
+__global__ void adam_l2_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                   float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                                   float wd, float gscale, const int* __restrict__ step_dev) {
+    __shared__ float s_lr_over_bc1, s_sqrt_bc2;
+    if (threadIdx.x == 0) {
+        const double t = (double)(*step_dev + 1);
+        s_lr_over_bc1 = (float)((double)lr / (1.0 - pow((double)beta1, t)));
+        s_sqrt_bc2 = (float)sqrt(1.0 - pow((double)beta2, t));
+    }
+    __syncthreads();
+    const float lr_over_bc1 = s_lr_over_bc1, sqrt_bc2 = s_sqrt_bc2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float pi = p[i];
+        float gi = fmaf(wd, pi, g[i] * gscale);
+        float mi = m[i];
+        mi = fmaf(1.0f - beta1, gi - mi, mi);
+        float vi = fmaf((1.0f - beta2) * gi, gi, beta2 * v[i]);
+        m[i] = mi;
+        v[i] = vi;
+        p[i] = pi - lr_over_bc1 * (mi / (sqrtf(vi) / sqrt_bc2 + eps));
+    }
+}
+__global__ void bump_counter_kernel(int* c, int delta) { *c += delta; }
+
+// Bootstrap batch assembly on the device (BootstrapIterator.__next__ + _consolidate_batches,
+// cmrl/util/transition_iterator.py:14-28,131-139): row b of member e = transitions[member_idx[e, order[start + b]]]
+__global__ void bootstrap_gather_kernel(const float* __restrict__ obs, const float* __restrict__ act,
+                                        const float* __restrict__ target, const int* __restrict__ member_idx,
+                                        const int* __restrict__ order, const int* __restrict__ start_dev, int B, int N,
+                                        int O, int A, int D, float* __restrict__ o_obs, float* __restrict__ o_act,
+                                        float* __restrict__ o_target) {
+    const int W = O + A + D;
+    const int e = blockIdx.y;
+    const int start = *start_dev;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * W; i += gridDim.x * blockDim.x) {
+        const int b = i / W, c = i - b * W;
+        const int pos = min(start + b, N - 1);
+        const long long src = member_idx[(long long)e * N + order[pos]];
+        const long long row = (long long)e * B + b;
+        if (c < O) o_obs[row * O + c] = obs[src * O + c];
+        else if (c < O + A) o_act[row * A + (c - O)] = act[src * A + (c - O)];
+        else o_target[row * D + (c - O - A)] = target[src * D + (c - O - A)];
+    }
+}
+
 }  // namespace cmrl
 
 using namespace cmrl;
+
+extern "C" int cmrl_adam_l2_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                                     float lr, float beta1, float beta2, float eps, float weight_decay,
+                                     float grad_scale, int* step_dev, void* stream) {
+    CMRL_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev, "adam_l2_step_dev: null pointer");
+    if (n == 0) return 0;
+    adam_l2_dev_kernel<<<ew_blocks(n), EW_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                            beta2, eps, weight_decay, grad_scale, step_dev);
+    CMRL_CHECK_LAUNCH("adam_l2_step_dev");
+    bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, 1);
+    CMRL_CHECK_LAUNCH("adam_l2_step_dev.bump");
+    return 0;
+}
+
+extern "C" int cmrl_bootstrap_gather(const float* obs, const float* act, const float* target, const int* member_idx,
+                                     const int* order, int* start_dev, int advance, int E, int B, int N, int O, int A,
+                                     int D, float* out_obs, float* out_act, float* out_target, void* stream) {
+    CMRL_REQUIRE(obs && act && target && member_idx && order && start_dev && out_obs && out_act && out_target,
+                 "bootstrap_gather: null pointer");
+    CMRL_REQUIRE(E >= 1 && B >= 1 && N >= 1, "bootstrap_gather: bad dims");
+    int bx = (B * (O + A + D) + 255) / 256;
+    if (bx > 64) bx = 64;
+    dim3 grid(bx, E);
+    bootstrap_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(obs, act, target, member_idx, order, start_dev, B, N, O, A,
+                                                                  D, out_obs, out_act, out_target);
+    CMRL_CHECK_LAUNCH("bootstrap_gather");
+    if (advance) {
+        bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(start_dev, advance);
+        CMRL_CHECK_LAUNCH("bootstrap_gather.advance");
+    }
+    return 0;
+}
 
 extern "C" int cmrl_gaussian_head_fwd(const float* raw, int layout, int E, int B, int D, const float* obs,
                                       long long obs_se, int obs_ld, const float* min_logvar, const float* max_logvar,

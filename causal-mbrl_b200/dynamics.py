@@ -189,7 +189,7 @@ class BaseDynamics:
         return (sums / float(n * d)).to(torch.float32).cpu()
 
     def train_step(self, mech: str, obs: torch.Tensor, act: torch.Tensor, target: torch.Tensor,
-                   want_loss: bool = True, grad_rows: Optional[int] = None):  # fmt: skip
+                   want_loss: bool = True, grad_rows: Optional[int] = None, graphable: bool = False):  # fmt: skip
         """One optimiser step on an ensemble batch (obs/act/target: [E,B,*] device tensors), equivalent to
         `loss = get_nll_loss(...); zero_grad(); loss.mean().backward(); step()` (base_dynamics.py:181-186).
         Returns the un-reduced loss [E,B,D] (None if not wanted).  grad_rows: global rows per member when the
@@ -238,7 +238,10 @@ class BaseDynamics:
             if i > 0:
                 dz = ops.ens_linear_bwd_dx(dz, w, zs[i - 1], kind)
         self._sync_grads(model)
-        optim.step()
+        if graphable:
+            optim.step_graphable()
+        else:
+            optim.step()
         return loss
 
     def enable_data_parallel(self, group=None):
@@ -258,6 +261,27 @@ class BaseDynamics:
 
             _, flat_grad = model.flat_parameters()
             dist.all_reduce(flat_grad[: model._n_trainable], op=dist.ReduceOp.SUM, group=self.dp_group)
+
+    def train_epoch_device(self, dataset: BootstrapIterator, mech: str = "transition", use_graph: bool = True):
+        """One pass over the bootstrap iterator with the training set, the bootstrap index table and the epoch order
+        resident on the device: batches are assembled by `cmrl_bootstrap_gather` and the whole optimiser step
+        (forward, NLL, backward, Adam; ~20 launches) is captured once in a CUDA graph and replayed per batch.
+        Consumes the iterator's RNG exactly like `train` (one permutation per epoch) and performs the same updates;
+        returns the mean train loss (what `learn` logs) instead of the [E,N,D] tensor."""
+        assert isinstance(dataset, BootstrapIterator)
+        model = getattr(self, mech)
+        optim = getattr(self, "{}_optimizer".format(mech))
+        fast = (not model.deterministic and self.dp_group is None and dataset._bootstrap_iter
+                and not any(q.requires_grad for q in model._bounds()))  # fmt: skip
+        if not fast:
+            return float(self.train(dataset, mech=mech).mean().item())
+        runner = self._epoch_runners.get(mech) if hasattr(self, "_epoch_runners") else None
+        if not hasattr(self, "_epoch_runners"):
+            self._epoch_runners = {}
+        if runner is None or runner.dataset is not dataset:
+            runner = _DeviceEpochRunner(self, mech, dataset, use_graph)
+            self._epoch_runners[mech] = runner
+        return runner.run_epoch()
 
     def train(self, dataset: TransitionIterator, mech: str = "transition"):
         """One pass over the bootstrap iterator; returns the un-reduced train loss [E, N_train, D] on the CPU
@@ -310,6 +334,74 @@ class BaseDynamics:
     def get_mach_by_variable(self, variable: str) -> str:
         assert variable in self._VARIABLE_TO_MECH
         return self._VARIABLE_TO_MECH[variable]
+
+
+class _DeviceEpochRunner:
+    """Device-resident training epoch: dataset + bootstrap tables in HBM, on-device batch gather,
+    CUDA-graph replay of the optimiser step."""
+
+    def __init__(self, dyn, mech, dataset, use_graph=True):
+        self.dyn, self.mech, self.dataset, self.use_graph = dyn, mech, dataset, use_graph
+        dev = dyn.device
+        data = dataset.transitions
+        target = dyn._batch_variable(data, dyn._MECH_TO_VARIABLE[mech])
+
+        def dev_f32(a):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            return torch.from_numpy(a.reshape(a.shape[0], -1)).to(dev)
+
+        self.obs, self.act, self.target = dev_f32(data.batch_obs), dev_f32(data.batch_action), dev_f32(target)
+        self.N = self.obs.shape[0]
+        self.member_idx = torch.from_numpy(np.ascontiguousarray(dataset.member_indices, dtype=np.int32)).to(dev)
+        self.order = torch.zeros(self.N, dtype=torch.int32, device=dev)
+        self.start = torch.zeros(1, dtype=torch.int32, device=dev)
+        E, B = dataset.ensemble_size, dataset.batch_size
+        self.E, self.B = E, B
+        self.b_obs = torch.empty((E, B, self.obs.shape[1]), device=dev)
+        self.b_act = torch.empty((E, B, self.act.shape[1]), device=dev)
+        self.b_tgt = torch.empty((E, B, self.target.shape[1]), device=dev)
+        self.loss_sum = torch.zeros((), device=dev, dtype=torch.float64)
+        self.graph = None
+
+    def _step(self):
+        ops.bootstrap_gather(self.obs, self.act, self.target, self.member_idx, self.order, self.start, self.B, self.B,
+                             self.b_obs, self.b_act, self.b_tgt)  # fmt: skip
+        loss = self.dyn.train_step(self.mech, self.b_obs, self.b_act, self.b_tgt, want_loss=True, graphable=True)
+        self.loss_sum += loss.sum(dtype=torch.float64)
+
+    def run_epoch(self):
+        ds = self.dataset
+        iter(ds)  # reshuffles exactly like the reference iterator (one rng.permutation per epoch)
+        self.order.copy_(torch.from_numpy(np.ascontiguousarray(ds._order, dtype=np.int32)), non_blocking=True)
+        self.start.zero_()
+        self.loss_sum.zero_()
+        model = getattr(self.dyn, self.mech)
+        model._nll_reg()  # host-side constant, cached before any capture
+        model.flat_parameters()
+        getattr(self.dyn, "{}_optimizer".format(self.mech)).prepare_graphable()
+        n_full = self.N // self.B
+        if self.use_graph and self.graph is None and n_full > 0:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._step()
+            self.graph = g
+        for _ in range(n_full):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._step()
+        total = n_full * self.B
+        rem = self.N - total
+        if rem > 0:  # ragged last batch: same rows the reference iterator would yield
+            idx = torch.from_numpy(np.ascontiguousarray(ds._order[total:], dtype=np.int64)).to(self.obs.device)
+            rows = self.member_idx.long()[:, idx]  # [E, rem]
+            loss = self.dyn.train_step(self.mech, self.obs[rows], self.act[rows], self.target[rows], want_loss=True,
+                                       graphable=True)  # fmt: skip
+            self.loss_sum += loss.sum(dtype=torch.float64)
+        ds._current_batch = len(ds)  # the iterator is exhausted, like after a `for batch in dataset` loop
+        denom = float(self.E * self.N * self.b_tgt.shape[-1])
+        return float(self.loss_sum.item()) / denom
 
 
 class PlainEnsembleDynamics(BaseDynamics):
@@ -369,7 +461,7 @@ class PlainEnsembleDynamics(BaseDynamics):
             best_val_loss = self._val_loss(val_dataset, mech)
 
             for epoch in epoch_iter:
-                train_loss = self.train(train_dataset, mech=mech)
+                train_loss = torch.tensor(self.train_epoch_device(train_dataset, mech=mech))
                 val_loss = self._val_loss(val_dataset, mech)
 
                 maybe_best_weights = self.maybe_get_best_weights(best_val_loss, val_loss, mech, improvement_threshold)

@@ -227,6 +227,19 @@ def adam_l2_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight
               _stream())  # fmt: skip
 
 
+def adam_l2_step_dev(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale=1.0):
+    _lib.call("cmrl_adam_l2_step_dev", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+              param.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale),
+              step_dev.data_ptr(), _stream())  # fmt: skip
+
+
+def bootstrap_gather(obs, act, target, member_idx, order, start_dev, advance, B, out_obs, out_act, out_target):
+    E, N = member_idx.shape
+    _lib.call("cmrl_bootstrap_gather", obs.data_ptr(), act.data_ptr(), target.data_ptr(), member_idx.data_ptr(),
+              order.data_ptr(), start_dev.data_ptr(), int(advance), E, B, N, obs.shape[1], act.shape[1], target.shape[1],
+              out_obs.data_ptr(), out_act.data_ptr(), out_target.data_ptr(), _stream())  # fmt: skip
+
+
 # ----------------------------------------------------------------------------- rollout
 def draw_member_noise(seed, stream_id, N, elite_u8, D, want_noise=True, device=None):
     device = elite_u8.device if device is None else device

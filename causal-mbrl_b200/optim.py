@@ -12,6 +12,7 @@ class FusedAdamL2(torch.optim.Optimizer):
         params = list(model.parameters())
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._step = 0
+        self._step_dev = None  # device copy of the step counter (CUDA-graph replayable steps)
         self._exp_avg = None
         self._exp_avg_sq = None
 
@@ -33,14 +34,36 @@ class FusedAdamL2(torch.optim.Optimizer):
         loss = closure() if closure is not None else None
         g = self.param_groups[0]
         p, grad = self._arena()
+        if self._step_dev is not None:  # a graph replay advanced the device counter
+            self._step = int(self._step_dev.item())
+            self._step_dev = None
         self._step += 1
         ops.adam_l2_step(p, grad, self._exp_avg, self._exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
                          g["weight_decay"], self._step, grad_scale)  # fmt: skip
         return loss
 
+    def prepare_graphable(self):
+        """Allocate the moment buffers and the device step counter (must happen outside a graph capture)."""
+        p, _ = self._arena()
+        if self._step_dev is None:
+            self._step_dev = torch.tensor([self._step], dtype=torch.int32, device=p.device)
+
+    @torch.no_grad()
+    def step_graphable(self, grad_scale: float = 1.0):
+        """Same update with the step counter on the device: safe to capture in a CUDA graph and replay."""
+        g = self.param_groups[0]
+        self.prepare_graphable()
+        p, grad = self._arena()
+        ops.adam_l2_step_dev(p, grad, self._exp_avg, self._exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                             g["weight_decay"], self._step_dev, grad_scale)  # fmt: skip
+
+    @property
+    def step_count(self):
+        return self._step if self._step_dev is None else int(self._step_dev.item())
+
     def state_dict(self):
         return {
-            "step": self._step,
+            "step": self.step_count,
             "exp_avg": None if self._exp_avg is None else self._exp_avg.clone(),
             "exp_avg_sq": None if self._exp_avg_sq is None else self._exp_avg_sq.clone(),
             "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],

@@ -121,6 +121,21 @@ int cmrl_adam_l2_step(float* param, const float* grad, float* exp_avg, float* ex
                       float beta1, float beta2, float eps, float weight_decay, float grad_scale, int step,
                       void* stream);
 
+/* Same update with the 1-based step counter kept in device memory (*step_dev is the number of steps already
+ * taken; incremented by the call), so a captured CUDA graph can be replayed step after step. */
+int cmrl_adam_l2_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, float grad_scale, int* step_dev,
+                          void* stream);
+
+/* Device-side bootstrap batch assembly (BootstrapIterator.__next__ + _consolidate_batches,
+ * cmrl/util/transition_iterator.py:14-28,131-139): for member e and row b < B
+ *   src = member_idx[e, order[min(*start_dev + b, N-1)]];  out_*[e,b,:] = {obs, act, target}[src,:]
+ * obs [N,O], act [N,A], target [N,D] are the device-resident training set; member_idx int32 [E,N], order int32 [N].
+ * advance != 0 adds it to *start_dev after the gather (graph-replayable epoch loop). */
+int cmrl_bootstrap_gather(const float* obs, const float* act, const float* target, const int* member_idx,
+                          const int* order, int* start_dev, int advance, int E, int B, int N, int O, int A, int D,
+                          float* out_obs, float* out_act, float* out_target, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K5  rollout step (VecFakeEnv.step_wait, cmrl/models/fake_env.py:97-142)
  * ------------------------------------------------------------------------------------------ */

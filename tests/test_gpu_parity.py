@@ -554,3 +554,35 @@ def test_tcgen05_pack_refreshes_on_weight_change(cm):
     b = env.predict_selected(m, obs, act, idx, noise)
     assert not torch.equal(a, b)
     assert "hidden_layers.0.0.weight" in m.state_dict() and all(v.dtype == torch.float32 for v in m.state_dict().values())
+
+
+# ------------------------------------------------------------------------------------------------ device-resident training
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_device_epoch_matches_host_iterator_path(cm, use_graph):
+    """train_epoch_device (on-device bootstrap gather + CUDA-graph replay, ragged last batch) performs the same
+    updates as the reference-shaped `train` loop over the host BootstrapIterator."""
+    g = load_golden("learn_small.npz")
+    from oracle.refshim import DuckReplayBuffer
+
+    buf = DuckReplayBuffer(g["obs"], g["act"], g["next_obs"], g["rew"], g["done"])
+    results = []
+    for device_path in (False, True):
+        tr = cm.PlainTransition(5, 1, hid_size=32, activation_fn_cfg=SILU, device=DEV)
+        load_sd(tr, params_of(g, "tr0."))
+        dyn = cm.PlainEnsembleDynamics(tr, learned_reward=False, optim_lr=1e-3)
+        seeds = iter(range(50, 60))
+        real = np.random.default_rng
+        with mock.patch("numpy.random.default_rng", lambda seed=None: real(next(seeds) if seed is None else seed)):
+            train_it, _ = dyn.dataset_split(buf, 0.2, 100)  # 512 train rows -> 5 full batches + ragged 12
+        losses = []
+        for epoch in range(3):
+            if device_path:
+                losses.append(dyn.train_epoch_device(train_it, "transition", use_graph=use_graph))
+            else:
+                losses.append(float(dyn.train(train_it, "transition").mean().item()))
+        assert dyn.transition_optimizer.step_count == 18
+        results.append((losses, {k: v.cpu().numpy() for k, v in tr.state_dict().items()}))
+    (l0, w0), (l1, w1) = results
+    assert rel_err(np.asarray(l1), np.asarray(l0)) < 1e-5
+    for k in w0:
+        assert rel_err(w1[k], w0[k]) < 1e-5, k
