@@ -61,7 +61,7 @@ class ClockSampler:
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)  # fmt: skip
         except Exception:
             self.proc = None
@@ -196,11 +196,11 @@ def run_native(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)  # > 126 MB L2
 
     # ---- device-resident steps (value) ------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # samples SM clocks / throttle reasons across all timed regions of this process
     for _ in range(args.warmup):
         env.step_device(act_dev)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = cm._lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for s in range(args.steps):
@@ -230,7 +230,6 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = N * world * args.steps / float(t.item())
-    clocks = sampler.stop()
     h2d = N * A * 4
     d2h = 2 * N * O * 4 + N * 4 + 2 * N + N * O * 4  # obs, terminal_obs, reward, done, trunc + next_obs for termination_fn
 
@@ -239,6 +238,7 @@ def run_native(args):
 
     # ---- training step (second half of the metric) ---------------------------------------------------------
     train = time_train(cm, dyn, dev, args, world, barrier)
+    clocks = sampler.stop()
 
     if rank == 0:
         cpu = None
@@ -407,7 +407,7 @@ def time_port_train(B, n_steps=30):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--envs", type=int, default=100_000)
