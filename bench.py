@@ -198,15 +198,16 @@ def run_native(args):
     # ---- device-resident steps (value) ------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()  # samples SM clocks / throttle reasons across all timed regions of this process
+    step_fn = env.step_device_graphed if args.graph else env.step_device
     for _ in range(args.warmup):
-        env.step_device(act_dev)
+        step_fn(act_dev)
     barrier()
     launches0 = cm._lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for s in range(args.steps):
         flush.fill_(float(s))  # L2 flush between timed iterations
         ev[s][0].record()
-        env.step_device(act_dev)
+        step_fn(act_dev)
         ev[s][1].record()
     barrier()
     launches = cm._lib.launch_count() - launches0
@@ -413,6 +414,7 @@ def main():
     ap.add_argument("--envs", type=int, default=100_000)
     ap.add_argument("--ref-envs", type=int, default=10_000)
     ap.add_argument("--precision", default="f16", choices=["fp32", "f16"])
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the step kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU port timing (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup

@@ -33,8 +33,9 @@ PROTOTYPES = {
     "cmrl_adam_l2_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _I, _P],
     "cmrl_adam_l2_step_dev": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _P, _P],
     "cmrl_bootstrap_gather": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
-    "cmrl_draw_member_noise": [_ULL, _ULL, _I, _P, _I, _I, _P, _P, _P],
-    "cmrl_draw_uniform_index": [_ULL, _ULL, _I, _I, _P, _P],
+    "cmrl_draw_member_noise": [_ULL, _ULL, _P, _I, _P, _I, _I, _P, _P, _P],
+    "cmrl_draw_uniform_index": [_ULL, _ULL, _P, _I, _I, _P, _P],
+    "cmrl_counter_add": [_P, _ULL, _P],
     "cmrl_member_bucket": [_P, _I, _I, _P, _P, _P, _P],
     "cmrl_gather_inputs": [_P, _P, _P, _I, _I, _I, _P, _P],
     "cmrl_sample_scatter": [_P, _I, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P],

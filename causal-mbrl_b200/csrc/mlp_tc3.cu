@@ -135,6 +135,19 @@ __device__ __forceinline__ void v3_ld8_issue(uint32_t taddr, uint32_t* r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking phase test
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void v3_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void v3_sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -158,39 +171,50 @@ __device__ __forceinline__ uint32_t v3_act_pack(float a, float b) {
 }
 
 // The work list of a cluster is a contiguous range of 128-row tiles in (p, member, tile) order; consecutive tiles of
-// the same net are processed two at a time.  Every role walks the list with this iterator.
+// the same net are processed two at a time.  Every role walks the list with this iterator (decode once, then step).
 struct V3Pair {
     int net, pp, n;       // net index, sub-net index, tiles in this pair (1 or 2)
     int row0[2], nrows[2];
 };
-__device__ __forceinline__ void v3_decode(const RolloutP& p, int item, int tiles_total, const int* s_off, int& pp, int& e, int& row0,
-                                          int& nrows) {
-    pp = item / tiles_total;
-    int t = item - pp * tiles_total;
-    row0 = 0;
-    nrows = 0;
-    for (e = 0; e < p.E; ++e) {
-        const int cnt = s_off[e + 1] - s_off[e];
-        const int nt = (cnt + V3_TILE - 1) / V3_TILE;
-        if (t < nt) {
-            row0 = s_off[e] + t * V3_TILE;
-            nrows = min(V3_TILE, cnt - t * V3_TILE);
-            return;
-        }
-        t -= nt;
+struct V3Iter {
+    int item, item_end, pp, e, t;  // next tile: sub-net pp, member e, tile t of that member
+};
+__device__ __forceinline__ int v3_tiles_of(const int* s_off, int e) { return (s_off[e + 1] - s_off[e] + V3_TILE - 1) / V3_TILE; }
+__device__ __forceinline__ void v3_iter_init(V3Iter& it, const RolloutP& p, int item_begin, int item_end, int tiles_total,
+                                             const int* s_off) {
+    it.item = item_begin;
+    it.item_end = item_end;
+    it.pp = tiles_total > 0 ? item_begin / tiles_total : 0;
+    int t = item_begin - it.pp * tiles_total;
+    it.e = 0;
+    while (it.e < p.E && t >= v3_tiles_of(s_off, it.e)) {
+        t -= v3_tiles_of(s_off, it.e);
+        ++it.e;
     }
+    it.t = t;
 }
-__device__ __forceinline__ int v3_next_pair(const RolloutP& p, int item, int item_end, int tiles_total, const int* s_off, V3Pair& pr) {
-    int e;
-    v3_decode(p, item, tiles_total, s_off, pr.pp, e, pr.row0[0], pr.nrows[0]);
-    pr.net = pr.pp * p.E + e;
-    pr.n = 1;
-    if (item + 1 < item_end) {
-        int pp2, e2;
-        v3_decode(p, item + 1, tiles_total, s_off, pp2, e2, pr.row0[1], pr.nrows[1]);
-        if (pp2 == pr.pp && e2 == e) pr.n = 2;
+// returns false when the range is exhausted
+__device__ __forceinline__ bool v3_iter_next(V3Iter& it, const RolloutP& p, const int* s_off, V3Pair& pr) {
+    if (it.item >= it.item_end) return false;
+    while (it.t >= v3_tiles_of(s_off, it.e)) {  // skip exhausted / empty members
+        it.t = 0;
+        if (++it.e >= p.E) {
+            it.e = 0;
+            ++it.pp;
+        }
     }
-    return item + pr.n;
+    const int nt = v3_tiles_of(s_off, it.e);
+    const int cnt = s_off[it.e + 1] - s_off[it.e];
+    pr.pp = it.pp;
+    pr.net = it.pp * p.E + it.e;
+    pr.n = (it.t + 1 < nt && it.item + 1 < it.item_end) ? 2 : 1;
+    for (int s = 0; s < pr.n; ++s) {
+        pr.row0[s] = s_off[it.e] + (it.t + s) * V3_TILE;
+        pr.nrows[s] = min(V3_TILE, cnt - (it.t + s) * V3_TILE);
+    }
+    it.t += pr.n;
+    it.item += pr.n;
+    return true;
 }
 
 template <int ACT>
@@ -250,8 +274,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
             int cur_net = -1;
             uint32_t n_w = 0;
             V3Pair pr;
-            for (int item = item_begin; item < item_end;) {
-                item = v3_next_pair(p, item, item_end, tiles_total, s_off, pr);
+            V3Iter it;
+            v3_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
+            while (v3_iter_next(it, p, s_off, pr)) {
                 if (pr.net == cur_net) continue;
                 if (cur_net != -1) mbar_wait(&bars[V3_W_EMPTY], (n_w - 1) & 1);
                 const __half* blob = p.packed + (long long)pr.net * p.blob_halfs;
@@ -284,8 +309,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
             const bool timing = p.dbg != nullptr && lane == 0 && s == 0;
             long long t_wa = 0, t_issue = 0, t_wx = 0, t_all = timing ? clock64() : 0, tt = 0;
             V3Pair pr;
-            for (int item = item_begin; item < item_end; ++n_pair) {
-                item = v3_next_pair(p, item, item_end, tiles_total, s_off, pr);
+            V3Iter it;
+            v3_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
+            for (; v3_iter_next(it, p, s_off, pr); ++n_pair) {
                 if (pr.net != cur_net) {
                     if (cur_net != -1) v3_commit_uni(&bars[V3_W_EMPTY]);
                     mbar_wait(&bars[V3_W_READY], n_w & 1);
@@ -356,8 +382,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
         const int in = p.O + p.A;
         uint32_t n_pair = 0, n_x[4] = {0, 0, 0, 0};
         V3Pair pr;
-        for (int item = item_begin; item < item_end; ++n_pair) {
-            item = v3_next_pair(p, item, item_end, tiles_total, s_off, pr);
+        V3Iter it;
+        v3_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
+        for (; v3_iter_next(it, p, s_off, pr); ++n_pair) {
             const int st = n_pair & 1;
             for (int s = 0; s < pr.n; ++s) {
                 mbar_wait(&bars[V3_X_EMPTY + st * 2 + s], (n_x[st * 2 + s] & 1) ^ 1);
@@ -402,8 +429,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
         const int D = p.head_dim;
         uint32_t n_h[2] = {0, 0};
         V3Pair pr;
-        for (int item = item_begin; item < item_end;) {
-            item = v3_next_pair(p, item, item_end, tiles_total, s_off, pr);
+        V3Iter it;
+        v3_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
+        while (v3_iter_next(it, p, s_off, pr)) {
             for (int s = 0; s < pr.n; ++s) {
                 const int grow = (int)rank * V3_ROWS + row;
                 const bool valid = grow < pr.nrows[s];
@@ -474,8 +502,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
         const int my_n = (n_chunks - cset + 3) >> 2;       // chunks of this warp: cset, cset+4, ...
         const int kc0 = h * n_chunks + cset;               // K chunk of the first one
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cset * 8;
-        const uint32_t a_addr[2] = {smem_u32(smem + sm.a_off[0]) + (uint32_t)(kc0 * V3_CHUNK + row * 16),
-                                    smem_u32(smem + sm.a_off[1]) + (uint32_t)(kc0 * V3_CHUNK + row * 16)};
+        const uint32_t a_addr0 = smem_u32(smem + sm.a_off[0]) + (uint32_t)(kc0 * V3_CHUNK + row * 16);
+        const uint32_t a_addr1 = smem_u32(smem + sm.a_off[1]) + (uint32_t)(kc0 * V3_CHUNK + row * 16);
         // does this thread own the ones column (fp16 1.0 at hidden unit H, the next layer's bias input)?
         const int ones_chunk = p.H >> 3;
         const int ones_rel = ones_chunk - kc0;
@@ -484,55 +512,80 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
         uint32_t n_d0 = 0, n_d1 = 0;
         const bool timing = p.dbg != nullptr && threadIdx.x == 0;
         long long t_wd = 0, t_loop = 0, t_pub = 0, t0 = timing ? clock64() : 0, tt = 0;
-        V3Pair pr;
-        for (int item = item_begin; item < item_end;) {
-            item = v3_next_pair(p, item, item_end, tiles_total, s_off, pr);
-            for (int l = 0; l < L; ++l) {
+        // A warp's chunks are processed in two halves (chunks {0,1} and {2,3}).  tcgen05.wait::ld waits for ALL of the
+        // thread's outstanding loads, so the loads of the next half are issued right after the wait for the current
+        // one and before its conversion: the TMEM load latency hides behind the SFU-bound conversion, also across the
+        // two tiles of the pair (when the other tile's accumulator is already complete).
+        uint32_t r0[2][8], r1[2][8];  // half 0 / half 1 staging registers
+        auto issue_half = [&](int s, int hf, uint32_t(&dst)[2][8]) {
+            const uint32_t d_addr = t_addr + v3_d_col(s) + (uint32_t)hf * 64;
+            __syncwarp();
+            if (2 * hf < my_n) v3_ld8_issue(d_addr, dst[0]);
+            if (2 * hf + 1 < my_n) v3_ld8_issue(d_addr + 32, dst[1]);
+        };
+        auto convert_half = [&](int s, int hf, const uint32_t(&src)[2][8]) {
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    if (s >= pr.n) break;
+            for (int i = 0; i < 2; ++i) {
+                if (2 * hf + i < my_n) {
+                    uint32_t hh[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) hh[j] = v3_act_pack<ACT>(__uint_as_float(src[i][2 * j]), __uint_as_float(src[i][2 * j + 1]));
+                    v3_sts128((s ? a_addr1 : a_addr0) + (uint32_t)((2 * hf + i) * 4 * V3_CHUNK), hh[0], hh[1], hh[2], hh[3]);
+                    // the ones column (fp16 1.0 = the next layer's bias input) goes out with the chunk that holds it, so it
+                    // is in place before that chunk's half is published
+                    if (owns_ones && (ones_rel >> 2) == 2 * hf + i) v3_sts16((s ? a_addr1 : a_addr0) + ones_off, (uint16_t)0x3C00);
+                }
+            }
+        };
+        V3Pair pr;
+        V3Iter it;
+        v3_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
+        while (v3_iter_next(it, p, s_off, pr)) {
+            const int n_steps = L * pr.n;  // tile-step ts -> layer ts / n, slot ts % n
+            bool have0 = false;            // half-0 loads of the current tile-step already in flight?
+            for (int ts = 0; ts < n_steps; ++ts) {
+                const int s = (pr.n == 2) ? (ts & 1) : 0;
+                // ---- half 0 ---------------------------------------------------------------------------------------------
+                if (!have0) {
                     if (timing) tt = clock64();
-                    if (s == 0) {
-                        mbar_wait(&bars[V3_D_FULL + 0], n_d0 & 1);
-                        ++n_d0;
-                    } else {
+                    if (s) {
                         mbar_wait(&bars[V3_D_FULL + 1], n_d1 & 1);
                         ++n_d1;
+                    } else {
+                        mbar_wait(&bars[V3_D_FULL + 0], n_d0 & 1);
+                        ++n_d0;
                     }
-                    if (timing) {
-                        long long t = clock64();
-                        t_wd += t - tt;
-                        tt = t;
-                    }
+                    if (timing) t_wd += clock64() - tt;
                     tc_fence_after();
-                    const uint32_t d_addr = t_addr + v3_d_col(s);
-                    uint32_t raw[4][8];
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (i < my_n) v3_ld8_issue(d_addr + i * 32, raw[i]);
-                    v3_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (i < my_n) {
-                            uint32_t hh[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) hh[j] = v3_act_pack<ACT>(__uint_as_float(raw[i][2 * j]), __uint_as_float(raw[i][2 * j + 1]));
-                            v3_sts128(a_addr[s] + (uint32_t)(i * 4 * V3_CHUNK), hh[0], hh[1], hh[2], hh[3]);
-                        }
-                    }
-                    if (owns_ones) v3_sts16(a_addr[s] + ones_off, (uint16_t)0x3C00);
-                    if (timing) {
-                        long long t = clock64();
-                        t_loop += t - tt;
-                        tt = t;
-                    }
-                    tc_fence_before();
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) v3_arrive_leader(&bars[V3_A_READY + s]);
-                    if (timing) t_pub += clock64() - tt;
+                    issue_half(s, 0, r0);
                 }
+                if (timing) tt = clock64();
+                v3_ld_wait();
+                issue_half(s, 1, r1);
+                convert_half(s, 0, r0);
+                // ---- half 1 (prefetch the other tile's half 0 if its accumulator is already complete) -----------------
+                v3_ld_wait();
+                have0 = false;
+                if (pr.n == 2 && ts + 1 < n_steps) {
+                    const int s2 = s ^ 1;
+                    if (s2 ? mbar_test(&bars[V3_D_FULL + 1], n_d1 & 1) : mbar_test(&bars[V3_D_FULL + 0], n_d0 & 1)) {
+                        if (s2) ++n_d1; else ++n_d0;
+                        tc_fence_after();
+                        issue_half(s2, 0, r0);
+                        have0 = true;
+                    }
+                }
+                convert_half(s, 1, r1);
+                if (timing) {
+                    long long t = clock64();
+                    t_loop += t - tt;
+                    tt = t;
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) v3_arrive_leader(&bars[V3_A_READY + s]);
+                if (timing) t_pub += clock64() - tt;
             }
         }
         if (timing) {

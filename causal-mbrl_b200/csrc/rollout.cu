@@ -42,11 +42,13 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float* n0, fl
 }
 
 // one thread per env: block 0 of the counter space draws the member, blocks 1.. draw 4 normals each
-__global__ void draw_member_noise_kernel(unsigned long long seed, unsigned long long stream_id, int N,
+__global__ void draw_member_noise_kernel(unsigned long long seed, unsigned long long stream_id,
+                                         const unsigned long long* __restrict__ stream_base, int N,
                                          const uint8_t* __restrict__ elite, int n_elite, int D,
                                          uint8_t* __restrict__ member_idx, float* __restrict__ noise) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
+    if (stream_base) stream_id += *stream_base;
     uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     uint32_t s_lo = (uint32_t)stream_id, s_hi = (uint32_t)(stream_id >> 32);
     uint4 r = philox4x32_10(make_uint4((uint32_t)n, 0u, s_lo, s_hi), key);
@@ -62,10 +64,12 @@ __global__ void draw_member_noise_kernel(unsigned long long seed, unsigned long 
     }
 }
 
-__global__ void draw_uniform_index_kernel(unsigned long long seed, unsigned long long stream_id, int N,
-                                          unsigned int upper, int* __restrict__ out) {
+__global__ void draw_uniform_index_kernel(unsigned long long seed, unsigned long long stream_id,
+                                          const unsigned long long* __restrict__ stream_base, int N, unsigned int upper,
+                                          int* __restrict__ out) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
+    if (stream_base) stream_id += *stream_base;
     uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     uint4 r = philox4x32_10(make_uint4((uint32_t)n, 0x7fffffffu, (uint32_t)stream_id, (uint32_t)(stream_id >> 32)), key);
     out[n] = (int)(((unsigned long long)r.x * (unsigned long long)upper) >> 32);
@@ -118,6 +122,8 @@ __global__ void bucket_scatter_kernel(const uint8_t* __restrict__ idx, int N, in
         if (e < E) perm[base[e] + atomicAdd(&h[e], 1)] = n;
     }
 }
+
+__global__ void bump_u64_kernel(unsigned long long* c, unsigned long long delta) { *c += delta; }
 
 __global__ void gather_inputs_kernel(const float* __restrict__ obs, const float* __restrict__ act,
                                      const int* __restrict__ perm, int N, int O, int A, float* __restrict__ x) {
@@ -240,24 +246,33 @@ __global__ void env_step_tail_kernel(const float* __restrict__ next_obs, const f
 
 using namespace cmrl;
 
-extern "C" int cmrl_draw_member_noise(unsigned long long seed, unsigned long long stream_id, int N,
-                                      const uint8_t* elite, int n_elite, int D, uint8_t* member_idx, float* noise,
-                                      void* stream) {
+extern "C" int cmrl_draw_member_noise(unsigned long long seed, unsigned long long stream_id,
+                                      const unsigned long long* stream_base_dev, int N, const uint8_t* elite, int n_elite,
+                                      int D, uint8_t* member_idx, float* noise, void* stream) {
     CMRL_REQUIRE(N >= 0 && D >= 0, "draw_member_noise: bad dims");
     CMRL_REQUIRE(!member_idx || (elite && n_elite >= 1), "draw_member_noise: elite list required");
     if (N == 0) return 0;
-    draw_member_noise_kernel<<<blocks_for(N), RT, 0, (cudaStream_t)stream>>>(seed, stream_id, N, elite, n_elite, D,
-                                                                           member_idx, noise);
+    draw_member_noise_kernel<<<blocks_for(N), RT, 0, (cudaStream_t)stream>>>(seed, stream_id, stream_base_dev, N, elite,
+                                                                           n_elite, D, member_idx, noise);
     CMRL_CHECK_LAUNCH("draw_member_noise");
     return 0;
 }
 
-extern "C" int cmrl_draw_uniform_index(unsigned long long seed, unsigned long long stream_id, int N, int upper,
-                                       int* out, void* stream) {
+extern "C" int cmrl_draw_uniform_index(unsigned long long seed, unsigned long long stream_id,
+                                       const unsigned long long* stream_base_dev, int N, int upper, int* out,
+                                       void* stream) {
     CMRL_REQUIRE(out && upper >= 1 && N >= 0, "draw_uniform_index: bad arguments");
     if (N == 0) return 0;
-    draw_uniform_index_kernel<<<blocks_for(N), RT, 0, (cudaStream_t)stream>>>(seed, stream_id, N, (unsigned)upper, out);
+    draw_uniform_index_kernel<<<blocks_for(N), RT, 0, (cudaStream_t)stream>>>(seed, stream_id, stream_base_dev, N,
+                                                                            (unsigned)upper, out);
     CMRL_CHECK_LAUNCH("draw_uniform_index");
+    return 0;
+}
+
+extern "C" int cmrl_counter_add(unsigned long long* counter_dev, unsigned long long delta, void* stream) {
+    CMRL_REQUIRE(counter_dev, "counter_add: null pointer");
+    bump_u64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter_dev, delta);
+    CMRL_CHECK_LAUNCH("counter_add");
     return 0;
 }
 

@@ -76,6 +76,8 @@ class VecFakeEnv(VecEnv):
         self._draw_counter = 0
         self._obs_dev = None
         self._env_len_dev = None
+        self._rng_base = None  # device counter added to the Philox stream ids (advanced inside captured step graphs)
+        self._step_graph = None
         self._pool_dev = None
         self._pool_rows = 0
         self._bufs = None
@@ -175,7 +177,7 @@ class VecFakeEnv(VecEnv):
         if self.rng_mode == "device":
             self._draw_counter += 1
             return ops.draw_member_noise(self._device_seed, self._draw_counter, N, self._elite_u8(mech), D,
-                                         want_noise=not self.deterministic)  # fmt: skip
+                                         want_noise=not self.deterministic, stream_base=self._rng_base)  # fmt: skip
         raise ValueError("rng_mode must be 'numpy' or 'device'")
 
     def _predict(self, mech, obs, act, all_member_out=None):
@@ -313,6 +315,40 @@ class VecFakeEnv(VecEnv):
                           b["term_obs"], None)  # fmt: skip
         return obs, b["reward_out"], b["done"], b["trunc"], b["term_obs"]
 
+    def step_device_graphed(self, actions: torch.Tensor):
+        """`step_device` captured once in a CUDA graph and replayed: one host call per step instead of ~15 launches.
+        The Philox stream ids baked into the graph are offset by a device-side counter that the graph itself advances,
+        so every replay draws fresh members / noise / reset rows.  Weights, elite lists and the reset pool are read at
+        replay time from the same device buffers; the graph is re-captured when the packed weights or the reset pool
+        were rebuilt (call `invalidate_step_graph()` after `set_elite_members`)."""
+        b = self._bufs
+        if self._reset_by_buffer and self._pool_dev is not None and self._pool_rows != self._upper_bound():
+            self._step_graph = None
+        if self._step_graph is None:
+            assert self.rng_mode == "device" and self.learned_reward
+            if self._rng_base is None:
+                self._rng_base = torch.zeros(1, dtype=torch.int64, device=self.device)
+            for mech in self.dynamics.learn_mech:  # everything that allocates or syncs happens before the capture
+                self._elite_u8(mech)
+                if self.precision == "f16":
+                    getattr(self.dynamics, mech).packed_f16()
+            self._device_reset_source()
+            b["act"].copy_(actions)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            c0 = self._draw_counter
+            with torch.cuda.graph(g):
+                self._graph_out = self.step_device(b["act"])
+                ops.counter_add(self._rng_base, self._draw_counter - c0)
+            self._step_graph = g
+        else:
+            b["act"].copy_(actions, non_blocking=True)
+        self._step_graph.replay()
+        return self._graph_out
+
+    def invalidate_step_graph(self):
+        self._step_graph = None
+
     def _make_infos(self, batch_truncate, done_idx, batch_next_obs):
         N = self.num_envs
         if self.infos_mode == "shared":
@@ -356,7 +392,8 @@ class VecFakeEnv(VecEnv):
                 rows = np.ascontiguousarray(np.asarray(self.get_init_obs_fn(size)).reshape(size, -1), dtype=np.float32)
                 self._pool_dev, self._pool_rows = torch.from_numpy(rows).to(self.device), size
         self._draw_counter += 1
-        idx = ops.draw_uniform_index(self._device_seed, self._draw_counter, N, self._pool_rows, self.device)
+        idx = ops.draw_uniform_index(self._device_seed, self._draw_counter, N, self._pool_rows, self.device,
+                                     stream_base=self._rng_base)  # fmt: skip
         return self._pool_dev, idx
 
     def reset(self, *, seed: Optional[int] = None, return_info: bool = False, options: Optional[dict] = None):

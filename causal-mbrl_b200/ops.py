@@ -241,18 +241,23 @@ def bootstrap_gather(obs, act, target, member_idx, order, start_dev, advance, B,
 
 
 # ----------------------------------------------------------------------------- rollout
-def draw_member_noise(seed, stream_id, N, elite_u8, D, want_noise=True, device=None):
+def draw_member_noise(seed, stream_id, N, elite_u8, D, want_noise=True, device=None, stream_base=None):
     device = elite_u8.device if device is None else device
     idx = torch.empty(N, device=device, dtype=torch.uint8)
     noise = torch.empty((N, D), device=device, dtype=torch.float32) if want_noise else None
-    _lib.call("cmrl_draw_member_noise", int(seed), int(stream_id), N, elite_u8.data_ptr(), elite_u8.numel(), D,
-              idx.data_ptr(), _ptr(noise), _stream())  # fmt: skip
+    _lib.call("cmrl_draw_member_noise", int(seed), int(stream_id), _ptr(stream_base), N, elite_u8.data_ptr(),
+              elite_u8.numel(), D, idx.data_ptr(), _ptr(noise), _stream())  # fmt: skip
     return idx, noise
 
 
-def draw_uniform_index(seed, stream_id, N, upper, device):
+def counter_add(counter, delta):
+    _lib.call("cmrl_counter_add", counter.data_ptr(), int(delta), _stream())
+
+
+def draw_uniform_index(seed, stream_id, N, upper, device, stream_base=None):
     out = torch.empty(N, device=device, dtype=torch.int32)
-    _lib.call("cmrl_draw_uniform_index", int(seed), int(stream_id), N, int(upper), out.data_ptr(), _stream())
+    _lib.call("cmrl_draw_uniform_index", int(seed), int(stream_id), _ptr(stream_base), N, int(upper), out.data_ptr(),
+              _stream())  # fmt: skip
     return out
 
 

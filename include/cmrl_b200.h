@@ -142,14 +142,18 @@ int cmrl_bootstrap_gather(const float* obs, const float* act, const float* targe
 /* Device RNG (throughput mode; the parity mode supplies numpy draws): Philox4x32-10 keyed by
  * (seed, stream_id), counter = (env, draw).  member_idx[n] = elite[u32 * n_elite >> 32] (uint8),
  * noise [N,D] ~ N(0,1) by Box-Muller.  Replaces Generator.choice + Generator.normal (fake_env.py:205-214,
- * mlp.py:40-44).  noise may be NULL (deterministic rollouts). */
-int cmrl_draw_member_noise(unsigned long long seed, unsigned long long stream_id, int N, const uint8_t* elite,
-                           int n_elite, int D, uint8_t* member_idx, float* noise, void* stream);
+ * mlp.py:40-44).  noise may be NULL (deterministic rollouts).  stream_base_dev: NULL, or a device counter whose value
+ * is added to stream_id (so a captured CUDA graph draws fresh numbers on every replay; see cmrl_counter_add). */
+int cmrl_draw_member_noise(unsigned long long seed, unsigned long long stream_id,
+                           const unsigned long long* stream_base_dev, int N, const uint8_t* elite, int n_elite, int D,
+                           uint8_t* member_idx, float* noise, void* stream);
 
 /* out[n] = uniform integer in [0, upper) (Philox): reset-row draw replacing np.random.randint at
  * fake_env.py:154,177 in throughput mode. */
-int cmrl_draw_uniform_index(unsigned long long seed, unsigned long long stream_id, int N, int upper, int* out,
-                            void* stream);
+int cmrl_draw_uniform_index(unsigned long long seed, unsigned long long stream_id,
+                            const unsigned long long* stream_base_dev, int N, int upper, int* out, void* stream);
+/* *counter_dev += delta (one-thread kernel): advances the RNG stream base inside a captured step graph. */
+int cmrl_counter_add(unsigned long long* counter_dev, unsigned long long delta, void* stream);
 
 /* Counting sort of envs by drawn member: perm [N] lists env ids grouped by member, offsets [E+1].
  * counters: int32 [2*(E+1)] scratch, zeroed by the call. */

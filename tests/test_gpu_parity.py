@@ -586,3 +586,28 @@ def test_device_epoch_matches_host_iterator_path(cm, use_graph):
     assert rel_err(np.asarray(l1), np.asarray(l0)) < 1e-5
     for k in w0:
         assert rel_err(w1[k], w0[k]) < 1e-5, k
+
+
+def test_step_device_graphed(cm):
+    """CUDA-graph replay of the device-resident step: episode bookkeeping advances, every replay draws fresh noise."""
+    g = load_golden("fake_env_truncate.npz")
+    for precision in ("fp32", "f16"):
+        env = _build_env(cm, g, rng_mode="device")
+        env.precision = precision
+        env.reset()
+        act = t(g["actions"][0])
+        seen = []
+        lengths = np.zeros(env.num_envs, dtype=int)
+        for step in range(7):
+            obs, rew, done, trunc, term_obs = env.step_device_graphed(act)
+            torch.cuda.synchronize()
+            lengths += 1
+            d = done.cpu().numpy().astype(bool)
+            assert np.array_equal(trunc.cpu().numpy().astype(bool), lengths >= 3) and np.all(d[lengths >= 3])
+            lengths[d] = 0
+            assert np.array_equal(env._envs_length, lengths)
+            assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+            seen.append(rew.cpu().numpy().copy())
+        assert all(not np.array_equal(seen[i], seen[i + 1]) for i in range(6))
+        # the all-replays reward noise is N(0, sigma): distinct draws -> low correlation between steps
+        assert abs(np.corrcoef(seen[1], seen[2])[0, 1]) < 0.6
