@@ -71,6 +71,8 @@ class VecFakeEnv(VecEnv):
         self.rng_mode = "numpy"
         self.infos_mode = "dicts"
         self.precision = "fp32"  # "fp32": CUDA-core tier (1e-5 parity); "f16": tcgen05 tier (1e-3 parity)
+        self.use_graph = True   # device rng_mode: replay the per-step launches from a CUDA graph
+        self._obs_flip = False
         self.init_obs_pool_size = None  # device rng_mode + get_init_obs_fn: size of the pre-drawn reset pool
         self._device_seed = 0
         self._draw_counter = 0
@@ -128,6 +130,9 @@ class VecFakeEnv(VecEnv):
         b["counters"] = torch.empty(2 * (E + 1), device=dev, dtype=torch.int32)
         # pinned host mirrors for the per-step device->host read of the SB3 return values
         b["h_obs"] = torch.empty((N, O), dtype=torch.float32).pin_memory()
+        b["h_obs2"] = torch.empty((N, O), dtype=torch.float32).pin_memory()
+        b["h_term_u8"] = torch.empty(N, dtype=torch.uint8).pin_memory()
+        b["term_u8"] = torch.empty(N, device=dev, dtype=torch.uint8)
         b["h_term_obs"] = torch.empty((N, O), dtype=torch.float32).pin_memory()
         b["h_reward"] = torch.empty(N, dtype=torch.float32).pin_memory()
         b["h_done"] = torch.empty(N, dtype=torch.uint8).pin_memory()
@@ -218,75 +223,119 @@ class VecFakeEnv(VecEnv):
         mn, mx = model._bounds()
         return ops.sample_scatter(raw, model._head_layout, perm, N, D, obs if model._residual() else None, mn, mx, noise)
 
+    def _predict_all(self, obs, act, need_all):
+        """transition (+ reward / termination mechs): the device part of a step before any host callback."""
+        all_out = {} if need_all else None
+        next_obs = self._predict("transition", obs, act, all_out)
+        reward = self._predict("reward_mech", obs, act) if self.learned_reward else None
+        terminal_f = self._predict("termination_mech", obs, act) if self.learned_termination else None
+        penalty = ops.mopo_penalty(all_out["mean"]) if need_all else None
+        return next_obs, reward, terminal_f, penalty
+
+    def _predict_all_graphed(self, obs, act, need_all):
+        """Same, replayed from a CUDA graph in device rng_mode (the graph is re-captured when packed weights, elite
+        sets or the precision changed)."""
+        key = (self.precision, self.deterministic, need_all) + tuple(
+            (id(getattr(self.dynamics, m)._packed.get("f16")), id(getattr(self.dynamics, m)._elite_members),
+             getattr(self.dynamics, m)._flat.data_ptr() if getattr(self.dynamics, m)._flat is not None else 0)
+            for m in self.dynamics.learn_mech)  # fmt: skip
+        cached = getattr(self, "_predict_graph", None)
+        if cached is None or cached[0] != key:
+            if self._rng_base is None:
+                self._rng_base = torch.zeros(1, dtype=torch.int64, device=self.device)
+            for mech in self.dynamics.learn_mech:
+                self._elite_u8(mech)
+                if self.precision == "f16":
+                    getattr(self.dynamics, mech).packed_f16()
+            key = (self.precision, self.deterministic, need_all) + tuple(
+                (id(getattr(self.dynamics, m)._packed.get("f16")), id(getattr(self.dynamics, m)._elite_members),
+                 getattr(self.dynamics, m)._flat.data_ptr() if getattr(self.dynamics, m)._flat is not None else 0)
+                for m in self.dynamics.learn_mech)  # fmt: skip
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            c0 = self._draw_counter
+            with torch.cuda.graph(g):
+                out = self._predict_all(obs, act, need_all)
+                ops.counter_add(self._rng_base, self._draw_counter - c0)
+            cached = (key, g, out)
+            self._predict_graph = cached
+        cached[1].replay()
+        return cached[2]
+
     def step_wait(self):
         assert self.has_set_up, "fake-env has not set up"
         assert len(self._current_batch_action.shape) == 2  # batch, action_dim
         b = self._bufs
         N = self.num_envs
         obs = self._obs_dev
-        b["act_pin"].copy_(torch.from_numpy(np.ascontiguousarray(self._current_batch_action, dtype=np.float32)))
+        stream = torch.cuda.current_stream()
+        b["act_pin"].numpy()[...] = self._current_batch_action
         act = b["act"]
         act.copy_(b["act_pin"], non_blocking=True)
 
         need_all = self.penalty_coeff != 0
-        all_out = {} if need_all else None
-        next_obs = self._predict("transition", obs, act, all_out)
-        host_obs = host_next = None
-        if self.learned_reward:
-            reward = self._predict("reward_mech", obs, act)
+        device_rng = self.rng_mode == "device"
+        if device_rng and self.use_graph:
+            next_obs, reward, terminal_f, penalty = self._predict_all_graphed(obs, act, need_all)
         else:
-            host_next, host_obs = next_obs.cpu().numpy(), self._current_batch_obs
-            r = np.asarray(self.reward_fn(host_next, host_obs, self._current_batch_action), dtype=np.float32)
-            reward = torch.from_numpy(r.reshape(N, 1)).to(self.device)
-        terminal_f = terminal_u8 = None
-        if self.learned_termination:
-            terminal_f = self._predict("termination_mech", obs, act)
-        else:
-            if host_next is None:
-                host_next, host_obs = next_obs.cpu().numpy(), self._current_batch_obs
-            t = np.asarray(self.termination_fn(host_next, host_obs, self._current_batch_action))
-            terminal_u8 = torch.from_numpy(np.ascontiguousarray(t.reshape(N) != 0, dtype=np.uint8)).to(self.device)
+            next_obs, reward, terminal_f, penalty = self._predict_all(obs, act, need_all)
+        if penalty is not None and self.logger is not None:
+            self.logger.record_mean("rollout/penalty", penalty.mean().item())
 
-        penalty = None
-        if need_all:
-            penalty = ops.mopo_penalty(all_out["mean"])
-            if self.logger is not None:
-                self.logger.record_mean("rollout/penalty", penalty.mean().item())
+        # ---- host callbacks (reward_fn / termination_fn of the real env), on pinned copies ----------------------
+        host_next = None
+        terminal_u8 = None
+        if not (self.learned_reward and self.learned_termination):
+            b["h_term_obs"].copy_(next_obs, non_blocking=True)
+            stream.synchronize()
+            host_next = b["h_term_obs"].numpy()
+            host_obs = self._current_batch_obs
+            if not self.learned_reward:
+                r = np.asarray(self.reward_fn(host_next, host_obs, self._current_batch_action), dtype=np.float32)
+                reward = torch.from_numpy(np.ascontiguousarray(r.reshape(N, 1))).to(self.device, non_blocking=True)
+            if not self.learned_termination:
+                t = np.asarray(self.termination_fn(host_next, host_obs, self._current_batch_action))
+                b["h_term_u8"].numpy()[...] = t.reshape(N) != 0
+                terminal_u8 = b["term_u8"]
+                terminal_u8.copy_(b["h_term_u8"], non_blocking=True)
 
-        device_reset = self.rng_mode == "device"
         reset_rows = reset_index = None
-        if device_reset:
+        if device_rng:
             reset_rows, reset_index = self._device_reset_source()
         ops.env_step_tail(next_obs, reward, terminal_f, terminal_u8, penalty, self.penalty_coeff, self._env_len_dev,
                           self.max_episode_steps, reset_rows, reset_index, obs, b["reward_out"], b["done"], b["trunc"],
-                          b["term_obs"], None)  # fmt: skip
+                          b["term_obs"] if host_next is None else None, None)  # fmt: skip
 
-        # ---- device -> host: the SB3 return values ------------------------------------------------------
-        b["h_term_obs"].copy_(b["term_obs"], non_blocking=True)
+        # ---- device -> host: the SB3 return values ------------------------------------------------------------------
+        if host_next is None:
+            b["h_term_obs"].copy_(b["term_obs"], non_blocking=True)
         b["h_reward"].copy_(b["reward_out"], non_blocking=True)
         b["h_done"].copy_(b["done"], non_blocking=True)
         b["h_trunc"].copy_(b["trunc"], non_blocking=True)
-        if device_reset:
-            b["h_obs"].copy_(obs, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        batch_done = b["h_done"].numpy().astype(bool)
-        batch_truncate = b["h_trunc"].numpy().astype(bool)
+        h_obs = b["h_obs"] if self._obs_flip else b["h_obs2"]  # ping-pong: the previous obs stays valid for callbacks
+        self._obs_flip = not self._obs_flip
+        if device_rng:
+            h_obs.copy_(obs, non_blocking=True)
+        stream.synchronize()
+        batch_done = b["h_done"].numpy().view(np.bool_)
+        batch_truncate = b["h_trunc"].numpy().view(np.bool_)
         batch_next_obs = b["h_term_obs"].numpy()
-        batch_reward = b["h_reward"].numpy()
         done_idx = np.nonzero(batch_done)[0]
-        if device_reset:
-            self._current_batch_obs = b["h_obs"].numpy().copy()
+        if device_rng:
+            self._current_batch_obs = h_obs.numpy()
         else:
             # host reset in the reference's order (ascending env index; fake_env.py:131-135,171-181)
-            self._current_batch_obs = batch_next_obs.copy()
+            cur = h_obs.numpy()
+            cur[...] = batch_next_obs
+            self._current_batch_obs = cur
             if done_idx.size:
                 rows = self._host_reset_rows(done_idx.size)
-                self._current_batch_obs[done_idx] = rows
+                cur[done_idx] = rows
                 di = torch.from_numpy(done_idx).to(self.device)
                 obs.index_copy_(0, di, torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)).to(self.device))
 
         infos = self._make_infos(batch_truncate, done_idx, batch_next_obs)
-        return self._current_batch_obs.copy(), batch_reward.copy(), batch_done.copy(), infos
+        return self._current_batch_obs.copy(), b["h_reward"].numpy().copy(), batch_done.copy(), infos
 
     def step_device(self, actions: torch.Tensor, termination=None):
         """Device-resident step for rollout collectors that keep their buffers on the GPU: `actions` is a CUDA

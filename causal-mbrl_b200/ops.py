@@ -10,7 +10,8 @@ from ._lib import ACT_IDENTITY, ACT_RELU, ACT_SILU, HEAD_PARALLEL, HEAD_PLAIN  #
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw handle of torch's current stream on the current device (fast path: one C call)
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def _req(t, name, dtype=torch.float32):
@@ -348,7 +349,7 @@ def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0), head_interleave
         _lib.call("cmrl_pack_layer_f16", w.data_ptr(), b.data_ptr(), _ptr(m), mask_str[0], mask_str[1], P, E,
                   w.shape[-2], w.shape[-1], layer_k[i], layer_n[i], inter, blob.data_ptr() + 2 * layer_off[i], off,
                   _stream())  # fmt: skip
-    return blob, layer_off, layer_k, layer_n
+    return [blob, layer_off, layer_k, layer_n]
 
 
 TC_VARIANT = 3  # 3: CTA pairs, two tiles in flight (default); 2: CTA pairs, one tile; 1: single-CTA streamed weights
@@ -358,14 +359,17 @@ def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, ga
                     min_logvar, max_logvar, noise, out=None):  # fmt: skip
     import ctypes
 
-    blob, layer_off, layer_k, layer_n = pack
+    blob, layer_off, layer_k, layer_n = pack[:4]
     N, O = obs.shape
     A = act.shape[1]
     L = len(layer_k) - 1
-    arr = ctypes.c_int * (L + 1)
+    if len(pack) < 5:  # ctypes views of the layer tables, built once per pack
+        arr = ctypes.c_int * (L + 1)
+        pack.append((arr(*layer_off), arr(*layer_k), arr(*layer_n)))
+    c_off, c_k, c_n = pack[4]
     pred = torch.empty((N, head_dim), device=obs.device, dtype=torch.float32) if out is None else out
     bounds_n = 0 if min_logvar is None else min_logvar.numel()
-    _lib.call("cmrl_mlp_rollout_f16", blob.data_ptr(), blob.shape[1], arr(*layer_off), arr(*layer_k), arr(*layer_n), L,
+    _lib.call("cmrl_mlp_rollout_f16", blob.data_ptr(), blob.shape[1], c_off, c_k, c_n, L,
               P, E, N, O, A, H, head_dim, layout, 1 if gaussian else 0, act_kind, obs.data_ptr(), act.data_ptr(),
               perm.data_ptr(), offsets.data_ptr(), 1 if residual else 0, _ptr(min_logvar), _ptr(max_logvar), bounds_n,
               _ptr(noise), pred.data_ptr(), TC_VARIANT, _stream())  # fmt: skip
