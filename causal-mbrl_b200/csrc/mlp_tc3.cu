@@ -217,6 +217,109 @@ __device__ __forceinline__ bool v3_iter_next(V3Iter& it, const RolloutP& p, cons
     return true;
 }
 
+// MMA issuer role of tile slot SLOT.  A function template (slot = compile-time constant) so that every descriptor is
+// provably warp-uniform: ptxas then keeps them in uniform registers (UIADD3) instead of moving vector registers to
+// uniform ones (R2UR) in front of every UTCHMMA -- the issue path is a single thread's dependent instruction chain
+// and directly bounds the MMA rate (54-cycle MMAs).
+// optional event trace (profiling): p.dbg + 4096 holds [3 roles][512] clock64 stamps of CTA 0
+__device__ __forceinline__ void v3_trace(const RolloutP& p, int role, int& n, bool on) {
+    if (on && n < 512) p.dbg[4096 + role * 512 + n++] = clock64();
+}
+
+template <int SLOT>
+__device__ __forceinline__ void v3_mma_role(const RolloutP& p, const V3Smem& sm, uint8_t* smem, uint64_t* bars, const int* s_off,
+                                            uint32_t tmem_base, uint32_t rank, int lane, int item_begin, int item_end,
+                                            int tiles_total) {
+    constexpr int s = SLOT;
+    const int L = p.num_layers;
+    const int HP = p.layer_n[0];
+    const int K0 = p.layer_k[0];
+    const int NH = p.layer_n[L];
+        if (rank == 0) {
+            int cur_net = -1;
+            uint32_t n_w = 0, n_pair = 0, n_a = 0, n_h = 0, n_x[2] = {0, 0};
+            const uint32_t idesc_h = umma_idesc_f16(V3_TILE, HP), idesc_head = umma_idesc_f16(V3_TILE, NH);
+            const uint32_t b_sbo0 = (uint32_t)(K0 / 8) * 128, b_sbo = (uint32_t)(HP / 8) * 128;
+            const uint64_t ad_a = umma_desc(smem_u32(smem + sm.a_off[s]), V3_CHUNK, 128);
+            const uint32_t a_hi = (uint32_t)(ad_a >> 32);
+            const bool timing = p.dbg != nullptr && lane == 0 && SLOT == 0;
+            const bool tracing = p.dbg != nullptr && lane == 0 && blockIdx.x == 0 && (p.dbg_flags & 16);
+            int n_tr = 0;
+            long long t_wa = 0, t_issue = 0, t_wx = 0, t_all = timing ? clock64() : 0, tt = 0;
+            V3Pair pr;
+            V3Iter it;
+            v3_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
+            for (; v3_iter_next(it, p, s_off, pr); ++n_pair) {
+                if (pr.net != cur_net) {
+                    if (cur_net != -1) v3_commit_uni(&bars[V3_W_EMPTY]);
+                    mbar_wait(&bars[V3_W_READY], n_w & 1);
+                    ++n_w;
+                    cur_net = pr.net;
+                }
+                if (s >= pr.n) continue;
+                const int st = n_pair & 1;
+                // ---- layer 0 ------------------------------------------------------------------------------------------
+                {
+                    if (timing) tt = clock64();
+                    mbar_wait(&bars[V3_X_READY + st * 2 + s], n_x[st] & 1);
+                    if (timing) t_wx += clock64() - tt;
+                    ++n_x[st];
+                    tc_fence_after();
+                    const uint64_t ad0 = umma_desc(smem_u32(smem + sm.x_off[st][s]), V3_CHUNK, 128);
+                    const uint64_t bd0 = umma_desc(smem_u32(smem + sm.w_off[0]), 128, b_sbo0);
+                    uint32_t a_lo = (uint32_t)ad0, b_lo = (uint32_t)bd0;
+                    const uint32_t b_hi = (uint32_t)(bd0 >> 32);
+                    for (int ks = 0; ks < K0 / 16; ++ks, a_lo += 2 * V3_CHUNK / 16, b_lo += 16)
+                        v3_mma_uni(tmem_base + v3_d_col(s), a_lo, (uint32_t)(ad0 >> 32), b_lo, b_hi, idesc_h, ks > 0);
+                    v3_commit_uni(&bars[V3_X_EMPTY + st * 2 + s]);
+                    v3_commit_uni(&bars[V3_D_FULL + s]);
+                }
+                // ---- layers 1..L (L = head) ------------------------------------------------------------------------------
+                for (int l = 1; l <= L; ++l) {
+                    const bool head = (l == L);
+                    const uint64_t bd0 = umma_desc(smem_u32(smem + sm.w_off[l]), 128, b_sbo);
+                    if (timing) tt = clock64();
+                    v3_trace(p, 1 + SLOT, n_tr, tracing);  // wait start
+                    mbar_wait(&bars[V3_A_READY + s], n_a & 1);
+                    ++n_a;
+                    if (head) {  // the head accumulator of this slot must have been drained by the head warps
+                        mbar_wait(&bars[V3_DH_EMPTY + s], (n_h & 1) ^ 1);
+                        ++n_h;
+                    }
+                    if (timing) {
+                        long long t = clock64();
+                        t_wa += t - tt;
+                        tt = t;
+                    }
+                    tc_fence_after();
+                    v3_trace(p, 1 + SLOT, n_tr, tracing);  // wait end / issue start
+                    const uint32_t d_tmem = tmem_base + (head ? v3_dh_col(s) : v3_d_col(s));
+                    const uint32_t idesc = head ? idesc_head : idesc_h;
+                    uint32_t a_lo = (uint32_t)ad_a, b_lo = (uint32_t)bd0;
+                    const uint32_t b_hi = (uint32_t)(bd0 >> 32);
+                    const int nks = HP / 16;
+                    v3_mma_uni(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, 0u);
+                    for (int ks = 1; ks < nks; ++ks) {
+                        a_lo += 2 * V3_CHUNK / 16;
+                        b_lo += 16;
+                        v3_mma_uni(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+                    }
+                    v3_commit_uni(head ? &bars[V3_DH_FULL + s] : &bars[V3_D_FULL + s]);
+                    v3_trace(p, 1 + SLOT, n_tr, tracing);  // issue end
+                    if (timing) t_issue += clock64() - tt;
+                }
+            }
+            if (timing) {
+                long long* d = p.dbg + (long long)blockIdx.x * 16;
+                d[0] = clock64() - t_all;
+                d[1] = t_wx;
+                d[2] = t_wa;
+                d[3] = t_issue;
+                d[4] = item_end - item_begin;
+            }
+        }
+}
+
 template <int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
     mlp_rollout_f16_v3_kernel(const RolloutP p, const V3Smem sm) {
@@ -294,89 +397,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
                 cur_net = pr.net;
             }
         }
-    } else if (warp == V3_WARP_MMA || warp == V3_WARP_MMA + 1) {
-        // ===================== MMA issuers: warp 20 drives tile slot 0, warp 21 slot 1 ================================
-        // The whole warp walks the (warp-uniform) schedule; one elected lane issues.  tcgen05.commit only tracks the
-        // MMAs of the issuing thread, so the two slots are independent pipelines sharing the tensor pipe.
-        if (rank == 0) {
-            const int s = warp - V3_WARP_MMA;
-            int cur_net = -1;
-            uint32_t n_w = 0, n_pair = 0, n_a = 0, n_h = 0, n_x[2] = {0, 0};
-            const uint32_t idesc_h = umma_idesc_f16(V3_TILE, HP), idesc_head = umma_idesc_f16(V3_TILE, NH);
-            const uint32_t b_sbo0 = (uint32_t)(K0 / 8) * 128, b_sbo = (uint32_t)(HP / 8) * 128;
-            const uint64_t ad_a = umma_desc(smem_u32(smem + sm.a_off[s]), V3_CHUNK, 128);
-            const uint32_t a_hi = (uint32_t)(ad_a >> 32);
-            const bool timing = p.dbg != nullptr && lane == 0 && s == 0;
-            long long t_wa = 0, t_issue = 0, t_wx = 0, t_all = timing ? clock64() : 0, tt = 0;
-            V3Pair pr;
-            V3Iter it;
-            v3_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
-            for (; v3_iter_next(it, p, s_off, pr); ++n_pair) {
-                if (pr.net != cur_net) {
-                    if (cur_net != -1) v3_commit_uni(&bars[V3_W_EMPTY]);
-                    mbar_wait(&bars[V3_W_READY], n_w & 1);
-                    ++n_w;
-                    cur_net = pr.net;
-                }
-                if (s >= pr.n) continue;
-                const int st = n_pair & 1;
-                // ---- layer 0 ------------------------------------------------------------------------------------------
-                {
-                    if (timing) tt = clock64();
-                    mbar_wait(&bars[V3_X_READY + st * 2 + s], n_x[st] & 1);
-                    if (timing) t_wx += clock64() - tt;
-                    ++n_x[st];
-                    tc_fence_after();
-                    const uint64_t ad0 = umma_desc(smem_u32(smem + sm.x_off[st][s]), V3_CHUNK, 128);
-                    const uint64_t bd0 = umma_desc(smem_u32(smem + sm.w_off[0]), 128, b_sbo0);
-                    uint32_t a_lo = (uint32_t)ad0, b_lo = (uint32_t)bd0;
-                    const uint32_t b_hi = (uint32_t)(bd0 >> 32);
-                    for (int ks = 0; ks < K0 / 16; ++ks, a_lo += 2 * V3_CHUNK / 16, b_lo += 16)
-                        v3_mma_uni(tmem_base + v3_d_col(s), a_lo, (uint32_t)(ad0 >> 32), b_lo, b_hi, idesc_h, ks > 0);
-                    v3_commit_uni(&bars[V3_X_EMPTY + st * 2 + s]);
-                    v3_commit_uni(&bars[V3_D_FULL + s]);
-                }
-                // ---- layers 1..L (L = head) ------------------------------------------------------------------------------
-                for (int l = 1; l <= L; ++l) {
-                    const bool head = (l == L);
-                    const uint64_t bd0 = umma_desc(smem_u32(smem + sm.w_off[l]), 128, b_sbo);
-                    if (timing) tt = clock64();
-                    mbar_wait(&bars[V3_A_READY + s], n_a & 1);
-                    ++n_a;
-                    if (head) {  // the head accumulator of this slot must have been drained by the head warps
-                        mbar_wait(&bars[V3_DH_EMPTY + s], (n_h & 1) ^ 1);
-                        ++n_h;
-                    }
-                    if (timing) {
-                        long long t = clock64();
-                        t_wa += t - tt;
-                        tt = t;
-                    }
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (head ? v3_dh_col(s) : v3_d_col(s));
-                    const uint32_t idesc = head ? idesc_head : idesc_h;
-                    uint32_t a_lo = (uint32_t)ad_a, b_lo = (uint32_t)bd0;
-                    const uint32_t b_hi = (uint32_t)(bd0 >> 32);
-                    const int nks = HP / 16;
-                    v3_mma_uni(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, 0u);
-                    for (int ks = 1; ks < nks; ++ks) {
-                        a_lo += 2 * V3_CHUNK / 16;
-                        b_lo += 16;
-                        v3_mma_uni(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
-                    }
-                    v3_commit_uni(head ? &bars[V3_DH_FULL + s] : &bars[V3_D_FULL + s]);
-                    if (timing) t_issue += clock64() - tt;
-                }
-            }
-            if (timing) {
-                long long* d = p.dbg + (long long)blockIdx.x * 16;
-                d[0] = clock64() - t_all;
-                d[1] = t_wx;
-                d[2] = t_wa;
-                d[3] = t_issue;
-                d[4] = item_end - item_begin;
-            }
-        }
+    } else if (warp == V3_WARP_MMA) {
+        v3_mma_role<0>(p, sm, smem, bars, s_off, tmem_base, rank, lane, item_begin, item_end, tiles_total);
+    } else if (warp == V3_WARP_MMA + 1) {
+        v3_mma_role<1>(p, sm, smem, bars, s_off, tmem_base, rank, lane, item_begin, item_end, tiles_total);
     } else if (warp == V3_WARP_X) {
         // ===================== layer-0 operand loader: two rows per lane, one pair ahead ===============================
         const int in = p.O + p.A;
@@ -511,6 +535,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
         const uint32_t ones_off = (uint32_t)(ones_rel * V3_CHUNK + (p.H & 7) * 2);
         uint32_t n_d0 = 0, n_d1 = 0;
         const bool timing = p.dbg != nullptr && threadIdx.x == 0;
+        const bool tracing = p.dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && (p.dbg_flags & 16);
+        int n_tr = 0;
         long long t_wd = 0, t_loop = 0, t_pub = 0, t0 = timing ? clock64() : 0, tt = 0;
         // A warp's chunks are processed in two halves (chunks {0,1} and {2,3}).  tcgen05.wait::ld waits for ALL of the
         // thread's outstanding loads, so the loads of the next half are issued right after the wait for the current
@@ -546,6 +572,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
             for (int ts = 0; ts < n_steps; ++ts) {
                 const int s = (pr.n == 2) ? (ts & 1) : 0;
                 // ---- half 0 ---------------------------------------------------------------------------------------------
+                v3_trace(p, 0, n_tr, tracing);  // step start
                 if (!have0) {
                     if (timing) tt = clock64();
                     if (s) {
@@ -560,6 +587,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
                     issue_half(s, 0, r0);
                 }
                 if (timing) tt = clock64();
+                v3_trace(p, 0, n_tr, tracing);  // accumulator available
                 v3_ld_wait();
                 issue_half(s, 1, r1);
                 convert_half(s, 0, r0);
@@ -585,6 +613,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) v3_arrive_leader(&bars[V3_A_READY + s]);
+                v3_trace(p, 0, n_tr, tracing);  // published
                 if (timing) t_pub += clock64() - tt;
             }
         }

@@ -19,7 +19,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // CTAS = 1: cta_group::1 (M=128); CTAS = 2: cluster of 2, cta_group::2 (M=256, B split by N across the pair)
 // mode bit0: run MMAs, bit1: run LDTM loops in `ld_warps` warps, bit2: LDTM loops also do 16 MUFU + 2 STS.128 per chunk
 template <int CTAS>
-__global__ void bench(int mode, int ld_warps, int n_mma, int n_ld, long long* out) {
+__global__ void bench(int mode, int ld_warps, int n_mma, int n_ld, long long* out, int m_total) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tslot;
@@ -52,15 +52,16 @@ __global__ void bench(int mode, int ld_warps, int n_mma, int n_ld, long long* ou
     const int N = 208;
     if (warp == 16) {  // MMA issuer warp
         if (lane == 0 && (mode & 1) && rank == 0) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((128 * CTAS) >> 4) << 24);
-            const uint64_t ad0 = make_desc(smem_u32(smem), 2048, 128), bd0 = make_desc(smem_u32(smem + 64 * 1024), 128, 26 * 128);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(m_total >> 4) << 24);
+            const int rows_cta = m_total / CTAS;
+            const uint64_t ad0 = make_desc(smem_u32(smem), rows_cta * 16, 128), bd0 = make_desc(smem_u32(smem + 64 * 1024), 128, 26 * 128);
             long long t0 = clock64();
             for (int i = 0; i < n_mma; ++i) {
                 const int ks = i % 13;
                 if (CTAS == 1)
-                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + 256), "l"(ad0 + (uint64_t)(ks * 256)), "l"(bd0 + (uint64_t)(ks * 16)), "r"(idesc), "r"((uint32_t)(ks > 0)) : "memory");
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + 256), "l"(ad0 + (uint64_t)(ks * (rows_cta * 32 / 16))), "l"(bd0 + (uint64_t)(ks * 16)), "r"(idesc), "r"((uint32_t)(ks > 0)) : "memory");
                 else
-                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + 256), "l"(ad0 + (uint64_t)(ks * 256)), "l"(bd0 + (uint64_t)(ks * 16)), "r"(idesc), "r"((uint32_t)(ks > 0)) : "memory");
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + 256), "l"(ad0 + (uint64_t)(ks * (rows_cta * 32 / 16))), "l"(bd0 + (uint64_t)(ks * 16)), "r"(idesc), "r"((uint32_t)(ks > 0)) : "memory");
             }
             if (CTAS == 1)
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -124,18 +125,18 @@ int main() {
         {3, 4, "MMA + LDTM 1 warp/SMSP"}, {3, 16, "MMA + LDTM 4 warps/SMSP"},
         {6, 16, "epilogue chunk (LDTM+SiLU+STS) 4 warps/SMSP, no MMA"}, {7, 16, "MMA + epilogue chunk 4 warps/SMSP"},
         {7, 8, "MMA + epilogue chunk 2 warps/SMSP"}, {7, 4, "MMA + epilogue chunk 1 warp/SMSP"}};
-    for (int ctas : {1, 2})
+    for (int ctas : {1, 2, 3})  // 3 = cta_group::2 with M=128 (64 rows per CTA)
     for (auto& c : cfgs) {
         for (int rep = 0; rep < 2; ++rep) {
             cudaMemset(out, 0, 64 * 8);
-            if (ctas == 1) bench<1><<<1, 17 * 32, smem>>>(c.mode, c.warps, n_mma, n_ld, out);
+            if (ctas == 1) bench<1><<<1, 17 * 32, smem>>>(c.mode, c.warps, n_mma, n_ld, out, 128);
             else {
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(2); cfg.blockDim = dim3(17 * 32); cfg.dynamicSmemBytes = smem;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
-                cudaLaunchKernelEx(&cfg, bench<2>, c.mode, c.warps, n_mma, n_ld, out);
+                cudaLaunchKernelEx(&cfg, bench<2>, c.mode, c.warps, n_mma, n_ld, out, ctas == 3 ? 128 : 256);
             }
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
@@ -144,7 +145,7 @@ int main() {
         cudaMemcpy(h, out, 64 * 8, cudaMemcpyDeviceToHost);
         double ld = 0; int nw = 0;
         for (int w = 0; w < c.warps; ++w) { ld += h[1 + w]; nw++; }
-        printf("cta_group::%d %-52s: MMA %.1f cyc/MMA", ctas, c.name, (double)h[0] / n_mma);
+        printf("cta_group::%d M=%d %-52s: MMA %.1f cyc/MMA", ctas == 1 ? 1 : 2, ctas == 1 ? 128 : (ctas == 3 ? 128 : 256), c.name, (double)h[0] / n_mma);
         if (nw) printf(" | chunk %.1f cyc per warp, %.1f per SMSP", ld / nw / n_ld, ld / nw / n_ld / (c.warps / 4));
         printf("\n");
     }
