@@ -51,125 +51,6 @@ enum {
     V3_BAR_COUNT = 19,
 };
 
-__device__ __forceinline__ uint32_t v3_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void v3_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void v3_arrive_leader(uint64_t* bar) {
-    asm volatile(
-        "{\n"
-        ".reg .b32 ra;\n"
-        "mapa.shared::cluster.u32 ra, %0, 0;\n"
-        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
-        "}\n" ::"r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void v3_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// same, descriptors passed as (lo, hi) words: only the low word (start-address field) changes between K steps, so the
-// issue loop is two 32-bit adds per MMA (a single thread issues dependent instructions at ~1 per 4-6 cycles; a long
-// per-MMA address computation makes the ISSUE, not the tensor pipe, the bottleneck -- measured 173 cycles per MMA)
-__device__ __forceinline__ void v3_mma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                            uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        ".reg .b64 da, db;\n"
-        "mov.b64 da, {%1, %2};\n"
-        "mov.b64 db, {%3, %4};\n"
-        "setp.ne.b32 p, %6, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Warp-uniform variants: executed by ALL lanes of the (converged) MMA warp with warp-uniform operands; one elected
-// lane issues.  Keeping the control flow uniform lets ptxas keep descriptors in uniform registers instead of emitting
-// an ELECT / R2UR.BROADCAST waterfall loop around every UTCHMMA.
-__device__ __forceinline__ void v3_mma_uni(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                           uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred pe, p;\n"
-        ".reg .b64 da, db;\n"
-        "elect.sync _|pe, 0xffffffff;\n"
-        "mov.b64 da, {%1, %2};\n"
-        "mov.b64 db, {%3, %4};\n"
-        "setp.ne.b32 p, %6, 0;\n"
-        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void v3_commit_uni(uint64_t* bar) {
-    asm volatile(
-        "{\n"
-        ".reg .pred pe;\n"
-        "elect.sync _|pe, 0xffffffff;\n"
-        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "h"((uint16_t)3)
-        : "memory");
-}
-__device__ __forceinline__ void v3_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(bar)),
-                 "h"((uint16_t)3)
-                 : "memory");
-}
-__device__ __forceinline__ void v3_ld8_issue(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking phase test
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void v3_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void v3_sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void v3_sts16(uint32_t saddr, uint16_t v) {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
-}
-
-template <int ACT>
-__device__ __forceinline__ uint32_t v3_act_pack(float a, float b) {
-    if (ACT == CMRL_ACT_SILU) {  // z*sigmoid(z) = 0.5z*(1 + tanh(0.5z)): one SFU op per element
-        float ha = 0.5f * a, hb = 0.5f * b, ta, tb;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(ha));
-        asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(hb));
-        return pack_h2(fmaf(ha, ta, ha), fmaf(hb, tb, hb));
-    } else if (ACT == CMRL_ACT_RELU) {
-        return pack_h2(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
-    }
-    return pack_h2(a, b);
-}
-
 // The work list of a cluster is a contiguous range of 128-row tiles in (p, member, tile) order; consecutive tiles of
 // the same net are processed two at a time.  Every role walks the list with this iterator (decode once, then step).
 struct V3Pair {

@@ -352,7 +352,11 @@ def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0), head_interleave
     return [blob, layer_off, layer_k, layer_n]
 
 
-TC_VARIANT = 3  # 3: CTA pairs, two tiles in flight (default); 2: CTA pairs, one tile; 1: single-CTA streamed weights
+# Kernel variant of the tensor-core tier.  None = first that accepts the shape: 4 (CTA pairs, 256-row tiles, chased
+# epilogue; head <= 32 columns), 3 (pairs, two 128-row tiles in flight; head <= 128 columns), 1 (single-CTA tiles,
+# per-layer streamed weights).  All need the padded hidden width to fit shared memory (hidden <= 207); wider models use
+# precision="fp32".  2 is the first pair kernel (kept for A/B).
+TC_VARIANT = None
 
 
 def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, gaussian, act_kind, residual,
@@ -369,8 +373,19 @@ def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, ga
     c_off, c_k, c_n = pack[4]
     pred = torch.empty((N, head_dim), device=obs.device, dtype=torch.float32) if out is None else out
     bounds_n = 0 if min_logvar is None else min_logvar.numel()
-    _lib.call("cmrl_mlp_rollout_f16", blob.data_ptr(), blob.shape[1], c_off, c_k, c_n, L,
-              P, E, N, O, A, H, head_dim, layout, 1 if gaussian else 0, act_kind, obs.data_ptr(), act.data_ptr(),
-              perm.data_ptr(), offsets.data_ptr(), 1 if residual else 0, _ptr(min_logvar), _ptr(max_logvar), bounds_n,
-              _ptr(noise), pred.data_ptr(), TC_VARIANT, _stream())  # fmt: skip
-    return pred
+    if len(pack) < 6:  # variant chosen once per pack (argument validation happens before any launch)
+        pack.append(None)
+    candidates = [TC_VARIANT] if TC_VARIANT is not None else ([pack[5]] if pack[5] else [4, 3, 1])
+    last = None
+    for variant in candidates:
+        try:
+            _lib.call("cmrl_mlp_rollout_f16", blob.data_ptr(), blob.shape[1], c_off, c_k, c_n, L,
+                      P, E, N, O, A, H, head_dim, layout, 1 if gaussian else 0, act_kind, obs.data_ptr(), act.data_ptr(),
+                      perm.data_ptr(), offsets.data_ptr(), 1 if residual else 0, _ptr(min_logvar), _ptr(max_logvar),
+                      bounds_n, _ptr(noise), pred.data_ptr(), variant, _stream())  # fmt: skip
+            if TC_VARIANT is None:
+                pack[5] = variant
+            return pred
+        except _lib.CmrlB200Error as e:  # shape not supported by this variant
+            last = e
+    raise _lib.CmrlB200Error("no tensor-core kernel variant supports this model (use precision='fp32'): %s" % last)

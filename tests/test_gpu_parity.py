@@ -509,7 +509,7 @@ def _tc_case(cm, kind, N, H, seed):
     return env, m, obs, act, idx, noise
 
 
-@pytest.fixture(params=[3, 2, 1], ids=["pingpong", "cta_pair", "single_cta"])
+@pytest.fixture(params=[None, 4, 3, 2, 1], ids=["auto", "pair256", "pingpong", "cta_pair", "single_cta"])
 def tc_variant(request, cm):
     old = cm.ops.TC_VARIANT
     cm.ops.TC_VARIANT = request.param
@@ -529,7 +529,7 @@ def test_tcgen05_rollout_vs_fp32_tier(cm, tc_variant, kind, N, H):
     out = env.predict_selected(m, obs, act, idx, noise)
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
-    print("tc variant %d %s N=%d H=%d rel_err %.2e" % (tc_variant, kind, N, H, rel_err(out.cpu().numpy(), ref.cpu().numpy())))
+    print("tc variant %s %s N=%d H=%d rel_err %.2e" % (tc_variant, kind, N, H, rel_err(out.cpu().numpy(), ref.cpu().numpy())))
     assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < TOL_TC
     # deterministic part only (no noise): isolates mean from logvar
     env.precision = "fp32"
@@ -611,3 +611,31 @@ def test_step_device_graphed(cm):
         assert all(not np.array_equal(seen[i], seen[i + 1]) for i in range(6))
         # the all-replays reward noise is N(0, sigma): distinct draws -> low correlation between steps
         assert abs(np.corrcoef(seen[1], seen[2])[0, 1]) < 0.6
+
+
+def test_tcgen05_wide_heads_and_hidden(cm):
+    """Shapes outside the default pair kernel: O=20 (head 48 columns -> variant 3); hidden 240 does not fit shared memory in
+    any tensor-core variant -> a loud error, never a silent fallback."""
+    torch.manual_seed(0)
+    np.random.seed(0)
+    rng = np.random.default_rng(0)
+    for O, A, H in ((20, 4, 200), (5, 1, 240), (17, 6, 128)):
+        N = 3000
+        m = cm.PlainTransition(O, A, hid_size=H, activation_fn_cfg=SILU, device=DEV)
+        dyn = cm.PlainEnsembleDynamics(m, learned_reward=False)
+        env = cm.VecFakeEnv(N, None, None)
+        env.set_up(dyn, reward_fn=lambda n, o, a: np.zeros((n.shape[0], 1), np.float32), termination_fn=lambda n, o, a: np.zeros((n.shape[0], 1), bool),
+                   get_init_obs_fn=lambda n: rng.normal(size=(n, O)).astype(np.float32))
+        env.reset()
+        act = t(rng.uniform(-1, 1, size=(N, A)).astype(np.float32))
+        idx = t(rng.choice(np.asarray(m.elite_members), size=N).astype(np.uint8))
+        noise = t(rng.normal(size=(N, O)).astype(np.float32))
+        env.precision = "fp32"
+        ref = env.predict_selected(m, env._obs_dev, act, idx, noise)
+        env.precision = "f16"
+        if H > 207:
+            with pytest.raises(cm._lib.CmrlB200Error):
+                env.predict_selected(m, env._obs_dev, act, idx, noise)
+            continue
+        out = env.predict_selected(m, env._obs_dev, act, idx, noise)
+        assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < TOL_TC
