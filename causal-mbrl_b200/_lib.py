@@ -84,5 +84,15 @@ def call(name, *args):
         raise CmrlB200Error("%s failed (code %d): %s" % (name, rc, msg))
 
 
+_replayed = 0
+
+
+def note_replayed(n):
+    """Kernels launched by replaying a captured CUDA graph (the C counter only sees them once, at capture)."""
+    global _replayed
+    _replayed += int(n)
+
+
 def launch_count():
-    return int(load().cmrl_launch_count())
+    """Kernels of this library launched so far: direct launches (counted in C) + graph-replayed ones."""
+    return int(load().cmrl_launch_count()) + _replayed

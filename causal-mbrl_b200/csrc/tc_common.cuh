@@ -71,6 +71,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > SPIN_LIMIT) __trap();
     }
 }
+// same, with a sleep between polls: for roles with slack (a spinning warp takes issue slots from the epilogue warps of
+// its SM sub-partition)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    unsigned long long spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (ns) __nanosleep(ns);
+        if (++spins > SPIN_LIMIT) __trap();
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -245,6 +266,35 @@ __device__ __forceinline__ void v3_sts128(uint32_t saddr, uint32_t a, uint32_t b
 }
 __device__ __forceinline__ void v3_sts16(uint32_t saddr, uint16_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
+}
+
+// ---- A operand in tensor memory (".ts" form): fp16 pairs packed in 32-bit columns, lane = row, 8 columns per K step ---
+__device__ __forceinline__ void v5_mma_ts_uni(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, p;\n"
+        ".reg .b64 db;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void v5_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void v5_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void v5_ld16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
 }
 
 template <int ACT>

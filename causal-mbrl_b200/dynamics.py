@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Tuple, Union
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .mlp import EnsembleMLP
 from .optim import FusedAdamL2
 from .reward_mech import BaseRewardMech
@@ -383,12 +383,15 @@ class _DeviceEpochRunner:
         if self.use_graph and self.graph is None and n_full > 0:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
+            l0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 self._step()
+            self.graph_launches = _lib.launch_count() - l0
             self.graph = g
         for _ in range(n_full):
             if self.graph is not None:
                 self.graph.replay()
+                _lib.note_replayed(self.graph_launches)
             else:
                 self._step()
         total = n_full * self.B

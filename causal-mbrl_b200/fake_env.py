@@ -23,7 +23,7 @@ from typing import Any, Dict, List, Optional, Type
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 
 try:  # the real SB3 base class when it is installed; an interface-compatible stand-in otherwise
     from stable_baselines3.common.vec_env.base_vec_env import VecEnv
@@ -254,12 +254,14 @@ class VecFakeEnv(VecEnv):
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             c0 = self._draw_counter
+            l0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 out = self._predict_all(obs, act, need_all)
                 ops.counter_add(self._rng_base, self._draw_counter - c0)
-            cached = (key, g, out)
+            cached = (key, g, out, _lib.launch_count() - l0)
             self._predict_graph = cached
         cached[1].replay()
+        _lib.note_replayed(cached[3])
         return cached[2]
 
     def step_wait(self):
@@ -386,13 +388,16 @@ class VecFakeEnv(VecEnv):
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             c0 = self._draw_counter
+            l0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 self._graph_out = self.step_device(b["act"])
                 ops.counter_add(self._rng_base, self._draw_counter - c0)
+            self._step_graph_launches = _lib.launch_count() - l0
             self._step_graph = g
         else:
             b["act"].copy_(actions, non_blocking=True)
         self._step_graph.replay()
+        _lib.note_replayed(self._step_graph_launches)
         return self._graph_out
 
     def invalidate_step_graph(self):

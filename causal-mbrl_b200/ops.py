@@ -352,7 +352,8 @@ def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0), head_interleave
     return [blob, layer_off, layer_k, layer_n]
 
 
-# Kernel variant of the tensor-core tier.  None = first that accepts the shape: 4 (CTA pairs, 256-row tiles, chased
+# Kernel variant of the tensor-core tier.  None = first that accepts the shape: 5 (CTA pairs, two 256-row tiles in
+# flight, A operand partly in tensor memory; head <= 16 columns for hidden 200), 4 (CTA pairs, 256-row tiles, chased
 # epilogue; head <= 32 columns), 3 (pairs, two 128-row tiles in flight; head <= 128 columns), 1 (single-CTA tiles,
 # per-layer streamed weights).  All need the padded hidden width to fit shared memory (hidden <= 207); wider models use
 # precision="fp32".  2 is the first pair kernel (kept for A/B).
@@ -375,7 +376,7 @@ def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, ga
     bounds_n = 0 if min_logvar is None else min_logvar.numel()
     if len(pack) < 6:  # variant chosen once per pack (argument validation happens before any launch)
         pack.append(None)
-    candidates = [TC_VARIANT] if TC_VARIANT is not None else ([pack[5]] if pack[5] else [4, 3, 1])
+    candidates = [TC_VARIANT] if TC_VARIANT is not None else ([pack[5]] if pack[5] else [5, 4, 3, 1])
     last = None
     for variant in candidates:
         try:
