@@ -299,9 +299,12 @@ def dominant_kernel_roofline(cm, env, tr, act_dev, args, flush):
         flops = float(FLOP_SUBNET) * O * N
         achieved = flops / (ms * 1e-3) / 1e12
         return {
-            "dtype": "f16", "kernel": "mlp_rollout_f16_kernel (fused 4x200 MLP + head + sampling, 5 sub-nets, tcgen05 kind::f16)",
+            "dtype": "f16", "kernel": "mlp_rollout_f16_v5_kernel (fused 4x200 MLP + head + sampling, 5 sub-nets, tcgen05 kind::f16)",
             "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": src + " bf16 burst",
+            "frac": achieved / pk["bf16_tflops"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch at N = 100000 (profiles/r1_ncu_mlp_f16_v5.csv)
+            "traffic": 11.70e6 if N == 100000 else None, "traffic_unit": "bytes per launch (ncu --set full)",
+            "peak_source": src + " bf16 burst",
             "flops_per_launch": flops, "ms_per_launch": ms,
             "note": "algorithmic FLOPs = 243200 per (sub-net, env) x 5 sub-nets x N envs (drawn member only, padding not counted)",
         }  # fmt: skip
