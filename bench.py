@@ -232,7 +232,7 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = N * world * args.steps / float(t.item())
     h2d = N * A * 4
-    d2h = 2 * N * O * 4 + N * 4 + 2 * N + N * O * 4  # obs, terminal_obs, reward, done, trunc + next_obs for termination_fn
+    d2h = N * O * 4 + N * 4 + 2 * N  # next_obs (for termination_fn; patched at reset rows it is also the returned obs), reward, done, trunc
 
     # ---- dominant kernel: K1 hidden layer (200->200) on the bucketed rows, timed alone ------------------
     roof = dominant_kernel_roofline(cm, env, tr, act_dev, args, flush)

@@ -285,12 +285,17 @@ class VecFakeEnv(VecEnv):
             self.logger.record_mean("rollout/penalty", penalty.mean().item())
 
         # ---- host callbacks (reward_fn / termination_fn of the real env), on pinned copies ----------------------
+        # The predicted next_obs lands in one of two pinned ping-pong buffers (the other one still holds the current
+        # obs for the callbacks); in device rng_mode that same buffer, patched at the few reset rows, becomes the
+        # current obs of the next step -- the full post-reset obs is never read back a second time.
         host_next = None
         terminal_u8 = None
+        h_next = b["h_obs"] if self._obs_flip else b["h_obs2"]
+        self._obs_flip = not self._obs_flip
         if not (self.learned_reward and self.learned_termination):
-            b["h_term_obs"].copy_(next_obs, non_blocking=True)
+            h_next.copy_(next_obs, non_blocking=True)
             stream.synchronize()
-            host_next = b["h_term_obs"].numpy()
+            host_next = h_next.numpy()
             host_obs = self._current_batch_obs
             if not self.learned_reward:
                 r = np.asarray(self.reward_fn(host_next, host_obs, self._current_batch_action), dtype=np.float32)
@@ -309,35 +314,39 @@ class VecFakeEnv(VecEnv):
                           b["term_obs"] if host_next is None else None, None)  # fmt: skip
 
         # ---- device -> host: the SB3 return values ------------------------------------------------------------------
-        if host_next is None:
-            b["h_term_obs"].copy_(b["term_obs"], non_blocking=True)
+        if host_next is None:  # fully learned step: the pre-reset next_obs comes back now
+            h_next.copy_(b["term_obs"], non_blocking=True)
         b["h_reward"].copy_(b["reward_out"], non_blocking=True)
         b["h_done"].copy_(b["done"], non_blocking=True)
         b["h_trunc"].copy_(b["trunc"], non_blocking=True)
-        h_obs = b["h_obs"] if self._obs_flip else b["h_obs2"]  # ping-pong: the previous obs stays valid for callbacks
-        self._obs_flip = not self._obs_flip
-        if device_rng:
-            h_obs.copy_(obs, non_blocking=True)
+        ret_obs = None
+        if host_next is not None:
+            ret_obs = host_next.copy()  # the returned copy is made while the tail kernel and the small copies run
         stream.synchronize()
+        if ret_obs is None:
+            host_next = h_next.numpy()
+            ret_obs = host_next.copy()
         batch_done = b["h_done"].numpy().view(np.bool_)
         batch_truncate = b["h_trunc"].numpy().view(np.bool_)
-        batch_next_obs = b["h_term_obs"].numpy()
         done_idx = np.nonzero(batch_done)[0]
-        if device_rng:
-            self._current_batch_obs = h_obs.numpy()
-        else:
-            # host reset in the reference's order (ascending env index; fake_env.py:131-135,171-181)
-            cur = h_obs.numpy()
-            cur[...] = batch_next_obs
-            self._current_batch_obs = cur
-            if done_idx.size:
-                rows = self._host_reset_rows(done_idx.size)
-                cur[done_idx] = rows
-                di = torch.from_numpy(done_idx).to(self.device)
-                obs.index_copy_(0, di, torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)).to(self.device))
+        terminal_rows = host_next[done_idx] if done_idx.size else None  # fancy index = copy, taken before the patch
+        if done_idx.size:
+            if device_rng:  # rows the fused tail wrote into the done envs
+                if done_idx.size * 4 < N:
+                    rows = obs.index_select(0, torch.from_numpy(done_idx).to(self.device)).cpu().numpy()
+                else:
+                    b["h_term_obs"].copy_(obs, non_blocking=True)
+                    stream.synchronize()
+                    rows = b["h_term_obs"].numpy()[done_idx]
+            else:  # host reset in the reference's order (ascending env index; fake_env.py:131-135,171-181)
+                rows = np.ascontiguousarray(self._host_reset_rows(done_idx.size), dtype=np.float32)
+                obs.index_copy_(0, torch.from_numpy(done_idx).to(self.device), torch.from_numpy(rows).to(self.device))
+            host_next[done_idx] = rows
+            ret_obs[done_idx] = rows
+        self._current_batch_obs = host_next
 
-        infos = self._make_infos(batch_truncate, done_idx, batch_next_obs)
-        return self._current_batch_obs.copy(), b["h_reward"].numpy().copy(), batch_done.copy(), infos
+        infos = self._make_infos(batch_truncate, done_idx, terminal_rows)
+        return ret_obs, b["h_reward"].numpy().copy(), batch_done.copy(), infos
 
     def step_device(self, actions: torch.Tensor, termination=None):
         """Device-resident step for rollout collectors that keep their buffers on the GPU: `actions` is a CUDA
@@ -403,19 +412,20 @@ class VecFakeEnv(VecEnv):
     def invalidate_step_graph(self):
         self._step_graph = None
 
-    def _make_infos(self, batch_truncate, done_idx, batch_next_obs):
+    def _make_infos(self, batch_truncate, done_idx, terminal_rows):
+        """`terminal_rows[k]` = pre-reset next_obs of env `done_idx[k]` (fake_env.py:126-135)."""
         N = self.num_envs
         if self.infos_mode == "shared":
             shared = {"TimeLimit.truncated": np.False_}
             infos = [shared] * N
             for i in np.nonzero(batch_truncate)[0]:
                 infos[i] = {"TimeLimit.truncated": np.True_}
-            for i in done_idx:
-                infos[i] = {"TimeLimit.truncated": batch_truncate[i], "terminal_observation": batch_next_obs[i].copy()}
+            for k, i in enumerate(done_idx):
+                infos[i] = {"TimeLimit.truncated": batch_truncate[i], "terminal_observation": terminal_rows[k]}
             return infos
         infos = [{"TimeLimit.truncated": t} for t in batch_truncate]
-        for i in done_idx:
-            infos[i]["terminal_observation"] = batch_next_obs[i].copy()
+        for k, i in enumerate(done_idx):
+            infos[i]["terminal_observation"] = terminal_rows[k]
         return infos
 
     # ------------------------------------------------------------------ resets (fake_env.py:144-181)

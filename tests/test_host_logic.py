@@ -194,11 +194,12 @@ def test_fake_env_host_side_contract():
     with pytest.raises(AssertionError):
         env.step_async(np.zeros((8, 1), np.float32))
         env.step_wait()
-    infos = env._make_infos(np.array([False, True] + [False] * 6), np.array([1, 3]), np.arange(16, dtype=np.float32).reshape(8, 2))
+    full = np.arange(16, dtype=np.float32).reshape(8, 2)  # third argument: the pre-reset rows of the done envs, in done_idx order
+    infos = env._make_infos(np.array([False, True] + [False] * 6), np.array([1, 3]), full[[1, 3]])
     assert [i["TimeLimit.truncated"] for i in infos] == [False, True] + [False] * 6
     assert "terminal_observation" in infos[1] and "terminal_observation" in infos[3] and "terminal_observation" not in infos[0]
     env.infos_mode = "shared"
-    infos2 = env._make_infos(np.array([False, True] + [False] * 6), np.array([1, 3]), np.arange(16, dtype=np.float32).reshape(8, 2))
+    infos2 = env._make_infos(np.array([False, True] + [False] * 6), np.array([1, 3]), full[[1, 3]])
     assert [bool(i["TimeLimit.truncated"]) for i in infos2] == [False, True] + [False] * 6
     assert np.array_equal(infos2[3]["terminal_observation"], [6.0, 7.0]) and infos2[0] is infos2[2]
 
