@@ -271,6 +271,8 @@ class VecFakeEnv(VecEnv):
         N = self.num_envs
         obs = self._obs_dev
         stream = torch.cuda.current_stream()
+        if self._current_batch_obs is None:  # device-resident steps ran in between
+            self.sync_host_obs()
         b["act_pin"].numpy()[...] = self._current_batch_action
         act = b["act"]
         act.copy_(b["act_pin"], non_blocking=True)
@@ -373,6 +375,7 @@ class VecFakeEnv(VecEnv):
         ops.env_step_tail(next_obs, reward, terminal_f, terminal_u8, penalty, self.penalty_coeff, self._env_len_dev,
                           self.max_episode_steps, reset_rows, reset_index, obs, b["reward_out"], b["done"], b["trunc"],
                           b["term_obs"], None)  # fmt: skip
+        self._current_batch_obs = None  # host mirror is stale now (refreshed lazily by step_wait / sync_host_obs)
         return obs, b["reward_out"], b["done"], b["trunc"], b["term_obs"]
 
     def step_device_graphed(self, actions: torch.Tensor):
@@ -392,7 +395,9 @@ class VecFakeEnv(VecEnv):
                 self._elite_u8(mech)
                 if self.precision == "f16":
                     getattr(self.dynamics, mech).packed_f16()
-            self._device_reset_source()
+            c_keep = self._draw_counter
+            self._device_reset_source()  # builds the reset pool; its draw is discarded so that the graph-replayed
+            self._draw_counter = c_keep  # steps use the same Philox streams as kernel-by-kernel `step_device` calls
             b["act"].copy_(actions)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -407,10 +412,77 @@ class VecFakeEnv(VecEnv):
             b["act"].copy_(actions, non_blocking=True)
         self._step_graph.replay()
         _lib.note_replayed(self._step_graph_launches)
+        self._current_batch_obs = None
         return self._graph_out
 
     def invalidate_step_graph(self):
         self._step_graph = None
+
+    def rollout_device(self, policy, n_steps: int, termination=None, out: Optional[Dict[str, torch.Tensor]] = None):
+        """Device-resident multi-step rollout into SB3 `ReplayBuffer`-layout slabs: replaces the
+        per-step host loop around `fake_env.py:97-142` + SB3's `_store_transition` for collectors that keep their
+        data on the GPU.  `policy(obs [N,O] cuda) -> actions [N,A] cuda` is called once per step; nothing is copied
+        to the host and nothing synchronises.  Returns (or fills `out` with) float32 CUDA tensors in the layout of
+        `stable_baselines3.common.buffers.ReplayBuffer` with `n_envs = num_envs`:
+        `observations`, `next_observations` [T,N,O] (next_observations is the PRE-reset next state, i.e. the
+        `terminal_observation` for done envs, as `OffPolicyAlgorithm._store_transition` stores it), `actions`
+        [T,N,A], `rewards`, `dones`, `timeouts` [T,N] (timeouts = `TimeLimit.truncated`).
+        Needs rng_mode == "device" and a learned reward mech; `termination` as in `step_device` (with a callable
+        the step is launched kernel by kernel, otherwise replayed from the captured graph)."""
+        assert self.has_set_up, "fake-env has not set up"
+        N, T = self.num_envs, int(n_steps)
+        O, A = self._obs_dev.shape[1], self._bufs["act"].shape[1]
+        dev = self.device
+        if out is None:
+            out = {
+                "observations": torch.empty((T, N, O), device=dev), "next_observations": torch.empty((T, N, O), device=dev),
+                "actions": torch.empty((T, N, A), device=dev), "rewards": torch.empty((T, N), device=dev),
+                "dones": torch.empty((T, N), device=dev), "timeouts": torch.empty((T, N), device=dev),
+            }  # fmt: skip
+        for t in range(T):
+            out["observations"][t].copy_(self._obs_dev)
+            actions = policy(self._obs_dev)
+            assert actions.is_cuda and actions.shape == (N, A), "policy must return a CUDA tensor [num_envs, action_dim]"
+            actions = actions.to(torch.float32).contiguous()
+            out["actions"][t].copy_(actions)
+            if termination is None and self.use_graph:
+                _, reward, done, trunc, term_obs = self.step_device_graphed(actions)
+            else:
+                _, reward, done, trunc, term_obs = self.step_device(actions, termination)
+            out["next_observations"][t].copy_(term_obs)
+            out["rewards"][t].copy_(reward)
+            out["dones"][t].copy_(done)
+            out["timeouts"][t].copy_(trunc)
+        return out
+
+    def sync_host_obs(self):
+        """Refresh the host mirror of the current observations after device-resident stepping."""
+        self._current_batch_obs = self._obs_dev.cpu().numpy()
+        return self._current_batch_obs.copy()
+
+    @staticmethod
+    def extend_replay_buffer(replay_buffer, slabs: Dict[str, torch.Tensor]):
+        """Append `rollout_device` slabs to an SB3-style `ReplayBuffer` (`observations/next_observations/actions/
+        rewards/dones/timeouts` arrays of shape [buffer_size, n_envs, ...], `pos`, `full`, `buffer_size`), with the
+        ring-buffer wrap-around of `ReplayBuffer.add` (one device->host copy per field instead of T x n_envs adds)."""
+        T = slabs["rewards"].shape[0]
+        cap = replay_buffer.buffer_size
+        fields = [k for k in ("observations", "next_observations", "actions", "rewards", "dones", "timeouts")
+                  if getattr(replay_buffer, k, None) is not None]  # fmt: skip
+        host = {k: slabs[k].cpu().numpy() for k in fields}
+        pos = int(replay_buffer.pos)
+        t = 0
+        while t < T:
+            n = min(T - t, cap - pos)
+            for k in fields:
+                dst = getattr(replay_buffer, k)
+                dst[pos:pos + n] = host[k][t:t + n].reshape((n,) + dst.shape[1:])
+            pos += n
+            t += n
+            if pos == cap:
+                replay_buffer.full = True
+                pos = 0
+        replay_buffer.pos = pos
 
     def _make_infos(self, batch_truncate, done_idx, terminal_rows):
         """`terminal_rows[k]` = pre-reset next_obs of env `done_idx[k]` (fake_env.py:126-135)."""

@@ -4,6 +4,7 @@
 Tolerances: fp32 tier 1e-5 relative (max|a-b| / max|b|) for outputs/losses; integer / flag outputs bit-exact."""
 import os
 import tempfile
+import types
 from unittest import mock
 
 import numpy as np
@@ -639,3 +640,72 @@ def test_tcgen05_wide_heads_and_hidden(cm):
             continue
         out = env.predict_selected(m, env._obs_dev, act, idx, noise)
         assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < TOL_TC
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# device-resident multi-step rollout into SB3 ReplayBuffer-layout slabs
+# ---------------------------------------------------------------------------------------------------------------------------
+def _rollout_env(cm, N, seed, max_steps=7):
+    torch.manual_seed(3)
+    tr = cm.PlainTransition(4, 2, hid_size=64, activation_fn_cfg=SILU, device=DEV)
+    rw = cm.PlainRewardMech(4, 2, hid_size=64, activation_fn_cfg=SILU, device=DEV)
+    tm = cm.PlainTerminationMech(4, 2, hid_size=64, activation_fn_cfg=SILU, device=DEV)
+    for m in (tr, rw, tm):  # the constructor draws the initial elite set from the global numpy RNG (mlp.py:27)
+        m.set_elite_members([0, 2, 3, 5, 6])
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw, learned_termination=True, termination_mech=tm)
+    rng = np.random.default_rng(5)
+    env = cm.VecFakeEnv(N, None, None)
+    env.set_up(dyn, get_init_obs_fn=lambda n: rng.normal(size=(n, 4)).astype(np.float32), max_episode_steps=max_steps)
+    env.rng_mode = "device"
+    env.seed(seed)
+    env.reset()
+    return env
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
+def test_rollout_device_slabs_equal_step_by_step(cm, precision):
+    """`rollout_device` (graph-replayed steps written into [T,N,.] slabs) == the same steps taken one by one through
+    `step_device`, bit for bit; slab layout follows SB3's ReplayBuffer (next_observations = pre-reset next state)."""
+    N, T = 333, 12
+    wp = torch.randn(4, 2, device=DEV)
+    policy = lambda obs: torch.tanh(obs @ wp)
+    env_a, env_b = _rollout_env(cm, N, 11), _rollout_env(cm, N, 11)
+    env_a.precision = env_b.precision = precision
+    slabs = env_a.rollout_device(policy, T)
+    assert slabs["observations"].shape == (T, N, 4) and slabs["actions"].shape == (T, N, 2) and slabs["rewards"].shape == (T, N)
+    for t in range(T):
+        obs_before = env_b._obs_dev.clone()
+        act = policy(env_b._obs_dev)
+        obs, reward, done, trunc, term_obs = env_b.step_device(act)
+        assert torch.equal(slabs["observations"][t], obs_before)
+        assert torch.equal(slabs["actions"][t], act)
+        assert torch.equal(slabs["next_observations"][t], term_obs)
+        assert torch.equal(slabs["rewards"][t], reward)
+        assert torch.equal(slabs["dones"][t], done.float()) and torch.equal(slabs["timeouts"][t], trunc.float())
+    assert torch.equal(env_a._obs_dev, env_b._obs_dev)
+    # SB3 invariants: where an env is not done its next_observation is the next step's observation; timeouts imply dones;
+    # every env is truncated at max_episode_steps at the latest
+    nd = slabs["dones"][:-1] == 0
+    assert torch.equal(slabs["next_observations"][:-1][nd], slabs["observations"][1:][nd])
+    assert bool((slabs["dones"] >= slabs["timeouts"]).all())
+    assert bool((slabs["dones"].cumsum(0)[6] >= 1).all())
+    # host step after device-resident stepping sees the current observations
+    host_obs = env_a.sync_host_obs()
+    assert np.array_equal(host_obs, env_a._obs_dev.cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_extend_replay_buffer_wraps_like_sb3(cm):
+    N, T, cap = 16, 10, 14
+    env = _rollout_env(cm, N, 2)
+    slabs = env.rollout_device(lambda obs: torch.zeros(N, 2, device=DEV), T)
+    buf = types.SimpleNamespace(buffer_size=cap, pos=9, full=False, observations=np.zeros((cap, N, 4), np.float32),
+                                next_observations=np.zeros((cap, N, 4), np.float32), actions=np.zeros((cap, N, 2), np.float32),
+                                rewards=np.zeros((cap, N), np.float32), dones=np.zeros((cap, N), np.float32),
+                                timeouts=np.zeros((cap, N), np.float32))  # fmt: skip
+    cm.VecFakeEnv.extend_replay_buffer(buf, slabs)
+    assert buf.full and buf.pos == (9 + T) % cap
+    rw = slabs["rewards"].cpu().numpy()
+    assert np.array_equal(buf.rewards[9:14], rw[:5]) and np.array_equal(buf.rewards[0:5], rw[5:10])
+    assert np.array_equal(buf.next_observations[0:5], slabs["next_observations"].cpu().numpy()[5:10])
