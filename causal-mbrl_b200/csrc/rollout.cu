@@ -78,48 +78,126 @@ __global__ void draw_uniform_index_kernel(unsigned long long seed, unsigned long
 // ------------------------------------------------------------------------------------------- bucketing
 constexpr int MAX_E = 256;
 
-__global__ void bucket_hist_kernel(const uint8_t* __restrict__ idx, int N, int E, int* __restrict__ counts) {
-    __shared__ int h[MAX_E];
-    for (int i = threadIdx.x; i < E; i += blockDim.x) h[i] = 0;
-    __syncthreads();
-    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
-        int e = idx[n];
-        if (e < E) atomicAdd(&h[e], 1);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < E; i += blockDim.x)
-        if (h[i]) atomicAdd(&counts[i], h[i]);
+// Counting sort of envs by drawn member in two launches, no global atomics, STABLE (ascending env id inside a member's
+// range, so the permutation is deterministic).  The env range is cut into W contiguous warp chunks (8 warps per block).
+//   pass 1: every warp counts its chunk per member (match.any groups the lanes of one member) -> counts[W][E]
+//   pass 2: every block reduces counts to its members' offsets and its warps' start positions, then every warp walks its
+//           chunk again and writes perm[start + rank]
+constexpr int BUCKET_WARPS = 8;
+constexpr int BUCKET_MAX_W = CMRL_BUCKET_SCRATCH_WARPS;
+
+__device__ __forceinline__ void bucket_warp_range(int N, int W, int gw, int& n0, int& n1) {
+    const int wchunk = (N + W - 1) / W;
+    n0 = min(N, gw * wchunk);
+    n1 = min(N, n0 + wchunk);
 }
 
-// each block owns a contiguous chunk of envs; reserves per-member ranges with one global atomic per member
-__global__ void bucket_scatter_kernel(const uint8_t* __restrict__ idx, int N, int E, const int* __restrict__ counts,
-                                      int* __restrict__ cursor, int* __restrict__ perm, int* __restrict__ offsets,
-                                      int chunk) {
-    __shared__ int h[MAX_E];     // local counts, then local cursors
-    __shared__ int base[MAX_E];  // global start of this block's range per member
-    for (int i = threadIdx.x; i < E; i += blockDim.x) h[i] = 0;
+__global__ void bucket_count_kernel(const uint8_t* __restrict__ idx, int N, int E, int W, int* __restrict__ counts) {
+    extern __shared__ int h[];  // [BUCKET_WARPS][E]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < BUCKET_WARPS * E; i += blockDim.x) h[i] = 0;
     __syncthreads();
-    const int n0 = blockIdx.x * chunk, n1 = min(N, n0 + chunk);
-    for (int n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
-        int e = idx[n];
-        if (e < E) atomicAdd(&h[e], 1);
+    const int gw = blockIdx.x * BUCKET_WARPS + warp;
+    int n0, n1;
+    bucket_warp_range(N, W, gw, n0, n1);
+    int* hw = h + warp * E;
+    for (int nb = n0; nb < n1; nb += 32) {
+        const int n = nb + lane;
+        const int e = n < n1 ? (int)idx[n] : 0x7fffffff;
+        const unsigned grp = __match_any_sync(0xffffffffu, e);
+        if (e < E && lane == __ffs(grp) - 1) hw[e] += __popc(grp);
+        __syncwarp();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    for (int i = threadIdx.x; i < BUCKET_WARPS * E; i += blockDim.x) counts[(size_t)blockIdx.x * BUCKET_WARPS * E + i] = h[i];
+}
+
+__global__ void bucket_place_kernel(const uint8_t* __restrict__ idx, int N, int E, int W, const int* __restrict__ counts,
+                                    int* __restrict__ perm, int* __restrict__ offsets) {
+    extern __shared__ int sm[];      // before[E] | total[E] | cur[BUCKET_WARPS][E] | red[8]
+    int* before = sm;                // envs of member e in the chunks of earlier blocks
+    int* total = sm + E;
+    int* cur = sm + 2 * E;
+    int* red = sm + 2 * E + BUCKET_WARPS * E;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w_first = blockIdx.x * BUCKET_WARPS;
+    if (E >= 64) {  // one thread per member walks all warp chunks
+        for (int e = threadIdx.x; e < E; e += blockDim.x) {
+            int bsum = 0, tsum = 0;
+            for (int w = 0; w < W; ++w) {
+                const int c = counts[(size_t)w * E + e];
+                tsum += c;
+                if (w < w_first) bsum += c;
+            }
+            before[e] = bsum;
+            total[e] = tsum;
+        }
+    } else {  // few members: block-wide reduction per member
+        for (int e = 0; e < E; ++e) {
+            int bsum = 0, tsum = 0;
+            for (int w = threadIdx.x; w < W; w += blockDim.x) {
+                const int c = counts[(size_t)w * E + e];
+                tsum += c;
+                if (w < w_first) bsum += c;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+                tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+            }
+            if (lane == 0) {
+                red[warp] = bsum;
+                red[BUCKET_WARPS + warp] = tsum;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int b2 = 0, t2 = 0;
+                for (int i = 0; i < BUCKET_WARPS; ++i) {
+                    b2 += red[i];
+                    t2 += red[BUCKET_WARPS + i];
+                }
+                before[e] = b2;
+                total[e] = t2;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // exclusive scan over members (E <= 256) -> start of every member's range
         int run = 0;
         for (int e = 0; e < E; ++e) {
-            int start = run;
-            run += counts[e];
-            if (blockIdx.x == 0) offsets[e] = start;
-            base[e] = start + (h[e] ? atomicAdd(&cursor[e], h[e]) : 0);
-            h[e] = 0;
+            const int t = total[e];
+            total[e] = run;
+            if (blockIdx.x == 0) offsets[e] = run;
+            run += t;
         }
         if (blockIdx.x == 0) offsets[E] = run;
     }
     __syncthreads();
-    for (int n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
-        int e = idx[n];
-        if (e < E) perm[base[e] + atomicAdd(&h[e], 1)] = n;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        int run = total[e] + before[e];
+        for (int w = 0; w < BUCKET_WARPS; ++w) {
+            cur[w * E + e] = run;
+            if (w_first + w < W) run += counts[(size_t)(w_first + w) * E + e];
+        }
+    }
+    __syncthreads();
+    const int gw = w_first + warp;
+    int n0, n1;
+    bucket_warp_range(N, W, gw, n0, n1);
+    int* cw = cur + warp * E;
+    for (int nb = n0; nb < n1; nb += 32) {
+        const int n = nb + lane;
+        const int e = n < n1 ? (int)idx[n] : 0x7fffffff;
+        const unsigned grp = __match_any_sync(0xffffffffu, e);
+        const int leader = __ffs(grp) - 1;
+        int start = 0;
+        if (e < E && lane == leader) {
+            start = cw[e];
+            cw[e] = start + __popc(grp);
+        }
+        start = __shfl_sync(0xffffffffu, start, leader);
+        if (e < E) perm[start + __popc(grp & ((1u << lane) - 1u))] = n;
+        __syncwarp();
     }
 }
 
@@ -281,18 +359,19 @@ extern "C" int cmrl_member_bucket(const uint8_t* member_idx, int N, int E, int* 
     CMRL_REQUIRE(member_idx && perm && offsets && counters, "member_bucket: null pointer");
     CMRL_REQUIRE(E >= 1 && E <= MAX_E, "member_bucket: E must be in [1,%d]", MAX_E);
     cudaStream_t st = (cudaStream_t)stream;
-    CMRL_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * 2 * (E + 1), st));
     if (N == 0) {
         CMRL_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int) * (E + 1), st));
         return 0;
     }
-    int nb = blocks_for(N, RT * 8);
-    if (nb > 4 * num_sms()) nb = 4 * num_sms();
-    bucket_hist_kernel<<<nb, RT, 0, st>>>(member_idx, N, E, counters);
-    CMRL_CHECK_LAUNCH("member_bucket.hist");
-    int chunk = (N + nb - 1) / nb;
-    bucket_scatter_kernel<<<nb, RT, 0, st>>>(member_idx, N, E, counters, counters + (E + 1), perm, offsets, chunk);
-    CMRL_CHECK_LAUNCH("member_bucket.scatter");
+    int W = (N + 63) / 64;  // >= 64 envs per warp chunk
+    if (W > BUCKET_MAX_W) W = BUCKET_MAX_W;
+    W = (W + BUCKET_WARPS - 1) / BUCKET_WARPS * BUCKET_WARPS;
+    const int nb = W / BUCKET_WARPS;
+    bucket_count_kernel<<<nb, BUCKET_WARPS * 32, sizeof(int) * BUCKET_WARPS * E, st>>>(member_idx, N, E, W, counters);
+    CMRL_CHECK_LAUNCH("member_bucket.count");
+    bucket_place_kernel<<<nb, BUCKET_WARPS * 32, sizeof(int) * (2 * E + BUCKET_WARPS * E + 2 * BUCKET_WARPS), st>>>(
+        member_idx, N, E, W, counters, perm, offsets);
+    CMRL_CHECK_LAUNCH("member_bucket.place");
     return 0;
 }
 

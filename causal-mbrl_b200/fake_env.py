@@ -127,7 +127,7 @@ class VecFakeEnv(VecEnv):
         b["perm"] = torch.empty(N, device=dev, dtype=torch.int32)
         E = self.dynamics.ensemble_num
         b["offsets"] = torch.empty(E + 1, device=dev, dtype=torch.int32)
-        b["counters"] = torch.empty(2 * (E + 1), device=dev, dtype=torch.int32)
+        b["counters"] = torch.empty(ops.BUCKET_SCRATCH_WARPS * E, device=dev, dtype=torch.int32)
         # pinned host mirrors for the per-step device->host read of the SB3 return values
         b["h_obs"] = torch.empty((N, O), dtype=torch.float32).pin_memory()
         b["h_obs2"] = torch.empty((N, O), dtype=torch.float32).pin_memory()

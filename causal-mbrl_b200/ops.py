@@ -262,12 +262,16 @@ def draw_uniform_index(seed, stream_id, N, upper, device, stream_base=None):
     return out
 
 
+BUCKET_SCRATCH_WARPS = 512  # CMRL_BUCKET_SCRATCH_WARPS (include/cmrl_b200.h)
+
+
 def member_bucket(member_idx, E, perm=None, offsets=None, counters=None):
     N = member_idx.numel()
     dev = member_idx.device
     perm = torch.empty(N, device=dev, dtype=torch.int32) if perm is None else perm
     offsets = torch.empty(E + 1, device=dev, dtype=torch.int32) if offsets is None else offsets
-    counters = torch.empty(2 * (E + 1), device=dev, dtype=torch.int32) if counters is None else counters
+    counters = torch.empty(BUCKET_SCRATCH_WARPS * E, device=dev, dtype=torch.int32) if counters is None else counters
+    assert counters.numel() >= BUCKET_SCRATCH_WARPS * E
     _lib.call("cmrl_member_bucket", member_idx.data_ptr(), N, E, perm.data_ptr(), offsets.data_ptr(),
               counters.data_ptr(), _stream())  # fmt: skip
     return perm, offsets

@@ -155,8 +155,10 @@ int cmrl_draw_uniform_index(unsigned long long seed, unsigned long long stream_i
 /* *counter_dev += delta (one-thread kernel): advances the RNG stream base inside a captured step graph. */
 int cmrl_counter_add(unsigned long long* counter_dev, unsigned long long delta, void* stream);
 
-/* Counting sort of envs by drawn member: perm [N] lists env ids grouped by member, offsets [E+1].
- * counters: int32 [2*(E+1)] scratch, zeroed by the call. */
+/* Counting sort of envs by drawn member: perm [N] lists env ids grouped by member (ascending env id inside a
+ * member: the sort is stable and deterministic), offsets [E+1].
+ * counters: int32 [CMRL_BUCKET_SCRATCH_WARPS * E] scratch (per-warp-chunk counts), overwritten by the call. */
+#define CMRL_BUCKET_SCRATCH_WARPS 512
 int cmrl_member_bucket(const uint8_t* member_idx, int N, int E, int* perm, int* offsets, int* counters,
                        void* stream);
 
