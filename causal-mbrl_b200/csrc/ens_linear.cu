@@ -8,28 +8,9 @@
 //   dx  : C[b,i] = (sum_o dz[b,o] W[i,o]) * act'(z_prev[b,i])        A k-contig, B k-contig
 //   dw  : C[i,o] = sum_b (x*mask)[b,i] dz[b,o];  db[o] = sum_b dz    A m-contig, B n-contig
 // The tensor-core tier (tcgen05) lives in mlp_tc.cu.
-#include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace cmrl {
-
-struct GemmP {
-    const float* A;
-    long long a_sp, a_se, a_sm, a_sk;
-    const float* Amask;  // optional multiplicative mask on A(m,k)
-    long long am_sp, am_se, am_sm, am_sk;
-    const float* B;
-    long long b_sp, b_se, b_sk, b_sn;
-    float* C;   // post-epilogue
-    float* C2;  // optional pre-activation copy (fwd)
-    long long c_sp, c_se, c_sm;
-    const float* bias;  // [P,E,N]
-    const float* emul;  // dx: z_prev, same layout as C
-    float* bsum;        // dw: db [P,E,N]
-    const int* row_offsets;
-    int M, N, K, P, E, act, accumulate;
-};
-
-enum { MODE_FWD = 0, MODE_DX = 1, MODE_DW = 2 };
 
 constexpr int BK = 16;
 constexpr int BN = 64;
@@ -239,8 +220,13 @@ __global__ void __launch_bounds__(NTHREADS) grouped_sgemm_kernel(const GemmP p) 
 }
 
 template <int MODE>
-static int launch_gemm(const GemmP& p, int total_rows, cudaStream_t st, const char* name) {
+static int launch_gemm(const GemmP& p, int total_rows, cudaStream_t st, const char* name, int tier = 0) {
     const bool ragged = p.row_offsets != nullptr;
+    CMRL_REQUIRE(tier == 0 || tier == 1 || tier == 3, "%s: tier must be 0 (fp32 FFMA), 1 (TF32) or 3 (3xTF32)", name);
+    if (tier != 0 && !ragged) {
+        const int rc = launch_gemm_tc<MODE>(p, tier, st, name);
+        if (rc != -2) return rc;  // -2: shape not eligible for the tensor-core kernel
+    }
     // small row counts -> 64-row tiles for more CTAs; large -> 128-row tiles
     const long long ctas128 = (long long)((total_rows + 127) / 128) * ((p.N + BN - 1) / BN) * (ragged ? p.P : p.P * p.E);
     const bool use64 = ctas128 < 2LL * num_sms();
@@ -266,7 +252,7 @@ using namespace cmrl;
 extern "C" int cmrl_ens_linear_fwd(const float* x, long long x_sp, long long x_se, const float* w, const float* b,
                                    float* y, float* z, int P, int E, int B, int in_size, int out_size,
                                    const float* mask, long long m_sp, long long m_se, long long m_sb,
-                                   const int* row_offsets, int act, void* stream) {
+                                   const int* row_offsets, int act, int tier, void* stream) {
     CMRL_REQUIRE(x && w && y, "ens_linear_fwd: null pointer");
     CMRL_REQUIRE(P >= 1 && E >= 1 && B >= 0 && in_size >= 1 && out_size >= 1, "ens_linear_fwd: bad dims");
     CMRL_REQUIRE(act >= 0 && act <= 2, "ens_linear_fwd: bad activation %d", act);
@@ -300,11 +286,11 @@ extern "C" int cmrl_ens_linear_fwd(const float* x, long long x_sp, long long x_s
     p.P = P;
     p.E = E;
     p.act = act;
-    return launch_gemm<MODE_FWD>(p, B, (cudaStream_t)stream, "ens_linear_fwd");
+    return launch_gemm<MODE_FWD>(p, B, (cudaStream_t)stream, "ens_linear_fwd", tier);
 }
 
 extern "C" int cmrl_ens_linear_bwd_dx(const float* dz, const float* w, const float* z_prev, float* dx, int P, int E,
-                                      int B, int in_size, int out_size, int act_prev, void* stream) {
+                                      int B, int in_size, int out_size, int act_prev, int tier, void* stream) {
     CMRL_REQUIRE(dz && w && dx, "ens_linear_bwd_dx: null pointer");
     CMRL_REQUIRE(P >= 1 && E >= 1 && B >= 0 && in_size >= 1 && out_size >= 1, "ens_linear_bwd_dx: bad dims");
     if (B == 0) return 0;
@@ -330,13 +316,13 @@ extern "C" int cmrl_ens_linear_bwd_dx(const float* dz, const float* w, const flo
     p.P = P;
     p.E = E;
     p.act = z_prev ? act_prev : CMRL_ACT_IDENTITY;
-    return launch_gemm<MODE_DX>(p, B, (cudaStream_t)stream, "ens_linear_bwd_dx");
+    return launch_gemm<MODE_DX>(p, B, (cudaStream_t)stream, "ens_linear_bwd_dx", tier);
 }
 
 extern "C" int cmrl_ens_linear_bwd_dw(const float* x, long long x_sp, long long x_se, const float* mask,
                                       long long m_sp, long long m_se, long long m_sb, const float* dz, float* dw,
                                       float* db, int P, int E, int B, int in_size, int out_size, int accumulate,
-                                      void* stream) {
+                                      int tier, void* stream) {
     CMRL_REQUIRE(x && dz && dw, "ens_linear_bwd_dw: null pointer");
     CMRL_REQUIRE(P >= 1 && E >= 1 && B >= 1 && in_size >= 1 && out_size >= 1, "ens_linear_bwd_dw: bad dims");
     GemmP p{};
@@ -366,5 +352,5 @@ extern "C" int cmrl_ens_linear_bwd_dw(const float* x, long long x_sp, long long 
     p.P = P;
     p.E = E;
     p.accumulate = accumulate;
-    return launch_gemm<MODE_DW>(p, in_size, (cudaStream_t)stream, "ens_linear_bwd_dw");
+    return launch_gemm<MODE_DW>(p, in_size, (cudaStream_t)stream, "ens_linear_bwd_dw", tier);
 }

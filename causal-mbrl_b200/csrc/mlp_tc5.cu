@@ -125,6 +125,8 @@ __device__ __forceinline__ void v5_mma_role(const RolloutP& p, const V5Lay& lay,
     const bool tracing = p.dbg != nullptr && lane == 0 && blockIdx.x == 0 && (p.dbg_flags & 256);
     int n_tr = 0;
     long long t_wa = 0, t_issue = 0, t_wx = 0, t_all = timing ? clock64() : 0, tt = 0;
+    unsigned long long g0 = 0;
+    if (timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     V5Pair pr;
     V5Iter it;
     v5_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
@@ -199,6 +201,9 @@ __device__ __forceinline__ void v5_mma_role(const RolloutP& p, const V5Lay& lay,
         d[2] = t_wa;
         d[3] = t_issue;
         d[4] = item_end - item_begin;
+        unsigned long long g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        d[5] = (long long)(g1 - g0);  // ns: with d[0] gives the SM clock the kernel really ran at
     }
 }
 

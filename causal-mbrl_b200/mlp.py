@@ -69,6 +69,13 @@ class _MseLossFn(torch.autograd.Function):
         return 2.0 * (mean - target) * g_loss, None
 
 
+class _NoGrad:
+    """marks a model whose forward was called under torch.no_grad()"""
+
+    def __init__(self, model):
+        self.model = model
+
+
 class _MechFn(torch.autograd.Function):
     """(obs, action) -> (mean, logvar) for one mechanism: 4x(K1 linear + fused activation) -> K1 head
     GEMM -> K2 Gaussian head.  Backward replays the chain with the K1/K2 backward kernels."""
@@ -77,6 +84,8 @@ class _MechFn(torch.autograd.Function):
     def forward(ctx, model, obs, act, *params):
         ops._req(obs, "batch_obs"), ops._req(act, "batch_action")
         need_grad = any(ctx.needs_input_grad)
+        if isinstance(model, _NoGrad):  # called under torch.no_grad(): inference, stays on the fp32 FFMA tier
+            model, need_grad = model.model, False
         E, B = model.ensemble_num, obs.shape[-2]
         shared = obs.dim() == 2 or obs.shape[0] == 1 or (obs.stride(0) == 0 and act.stride(0) == 0)
         if shared:  # same rows for every member (query / evaluate): never replicated
@@ -262,7 +271,9 @@ class EnsembleMLP(nn.Module):
         return ps
 
     def _mech_forward(self, batch_obs, batch_action):
-        return _MechFn.apply(self, batch_obs, batch_action, *self._stack_params())
+        # the outer grad mode is read here: inside Function.forward autograd is always off
+        model = self if torch.is_grad_enabled() else _NoGrad(self)
+        return _MechFn.apply(model, batch_obs, batch_action, *self._stack_params())
 
     # ------------------------------------------------------------------ losses (mlp.py:68-76)
     def get_mse_loss(self, model_in: Dict[(str, torch.Tensor)], target: torch.Tensor) -> torch.Tensor:

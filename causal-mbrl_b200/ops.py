@@ -59,9 +59,28 @@ def mask_strides(mask, P, E, B):
     raise AssertionError("input mask must have 2..4 dims")
 
 
-def ens_linear_fwd(x, w, b, act=ACT_IDENTITY, mask=None, mask_str=(0, 0, 0), want_z=False, row_offsets=None):
+# GEMM tier of the TRAINING path (forward with saved pre-activations, dx, dw): 0 = fp32 FFMA, 1 = tcgen05 TF32 (1e-3
+# tier), 3 = 3xTF32 error-compensated tcgen05 (fp32-grade), "auto" = 3 where the tensor-core kernel is faster than the
+# FFMA kernel and 0 elsewhere (measured, profiles/tools/gemm_tier_time.py: forward and dx from ~1k rows per member on --
+# 2.2x / 1.3-1.9x at 4k-64k rows; at the reference batch size of 256 rows both kernels are latency bound at ~17 us and
+# dw, whose K dimension is the batch, is not faster at any size).  Inference forwards (query / evaluate / the fp32
+# rollout tier) always run tier 0, whose row results do not depend on tile placement (selected-member rollouts stay
+# bit-identical to the all-member path).
+TRAIN_GEMM_TIER = "auto"
+TRAIN_GEMM_TC_MIN_ROWS = 1024
+
+
+def _train_tier(kind, rows):
+    if TRAIN_GEMM_TIER != "auto":
+        return int(TRAIN_GEMM_TIER)
+    return 3 if (kind != "dw" and rows >= TRAIN_GEMM_TC_MIN_ROWS) else 0
+
+
+def ens_linear_fwd(x, w, b, act=ACT_IDENTITY, mask=None, mask_str=(0, 0, 0), want_z=False, row_offsets=None, tier=None):
     """y = act((x*mask) @ w + b).  w: [E,in,out] or [P,E,in,out]; x: [B,in] | [E,B,in] | [P,E,B,in]
     (broadcast dims allowed).  Ragged mode: x [N,in] flat + int32 row_offsets [E+1] -> y [N,out] / [P,N,out]."""
+    if tier is None:
+        tier = _train_tier("fwd", x.shape[-2]) if (want_z and row_offsets is None) else 0
     _req(x, "x"), _req(w, "weight")
     parallel = w.dim() == 4
     P = w.shape[0] if parallel else 1
@@ -85,13 +104,14 @@ def ens_linear_fwd(x, w, b, act=ACT_IDENTITY, mask=None, mask_str=(0, 0, 0), wan
         mask = _req(mask, "mask").contiguous()
     _lib.call(
         "cmrl_ens_linear_fwd", x.data_ptr(), x_sp, x_se, w.data_ptr(), _ptr(b), y.data_ptr(), _ptr(z), P, E, B,
-        in_size, out_size, _ptr(mask), mask_str[0], mask_str[1], mask_str[2], _ptr(row_offsets), act, _stream(),
+        in_size, out_size, _ptr(mask), mask_str[0], mask_str[1], mask_str[2], _ptr(row_offsets), act, tier, _stream(),
     )  # fmt: skip
     return (y, z) if want_z else y
 
 
-def ens_linear_bwd_dx(dz, w, z_prev, act_prev):
+def ens_linear_bwd_dx(dz, w, z_prev, act_prev, tier=None):
     """dx = (dz @ w^T) * act'(z_prev); dz [(P,)E,B,out] dense."""
+    tier = _train_tier("dx", dz.shape[-2]) if tier is None else tier
     dz = _req(dz, "dz").contiguous()
     w = w.contiguous()
     parallel = w.dim() == 4
@@ -103,13 +123,15 @@ def ens_linear_bwd_dx(dz, w, z_prev, act_prev):
         z_prev = z_prev.contiguous()
     _lib.call(
         "cmrl_ens_linear_bwd_dx", dz.data_ptr(), w.data_ptr(), _ptr(z_prev), dx.data_ptr(), P, E, B, in_size,
-        out_size, act_prev, _stream(),
+        out_size, act_prev, tier, _stream(),
     )  # fmt: skip
     return dx
 
 
-def ens_linear_bwd_dw(x, dz, w_shape, mask=None, mask_str=(0, 0, 0), dw=None, db=None, want_db=True, accumulate=False):
+def ens_linear_bwd_dw(x, dz, w_shape, mask=None, mask_str=(0, 0, 0), dw=None, db=None, want_db=True, accumulate=False,
+                      tier=None):
     """dw = (x*mask)^T @ dz, db = sum_b dz, written into dw/db when given (flat-arena views)."""
+    tier = _train_tier("dw", dz.shape[-2]) if tier is None else tier
     dz = _req(dz, "dz").contiguous()
     x = _rows_contig(_req(x, "x"), "x")
     parallel = len(w_shape) == 4
@@ -125,7 +147,7 @@ def ens_linear_bwd_dw(x, dz, w_shape, mask=None, mask_str=(0, 0, 0), dw=None, db
     assert dw.is_contiguous() and (db is None or db.is_contiguous())
     _lib.call(
         "cmrl_ens_linear_bwd_dw", x.data_ptr(), x_sp, x_se, _ptr(mask), mask_str[0], mask_str[1], mask_str[2],
-        dz.data_ptr(), dw.data_ptr(), _ptr(db), P, E, B, in_size, out_size, 1 if accumulate else 0, _stream(),
+        dz.data_ptr(), dw.data_ptr(), _ptr(db), P, E, B, in_size, out_size, 1 if accumulate else 0, tier, _stream(),
     )  # fmt: skip
     return dw, db
 

@@ -55,25 +55,28 @@ long long cmrl_launch_count(void);
  *  row_offsets NULL, or int32 [E+1] (device): ragged mode -- member e owns rows
  *       [row_offsets[e], row_offsets[e+1]) of a flat [B,in] x and [P,B,out] y (x_se ignored);
  *       used by selected-member rollouts (VecFakeEnv.get_dynamics_predict, fake_env.py:195-215).
+ *  tier (all three K1 entry points): 0 = fp32 FFMA, ascending-k accumulation (row results independent of
+ *       tile placement); 1 = tcgen05 kind::tf32 (1e-3 tier); 3 = 3xTF32 error-compensated tcgen05 (operands split
+ *       into tf32 hi + lo, three MMAs per K step: fp32-grade, 1e-5 tier).  Ragged calls always use tier 0.
  * ------------------------------------------------------------------------------------------ */
 int cmrl_ens_linear_fwd(const float* x, long long x_sp, long long x_se, const float* w, const float* b,
                         float* y, float* z, int P, int E, int B, int in_size, int out_size,
                         const float* mask, long long m_sp, long long m_se, long long m_sb,
-                        const int* row_offsets, int act, void* stream);
+                        const int* row_offsets, int act, int tier, void* stream);
 
 /* Backward of K1 w.r.t. the input, fused with the previous layer's activation derivative
  * (autograd of layers.py:61 + the activation; base_dynamics.py:185 `.backward()`):
  *   dx[p,e,b,i] = (sum_o dz[p,e,b,o] * w[p,e,i,o]) * act'(z_prev[p,e,b,i])
  * z_prev NULL or act_prev == IDENTITY -> plain dz.W^T. */
 int cmrl_ens_linear_bwd_dx(const float* dz, const float* w, const float* z_prev, float* dx, int P, int E,
-                           int B, int in_size, int out_size, int act_prev, void* stream);
+                           int B, int in_size, int out_size, int act_prev, int tier, void* stream);
 
 /* Backward of K1 w.r.t. weight and bias:
  *   dw[p,e,i,o] = sum_b (x*mask)[p,e,b,i] * dz[p,e,b,o];   db[p,e,0,o] = sum_b dz[p,e,b,o]
  * db may be NULL.  accumulate != 0 adds into dw/db instead of overwriting. */
 int cmrl_ens_linear_bwd_dw(const float* x, long long x_sp, long long x_se, const float* mask, long long m_sp,
                            long long m_se, long long m_sb, const float* dz, float* dw, float* db, int P,
-                           int E, int B, int in_size, int out_size, int accumulate, void* stream);
+                           int E, int B, int in_size, int out_size, int accumulate, int tier, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2  Gaussian head: split, double soft-clamp, residual (and the ExternalMask transpose)

@@ -201,9 +201,18 @@ def _build_for_train(cm, name, g):
     return m
 
 
+@pytest.fixture(params=["auto", 3], ids=["auto_tier", "3xtf32"])
+def train_tier(request, cm):
+    """training GEMM tier: the size-based default, and the tcgen05 3xTF32 kernels forced for every GEMM"""
+    old = cm.ops.TRAIN_GEMM_TIER
+    cm.ops.TRAIN_GEMM_TIER = request.param
+    yield request.param
+    cm.ops.TRAIN_GEMM_TIER = old
+
+
 @pytest.mark.parametrize("name", ["plain_train.npz", "plain_relu_train.npz", "reward_train.npz", "extmask_train.npz", "plain_learnbounds_train.npz"])
 @pytest.mark.parametrize("path", ["fused", "autograd"])
-def test_train_steps_golden(cm, name, path):
+def test_train_steps_golden(cm, name, path, train_tier):
     g = load_golden(name)
     m = _build_for_train(cm, name, g)
     mech = "reward_mech" if name.startswith("reward") else "transition"
@@ -709,3 +718,41 @@ def test_extend_replay_buffer_wraps_like_sb3(cm):
     rw = slabs["rewards"].cpu().numpy()
     assert np.array_equal(buf.rewards[9:14], rw[:5]) and np.array_equal(buf.rewards[0:5], rw[5:10])
     assert np.array_equal(buf.next_observations[0:5], slabs["next_observations"].cpu().numpy()[5:10])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# K1 tensor-core training tier (tcgen05 kind::tf32, 3xTF32) vs the fp32 FFMA tier
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,E,B,i,o", [(1, 7, 256, 6, 200), (1, 7, 256, 200, 200), (1, 7, 256, 200, 10), (5, 7, 100, 6, 200),
+                                       (5, 3, 77, 200, 2), (2, 2, 300, 130, 300), (1, 1, 5, 3, 1), (1, 2, 1000, 128, 64)])
+def test_train_gemm_tensor_core_tiers(cm, P, E, B, i, o):
+    """fwd (+pre-activation), dx (fused act'), dw (+db, accumulate) on tcgen05: tier 3 (3xTF32) is fp32-grade (1e-5 tier),
+    tier 1 (plain TF32) is the 1e-3 tier.  Shapes cover K tails (6, 130, 3), N tails (10, 2, 300 > one 256-wide tile),
+    M tails, shared / per-member inputs and input masks."""
+    g = torch.Generator(device=DEV).manual_seed(P * 1000 + B + i)
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    lead = (P, E) if P > 1 else (E,)
+    w, b = rnd(*lead, i, o) / np.sqrt(i), rnd(*lead, 1, o)
+    x = rnd(E, B, i) if P > 1 else rnd(*lead, B, i)  # P > 1: rows shared by the sub-nets (ExternalMask layer 1)
+    mask = (torch.rand(P, i, device=DEV, generator=g) < 0.6).float() if P > 1 else None
+    mstr = cm.ops.mask_strides(mask, P, E, B) if mask is not None else (0, 0, 0)
+    dz = rnd(*lead, B, o)
+    ref_y, ref_z = cm.ops.ens_linear_fwd(x, w, b, cm.ops.ACT_SILU, mask, mstr, want_z=True, tier=0)
+    x_full = x if P == 1 else x.expand(P, E, B, i)
+    ref_dx = cm.ops.ens_linear_bwd_dx(dz, w, None, cm.ops.ACT_IDENTITY, tier=0)
+    z_in = rnd(*lead, B, i)
+    ref_dx2 = cm.ops.ens_linear_bwd_dx(dz, w, z_in, cm.ops.ACT_SILU, tier=0)
+    ref_dw, ref_db = cm.ops.ens_linear_bwd_dw(x_full, dz, w.shape, mask, mstr, tier=0)
+    for tier, tol in ((3, 1e-5), (1, 2e-3)):
+        y, z = cm.ops.ens_linear_fwd(x, w, b, cm.ops.ACT_SILU, mask, mstr, want_z=True, tier=tier)
+        assert rel_err(z.cpu().numpy(), ref_z.cpu().numpy()) < tol and rel_err(y.cpu().numpy(), ref_y.cpu().numpy()) < tol
+        dx = cm.ops.ens_linear_bwd_dx(dz, w, None, cm.ops.ACT_IDENTITY, tier=tier)
+        assert rel_err(dx.cpu().numpy(), ref_dx.cpu().numpy()) < tol
+        dx2 = cm.ops.ens_linear_bwd_dx(dz, w, z_in, cm.ops.ACT_SILU, tier=tier)
+        assert rel_err(dx2.cpu().numpy(), ref_dx2.cpu().numpy()) < tol
+        dw, db = cm.ops.ens_linear_bwd_dw(x_full, dz, w.shape, mask, mstr, tier=tier)
+        assert rel_err(dw.cpu().numpy(), ref_dw.cpu().numpy()) < tol and rel_err(db.cpu().numpy(), ref_db.cpu().numpy()) < tol
+        dw2, db2 = dw.clone(), db.clone()  # accumulate mode adds into the given buffers
+        cm.ops.ens_linear_bwd_dw(x_full, dz, w.shape, mask, mstr, dw=dw2, db=db2, accumulate=True, tier=tier)
+        assert rel_err(dw2.cpu().numpy(), 2 * ref_dw.cpu().numpy()) < tol and rel_err(db2.cpu().numpy(), 2 * ref_db.cpu().numpy()) < tol

@@ -27,7 +27,7 @@ def test_abi_exports_every_declared_symbol():
     bound = set(cm._lib.PROTOTYPES) | {"cmrl_abi_version", "cmrl_last_error", "cmrl_launch_count"}
     assert declared == bound, declared ^ bound
     # argument validation happens before any CUDA call
-    rc = lib.cmrl_ens_linear_fwd(None, 0, 0, None, None, None, None, 1, 1, 1, 1, 1, None, 0, 0, 0, None, 0, None)
+    rc = lib.cmrl_ens_linear_fwd(None, 0, 0, None, None, None, None, 1, 1, 1, 1, 1, None, 0, 0, 0, None, 0, 0, None)
     assert rc < 0 and b"null pointer" in lib.cmrl_last_error()
 
 
