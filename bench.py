@@ -239,6 +239,8 @@ def run_native(args):
 
     # ---- training step (second half of the metric) ---------------------------------------------------------
     train = time_train(cm, dyn, dev, args, world, barrier)
+    # throughput point of the SURVEY 8d sweep (4 096 rows per member): the tensor-core training GEMMs take over here
+    train["bs4096"] = time_train(cm, dyn, dev, args, world, barrier, B=4096, n_batches=12, with_cpu=False)
     clocks = sampler.stop()
 
     if rank == 0:
@@ -337,7 +339,7 @@ def dominant_kernel_roofline(cm, env, tr, act_dev, args, flush):
     }  # fmt: skip
 
 
-def time_train(cm, dyn_unused, dev, args, world, barrier):
+def time_train(cm, dyn_unused, dev, args, world, barrier, B=256, n_batches=200, with_cpu=True):
     """Second half of the metric: ensemble train member-samples/s.  C4-shaped: PlainTransition E=7 (4x200, SiLU, O=5,
     A=1), bs 256 per member, fp32 tier, one device-resident epoch (on-device bootstrap gather + CUDA-graph replay of
     the optimiser step) over a synthetic training set; replicas per GPU (gradient all-reduce is exercised by
@@ -347,7 +349,6 @@ def time_train(cm, dyn_unused, dev, args, world, barrier):
 
     from oracle.refshim import DuckReplayBuffer
 
-    B, n_batches = 256, 200
     N = int(B * n_batches / 0.8)
     rng = np.random.default_rng(7)
     obs = rng.normal(size=(N, O)).astype(np.float32)
@@ -375,9 +376,11 @@ def time_train(cm, dyn_unused, dev, args, world, barrier):
     ms = float(t.item()) / steps
     out = {"metric": "ensemble_train_member_samples_per_sec", "value": E * B * world / (ms * 1e-3), "unit": "member-samples/s",
            "ms_per_step": ms, "steps_per_epoch": steps, "epoch_mean_nll": loss,
-           "config": "C4-shaped: PlainTransition E=7 4x200 SiLU O=5 A=1, bs 256 per member per GPU, fp32 tier, "
-                     "device-resident epoch (on-device bootstrap gather + CUDA-graph replay), replicas"}  # fmt: skip
-    if not args.no_cpu_baseline and int(os.environ.get("RANK", "0")) == 0:
+           "config": "C4-shaped: PlainTransition E=7 4x200 SiLU O=5 A=1, bs %d per member per GPU, fp32-grade tier "
+                     "(GEMM tier %s: %s), device-resident epoch (on-device bootstrap gather + CUDA-graph replay), replicas"
+                     % (B, cm.ops.TRAIN_GEMM_TIER, "tcgen05 3xTF32 forward/dx, FFMA dw" if B >= cm.ops.TRAIN_GEMM_TC_MIN_ROWS
+                        else "FFMA: latency bound at this batch size")}  # fmt: skip
+    if with_cpu and not args.no_cpu_baseline and int(os.environ.get("RANK", "0")) == 0:
         out["cpu_baseline"] = time_port_train(B)
     return out
 
