@@ -95,6 +95,8 @@ class BaseDynamics:
 
         # data-parallel training (optional): torch.distributed process group + this rank's row slice
         self.dp_group = None
+        self.overlap_dw = True   # train_step: weight-gradient GEMMs on a side stream next to the dz chain
+        self._side_stream = None
 
     def _make_optimizer(self, model):
         return FusedAdamL2(model, lr=self.optim_lr, weight_decay=self.weight_decay, eps=self.optim_eps)
@@ -229,14 +231,31 @@ class BaseDynamics:
         rows = B if grad_rows is None else grad_rows
         g_mean, g_logvar = ops.nll_loss_bwd(mean, logvar, target, g_scalar=1.0 / float(E * rows * D))
         dz = ops.gaussian_head_bwd(raw, model._head_layout, E, B, D, mn, mx, g_mean, g_logvar)
+        # Backward: dW_i and dx_i both need only dz_i, so the weight-gradient GEMMs run on a side stream next to the
+        # dz chain (at the reference batch size every GEMM is a latency-bound ~17 us launch on < 148 CTAs: the critical
+        # path shrinks from 2L+1 to L+1 GEMMs).  Works under CUDA-graph capture (fork / join through events).
+        main = torch.cuda.current_stream()
+        side = self._side_stream if self.overlap_dw else None
+        if side is None and self.overlap_dw:
+            side = self._side_stream = torch.cuda.Stream(device=obs.device)
+        keep = []  # dz tensors stay referenced until the join: the side stream reads them
         for i in range(L, -1, -1):
             w, b = params[2 * i], params[2 * i + 1]
             h_in = hs[i]
             if i == 0 and h_in.dim() < w.dim():
                 h_in = h_in.expand(tuple(w.shape[:-2]) + tuple(h_in.shape[-2:]))
-            ops.ens_linear_bwd_dw(h_in, dz, w.shape, mask if i == 0 else None, mask_str, dw=w.grad, db=b.grad)
+            if side is not None:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    ops.ens_linear_bwd_dw(h_in, dz, w.shape, mask if i == 0 else None, mask_str, dw=w.grad, db=b.grad)
+                keep.append(dz)
+            else:
+                ops.ens_linear_bwd_dw(h_in, dz, w.shape, mask if i == 0 else None, mask_str, dw=w.grad, db=b.grad)
             if i > 0:
                 dz = ops.ens_linear_bwd_dx(dz, w, zs[i - 1], kind)
+        if side is not None:
+            main.wait_stream(side)
+        del keep
         self._sync_grads(model)
         if graphable:
             optim.step_graphable()
