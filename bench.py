@@ -133,6 +133,9 @@ def time_port(n_envs, steps, warmup):
     return n_envs * steps / dt, dt / steps * 1e3, threads
 
 
+WORKLOAD = "C2: ExternalMaskTransition P=5 E=7 (5 elites) 4x200 SiLU fixed 2-D mask + PlainRewardMech, %d fake envs per GPU"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -144,7 +147,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 ExternalMaskTransition P=5 E=7 4x200 SiLU + PlainRewardMech; CPU sample of %d envs" % n},
+        "config": {"workload": WORKLOAD % args.envs, "envs_per_gpu": args.envs, "precision": "fp32 (reference torch CPU)",
+                   "sample": "each step advances a bounded sample of %d of the %d envs on the host cores" % (n, args.envs)},
         "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -254,8 +258,7 @@ def run_native(args):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": roof.pop("dtype"), "data": "synthetic",
             "config": {
-                "workload": "C2: ExternalMaskTransition P=5 E=7 (5 elites) 4x200 SiLU fixed 2-D mask + PlainRewardMech, "
-                            "%d fake envs per GPU, selected-member evaluation, device Philox draws" % N,
+                "workload": WORKLOAD % N, "evaluation": "selected-member (drawn member only), device Philox draws",
                 "envs_per_gpu": N, "precision": args.precision, "l2": "flushed (256 MB write) between timed steps",
                 "flop_per_transition": FLOP_PER_TRANSITION_SELECTED,
             },
