@@ -756,3 +756,64 @@ def test_train_gemm_tensor_core_tiers(cm, P, E, B, i, o):
         dw2, db2 = dw.clone(), db.clone()  # accumulate mode adds into the given buffers
         cm.ops.ens_linear_bwd_dw(x_full, dz, w.shape, mask, mstr, dw=dw2, db=db2, accumulate=True, tier=tier)
         assert rel_err(dw2.cpu().numpy(), 2 * ref_dw.cpu().numpy()) < tol and rel_err(db2.cpu().numpy(), 2 * ref_db.cpu().numpy()) < tol
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# C5 at full size (O = P = 100, A = 20, E = 16, H = 512, per-member 3-D mask: 1 600 sub-nets, 1.36 G parameters)
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_c5_full_size_forward_and_rollout(cm):
+    """Maximum configuration of BASELINE.json: parity against the oracle on sampled (sub-net, member) pairs (a sub-net's
+    output column depends only on its own weights and mask row), selected-member rollout == all-member path bit for bit,
+    and the tensor-core tier refuses the width loudly instead of falling back."""
+    O, A, E, H, B = 100, 20, 16, 512, 48
+    torch.manual_seed(5)
+    rng = np.random.default_rng(5)
+    m = cm.ExternalMaskTransition(O, A, ensemble_num=E, elite_num=12, hid_size=H, activation_fn_cfg=SILU, device=DEV)
+    mask = (rng.uniform(size=(O, E, O + A)) < 0.3).astype(np.float32)
+    mask[np.arange(O), :, np.arange(O)] = 1.0
+    m.set_input_mask(torch.from_numpy(mask))
+    m.set_elite_members(list(range(12)))
+    assert sum(p.numel() for p in m.parameters()) > 1.3e9
+    obs = rng.normal(size=(E, B, O)).astype(np.float32)
+    act = rng.uniform(-1, 1, size=(E, B, A)).astype(np.float32)
+    with torch.no_grad():
+        mean, logvar = m.forward(t(obs), t(act))
+    assert mean.shape == logvar.shape == (E, B, O)
+    sd = {k: v for k, v in m.state_dict().items()}
+    for p_i, e_i in ((0, 0), (57, 3), (99, 15)):
+        sub = {}
+        for k, v in sd.items():  # one (sub-net, member) slice as a P = E = 1 ExternalMask model for the oracle
+            if v.dim() == 4:
+                sub[k] = v[p_i:p_i + 1, e_i:e_i + 1].cpu().numpy()
+        sub["min_logvar"], sub["max_logvar"] = sd["min_logvar"][p_i:p_i + 1].cpu().numpy(), sd["max_logvar"][p_i:p_i + 1].cpu().numpy()
+        x = np.concatenate([obs[e_i], act[e_i]], -1) * mask[p_i, e_i]
+        h = x[None, None]
+        for l in range(4):
+            h = oc.activation(oc.ens_linear(h, sub["hidden_layers.%d.0.weight" % l], sub["hidden_layers.%d.0.bias" % l]), oc.ACT_SILU)
+        raw = oc.ens_linear(h, sub["mean_and_logvar.weight"], sub["mean_and_logvar.bias"])[0, 0]
+        ref_mean = raw[:, 0] + obs[e_i][:, p_i]
+        ref_lv = oc.soft_clamp_logvar(raw[:, 1], sub["min_logvar"].reshape(-1)[0], sub["max_logvar"].reshape(-1)[0])
+        assert rel_err(mean[e_i, :, p_i].cpu().numpy(), ref_mean) < TOL
+        assert rel_err(logvar[e_i, :, p_i].cpu().numpy(), ref_lv) < TOL
+    # rollout: 1 024 envs, selected-member evaluation on the ragged fp32 kernels == query-and-gather
+    N = 1024
+    dyn = cm.PlainEnsembleDynamics(m, learned_reward=False)
+    env = cm.VecFakeEnv(N, None, None)
+    env.set_up(dyn, reward_fn=lambda n, o, a: np.zeros((n.shape[0], 1), np.float32),
+               termination_fn=lambda n, o, a: np.zeros((n.shape[0], 1), bool),
+               get_init_obs_fn=lambda n: rng.normal(size=(n, O)).astype(np.float32))
+    env.reset()
+    a_dev = t(rng.uniform(-1, 1, size=(N, A)).astype(np.float32))
+    idx = t(rng.choice(np.arange(12), size=N).astype(np.uint8))
+    noise = t(rng.normal(size=(N, O)).astype(np.float32))
+    sel = env.predict_selected(m, env._obs_dev, a_dev, idx, noise)
+    with torch.no_grad():
+        am, alv = m.forward(env._obs_dev.unsqueeze(0), a_dev.unsqueeze(0))
+    assert torch.equal(sel, cm.ops.select_sample(am, alv, idx, noise))
+    env.precision = "f16"
+    with pytest.raises(cm._lib.CmrlB200Error):
+        env.predict_selected(m, env._obs_dev, a_dev, idx, noise)
+    env.precision = "fp32"
+    o2, r2, d2, infos = env.step(rng.uniform(-1, 1, size=(N, A)).astype(np.float32))
+    assert o2.shape == (N, O) and r2.shape == (N,) and d2.shape == (N,) and len(infos) == N and np.isfinite(o2).all()
