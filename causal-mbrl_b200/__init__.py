@@ -5,6 +5,7 @@ signatures, attributes, state_dict keys and checkpoint files; the arithmetic run
 (include/cmrl_b200.h).  Import as `cmrl_b200` (the on-disk directory is `causal-mbrl_b200/`).
 """
 from . import _lib, ops  # noqa: F401
+from .cmi_test import TransitionConditionalMutualInformationTest  # noqa: F401
 from .dynamics import BaseDynamics, ConstraintBasedDynamics, PlainEnsembleDynamics  # noqa: F401
 from .fake_env import VecFakeEnv  # noqa: F401
 from .layers import EnsembleLinearLayer, ParallelEnsembleLinearLayer, truncated_normal_init  # noqa: F401

@@ -88,7 +88,12 @@ class _MechFn(torch.autograd.Function):
             model, need_grad = model.model, False
         E, B = model.ensemble_num, obs.shape[-2]
         shared = obs.dim() == 2 or obs.shape[0] == 1 or (obs.stride(0) == 0 and act.stride(0) == 0)
-        if shared:  # same rows for every member (query / evaluate): never replicated
+        if obs.dim() == 4:  # one observation set per sub-net (CMI_test.py:103-105): [P,E,B,O]
+            obs_c = obs.contiguous()
+            x = torch.cat([obs_c, act.contiguous().expand(obs.shape[0], -1, -1, -1)], dim=-1).contiguous()
+            res_obs = obs_c
+            shared = False
+        elif shared:  # same rows for every member (query / evaluate): never replicated
             o2 = obs if obs.dim() == 2 else obs[0]
             a2 = act if act.dim() == 2 else act[0]
             x = ops.gather_inputs(o2.contiguous(), a2.contiguous(), None)
@@ -110,11 +115,7 @@ class _MechFn(torch.autograd.Function):
             hs.append(h)
             zs.append(z)
         raw = ops.ens_linear_fwd(h, params[2 * n_layers], params[2 * n_layers + 1], ops.ACT_IDENTITY)
-        mn, mx = model._bounds()
-        mean, logvar = ops.gaussian_head_fwd(
-            raw, model._head_layout, E, B, model._head_dim, res_obs if model._residual() else None, mn, mx,
-            deterministic=model.deterministic,
-        )  # fmt: skip
+        mean, logvar = model._head_fwd(raw, res_obs if model._residual() else None, E, B)
         if need_grad:
             ctx.model, ctx.n_layers, ctx.mask, ctx.mask_str, ctx.shared = model, n_layers, mask, mask_str, shared
             ctx.save_for_backward(raw, *hs, *zs, *params)
@@ -133,8 +134,7 @@ class _MechFn(torch.autograd.Function):
         if n_bounds and (ctx.needs_input_grad[3 + 2 * (L + 1)] or ctx.needs_input_grad[3 + 2 * (L + 1) + 1]):
             d_min, d_max = torch.zeros_like(mn), torch.zeros_like(mx)
             grads[2 * (L + 1)], grads[2 * (L + 1) + 1] = d_min, d_max
-        dz = ops.gaussian_head_bwd(raw, model._head_layout, E, B, model._head_dim, mn, mx, g_mean,
-                                   None if model.deterministic else g_logvar, d_min, d_max)  # fmt: skip
+        dz = model._head_bwd(raw, E, B, g_mean, None if model.deterministic else g_logvar, d_min, d_max)
         kind = model._act_kind
         for i in range(L, -1, -1):
             w = params[2 * i]
@@ -260,6 +260,16 @@ class EnsembleMLP(nn.Module):
         if self.deterministic:
             return None, None
         return self.min_logvar, self.max_logvar
+
+    def _head_fwd(self, raw, res_obs, E, B):
+        """K2: raw head output -> (mean, logvar); specialised by models with another output layout."""
+        mn, mx = self._bounds()
+        return ops.gaussian_head_fwd(raw, self._head_layout, E, B, self._head_dim, res_obs, mn, mx,
+                                     deterministic=self.deterministic)  # fmt: skip
+
+    def _head_bwd(self, raw, E, B, g_mean, g_logvar, d_min, d_max):
+        mn, mx = self._bounds()
+        return ops.gaussian_head_bwd(raw, self._head_layout, E, B, self._head_dim, mn, mx, g_mean, g_logvar, d_min, d_max)
 
     def _stack_params(self):
         ps = []

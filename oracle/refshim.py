@@ -104,6 +104,7 @@ def load_reference():
     from cmrl.models.fake_env import VecFakeEnv
     from cmrl.util.transition_iterator import BootstrapIterator, TransitionIterator
     from cmrl.types import InteractionBatch
+    from cmrl.models.causal_discovery.CMI_test import TransitionConditionalMutualInformationTest
 
     for k, v in list(locals().items()):
         if k not in ("ns",):

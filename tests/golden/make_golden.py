@@ -87,6 +87,35 @@ def train_fixture(name, model, rng, B, target_dim, steps=3, extra=None):
     print(name, "train steps", steps)
 
 
+def cmi_fixtures():
+    """CMI-test network (causal_discovery/CMI_test.py:15-130): P = O+A+1 leave-one-out sub-nets, outputs [P,E,B,O]."""
+    torch.manual_seed(11)
+    np.random.seed(11)
+    rng = np.random.default_rng(11)
+    O, A, E, B = 4, 2, 5, 30
+    for name, kw in (("cmi_relu", {}), ("cmi_silu", {"activation_fn_cfg": SILU}), ("cmi_noresidual", {"activation_fn_cfg": SILU, "residual": False})):
+        m = ref.TransitionConditionalMutualInformationTest(O, A, ensemble_num=E, elite_num=3, hid_size=24, **kw)
+        obs, act = make_inputs(rng, E, B, O, A, True)
+        target = (obs + 0.1 * rng.normal(size=(E, B, O))).astype(np.float32)
+        with torch.no_grad():
+            mean, logvar = m.forward(torch.from_numpy(obs.copy()), torch.from_numpy(act.copy()))
+            nll = m.get_nll_loss({"batch_obs": torch.from_numpy(obs.copy()), "batch_action": torch.from_numpy(act.copy())},
+                                 torch.from_numpy(target))
+            # 4-D observations (one per sub-net): forward accepts [P,E,B,O] (CMI_test.py:103-105)
+            obs4 = rng.normal(size=(O + A + 1, E, B, O)).astype(np.float32)
+            mean4, logvar4 = m.forward(torch.from_numpy(obs4.copy()), torch.from_numpy(act.copy()))
+        out = sd_np(m)
+        out.update(obs=obs, act=act, target=target, mean=mean.numpy(), logvar=logvar.numpy(), nll=nll.numpy(),
+                   obs4=obs4, mean4=mean4.numpy(), logvar4=logvar4.numpy(), input_mask=m.input_mask.numpy())
+        np.savez_compressed(os.path.join(HERE, name + "_forward.npz"), **out)
+        print(name, mean.shape, nll.shape)
+    m = ref.TransitionConditionalMutualInformationTest(O, A, ensemble_num=E, elite_num=3, hid_size=24, activation_fn_cfg=SILU)
+    train_fixture("cmi_train.npz", m, rng, B=32, target_dim=O, steps=3)
+    m = ref.TransitionConditionalMutualInformationTest(O, A, ensemble_num=E, elite_num=3, hid_size=24, activation_fn_cfg=SILU,
+                                                       learn_logvar_bounds=True)
+    train_fixture("cmi_learnbounds_train.npz", m, rng, B=32, target_dim=O, steps=3)
+
+
 def synth_dataset(rng, N, O, A):
     """SURVEY 8(d) synthetic transitions."""
     obs = rng.normal(size=(N, O)).astype(np.float32)
@@ -270,4 +299,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--only-cmi" in sys.argv:
+        cmi_fixtures()
+    else:
+        main()
+        cmi_fixtures()

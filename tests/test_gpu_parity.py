@@ -817,3 +817,67 @@ def test_c5_full_size_forward_and_rollout(cm):
     env.precision = "fp32"
     o2, r2, d2, infos = env.step(rng.uniform(-1, 1, size=(N, A)).astype(np.float32))
     assert o2.shape == (N, O) and r2.shape == (N,) and d2.shape == (N,) and len(infos) == N and np.isfinite(o2).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the CMI-test network (causal_discovery/CMI_test.py) on the grouped masked-GEMM kernels
+# ---------------------------------------------------------------------------------------------------------------------------
+def _build_cmi(cm, g, prefix="p.", **kw):
+    p = params_of(g, prefix)
+    m = cm.TransitionConditionalMutualInformationTest(4, 2, ensemble_num=5, elite_num=3,
+                                                      hid_size=p["hidden_layers.0.0.weight"].shape[-1], device=DEV, **kw)
+    load_sd(m, p)
+    return m
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw", [("cmi_relu", {}), ("cmi_silu", {"activation_fn_cfg": SILU}),
+                                     ("cmi_noresidual", {"activation_fn_cfg": SILU, "residual": False})])
+def test_cmi_test_network_forward_golden(cm, name, kw):
+    g = load_golden(name + "_forward.npz")
+    m = _build_cmi(cm, g, **kw)
+    assert m.parallel_num == 7 and torch.equal(m.input_mask.cpu(), torch.from_numpy(g["input_mask"]))
+    with torch.no_grad():
+        mean, logvar = m.forward(t(g["obs"]), t(g["act"]))
+        nll = m.get_nll_loss({"batch_obs": t(g["obs"]), "batch_action": t(g["act"])}, t(g["target"]))
+        mean4, logvar4 = m.forward(t(g["obs4"]), t(g["act"]))
+    assert mean.shape == logvar.shape == nll.shape == (7, 5, 30, 4)
+    assert rel_err(mean.cpu().numpy(), g["mean"]) < TOL and rel_err(logvar.cpu().numpy(), g["logvar"]) < TOL
+    assert rel_err(nll.cpu().numpy(), g["nll"]) < 3e-5
+    assert rel_err(mean4.cpu().numpy(), g["mean4"]) < TOL and rel_err(logvar4.cpu().numpy(), g["logvar4"]) < TOL
+    # leave-one-out property: sub-net p ignores input column p (the last sub-net sees everything)
+    obs2 = g["obs"].copy()
+    obs2[..., 1] += 3.0
+    with torch.no_grad():
+        mean2, _ = m.forward(t(obs2), t(g["act"]))
+    res = 3.0 if m.residual else 0.0  # the residual adds the raw observation back
+    d = (mean2 - mean).cpu().numpy()
+    d[..., 1] -= res
+    assert np.abs(d[1]).max() < 1e-5 and np.abs(d[0]).max() > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cmi_train.npz", "cmi_learnbounds_train.npz"])
+def test_cmi_test_network_train_golden(cm, name):
+    """three optimiser steps (NLL.mean().backward() + Adam with L2) against the reference run"""
+    g = load_golden(name)
+    m = _build_cmi(cm, g, "p0.", activation_fn_cfg=SILU, learn_logvar_bounds="learnbounds" in name)
+    optim = cm.FusedAdamL2(m, lr=1e-4, weight_decay=1e-5, eps=1e-8)
+    steps = int(g["steps"])
+    for s in range(steps):
+        loss = m.get_nll_loss({"batch_obs": t(g["obs%d" % s]), "batch_action": t(g["act%d" % s])}, t(g["target%d" % s]))
+        optim.zero_grad()
+        loss.mean().backward()
+        if s == 0:
+            for k, prm in m.named_parameters():
+                if prm.requires_grad:
+                    assert rel_err(prm.grad.cpu().numpy(), g["g0." + k]) < 1e-4, k
+        optim.step()
+        assert rel_err(loss.detach().cpu().numpy(), g["loss%d" % s]) < 3e-5
+    ref = params_of(g, "p%d." % steps)
+    sd = m.state_dict()
+    for k in ref:
+        mine = sd[k].cpu().numpy()
+        if k.endswith("weight"):
+            assert rel_err(mine, ref[k]) < TOL, k
+        assert rel_err(mine - g["p0." + k], ref[k] - g["p0." + k]) < 2e-3 or np.array_equal(mine, ref[k]), k

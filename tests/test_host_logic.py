@@ -141,7 +141,9 @@ def test_iterators_match_reference_bit_for_bit():
 
 @pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted (GPU box)")
 @pytest.mark.parametrize("cls,kw", [("PlainTransition", {}), ("ExternalMaskTransition", {}), ("PlainRewardMech", {}),
-                                     ("PlainTransition", {"activation_fn_cfg": None, "deterministic": True})])
+                                     ("PlainTransition", {"activation_fn_cfg": None, "deterministic": True}),
+                                     ("TransitionConditionalMutualInformationTest", {}),
+                                     ("TransitionConditionalMutualInformationTest", {"activation_fn_cfg": None, "learn_logvar_bounds": True})])
 def test_same_seed_gives_the_reference_initial_weights(cls, kw):
     """Constructing with the same torch / numpy seeds reproduces the reference's init (truncated normal
     resampling order, layers.py:8-28) and its random initial elites (mlp.py:27) exactly."""
@@ -159,6 +161,10 @@ def test_same_seed_gives_the_reference_initial_weights(cls, kw):
     for k in sa:
         assert torch.equal(sa[k], sb[k]), k
     assert list(a.elite_members) == list(b.elite_members)
+    assert [p.requires_grad for p in a.parameters()] == [p.requires_grad for p in b.parameters()]
+    assert a.model_file_name == b.model_file_name
+    if hasattr(b, "input_mask"):
+        assert torch.equal(a.input_mask.cpu(), b.input_mask.cpu())
 
 
 def test_dynamics_host_logic_without_gpu():
