@@ -484,15 +484,19 @@ int launch_rollout_v5(const RolloutP& p, cudaStream_t st) {
                  "mlp_rollout_f16 v5: accumulators of two tiles (2 x %d + 2 x %d columns) do not fit tensor memory", HP, NH);
     V5Lay lay{};
     const int n_ks = HP / 16;
-    int kt = (512 - 2 * HP - 2 * NH) / 16;  // A-operand K steps per slot that fit the remaining TMEM columns
+    // TMEM columns: [D slot 0 | D slot 1 | A (K steps 0..kt-1) slot 0 | slot 1 | head slot 0 | slot 1]
+    int d1 = HP;
+    if (p.dbg_flags & 1024) d1 = (HP + 31) / 32 * 32;  // profiling experiment: 32-column aligned second accumulator
+    int kt = (512 - d1 - HP - 2 * NH) / 16;  // A-operand K steps per slot that fit the remaining TMEM columns
     if (kt > n_ks) kt = n_ks;
     if (kt > p.H / 16) kt = p.H / 16;  // the K step that holds the ones column (hidden unit H) stays in shared memory
+    CMRL_REQUIRE(kt >= 0, "mlp_rollout_f16 v5: tensor memory layout does not fit");
     lay.kt = kt;
     lay.d_col[0] = 0;
-    lay.d_col[1] = (uint32_t)HP;
-    lay.at_col[0] = 2u * HP;
-    lay.at_col[1] = 2u * HP + 8u * kt;
-    lay.dh_col[0] = 2u * HP + 16u * kt;
+    lay.d_col[1] = (uint32_t)d1;
+    lay.at_col[0] = (uint32_t)(d1 + HP);
+    lay.at_col[1] = lay.at_col[0] + 8u * kt;
+    lay.dh_col[0] = lay.at_col[0] + 16u * kt;
     lay.dh_col[1] = lay.dh_col[0] + (uint32_t)NH;
     uint32_t off = 0;
     for (int l = 0; l <= L; ++l) {

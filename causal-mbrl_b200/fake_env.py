@@ -72,6 +72,9 @@ class VecFakeEnv(VecEnv):
         self.infos_mode = "dicts"
         self.precision = "fp32"  # "fp32": CUDA-core tier (1e-5 parity); "f16": tcgen05 tier (1e-3 parity)
         self.use_graph = True   # device rng_mode: replay the per-step launches from a CUDA graph
+        self.overlap_prepare = True  # device rng_mode: reward / termination / reset draws + buckets on a side stream
+        self._side_stream = None
+        self._prep_reset = None
         self._obs_flip = False
         self.init_obs_pool_size = None  # device rng_mode + get_init_obs_fn: size of the pre-drawn reset pool
         self._device_seed = 0
@@ -124,10 +127,11 @@ class VecFakeEnv(VecEnv):
         b["trunc"] = torch.empty(N, device=dev, dtype=torch.uint8)
         b["term_obs"] = torch.empty((N, O), device=dev, dtype=torch.float32)
         b["n_done"] = torch.zeros(1, device=dev, dtype=torch.int32)
-        b["perm"] = torch.empty(N, device=dev, dtype=torch.int32)
         E = self.dynamics.ensemble_num
-        b["offsets"] = torch.empty(E + 1, device=dev, dtype=torch.int32)
-        b["counters"] = torch.empty(ops.BUCKET_SCRATCH_WARPS * E, device=dev, dtype=torch.int32)
+        for k in ("", "@transition", "@reward_mech", "@termination_mech"):  # one bucket workspace per mechanism (+ a shared one)
+            b["perm" + k] = torch.empty(N, device=dev, dtype=torch.int32)
+            b["offsets" + k] = torch.empty(E + 1, device=dev, dtype=torch.int32)
+            b["counters" + k] = torch.empty(ops.BUCKET_SCRATCH_WARPS * E, device=dev, dtype=torch.int32)
         # pinned host mirrors for the per-step device->host read of the SB3 return values
         b["h_obs"] = torch.empty((N, O), dtype=torch.float32).pin_memory()
         b["h_obs2"] = torch.empty((N, O), dtype=torch.float32).pin_memory()
@@ -185,11 +189,32 @@ class VecFakeEnv(VecEnv):
                                          want_noise=not self.deterministic, stream_base=self._rng_base)  # fmt: skip
         raise ValueError("rng_mode must be 'numpy' or 'device'")
 
-    def _predict(self, mech, obs, act, all_member_out=None):
+    def _selected_path(self, model, need_all):
+        mask = model._kernel_mask()
+        per_sample_mask = mask is not None and (mask.dim() == 4 or (mask.dim() == 3 and mask.shape[1] != model.ensemble_num))
+        return not (need_all or per_sample_mask)
+
+    def _prepare(self, mech, need_all=False):
+        """Everything of a mechanism's prediction that does not depend on the observations: the member / noise draw and
+        (selected-member path) the counting sort of the envs by drawn member, into this mechanism's own workspace."""
+        model = getattr(self.dynamics, mech)
+        idx, noise = self._draw(mech, model._head_dim)
+        bucket = None
+        if self._selected_path(model, need_all):
+            b = self._bufs
+            bucket = ops.member_bucket(idx, model.ensemble_num, b["perm@" + mech], b["offsets@" + mech], b["counters@" + mech])
+        return idx, noise, bucket
+
+    def _predict(self, mech, obs, act, all_member_out=None, prep=None):
         """next value of `mech`'s variable for every env: [N,D] device tensor."""
         model = getattr(self.dynamics, mech)
         N, D = self.num_envs, model._head_dim
-        idx, noise = self._draw(mech, D)
+        if prep is not None:
+            idx, noise, bucket = prep
+            if bucket is not None:
+                return self.predict_selected(model, obs, act, idx, noise, bucket)
+        else:
+            idx, noise = self._draw(mech, D)
         mask = model._kernel_mask()
         per_sample_mask = mask is not None and (mask.dim() == 4 or (mask.dim() == 3 and mask.shape[1] != model.ensemble_num))
         if all_member_out is not None or per_sample_mask:
@@ -200,11 +225,11 @@ class VecFakeEnv(VecEnv):
             return ops.select_sample(mean, logvar, idx, noise)
         return self.predict_selected(model, obs, act, idx, noise)
 
-    def predict_selected(self, model, obs, act, idx, noise):
+    def predict_selected(self, model, obs, act, idx, noise, bucket=None):
         """Selected-member evaluation: bucket envs by drawn member, run the MLP on each member's rows only."""
         b = self._bufs
         N, D, E = obs.shape[0], model._head_dim, model.ensemble_num
-        perm, offsets = ops.member_bucket(idx, E, b["perm"], b["offsets"], b["counters"])
+        perm, offsets = bucket if bucket is not None else ops.member_bucket(idx, E, b["perm"], b["offsets"], b["counters"])
         if self.precision == "f16":
             mn, mx = model._bounds()
             return ops.mlp_rollout_f16(model.packed_f16(), model._parallel_num(), E, obs, act, perm, offsets,
@@ -226,11 +251,53 @@ class VecFakeEnv(VecEnv):
     def _predict_all(self, obs, act, need_all):
         """transition (+ reward / termination mechs): the device part of a step before any host callback."""
         all_out = {} if need_all else None
-        next_obs = self._predict("transition", obs, act, all_out)
-        reward = self._predict("reward_mech", obs, act) if self.learned_reward else None
-        terminal_f = self._predict("termination_mech", obs, act) if self.learned_termination else None
+        preps = self._prepare_all(need_all)
+        next_obs = self._predict("transition", obs, act, all_out, prep=preps.get("transition"))
+        self._join_prepare()
+        reward = self._predict("reward_mech", obs, act, prep=preps.get("reward_mech")) if self.learned_reward else None
+        terminal_f = (self._predict("termination_mech", obs, act, prep=preps.get("termination_mech"))
+                      if self.learned_termination else None)
         penalty = ops.mopo_penalty(all_out["mean"]) if need_all else None
         return next_obs, reward, terminal_f, penalty
+
+    def _prepare_all(self, need_all, reset_source=False):
+        """device rng_mode: the draws and member buckets of every mechanism (and the reset-row draw) are independent of
+        the transition network, so all but the transition's own run on a side stream while the fused transition kernel
+        computes (~20 us of small launches per step off the critical path; fork / join through events, also under
+        CUDA-graph capture).  The Philox stream ids are assigned here in the fixed order transition, reward,
+        termination, reset -- independent of the execution order.  Returns {mech: (idx, noise, bucket)}."""
+        self._prep_reset = None
+        if self.rng_mode != "device":
+            return {}
+        preps = {"transition": self._prepare("transition", need_all)}
+        others = [m for m, on in (("reward_mech", self.learned_reward), ("termination_mech", self.learned_termination)) if on]
+        if not self.overlap_prepare:
+            for m in others:
+                preps[m] = self._prepare(m)
+            if reset_source:
+                self._prep_reset = self._device_reset_source()
+            return preps
+        main = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side = self._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for m in others:
+                preps[m] = self._prepare(m)
+                for x in preps[m][:2]:
+                    if x is not None:
+                        x.record_stream(main)  # allocated on the side stream, consumed on the main one
+            if reset_source:
+                self._prep_reset = self._device_reset_source()
+                self._prep_reset[1].record_stream(main)
+        self._prep_forked = True
+        return preps
+
+    def _join_prepare(self):
+        if getattr(self, "_prep_forked", False):
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+            self._prep_forked = False
 
     def _predict_all_graphed(self, obs, act, need_all):
         """Same, replayed from a CUDA graph in device rng_mode (the graph is re-captured when packed weights, elite
@@ -363,15 +430,17 @@ class VecFakeEnv(VecEnv):
         obs = self._obs_dev
         need_all = self.penalty_coeff != 0
         all_out = {} if need_all else None
-        next_obs = self._predict("transition", obs, actions, all_out)
-        reward = self._predict("reward_mech", obs, actions)
+        preps = self._prepare_all(need_all, reset_source=True)
+        next_obs = self._predict("transition", obs, actions, all_out, prep=preps.get("transition"))
+        self._join_prepare()
+        reward = self._predict("reward_mech", obs, actions, prep=preps.get("reward_mech"))
         terminal_f = terminal_u8 = None
         if self.learned_termination:
-            terminal_f = self._predict("termination_mech", obs, actions)
+            terminal_f = self._predict("termination_mech", obs, actions, prep=preps.get("termination_mech"))
         elif termination is not None:
             terminal_u8 = termination(next_obs, obs, actions).to(torch.uint8).contiguous()
         penalty = ops.mopo_penalty(all_out["mean"]) if need_all else None
-        reset_rows, reset_index = self._device_reset_source()
+        reset_rows, reset_index = self._prep_reset
         ops.env_step_tail(next_obs, reward, terminal_f, terminal_u8, penalty, self.penalty_coeff, self._env_len_dev,
                           self.max_episode_steps, reset_rows, reset_index, obs, b["reward_out"], b["done"], b["trunc"],
                           b["term_obs"], None)  # fmt: skip
