@@ -9,6 +9,9 @@ dev = 'cuda:0'
 peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6557.8
 
 def timeit(f, reps=20):
+    if os.environ.get("HBM_NCU"):  # under ncu: two eager launches per kernel, the profiler times them
+        f(); f(); torch.cuda.synchronize()
+        return 1.0
     for _ in range(2): f()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
