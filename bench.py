@@ -290,17 +290,18 @@ def dominant_kernel_roofline(cm, env, tr, act_dev, args, flush):
         perm, offsets = cm.ops.member_bucket(idx, E)
         mn, mx = tr._bounds()
         pack = tr.packed_f16()
-        tot = 0.0
-        for r in range(reps):
+        # flush, event, kernel, event -- all reps queued before the one synchronize, so that an event pair brackets the
+        # kernel and not the host-side launch latency of an idle GPU
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        torch.cuda.synchronize()
+        for a, c in evs:
             flush.fill_(1.0)
-            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             cm.ops.mlp_rollout_f16(pack, O, E, obs, act_dev, perm, offsets, H, O, cm.ops.HEAD_PARALLEL, True,
                                    cm.ops.ACT_SILU, True, mn, mx, noise)
             c.record()
-            torch.cuda.synchronize()
-            tot += a.elapsed_time(c)
-        ms = tot / reps
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(c) for a, c in evs) / reps
         flops = float(FLOP_SUBNET) * O * N
         achieved = flops / (ms * 1e-3) / 1e12
         return {

@@ -223,6 +223,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
     const int lane = threadIdx.x & 31;
     const uint32_t ns_slack = (p.dbg_flags & 8) ? 256u : 0u;  // poll interval of the roles with slack (head, weights, layer-0 loader)
 
+    if (p.dbg != nullptr && threadIdx.x == 0) {  // profiling: wall-clock (ns) at kernel entry / exit of every CTA
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        p.dbg[(long long)blockIdx.x * 16 + 6] = (long long)g;
+    }
     for (int i = threadIdx.x; i <= p.E; i += blockDim.x) s_off[i] = p.offsets[i];
     if (threadIdx.x == 0) {
         mbar_init(&bars[V5_W_FULL], 1);
@@ -473,6 +478,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
     v3_cluster_sync();
     if (warp == V5_WARP_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+    if (p.dbg != nullptr && threadIdx.x == 0) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        p.dbg[(long long)blockIdx.x * 16 + 7] = (long long)g;
     }
 }
 

@@ -57,4 +57,8 @@ for v in variants:
     print('  MMA slot0 (leader): total, wait_x, wait_a, issue | items', lead[:, :4].mean(0).astype(int), int(items), ' per item:', (lead[:, :4].mean(0) / items).astype(int))
     print('  per-cluster total cycles: min %d mean %d max %d; items min %d max %d' % (lead[:, 0].min(), lead[:, 0].mean(), lead[:, 0].max(), lead[:, 4].min(), lead[:, 4].max()))
     if lead[:, 5].max() > 0: print('  SM clock during the kernel: %.0f MHz (cycles / globaltimer ns)' % (1e3 * lead[:, 0].sum() / lead[:, 5].sum()))
+    if d[:, 6].max() > 0:
+        st, en = d[:, 6], d[:, 7]
+        print('  wall clock (globaltimer): first CTA entry -> last CTA exit %.1f us; entry spread %.1f us; exit spread %.1f us; mean CTA lifetime %.1f us'
+              % ((en.max() - st.min()) / 1e3, (st.max() - st.min()) / 1e3, (en.max() - en.min()) / 1e3, (en - st).mean() / 1e3))
     print('  epilogue warp0: total, wait_d, loop, -, -, -, publish', d[:, 8:15].mean(0).astype(int), ' per item:', (d[:, 8:15].mean(0) / items).astype(int))
