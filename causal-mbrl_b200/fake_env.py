@@ -74,6 +74,7 @@ class VecFakeEnv(VecEnv):
         self.use_graph = True   # device rng_mode: replay the per-step launches from a CUDA graph
         self.overlap_prepare = True  # device rng_mode: reward / termination / reset draws + buckets on a side stream
         self._side_stream = None
+        self._copy_stream = None
         self._prep_reset = None
         self._obs_flip = False
         self.init_obs_pool_size = None  # device rng_mode + get_init_obs_fn: size of the pre-drawn reset pool
@@ -248,11 +249,14 @@ class VecFakeEnv(VecEnv):
         mn, mx = model._bounds()
         return ops.sample_scatter(raw, model._head_layout, perm, N, D, obs if model._residual() else None, mn, mx, noise)
 
-    def _predict_all(self, obs, act, need_all):
-        """transition (+ reward / termination mechs): the device part of a step before any host callback."""
+    def _predict_all(self, obs, act, need_all, after_transition=None):
+        """transition (+ reward / termination mechs): the device part of a step before any host callback.
+        `after_transition(next_obs)` is called as soon as the transition prediction is enqueued."""
         all_out = {} if need_all else None
         preps = self._prepare_all(need_all)
         next_obs = self._predict("transition", obs, act, all_out, prep=preps.get("transition"))
+        if after_transition is not None:
+            after_transition(next_obs)
         self._join_prepare()
         reward = self._predict("reward_mech", obs, act, prep=preps.get("reward_mech")) if self.learned_reward else None
         terminal_f = (self._predict("termination_mech", obs, act, prep=preps.get("termination_mech"))
@@ -299,9 +303,22 @@ class VecFakeEnv(VecEnv):
             torch.cuda.current_stream().wait_stream(self._side_stream)
             self._prep_forked = False
 
-    def _predict_all_graphed(self, obs, act, need_all):
+    def _predict_all_graphed(self, obs, act, need_all, host_next_buf=None):
         """Same, replayed from a CUDA graph in device rng_mode (the graph is re-captured when packed weights, elite
-        sets or the precision changed)."""
+        sets or the precision changed).  host_next_buf: pinned [N,O] tensor that receives next_obs -- the copy is a
+        node of the graph on a branch that starts right after the transition kernel, so it overlaps the reward /
+        termination mechanisms (one graph per destination buffer: the host side ping-pongs between two)."""
+        graphs = getattr(self, "_predict_graphs", None)
+        if graphs is None:
+            graphs = self._predict_graphs = {}
+        slot = 0 if host_next_buf is None else host_next_buf.data_ptr()
+        self._predict_graph = graphs.get(slot)
+        try:
+            return self._predict_all_graphed_one(obs, act, need_all, host_next_buf)
+        finally:
+            graphs[slot] = self._predict_graph
+
+    def _predict_all_graphed_one(self, obs, act, need_all, host_next_buf):
         key = (self.precision, self.deterministic, need_all) + tuple(
             (id(getattr(self.dynamics, m)._packed.get("f16")), id(getattr(self.dynamics, m)._elite_members),
              getattr(self.dynamics, m)._flat.data_ptr() if getattr(self.dynamics, m)._flat is not None else 0)
@@ -322,9 +339,22 @@ class VecFakeEnv(VecEnv):
             g = torch.cuda.CUDAGraph()
             c0 = self._draw_counter
             l0 = _lib.launch_count()
+            copy_stream = None
+            if host_next_buf is not None:
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=self.device)
+                copy_stream = self._copy_stream
+
+            def early_copy(next_obs):
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(copy_stream):
+                    host_next_buf.copy_(next_obs, non_blocking=True)
+
             with torch.cuda.graph(g):
-                out = self._predict_all(obs, act, need_all)
+                out = self._predict_all(obs, act, need_all, early_copy if copy_stream is not None else None)
                 ops.counter_add(self._rng_base, self._draw_counter - c0)
+                if copy_stream is not None:
+                    torch.cuda.current_stream().wait_stream(copy_stream)
             cached = (key, g, out, _lib.launch_count() - l0)
             self._predict_graph = cached
         cached[1].replay()
@@ -346,8 +376,13 @@ class VecFakeEnv(VecEnv):
 
         need_all = self.penalty_coeff != 0
         device_rng = self.rng_mode == "device"
+        h_next = b["h_obs"] if self._obs_flip else b["h_obs2"]
+        self._obs_flip = not self._obs_flip
+        host_callbacks = not (self.learned_reward and self.learned_termination)
+        copied_in_graph = False
         if device_rng and self.use_graph:
-            next_obs, reward, terminal_f, penalty = self._predict_all_graphed(obs, act, need_all)
+            next_obs, reward, terminal_f, penalty = self._predict_all_graphed(obs, act, need_all, h_next if host_callbacks else None)
+            copied_in_graph = host_callbacks
         else:
             next_obs, reward, terminal_f, penalty = self._predict_all(obs, act, need_all)
         if penalty is not None and self.logger is not None:
@@ -359,10 +394,9 @@ class VecFakeEnv(VecEnv):
         # current obs of the next step -- the full post-reset obs is never read back a second time.
         host_next = None
         terminal_u8 = None
-        h_next = b["h_obs"] if self._obs_flip else b["h_obs2"]
-        self._obs_flip = not self._obs_flip
-        if not (self.learned_reward and self.learned_termination):
-            h_next.copy_(next_obs, non_blocking=True)
+        if host_callbacks:
+            if not copied_in_graph:
+                h_next.copy_(next_obs, non_blocking=True)
             stream.synchronize()
             host_next = h_next.numpy()
             host_obs = self._current_batch_obs
