@@ -527,7 +527,7 @@ def tc_variant(request, cm):
     cm.ops.TC_VARIANT = old
 
 
-@pytest.mark.parametrize("kind,N,H", [("plain", 300, 200), ("extmask", 1000, 200), ("reward", 777, 200), ("plain_relu", 130, 64),
+@pytest.mark.parametrize("kind,N,H", [("plain", 3, 200), ("reward", 1, 200), ("extmask", 257, 200), ("plain", 300, 200), ("extmask", 1000, 200), ("reward", 777, 200), ("plain_relu", 130, 64),
                                       ("extmask", 5, 40), ("plain", 20000, 200), ("extmask", 100000, 200)])
 def test_tcgen05_rollout_vs_fp32_tier(cm, tc_variant, kind, N, H):
     """The fused tcgen05 kernel (fp16 operands, fp32 accumulate) against the fp32 tier on the same draws:
