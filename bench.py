@@ -272,7 +272,13 @@ def run_native(args):
         }  # fmt: skip
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured the NCCL all-reduce (data-parallel training) still reference the communicator and can
+        # stall an orderly destroy_process_group(): synchronise, flush and leave
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def dominant_kernel_roofline(cm, env, tr, act_dev, args, flush):
@@ -353,7 +359,8 @@ def time_train(cm, dyn_unused, dev, args, world, barrier, B=256, n_batches=200, 
 
     from oracle.refshim import DuckReplayBuffer
 
-    N = int(B * n_batches / 0.8)
+    Bg = B * world  # data parallel: the global batch is sharded by rows, B rows per member stay on every GPU (weak scaling)
+    N = int(Bg * n_batches / 0.8)
     rng = np.random.default_rng(7)
     obs = rng.normal(size=(N, O)).astype(np.float32)
     act = rng.uniform(-1, 1, size=(N, A)).astype(np.float32)
@@ -365,7 +372,9 @@ def time_train(cm, dyn_unused, dev, args, world, barrier, B=256, n_batches=200, 
     torch.manual_seed(1)
     tr = cm.PlainTransition(O, A, ensemble_num=E, elite_num=ELITE, hid_size=H, activation_fn_cfg=SILU, device=dev)
     dyn = cm.PlainEnsembleDynamics(tr, learned_reward=False)
-    train_it, _ = dyn.dataset_split(buf, 0.2, B)
+    if world > 1:
+        dyn.enable_data_parallel()  # one NCCL all-reduce (sum) of the flat gradient arena per step, inside the captured graph
+    train_it, _ = dyn.dataset_split(buf, 0.2, Bg)
     steps = len(train_it)
     dyn.train_epoch_device(train_it, "transition")  # warm-up epoch: uploads the set, captures the graph
     barrier()
@@ -381,9 +390,11 @@ def time_train(cm, dyn_unused, dev, args, world, barrier, B=256, n_batches=200, 
     out = {"metric": "ensemble_train_member_samples_per_sec", "value": E * B * world / (ms * 1e-3), "unit": "member-samples/s",
            "ms_per_step": ms, "steps_per_epoch": steps, "epoch_mean_nll": loss,
            "config": "C4-shaped: PlainTransition E=7 4x200 SiLU O=5 A=1, bs %d per member per GPU, fp32-grade tier "
-                     "(GEMM tier %s: %s), device-resident epoch (on-device bootstrap gather + CUDA-graph replay), replicas"
+                     "(GEMM tier %s: %s), device-resident epoch (on-device bootstrap gather + CUDA-graph replay), %s"
                      % (B, cm.ops.TRAIN_GEMM_TIER, "tcgen05 3xTF32 forward/dx, FFMA dw" if B >= cm.ops.TRAIN_GEMM_TC_MIN_ROWS
-                        else "FFMA: latency bound at this batch size")}  # fmt: skip
+                        else "FFMA: latency bound at this batch size",
+                        "single GPU" if world == 1 else "data parallel over %d GPUs: global batch %d rows per member sharded by rows, "
+                        "one NCCL all-reduce of the flat gradient arena per step" % (world, Bg))}  # fmt: skip
     if with_cpu and not args.no_cpu_baseline and int(os.environ.get("RANK", "0")) == 0:
         out["cpu_baseline"] = time_port_train(B)
     return out

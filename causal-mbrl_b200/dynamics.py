@@ -290,7 +290,7 @@ class BaseDynamics:
         assert isinstance(dataset, BootstrapIterator)
         model = getattr(self, mech)
         optim = getattr(self, "{}_optimizer".format(mech))
-        fast = (not model.deterministic and self.dp_group is None and dataset._bootstrap_iter
+        fast = (not model.deterministic and dataset._bootstrap_iter
                 and not any(q.requires_grad for q in model._bounds()))  # fmt: skip
         if not fast:
             return float(self.train(dataset, mech=mech).mean().item())
@@ -376,23 +376,29 @@ class _DeviceEpochRunner:
         self.start = torch.zeros(1, dtype=torch.int32, device=dev)
         E, B = dataset.ensemble_size, dataset.batch_size
         self.E, self.B = E, B
-        self.b_obs = torch.empty((E, B, self.obs.shape[1]), device=dev)
-        self.b_act = torch.empty((E, B, self.act.shape[1]), device=dev)
-        self.b_tgt = torch.empty((E, B, self.target.shape[1]), device=dev)
+        # data parallel (every rank holds the same set and epoch order): this rank gathers and trains only its row slice
+        # of each batch; train_step all-reduces the flat gradient arena and scales the loss by the global row count
+        self.row_slice = dp_row_slice(B, dyn.dp_world, dyn.dp_rank) if dyn.dp_group is not None else slice(0, B)
+        Bl = self.Bl = self.row_slice.stop - self.row_slice.start
+        self.b_obs = torch.empty((E, Bl, self.obs.shape[1]), device=dev)
+        self.b_act = torch.empty((E, Bl, self.act.shape[1]), device=dev)
+        self.b_tgt = torch.empty((E, Bl, self.target.shape[1]), device=dev)
         self.loss_sum = torch.zeros((), device=dev, dtype=torch.float64)
         self.graph = None
 
     def _step(self):
-        ops.bootstrap_gather(self.obs, self.act, self.target, self.member_idx, self.order, self.start, self.B, self.B,
+        # `start` points at this rank's first row of the batch and advances by the global batch size
+        ops.bootstrap_gather(self.obs, self.act, self.target, self.member_idx, self.order, self.start, self.B, self.Bl,
                              self.b_obs, self.b_act, self.b_tgt)  # fmt: skip
-        loss = self.dyn.train_step(self.mech, self.b_obs, self.b_act, self.b_tgt, want_loss=True, graphable=True)
+        loss = self.dyn.train_step(self.mech, self.b_obs, self.b_act, self.b_tgt, want_loss=True, graphable=True,
+                                   grad_rows=self.B if self.dyn.dp_group is not None else None)  # fmt: skip
         self.loss_sum += loss.sum(dtype=torch.float64)
 
     def run_epoch(self):
         ds = self.dataset
         iter(ds)  # reshuffles exactly like the reference iterator (one rng.permutation per epoch)
         self.order.copy_(torch.from_numpy(np.ascontiguousarray(ds._order, dtype=np.int32)), non_blocking=True)
-        self.start.zero_()
+        self.start.fill_(self.row_slice.start)
         self.loss_sum.zero_()
         model = getattr(self.dyn, self.mech)
         model._nll_reg()  # host-side constant, cached before any capture
@@ -400,6 +406,9 @@ class _DeviceEpochRunner:
         getattr(self.dyn, "{}_optimizer".format(self.mech)).prepare_graphable()
         n_full = self.N // self.B
         if self.use_graph and self.graph is None and n_full > 0:
+            if self.dyn.dp_group is not None:
+                self._step()  # one eager step first: NCCL sets its communicator up outside the capture
+                n_full -= 1
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             l0 = _lib.launch_count()
@@ -413,15 +422,21 @@ class _DeviceEpochRunner:
                 _lib.note_replayed(self.graph_launches)
             else:
                 self._step()
-        total = n_full * self.B
+        total = (self.N // self.B) * self.B
         rem = self.N - total
         if rem > 0:  # ragged last batch: same rows the reference iterator would yield
-            idx = torch.from_numpy(np.ascontiguousarray(ds._order[total:], dtype=np.int64)).to(self.obs.device)
-            rows = self.member_idx.long()[:, idx]  # [E, rem]
+            dp = self.dyn.dp_group is not None
+            sl = dp_row_slice(rem, self.dyn.dp_world, self.dyn.dp_rank) if dp else slice(0, rem)
+            idx = torch.from_numpy(np.ascontiguousarray(ds._order[total:][sl], dtype=np.int64)).to(self.obs.device)
+            rows = self.member_idx.long()[:, idx]  # [E, local rem]
             loss = self.dyn.train_step(self.mech, self.obs[rows], self.act[rows], self.target[rows], want_loss=True,
-                                       graphable=True)  # fmt: skip
+                                       graphable=True, grad_rows=rem if dp else None)  # fmt: skip
             self.loss_sum += loss.sum(dtype=torch.float64)
         ds._current_batch = len(ds)  # the iterator is exhausted, like after a `for batch in dataset` loop
+        if self.dyn.dp_group is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(self.loss_sum, op=dist.ReduceOp.SUM, group=self.dyn.dp_group)
         denom = float(self.E * self.N * self.b_tgt.shape[-1])
         return float(self.loss_sum.item()) / denom
 

@@ -10,6 +10,12 @@ import cmrl_b200 as cm
 from cmrl_b200.dynamics import dp_row_slice
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+_logf = open(os.path.join(os.environ.get("GRAFT_REPO_ROOT", "."), "gpurun_out", "dp_rank%d.log" % rank), "w") if os.path.isdir(os.path.join(os.environ.get("GRAFT_REPO_ROOT", "."), "gpurun_out")) else sys.stderr
+
+
+def mark(*a):
+    print(*a, file=_logf, flush=True)
+
 torch.cuda.set_device(local)
 dev = "cuda:%d" % local
 dist.init_process_group("nccl", device_id=torch.device(dev))
@@ -52,6 +58,42 @@ if rank == 0:
     print("DP over NCCL, world %d: weights identical on all ranks: %s; weights vs single-process full batch: rel %.2e; "
           "update (20 Adam steps) rel %.2e; %.3f ms per DP step (bs %d per member, eager launches)"
           % (world, same, float((flat_dp - flat_1).abs().max() / flat_1.abs().max()), upd_err, dt * 1e3, B))
+# ---- device-resident epoch (graph-captured step with the all-reduce inside) vs the same epoch on one process ----------
+from oracle.refshim import DuckReplayBuffer
+
+def epoch_weights(dp):
+    dyn2 = build()
+    if dp:
+        dyn2.enable_data_parallel()
+    r2 = np.random.default_rng(3)
+    n = 256 * 12
+    o = r2.normal(size=(n, O)).astype(np.float32); a = r2.uniform(-1, 1, size=(n, A)).astype(np.float32)
+    buf = DuckReplayBuffer(o, a, (o + 0.1 * np.tanh(o)).astype(np.float32), np.zeros(n, np.float32), np.zeros(n, bool))
+    real = np.random.default_rng
+    seeds = iter(range(500, 600))
+    np.random.default_rng = lambda seed=None: real(next(seeds) if seed is None else seed)
+    try:
+        it, _ = dyn2.dataset_split(buf, 0.2, 256)
+        mark('split done, dp', dp)
+        loss = dyn2.train_epoch_device(it, "transition")
+        mark('epoch 1 done', loss)
+        loss = dyn2.train_epoch_device(it, "transition")
+        mark('epoch 2 done', loss)
+    finally:
+        np.random.default_rng = real
+    return dyn2.transition.flat_parameters()[0].clone(), loss
+
+mark('starting DP device epochs')
+w_dp, loss_dp = epoch_weights(True)
+mark('DP device epochs done')
+if rank == 0:
+    w_1, loss_1 = epoch_weights(False)
+    print("device-resident epochs (CUDA graph with the NCCL all-reduce captured): DP loss %.6f vs single %.6f; weights rel %.2e"
+          % (loss_dp, loss_1, float((w_dp - w_1).abs().max() / w_1.abs().max())))
 same_t = torch.tensor([1 if same else 0], device=dev); dist.all_reduce(same_t, op=dist.ReduceOp.MIN)
 assert int(same_t.item()) == 1
-dist.destroy_process_group()
+dist.barrier()
+torch.cuda.synchronize()
+mark('done')
+sys.stdout.flush()
+os._exit(0)  # captured graphs still reference the NCCL communicator: skip the orderly teardown
