@@ -349,6 +349,16 @@ def dominant_kernel_roofline(cm, env, tr, act_dev, args, flush):
     }  # fmt: skip
 
 
+class _ReplayBufferFields:
+    """The SB3 `ReplayBuffer` fields `BaseDynamics.dataset_split` reads (base_dynamics.py:131-138), n_envs = 1."""
+
+    def __init__(self, obs, act, next_obs, rew, done):
+        n = obs.shape[0]
+        self.buffer_size, self.full, self.pos = n, True, 0
+        self.observations, self.next_observations = obs[:, None, :], next_obs[:, None, :]
+        self.actions, self.rewards, self.dones = act[:, None, :], rew.reshape(n, 1), done.reshape(n, 1)
+
+
 def time_train(cm, dyn_unused, dev, args, world, barrier, B=256, n_batches=200, with_cpu=True):
     """Second half of the metric: ensemble train member-samples/s.  C4-shaped: PlainTransition E=7 (4x200, SiLU, O=5,
     A=1), bs 256 per member, fp32 tier, one device-resident epoch (on-device bootstrap gather + CUDA-graph replay of
@@ -356,8 +366,6 @@ def time_train(cm, dyn_unused, dev, args, world, barrier, B=256, n_batches=200, 
     `enable_data_parallel`, not timed here)."""
     import torch
     import torch.distributed as dist
-
-    from oracle.refshim import DuckReplayBuffer
 
     Bg = B * world  # data parallel: the global batch is sharded by rows, B rows per member stay on every GPU (weak scaling)
     N = int(Bg * n_batches / 0.8)
@@ -368,7 +376,7 @@ def time_train(cm, dyn_unused, dev, args, world, barrier, B=256, n_batches=200, 
     K = rng.normal(size=(A, O)).astype(np.float32)
     nxt = (obs + 0.1 * np.tanh(obs @ M + act @ K) + 0.01 * rng.normal(size=(N, O))).astype(np.float32)
     rew = (np.cos(obs[:, 0]) - 0.1 * (act**2).sum(-1)).astype(np.float32)
-    buf = DuckReplayBuffer(obs, act, nxt, rew, np.zeros(N, bool))
+    buf = _ReplayBufferFields(obs, act, nxt, rew, np.zeros(N, bool))
     torch.manual_seed(1)
     tr = cm.PlainTransition(O, A, ensemble_num=E, elite_num=ELITE, hid_size=H, activation_fn_cfg=SILU, device=dev)
     dyn = cm.PlainEnsembleDynamics(tr, learned_reward=False)

@@ -59,7 +59,14 @@ if rank == 0:
           "update (20 Adam steps) rel %.2e; %.3f ms per DP step (bs %d per member, eager launches)"
           % (world, same, float((flat_dp - flat_1).abs().max() / flat_1.abs().max()), upd_err, dt * 1e3, B))
 # ---- device-resident epoch (graph-captured step with the all-reduce inside) vs the same epoch on one process ----------
-from oracle.refshim import DuckReplayBuffer
+
+class DuckReplayBuffer:  # the SB3 ReplayBuffer fields dataset_split reads (base_dynamics.py:131-138)
+    def __init__(self, obs, act, next_obs, rew, done):
+        n = obs.shape[0]
+        self.buffer_size, self.full, self.pos = n, True, 0
+        self.observations, self.next_observations = obs[:, None, :], next_obs[:, None, :]
+        self.actions, self.rewards, self.dones = act[:, None, :], rew.reshape(n, 1), done.reshape(n, 1)
+
 
 def epoch_weights(dp):
     dyn2 = build()

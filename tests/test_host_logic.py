@@ -2,6 +2,7 @@
 mounted) drop-in equivalences against the unmodified reference classes.  No CUDA compute calls."""
 import ctypes
 import os
+import sys
 import re
 import tempfile
 
@@ -37,6 +38,21 @@ def test_no_cpu_fallback():
         m.forward(torch.zeros(7, 3, 5), torch.zeros(7, 3, 1))
     with pytest.raises(cm._lib.CmrlB200Error):
         cm.EnsembleLinearLayer(3, 4, ensemble_num=2)(torch.zeros(2, 5, 3))
+
+
+def test_oracle_is_test_infrastructure_only():
+    """Nothing in the product package, and nothing on the measured (native) arm of bench.py, touches oracle/."""
+    import glob
+    import inspect
+    import re
+
+    for f in glob.glob(os.path.join(ROOT, "causal-mbrl_b200", "*.py")) + glob.glob(os.path.join(ROOT, "cmrl_b200", "*.py")):
+        assert not re.search(r"^\s*(from|import)\s+oracle", open(f).read(), re.M), f
+    sys.path.insert(0, ROOT)
+    import bench
+
+    for fn in (bench.run_native, bench.time_train, bench.dominant_kernel_roofline):
+        assert not re.search(r"(from|import)\s+oracle", inspect.getsource(fn)), fn.__name__
 
 
 def test_unsupported_activation_is_loud():
