@@ -76,6 +76,7 @@ class VecFakeEnv(VecEnv):
         self._side_stream = None
         self._copy_stream = None
         self._prep_reset = None
+        self._tail_graphs = {}
         self._obs_flip = False
         self.init_obs_pool_size = None  # device rng_mode + get_init_obs_fn: size of the pre-drawn reset pool
         self._device_seed = 0
@@ -402,26 +403,55 @@ class VecFakeEnv(VecEnv):
             host_obs = self._current_batch_obs
             if not self.learned_reward:
                 r = np.asarray(self.reward_fn(host_next, host_obs, self._current_batch_action), dtype=np.float32)
-                reward = torch.from_numpy(np.ascontiguousarray(r.reshape(N, 1))).to(self.device, non_blocking=True)
+                reward = b["reward"]
+                reward.copy_(torch.from_numpy(np.ascontiguousarray(r.reshape(N, 1))), non_blocking=False)
             if not self.learned_termination:
                 t = np.asarray(self.termination_fn(host_next, host_obs, self._current_batch_action))
                 b["h_term_u8"].numpy()[...] = t.reshape(N) != 0
-                terminal_u8 = b["term_u8"]
-                terminal_u8.copy_(b["h_term_u8"], non_blocking=True)
+                terminal_u8 = b["term_u8"]  # uploaded by tail_and_readback()
 
-        reset_rows = reset_index = None
-        if device_rng:
-            reset_rows, reset_index = self._device_reset_source()
-        ops.env_step_tail(next_obs, reward, terminal_f, terminal_u8, penalty, self.penalty_coeff, self._env_len_dev,
-                          self.max_episode_steps, reset_rows, reset_index, obs, b["reward_out"], b["done"], b["trunc"],
-                          b["term_obs"] if host_next is None else None, None)  # fmt: skip
+        def tail_and_readback():
+            """reset-row draw, fused tail, device -> host copies of the SB3 return values (all asynchronous)"""
+            if terminal_u8 is not None:
+                terminal_u8.copy_(b["h_term_u8"], non_blocking=True)
+            reset_rows = reset_index = None
+            if device_rng:
+                reset_rows, reset_index = self._device_reset_source(tail=True)
+            ops.env_step_tail(next_obs, reward, terminal_f, terminal_u8, penalty, self.penalty_coeff, self._env_len_dev,
+                              self.max_episode_steps, reset_rows, reset_index, obs, b["reward_out"], b["done"], b["trunc"],
+                              b["term_obs"] if host_next is None else None, None)  # fmt: skip
+            if host_next is None:  # fully learned step: the pre-reset next_obs comes back now
+                h_next.copy_(b["term_obs"], non_blocking=True)
+            b["h_reward"].copy_(b["reward_out"], non_blocking=True)
+            b["h_done"].copy_(b["done"], non_blocking=True)
+            b["h_trunc"].copy_(b["trunc"], non_blocking=True)
+
+        if device_rng and self.use_graph and copied_in_graph == host_callbacks and (self.learned_reward or reward is b["reward"]):
+            # second half of the step as one graph replay (5-6 launches / copies otherwise issued one by one from Python);
+            # every operand is a fixed buffer: the predict graph's outputs, the pinned mirrors, this step's h_next
+            if self._pool_dev is None or (self._reset_by_buffer and self._pool_rows != self._upper_bound()):
+                c_keep = self._draw_counter
+                self._device_reset_source(tail=True)  # (re)builds the reset pool outside any capture
+                self._draw_counter = c_keep
+            key = (id(next_obs), id(reward), id(terminal_f), terminal_u8 is not None, id(penalty), host_next is None,
+                   h_next.data_ptr() if host_next is None else 0, self._pool_dev.data_ptr(), self._pool_rows,
+                   self.penalty_coeff, self.max_episode_steps)
+            tg = self._tail_graphs.get(key)
+            if tg is None:
+                if len(self._tail_graphs) >= 4:
+                    self._tail_graphs.clear()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                l0 = _lib.launch_count()
+                with torch.cuda.graph(g):
+                    tail_and_readback()
+                tg = self._tail_graphs[key] = (g, _lib.launch_count() - l0)
+            tg[0].replay()
+            _lib.note_replayed(tg[1])
+        else:
+            tail_and_readback()
 
         # ---- device -> host: the SB3 return values ------------------------------------------------------------------
-        if host_next is None:  # fully learned step: the pre-reset next_obs comes back now
-            h_next.copy_(b["term_obs"], non_blocking=True)
-        b["h_reward"].copy_(b["reward_out"], non_blocking=True)
-        b["h_done"].copy_(b["done"], non_blocking=True)
-        b["h_trunc"].copy_(b["trunc"], non_blocking=True)
         ret_obs = None
         if host_next is not None:
             ret_obs = host_next.copy()  # the returned copy is made while the tail kernel and the small copies run
@@ -617,8 +647,11 @@ class VecFakeEnv(VecEnv):
         assert self.get_init_obs_fn is not None
         return np.asarray(self.get_init_obs_fn(n)).reshape(n, -1)
 
-    def _device_reset_source(self):
-        """(rows [R,O] device, reset_index [N] device) for the fused tail in device rng_mode."""
+    def _device_reset_source(self, tail=False):
+        """(rows [R,O] device, reset_index [N] device) for the fused tail in device rng_mode.  tail=True (host-facing
+        step): the draw may be replayed from its own CUDA graph, where its stream id is a capture-time constant plus the
+        device-side base the predict graph advances -- a disjoint id range (bit 40) keeps it from ever coinciding with a
+        member / noise draw of another step."""
         N = self.num_envs
         if self._reset_by_buffer:
             ub = self._upper_bound()
@@ -631,8 +664,8 @@ class VecFakeEnv(VecEnv):
                 rows = np.ascontiguousarray(np.asarray(self.get_init_obs_fn(size)).reshape(size, -1), dtype=np.float32)
                 self._pool_dev, self._pool_rows = torch.from_numpy(rows).to(self.device), size
         self._draw_counter += 1
-        idx = ops.draw_uniform_index(self._device_seed, self._draw_counter, N, self._pool_rows, self.device,
-                                     stream_base=self._rng_base)  # fmt: skip
+        idx = ops.draw_uniform_index(self._device_seed, self._draw_counter + ((1 << 40) if tail else 0), N, self._pool_rows,
+                                     self.device, stream_base=self._rng_base)  # fmt: skip
         return self._pool_dev, idx
 
     def reset(self, *, seed: Optional[int] = None, return_info: bool = False, options: Optional[dict] = None):
