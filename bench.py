@@ -191,6 +191,7 @@ def run_native(args):
                get_init_obs_fn=lambda n: rng.normal(size=(n, O)).astype(np.float32), max_episode_steps=1000)  # fmt: skip
     env.rng_mode = "device"
     env.infos_mode = "shared"
+    env.return_views = True  # step() returns the pinned observation ring buffer itself (valid for two steps), no 2 MB host copy
     if hasattr(env, "precision"):
         env.precision = args.precision
     env.seed(rank)
@@ -264,7 +265,7 @@ def run_native(args):
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "VecFakeEnv.step_async/step_wait, rng_mode=device, infos_mode=shared, host termination_fn"},
+                    "api": "VecFakeEnv.step_async/step_wait, rng_mode=device, infos_mode=shared, return_views=True, host termination_fn"},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,

@@ -72,6 +72,7 @@ class VecFakeEnv(VecEnv):
         self.infos_mode = "dicts"
         self.precision = "fp32"  # "fp32": CUDA-core tier (1e-5 parity); "f16": tcgen05 tier (1e-3 parity)
         self.use_graph = True   # device rng_mode: replay the per-step launches from a CUDA graph
+        self.return_views = False    # step(): hand out the pinned observation buffer itself instead of a copy (opt-in)
         self.overlap_prepare = True  # device rng_mode: reward / termination / reset draws + buckets on a side stream
         self._side_stream = None
         self._copy_stream = None
@@ -453,12 +454,15 @@ class VecFakeEnv(VecEnv):
 
         # ---- device -> host: the SB3 return values ------------------------------------------------------------------
         ret_obs = None
-        if host_next is not None:
+        if host_next is not None and not self.return_views:
             ret_obs = host_next.copy()  # the returned copy is made while the tail kernel and the small copies run
         stream.synchronize()
-        if ret_obs is None:
+        if host_next is None:
             host_next = h_next.numpy()
-            ret_obs = host_next.copy()
+        if ret_obs is None:
+            # return_views: the observation array handed out IS the pinned ping-pong buffer (valid until the step after
+            # the next one, which is how SB3's collectors use it: `_last_obs` is replaced after every step)
+            ret_obs = host_next if self.return_views else host_next.copy()
         batch_done = b["h_done"].numpy().view(np.bool_)
         batch_truncate = b["h_trunc"].numpy().view(np.bool_)
         done_idx = np.nonzero(batch_done)[0]
@@ -475,7 +479,8 @@ class VecFakeEnv(VecEnv):
                 rows = np.ascontiguousarray(self._host_reset_rows(done_idx.size), dtype=np.float32)
                 obs.index_copy_(0, torch.from_numpy(done_idx).to(self.device), torch.from_numpy(rows).to(self.device))
             host_next[done_idx] = rows
-            ret_obs[done_idx] = rows
+            if ret_obs is not host_next:
+                ret_obs[done_idx] = rows
         self._current_batch_obs = host_next
 
         infos = self._make_infos(batch_truncate, done_idx, terminal_rows)

@@ -881,3 +881,42 @@ def test_cmi_test_network_train_golden(cm, name):
         if k.endswith("weight"):
             assert rel_err(mine, ref[k]) < TOL, k
         assert rel_err(mine - g["p0." + k], ref[k] - g["p0." + k]) < 2e-3 or np.array_equal(mine, ref[k]), k
+
+
+def _host_term_env(cm, N, seed, max_steps):
+    torch.manual_seed(3)
+    tr = cm.PlainTransition(4, 2, hid_size=64, activation_fn_cfg=SILU, device=DEV)
+    rw = cm.PlainRewardMech(4, 2, hid_size=64, activation_fn_cfg=SILU, device=DEV)
+    for m in (tr, rw):
+        m.set_elite_members([0, 2, 3, 5, 6])
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw)
+    rng = np.random.default_rng(5)
+    env = cm.VecFakeEnv(N, None, None)
+    env.set_up(dyn, termination_fn=lambda n, o, a: np.abs(n[:, :1]) > 1.5,
+               get_init_obs_fn=lambda n: rng.normal(size=(n, 4)).astype(np.float32), max_episode_steps=max_steps)
+    env.rng_mode = "device"
+    env.seed(seed)
+    env.reset()
+    return env
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("make", [_rollout_env, _host_term_env], ids=["learned_termination", "host_termination_fn"])
+def test_step_return_views_equals_copies(cm, make):
+    """`return_views=True` hands out the pinned observation ring buffer instead of a copy: same values, and the array of
+    step t stays intact while step t+1 runs (two-buffer ring), which is what SB3's collectors rely on."""
+    N = 500
+    env_a, env_b = make(cm, N, 4, max_steps=3), make(cm, N, 4, max_steps=3)
+    env_b.return_views = True
+    rng = np.random.default_rng(0)
+    prev = None
+    for t_ in range(5):
+        act = rng.uniform(-1, 1, size=(N, 2)).astype(np.float32)
+        oa, ra, da, ia = env_a.step(act)
+        ob, rb, db, ib = env_b.step(act)
+        assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and np.array_equal(da, db)
+        for i in np.nonzero(da)[0][:20]:
+            assert np.array_equal(ia[i]["terminal_observation"], ib[i]["terminal_observation"])
+        if prev is not None:
+            assert np.array_equal(prev[0], prev[1])  # last step's view was not overwritten by this step
+        prev = (oa.copy(), ob)
