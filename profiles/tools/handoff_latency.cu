@@ -7,7 +7,7 @@
 //   F  13 such MMAs + commit -> wait
 //   G  full hand-off loop of the kernels: [32 warps arrive on the leader barrier] -> issuer wakes -> 13 MMAs + commit ->
 //      all warps of both CTAs wake -> arrive again ... (cycles per loop = the floor of one layer step of one tile slot)
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/handoff profiles/tools/handoff_latency.cu && /tmp/handoff
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o profiles/tools/handoff_bin profiles/tools/handoff_latency.cu && profiles/tools/handoff_bin  (the binary is git-ignored)
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
