@@ -290,6 +290,7 @@ int launch_rollout_v2(const RolloutP& p, cudaStream_t st);
 int launch_rollout_v3(const RolloutP& p, cudaStream_t st);
 int launch_rollout_v4(const RolloutP& p, cudaStream_t st);
 int launch_rollout_v5(const RolloutP& p, cudaStream_t st);
+int launch_rollout_v6(const RolloutP& p, cudaStream_t st);
 }
 }  // namespace cmrl
 
@@ -338,12 +339,14 @@ extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, co
         p.layer_off[l] = layer_off_halfs[l];
         p.layer_k[l] = layer_k[l];
         p.layer_n[l] = layer_n[l];
-        CMRL_REQUIRE(layer_k[l] % 16 == 0 && layer_n[l] % 16 == 0 && layer_n[l] <= 256 && layer_n[l] >= 16,
-                     "mlp_rollout_f16: layer %d dims must be multiples of 16 with N <= 256", l);
-        if (l >= 1) CMRL_REQUIRE(layer_k[l] == HP, "mlp_rollout_f16: hidden width must be uniform");
-        if (l < num_layers) CMRL_REQUIRE(layer_n[l] == HP, "mlp_rollout_f16: hidden width must be uniform");
+        CMRL_REQUIRE(layer_k[l] % 16 == 0 && layer_n[l] % 16 == 0 && layer_n[l] <= (variant == 6 ? 512 : 256) && layer_n[l] >= 16,
+                     "mlp_rollout_f16: layer %d dims must be multiples of 16 with N <= 256 (512 for variant 6)", l);
+        if (variant != 6) {
+            if (l >= 1) CMRL_REQUIRE(layer_k[l] == HP, "mlp_rollout_f16: hidden width must be uniform");
+            if (l < num_layers) CMRL_REQUIRE(layer_n[l] == HP, "mlp_rollout_f16: hidden width must be uniform");
+        }
     }
-    CMRL_REQUIRE(H < HP, "mlp_rollout_f16: padded width must leave a bias slot (H < HP)");
+    CMRL_REQUIRE(variant == 6 || H < HP, "mlp_rollout_f16: padded width must leave a bias slot (H < HP)");
     CMRL_REQUIRE(layout == CMRL_HEAD_PLAIN ? layer_n[num_layers] >= (gaussian ? 2 : 1) * head_dim : true,
                  "mlp_rollout_f16: head too narrow");
     p.num_layers = num_layers;
@@ -369,11 +372,12 @@ extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, co
     p.pred = pred;
     p.dbg = g_dbg_buffer;
     p.dbg_flags = g_dbg_flags;
+    if (variant == 6) return tc::launch_rollout_v6(p, (cudaStream_t)stream);
     if (variant == 5) return tc::launch_rollout_v5(p, (cudaStream_t)stream);
     if (variant == 4) return tc::launch_rollout_v4(p, (cudaStream_t)stream);
     if (variant == 3) return tc::launch_rollout_v3(p, (cudaStream_t)stream);
     if (variant == 2) return tc::launch_rollout_v2(p, (cudaStream_t)stream);
-    CMRL_REQUIRE(variant == 1, "mlp_rollout_f16: variant must be 1 (streamed weights), 2 / 4 (weight-stationary CTA pairs, 256-row tiles), 3 (pairs, two 128-row tiles in flight) or 5 (pairs, two 256-row tiles, A operand partly in TMEM)");
+    CMRL_REQUIRE(variant == 1, "mlp_rollout_f16: variant must be 1 (streamed weights), 2 / 4 (weight-stationary CTA pairs, 256-row tiles), 3 (pairs, two 128-row tiles in flight), 5 (pairs, two 256-row tiles, A operand partly in TMEM) or 6 (pairs, streamed weights, wide hidden)");
     size_t w_stage = 0;
     int kmax = 0;
     for (int l = 0; l <= num_layers; ++l) {

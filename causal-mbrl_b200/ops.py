@@ -360,9 +360,14 @@ def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0), head_interleave
         layer_n.append(n_pad)
         layer_off.append(off)
         off += k_pad * n_pad
-    # hidden outputs feed the next layer's K (incl. the bias slot): widen N of hidden layers to the next K
-    for i in range(len(weights) - 1):
-        layer_n[i] = layer_k[i + 1]
+    # Wide models (hidden a multiple of 16 whose padded width no longer fits the weight-stationary kernels) keep N = hidden:
+    # the streamed-weights kernel (variant 6) carries the bias input in a K step of its own.  Otherwise hidden outputs
+    # feed the next layer's K including the bias slot: widen N of hidden layers to the next K.
+    hid = weights[0].shape[-1]
+    wide = len(weights) > 1 and hid % 16 == 0 and hid > 207 and all(w.shape[-1] == hid for w in weights[:-1])
+    if not wide:
+        for i in range(len(weights) - 1):
+            layer_n[i] = layer_k[i + 1]
     layer_off, off = [], 0
     for k_pad, n_pad in zip(layer_k, layer_n):
         layer_off.append(off)
@@ -381,7 +386,8 @@ def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0), head_interleave
 # Kernel variant of the tensor-core tier.  None = first that accepts the shape: 5 (CTA pairs, two 256-row tiles in
 # flight, A operand partly in tensor memory; head <= 16 columns for hidden 200), 4 (CTA pairs, 256-row tiles, chased
 # epilogue; head <= 32 columns), 3 (pairs, two 128-row tiles in flight; head <= 128 columns), 1 (single-CTA tiles,
-# per-layer streamed weights).  All need the padded hidden width to fit shared memory (hidden <= 207); wider models use
+# per-layer streamed weights) -- these need the padded hidden width to fit shared memory (hidden <= 207) -- and, for wide
+# models (hidden a multiple of 16, 208 .. 512), 6 (CTA pairs, weights streamed in K chunks).  Other widths use
 # precision="fp32".  2 is the first pair kernel (kept for A/B).
 TC_VARIANT = None
 
@@ -402,7 +408,8 @@ def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, ga
     bounds_n = 0 if min_logvar is None else min_logvar.numel()
     if len(pack) < 6:  # variant chosen once per pack (argument validation happens before any launch)
         pack.append(None)
-    candidates = [TC_VARIANT] if TC_VARIANT is not None else ([pack[5]] if pack[5] else [5, 4, 3, 1])
+    wide = L >= 1 and layer_n[0] == H  # un-widened (streamed-weights) packing
+    candidates = [TC_VARIANT] if TC_VARIANT is not None else ([pack[5]] if pack[5] else ([6] if wide else [5, 4, 3, 1]))
     last = None
     for variant in candidates:
         try:

@@ -624,12 +624,12 @@ def test_step_device_graphed(cm):
 
 
 def test_tcgen05_wide_heads_and_hidden(cm):
-    """Shapes outside the default pair kernel: O=20 (head 48 columns -> variant 3); hidden 240 does not fit shared memory in
-    any tensor-core variant -> a loud error, never a silent fallback."""
+    """Shapes outside the default pair kernel: O=20 (head 48 columns -> variant 3); hidden 250 (wider than the weight-stationary
+    kernels take and not a multiple of 16) -> a loud error, never a silent fallback."""
     torch.manual_seed(0)
     np.random.seed(0)
     rng = np.random.default_rng(0)
-    for O, A, H in ((20, 4, 200), (5, 1, 240), (17, 6, 128)):
+    for O, A, H in ((20, 4, 200), (5, 1, 250), (17, 6, 128)):
         N = 3000
         m = cm.PlainTransition(O, A, hid_size=H, activation_fn_cfg=SILU, device=DEV)
         dyn = cm.PlainEnsembleDynamics(m, learned_reward=False)
@@ -765,7 +765,7 @@ def test_train_gemm_tensor_core_tiers(cm, P, E, B, i, o):
 def test_c5_full_size_forward_and_rollout(cm):
     """Maximum configuration of BASELINE.json: parity against the oracle on sampled (sub-net, member) pairs (a sub-net's
     output column depends only on its own weights and mask row), selected-member rollout == all-member path bit for bit,
-    and the tensor-core tier refuses the width loudly instead of falling back."""
+    and the tensor-core tier (streamed weights) against the fp32 tier."""
     O, A, E, H, B = 100, 20, 16, 512, 48
     torch.manual_seed(5)
     rng = np.random.default_rng(5)
@@ -811,10 +811,9 @@ def test_c5_full_size_forward_and_rollout(cm):
     with torch.no_grad():
         am, alv = m.forward(env._obs_dev.unsqueeze(0), a_dev.unsqueeze(0))
     assert torch.equal(sel, cm.ops.select_sample(am, alv, idx, noise))
-    env.precision = "f16"
-    with pytest.raises(cm._lib.CmrlB200Error):
-        env.predict_selected(m, env._obs_dev, a_dev, idx, noise)
-    env.precision = "fp32"
+    env.precision = "f16"  # hidden 512: the streamed-weights tensor-core kernel (variant 6)
+    out16 = env.predict_selected(m, env._obs_dev, a_dev, idx, noise)
+    assert m.packed_f16()[5] == 6 and rel_err(out16.cpu().numpy(), sel.cpu().numpy()) < TOL_TC
     o2, r2, d2, infos = env.step(rng.uniform(-1, 1, size=(N, A)).astype(np.float32))
     assert o2.shape == (N, O) and r2.shape == (N,) and d2.shape == (N,) and len(infos) == N and np.isfinite(o2).all()
 
@@ -920,3 +919,45 @@ def test_step_return_views_equals_copies(cm, make):
         if prev is not None:
             assert np.array_equal(prev[0], prev[1])  # last step's view was not overwritten by this step
         prev = (oa.copy(), ob)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# tensor-core tier for WIDE hidden layers (streamed weights, variant 6)
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,O,A,H,N", [("plain", 5, 1, 240, 700), ("plain", 20, 4, 256, 3000), ("reward", 9, 3, 320, 1500),
+                                          ("extmask", 8, 3, 512, 2500), ("plain_relu", 30, 6, 512, 513)])
+def test_tcgen05_wide_hidden_streamed_weights(cm, kind, O, A, H, N):
+    """hidden 208..512 (a multiple of 16): the streamed-weights pair kernel against the fp32 tier on the same draws"""
+    torch.manual_seed(1)
+    rng = np.random.default_rng(1)
+    act_cfg_ = None if kind == "plain_relu" else SILU
+    if kind == "extmask":
+        m = cm.ExternalMaskTransition(O, A, hid_size=H, activation_fn_cfg=act_cfg_, device=DEV)
+        mask = (rng.uniform(size=(O, 7, O + A)) < 0.5).astype(np.float32)
+        m.set_input_mask(torch.from_numpy(mask))
+        dyn = cm.PlainEnsembleDynamics(m, learned_reward=False)
+    elif kind == "reward":
+        tr = cm.PlainTransition(O, A, hid_size=16, device=DEV)
+        m = cm.PlainRewardMech(O, A, hid_size=H, activation_fn_cfg=act_cfg_, device=DEV)
+        dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=m)
+    else:
+        m = cm.PlainTransition(O, A, hid_size=H, activation_fn_cfg=act_cfg_, device=DEV)
+        dyn = cm.PlainEnsembleDynamics(m, learned_reward=False)
+    env = cm.VecFakeEnv(N, None, None)
+    env.set_up(dyn, reward_fn=lambda n, o, a: np.zeros((n.shape[0], 1), np.float32), termination_fn=lambda n, o, a: np.zeros((n.shape[0], 1), bool),
+               get_init_obs_fn=lambda n: rng.normal(size=(n, O)).astype(np.float32))
+    env.reset()
+    act = t(rng.uniform(-1, 1, size=(N, A)).astype(np.float32))
+    idx = t(rng.choice(np.asarray(m.elite_members), size=N).astype(np.uint8))
+    noise = t(rng.normal(size=(N, m._head_dim)).astype(np.float32))
+    env.precision = "fp32"
+    ref = env.predict_selected(m, env._obs_dev, act, idx, noise)
+    ref_m = env.predict_selected(m, env._obs_dev, act, idx, None)
+    env.precision = "f16"
+    out = env.predict_selected(m, env._obs_dev, act, idx, noise)
+    assert m.packed_f16()[5] == 6
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < TOL_TC
+    out_m = env.predict_selected(m, env._obs_dev, act, idx, None)
+    base = env._obs_dev if kind != "reward" else 0.0
+    assert rel_err((out_m - base).cpu().numpy(), (ref_m - base).cpu().numpy()) < 6e-3  # raw head output alone
