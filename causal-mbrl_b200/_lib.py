@@ -23,7 +23,7 @@ _F = _c.c_float
 PROTOTYPES = {
     "cmrl_ens_linear_fwd": [_P, _LL, _LL, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _LL, _LL, _LL, _P, _I, _I, _P],
     "cmrl_ens_linear_bwd_dx": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "cmrl_ens_linear_bwd_dw": [_P, _LL, _LL, _P, _LL, _LL, _LL, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "cmrl_ens_linear_bwd_dw": [_P, _LL, _LL, _P, _LL, _LL, _LL, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _P],
     "cmrl_gaussian_head_fwd": [_P, _I, _I, _I, _I, _P, _LL, _I, _P, _P, _I, _P, _P, _P],
     "cmrl_gaussian_head_bwd": [_P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     "cmrl_nll_loss_fwd": [_P, _P, _P, _LL, _I, _LL, _F, _P, _P],

@@ -220,11 +220,12 @@ __global__ void __launch_bounds__(NTHREADS) grouped_sgemm_kernel(const GemmP p) 
 }
 
 template <int MODE>
-static int launch_gemm(const GemmP& p, int total_rows, cudaStream_t st, const char* name, int tier = 0) {
+static int launch_gemm(const GemmP& p, int total_rows, cudaStream_t st, const char* name, int tier = 0,
+                       float* workspace = nullptr, long long workspace_floats = 0) {
     const bool ragged = p.row_offsets != nullptr;
     CMRL_REQUIRE(tier == 0 || tier == 1 || tier == 3, "%s: tier must be 0 (fp32 FFMA), 1 (TF32) or 3 (3xTF32)", name);
     if (tier != 0 && !ragged) {
-        const int rc = launch_gemm_tc<MODE>(p, tier, st, name);
+        const int rc = launch_gemm_tc<MODE>(p, tier, st, name, workspace, workspace_floats);
         if (rc != -2) return rc;  // -2: shape not eligible for the tensor-core kernel
     }
     // small row counts -> 64-row tiles for more CTAs; large -> 128-row tiles
@@ -322,7 +323,7 @@ extern "C" int cmrl_ens_linear_bwd_dx(const float* dz, const float* w, const flo
 extern "C" int cmrl_ens_linear_bwd_dw(const float* x, long long x_sp, long long x_se, const float* mask,
                                       long long m_sp, long long m_se, long long m_sb, const float* dz, float* dw,
                                       float* db, int P, int E, int B, int in_size, int out_size, int accumulate,
-                                      int tier, void* stream) {
+                                      int tier, float* workspace, long long workspace_floats, void* stream) {
     CMRL_REQUIRE(x && dz && dw, "ens_linear_bwd_dw: null pointer");
     CMRL_REQUIRE(P >= 1 && E >= 1 && B >= 1 && in_size >= 1 && out_size >= 1, "ens_linear_bwd_dw: bad dims");
     GemmP p{};
@@ -352,5 +353,5 @@ extern "C" int cmrl_ens_linear_bwd_dw(const float* x, long long x_sp, long long 
     p.P = P;
     p.E = E;
     p.accumulate = accumulate;
-    return launch_gemm<MODE_DW>(p, in_size, (cudaStream_t)stream, "ens_linear_bwd_dw", tier);
+    return launch_gemm<MODE_DW>(p, in_size, (cudaStream_t)stream, "ens_linear_bwd_dw", tier, workspace, workspace_floats);
 }

@@ -26,6 +26,7 @@ enum { MODE_FWD = 0, MODE_DX = 1, MODE_DW = 2 };
 // tcgen05 kind::tf32 tier (gemm_tc.cu): passes = 1 (TF32, 1e-3 tier) or 3 (3xTF32 error-compensated, fp32-grade).
 // Returns -2 when the shape is not eligible (caller falls back to the FFMA kernel).
 template <int MODE>
-int launch_gemm_tc(const GemmP& p, int passes, cudaStream_t st, const char* name);
+int launch_gemm_tc(const GemmP& p, int passes, cudaStream_t st, const char* name, float* workspace = nullptr,
+                   long long workspace_floats = 0);
 
 }  // namespace cmrl

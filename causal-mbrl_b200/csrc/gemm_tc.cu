@@ -37,6 +37,10 @@ struct TgLay {
     uint32_t stage;           // bytes of one stage
     uint32_t bar_off, total;
     uint32_t tmem_cols;
+    int ksplit;           // dw only: the K (= batch) range is cut into ksplit slices, one CTA each, partial tiles go to `ws`
+    int k_per_split;      // multiple of TG_KC
+    float* ws;            // [ksplit][G][Mtot][N] partial results (Mtot = M + 1 with the db row)
+    int m_tot;
 };
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -63,10 +67,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tc_kernel(const GemmP p, c
     const int NT = lay.NT;
 
     const int pe_p = blockIdx.z / p.E, pe_e = blockIdx.z % p.E;
-    const int m0 = blockIdx.x * TG_BM, n0 = blockIdx.y * NT;
-    const float* A = p.A + pe_p * p.a_sp + pe_e * p.a_se;
-    const float* Am = p.Amask ? p.Amask + pe_p * p.am_sp + pe_e * p.am_se : nullptr;
-    const float* Bp = p.B + pe_p * p.b_sp + pe_e * p.b_se;
+    const int split = lay.ksplit > 1 ? (int)blockIdx.x % lay.ksplit : 0;
+    const int m_tile = lay.ksplit > 1 ? (int)blockIdx.x / lay.ksplit : (int)blockIdx.x;
+    const int kbase = split * lay.k_per_split;
+    const int Kloc = lay.ksplit > 1 ? min(p.K - kbase, lay.k_per_split) : p.K;  // this CTA's slice of the K range
+    const int m0 = m_tile * TG_BM, n0 = blockIdx.y * NT;
+    const float* A = p.A + pe_p * p.a_sp + pe_e * p.a_se + (long long)kbase * p.a_sk;
+    const float* Am = p.Amask ? p.Amask + pe_p * p.am_sp + pe_e * p.am_se + (long long)kbase * p.am_sk : nullptr;
+    const float* Bp = p.B + pe_p * p.b_sp + pe_e * p.b_se + (long long)kbase * p.b_sk;
     const long long c_off = pe_p * p.c_sp + pe_e * p.c_se;
     const long long g = (long long)pe_p * p.E + pe_e;
     const bool ones_row = (MODE == MODE_DW) && p.bsum != nullptr;  // A row index M (= in) is all ones -> C row M = db
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tc_kernel(const GemmP p, c
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         float x = 0.f;
-                        if (full || k0 + a_k[j] + u < p.K) {
+                        if (full || k0 + a_k[j] + u < Kloc) {
                             x = a_ptr[j][(long long)u * p.a_sk];
                             if (Am) x *= am_ptr[j][(long long)u * p.am_sk];
                         }
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tc_kernel(const GemmP p, c
                 }
             } else if (a_kind[j] == 2) {
                 const int kk = k0 + a_k[j];
-                v = make_float4(kk < p.K ? 1.f : 0.f, kk + 1 < p.K ? 1.f : 0.f, kk + 2 < p.K ? 1.f : 0.f, kk + 3 < p.K ? 1.f : 0.f);
+                v = make_float4(kk < Kloc ? 1.f : 0.f, kk + 1 < Kloc ? 1.f : 0.f, kk + 2 < Kloc ? 1.f : 0.f, kk + 3 < Kloc ? 1.f : 0.f);
             }
             ra[j] = v;
             a_ptr[j] += a_step;
@@ -169,7 +177,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tc_kernel(const GemmP p, c
                 } else {
                     float e[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) e[u] = (full || k0 + b_k[j] + u < p.K) ? b_ptr[j][(long long)u * p.b_sk] : 0.f;
+                    for (int u = 0; u < 4; ++u) e[u] = (full || k0 + b_k[j] + u < Kloc) ? b_ptr[j][(long long)u * p.b_sk] : 0.f;
                     v = make_float4(e[0], e[1], e[2], e[3]);
                 }
             }
@@ -200,10 +208,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tc_kernel(const GemmP p, c
 
     // ---- main loop: chunk kc is stored from one register set while the loads of chunk kc+1 (other set) are in flight;
     // two shared-memory stages, the MMAs of chunk kc run while chunk kc+1 is stored
-    const int nk = (p.K + TG_KC - 1) / TG_KC;
+    const int nk = (Kloc + TG_KC - 1) / TG_KC;
     const uint32_t idesc = umma_idesc_tf32(TG_BM, NT);
-    load_chunk(0, TG_KC <= p.K, ra0, rb0);
-    if (nk > 1) load_chunk(TG_KC, 2 * TG_KC <= p.K, ra1, rb1);
+    load_chunk(0, TG_KC <= Kloc, ra0, rb0);
+    if (nk > 1) load_chunk(TG_KC, 2 * TG_KC <= Kloc, ra1, rb1);
     for (int kc = 0; kc < nk; ++kc) {
         const int s = kc & 1;
         if (kc >= 2) mbar_wait(&bars[s], ((kc >> 1) - 1) & 1);  // the MMAs that read this stage two chunks ago are done
@@ -211,15 +219,15 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tc_kernel(const GemmP p, c
         fence_proxy_async();
         __syncthreads();
         if (kc + 2 < nk) {
-            if (s == 0) load_chunk((kc + 2) * TG_KC, (kc + 3) * TG_KC <= p.K, ra0, rb0);
-            else load_chunk((kc + 2) * TG_KC, (kc + 3) * TG_KC <= p.K, ra1, rb1);
+            if (s == 0) load_chunk((kc + 2) * TG_KC, (kc + 3) * TG_KC <= Kloc, ra0, rb0);
+            else load_chunk((kc + 2) * TG_KC, (kc + 3) * TG_KC <= Kloc, ra1, rb1);
         }
         if (tid == 0) {
             tc_fence_after();
             const uint32_t base = smem_base + (uint32_t)s * lay.stage;
             const uint32_t a_hi = base, a_lo = base + lay.a_part;
             const uint32_t b_hi = base + (uint32_t)lay.parts * lay.a_part, b_lo = b_hi + lay.b_part;
-            const int ksteps = min(TG_KC / 8, (p.K - kc * TG_KC + 7) / 8);
+            const int ksteps = min(TG_KC / 8, (Kloc - kc * TG_KC + 7) / 8);
             for (int ks = 0; ks < ksteps; ++ks) {
                 const uint32_t ao = (uint32_t)(2 * ks) * lay.a_gstride, bo = (uint32_t)(2 * ks) * lay.b_gstride;
                 const uint64_t dah = umma_desc(a_hi + ao, lay.a_gstride, 128), dbh = umma_desc(b_hi + bo, lay.b_gstride, 128);
@@ -267,6 +275,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tc_kernel(const GemmP p, c
                 const int gn = n0 + col;
                 if (gn >= p.N) continue;
                 float x = otile[(size_t)row * ostride + col];
+                if (lay.ksplit > 1) {  // partial tile of this K slice; splitk_reduce_kernel applies accumulate / db
+                    lay.ws[(((long long)split * gridDim.z + blockIdx.z) * lay.m_tot + gm) * p.N + gn] = x;
+                    continue;
+                }
                 if (row_ok) {
                     const long long off = c_off + (long long)gm * p.c_sm + gn;
                     if (MODE == MODE_FWD) {
@@ -291,8 +303,23 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tc_kernel(const GemmP p, c
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(lay.tmem_cols) : "memory");
 }
 
+// sums the K-slice partials in slice order (deterministic) into dw (rows < M) and db (row M)
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int S, long long G, int m_tot, int M, int N, float* __restrict__ C,
+                                     float* __restrict__ bsum, int accumulate) {
+    const long long total = G * m_tot * N, slice = total;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += ws[s * slice + i];
+        const int n = (int)(i % N);
+        const int r = (int)((i / N) % m_tot);
+        const long long g = i / ((long long)N * m_tot);
+        float* dst = r < M ? &C[(g * M + r) * N + n] : &bsum[g * N + n];
+        *dst = accumulate ? *dst + acc : acc;
+    }
+}
+
 template <int MODE>
-int launch_gemm_tc(const GemmP& p, int passes, cudaStream_t st, const char* name) {
+int launch_gemm_tc(const GemmP& p, int passes, cudaStream_t st, const char* name, float* workspace, long long workspace_floats) {
     if (p.row_offsets != nullptr) return -2;
     if (MODE == MODE_DW && p.bsum != nullptr && p.M % TG_BM == 0) return -2;  // no spare tile row for the ones row (db)
     if (p.M < 1 || p.N < 1 || p.K < 1) return -2;
@@ -304,7 +331,8 @@ int launch_gemm_tc(const GemmP& p, int passes, cudaStream_t st, const char* name
         const int m_rows0 = p.M + ((MODE == MODE_DW && p.bsum) ? 1 : 0);
         const long long ctas = (long long)((m_rows0 + TG_BM - 1) / TG_BM) * p.P * p.E;
         const int want = (int)((num_sms() + ctas - 1) / ctas);           // N tiles for ~one CTA per SM
-        if (want > 1) {
+        const bool will_split_k = MODE == MODE_DW && workspace != nullptr && p.K >= 2048;  // parallelism comes from K slices instead
+        if (want > 1 && !will_split_k) {
             int nt = ((p.N + want - 1) / want + 15) / 16 * 16;
             if (nt < 32) nt = 32;
             if (nt < NT) NT = nt;
@@ -334,13 +362,40 @@ int launch_gemm_tc(const GemmP& p, int passes, cudaStream_t st, const char* name
     const int m_rows = p.M + ((MODE == MODE_DW && p.bsum) ? 1 : 0);
     dim3 grid((m_rows + TG_BM - 1) / TG_BM, (p.N + NT - 1) / NT, p.P * p.E);
     CMRL_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "%s: too many nets/columns for one launch", name);
+    lay.ksplit = 1;
+    if (MODE == MODE_DW && workspace != nullptr && p.K >= 2048) {
+        // dw: K is the batch.  Cut it into slices so that the launch fills the chip; partial tiles go to the caller's
+        // workspace and are summed in slice order (contiguous dw [G,M,N] / db [G,N] as the Python layer passes them)
+        const long long ctas = (long long)grid.x * grid.y * grid.z;
+        int S = (int)((2LL * num_sms() + ctas - 1) / ctas);
+        const long long per_slice = (long long)grid.z * m_rows * p.N;
+        if (S > workspace_floats / per_slice) S = (int)(workspace_floats / per_slice);
+        if (S > 32) S = 32;
+        const bool contiguous = p.c_sm == p.N && p.c_se == (long long)p.M * p.N && (p.P == 1 || p.c_sp == (long long)p.E * p.M * p.N);
+        if (S >= 2 && contiguous) {
+            int kps = ((p.K + S - 1) / S + TG_KC - 1) / TG_KC * TG_KC;
+            S = (p.K + kps - 1) / kps;
+            lay.ksplit = S;
+            lay.k_per_split = kps;
+            lay.ws = workspace;
+            lay.m_tot = m_rows;
+            grid.x *= S;
+        }
+    }
     gemm_tc_kernel<MODE><<<grid, TG_THREADS, lay.total, st>>>(p, lay);
     CMRL_CHECK_LAUNCH(name);
+    if (lay.ksplit > 1) {
+        const long long total = (long long)grid.z * m_rows * p.N;
+        int nb = (int)((total + 255) / 256);
+        if (nb > 8 * num_sms()) nb = 8 * num_sms();
+        splitk_reduce_kernel<<<nb, 256, 0, st>>>(workspace, lay.ksplit, grid.z, m_rows, p.M, p.N, p.C, p.bsum, p.accumulate);
+        CMRL_CHECK_LAUNCH("ens_linear_bwd_dw.splitk_reduce");
+    }
     return 0;
 }
 
-template int launch_gemm_tc<MODE_FWD>(const GemmP&, int, cudaStream_t, const char*);
-template int launch_gemm_tc<MODE_DX>(const GemmP&, int, cudaStream_t, const char*);
-template int launch_gemm_tc<MODE_DW>(const GemmP&, int, cudaStream_t, const char*);
+template int launch_gemm_tc<MODE_FWD>(const GemmP&, int, cudaStream_t, const char*, float*, long long);
+template int launch_gemm_tc<MODE_DX>(const GemmP&, int, cudaStream_t, const char*, float*, long long);
+template int launch_gemm_tc<MODE_DW>(const GemmP&, int, cudaStream_t, const char*, float*, long long);
 
 }  // namespace cmrl

@@ -62,8 +62,8 @@ def mask_strides(mask, P, E, B):
 # GEMM tier of the TRAINING path (forward with saved pre-activations, dx, dw): 0 = fp32 FFMA, 1 = tcgen05 TF32 (1e-3
 # tier), 3 = 3xTF32 error-compensated tcgen05 (fp32-grade), "auto" = 3 where the tensor-core kernel is faster than the
 # FFMA kernel and 0 elsewhere (measured, profiles/tools/gemm_tier_time.py: forward and dx from ~1k rows per member on --
-# 2.2x / 1.3-1.9x at 4k-64k rows; at the reference batch size of 256 rows both kernels are latency bound at ~17 us and
-# dw, whose K dimension is the batch, is not faster at any size).  Inference forwards (query / evaluate / the fp32
+# 2.2x / 1.3-1.9x at 4k-64k rows -- and dw, whose K dimension is the batch, from 2k rows on with split-K, 3x; at the
+# reference batch size of 256 rows both kernels are latency bound at ~17 us).  Inference forwards (query / evaluate / the fp32
 # rollout tier) always run tier 0, whose row results do not depend on tile placement (selected-member rollouts stay
 # bit-identical to the all-member path).
 TRAIN_GEMM_TIER = "auto"
@@ -73,7 +73,9 @@ TRAIN_GEMM_TC_MIN_ROWS = 1024
 def _train_tier(kind, rows):
     if TRAIN_GEMM_TIER != "auto":
         return int(TRAIN_GEMM_TIER)
-    return 3 if (kind != "dw" and rows >= TRAIN_GEMM_TC_MIN_ROWS) else 0
+    if kind == "dw":  # K of the dw GEMM is the batch: the tensor-core kernel pays once the batch is split over CTAs
+        return 3 if rows >= 2048 else 0
+    return 3 if rows >= TRAIN_GEMM_TC_MIN_ROWS else 0
 
 
 def ens_linear_fwd(x, w, b, act=ACT_IDENTITY, mask=None, mask_str=(0, 0, 0), want_z=False, row_offsets=None, tier=None):
@@ -145,9 +147,17 @@ def ens_linear_bwd_dw(x, dz, w_shape, mask=None, mask_str=(0, 0, 0), dw=None, db
     if db is None and want_db:
         db = torch.empty(tuple(w_shape[:-2]) + (1, out_size), device=dz.device, dtype=torch.float32)
     assert dw.is_contiguous() and (db is None or db.is_contiguous())
+    ws, ws_floats = None, 0
+    if tier and B >= 2048:  # split-K workspace: one partial [P*E, in+1, out] per batch slice (capped at 256 MB)
+        per_slice = P * E * (in_size + 1) * out_size
+        slices = min(32, (256 << 20) // (4 * per_slice))
+        if slices >= 2:
+            ws = torch.empty(slices * per_slice, device=dz.device, dtype=torch.float32)
+            ws_floats = ws.numel()
     _lib.call(
         "cmrl_ens_linear_bwd_dw", x.data_ptr(), x_sp, x_se, _ptr(mask), mask_str[0], mask_str[1], mask_str[2],
-        dz.data_ptr(), dw.data_ptr(), _ptr(db), P, E, B, in_size, out_size, 1 if accumulate else 0, tier, _stream(),
+        dz.data_ptr(), dw.data_ptr(), _ptr(db), P, E, B, in_size, out_size, 1 if accumulate else 0, tier, _ptr(ws),
+        ws_floats, _stream(),
     )  # fmt: skip
     return dw, db
 

@@ -73,10 +73,14 @@ int cmrl_ens_linear_bwd_dx(const float* dz, const float* w, const float* z_prev,
 
 /* Backward of K1 w.r.t. weight and bias:
  *   dw[p,e,i,o] = sum_b (x*mask)[p,e,b,i] * dz[p,e,b,o];   db[p,e,0,o] = sum_b dz[p,e,b,o]
- * db may be NULL.  accumulate != 0 adds into dw/db instead of overwriting. */
+ * db may be NULL.  accumulate != 0 adds into dw/db instead of overwriting.
+ * workspace (optional, caller-owned device floats; NULL / 0 = none): with tier 1 / 3 and B >= 2048 the batch (= the K
+ * dimension of this GEMM) is cut into up to 32 slices that run as separate CTAs; each slice needs
+ * P*E*(in_size+1)*out_size floats and the slices are summed in order (deterministic). */
 int cmrl_ens_linear_bwd_dw(const float* x, long long x_sp, long long x_se, const float* mask, long long m_sp,
                            long long m_se, long long m_sb, const float* dz, float* dw, float* db, int P,
-                           int E, int B, int in_size, int out_size, int accumulate, int tier, void* stream);
+                           int E, int B, int in_size, int out_size, int accumulate, int tier, float* workspace,
+                           long long workspace_floats, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2  Gaussian head: split, double soft-clamp, residual (and the ExternalMask transpose)

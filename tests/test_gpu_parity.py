@@ -725,7 +725,8 @@ def test_extend_replay_buffer_wraps_like_sb3(cm):
 # ---------------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("P,E,B,i,o", [(1, 7, 256, 6, 200), (1, 7, 256, 200, 200), (1, 7, 256, 200, 10), (5, 7, 100, 6, 200),
-                                       (5, 3, 77, 200, 2), (2, 2, 300, 130, 300), (1, 1, 5, 3, 1), (1, 2, 1000, 128, 64)])
+                                       (5, 3, 77, 200, 2), (2, 2, 300, 130, 300), (1, 1, 5, 3, 1), (1, 2, 1000, 128, 64),
+                                       (1, 7, 4096, 200, 200), (2, 3, 2500, 64, 130)])  # the last two: split-K dw
 def test_train_gemm_tensor_core_tiers(cm, P, E, B, i, o):
     """fwd (+pre-activation), dx (fused act'), dw (+db, accumulate) on tcgen05: tier 3 (3xTF32) is fp32-grade (1e-5 tier),
     tier 1 (plain TF32) is the 1e-3 tier.  Shapes cover K tails (6, 130, 3), N tails (10, 2, 300 > one 256-wide tile),
