@@ -12,13 +12,14 @@
 
 namespace cmrl {
 
-constexpr int BK = 16;
 constexpr int BN = 64;
 constexpr int TN = 4;
 constexpr int NTHREADS = 256;
 constexpr int PAD = 4;
 
-template <int MODE, int BM>
+// BK: K depth of one shared-memory tile.  Small grids (one wave of 64-row tiles, the reference batch size) are bound by the
+// global-load round trip per K tile, so they run BK = 32 (half as many round trips); large ones BK = 16 with 128-row tiles.
+template <int MODE, int BM, int BK>
 __global__ void __launch_bounds__(NTHREADS) grouped_sgemm_kernel(const GemmP p) {
     constexpr int TM = BM / 16;
     constexpr bool A_KCONTIG = (MODE != MODE_DW);
@@ -239,9 +240,9 @@ static int launch_gemm(const GemmP& p, int total_rows, cudaStream_t st, const ch
     if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
     CMRL_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "%s: too many nets/columns for one launch", name);
     if (use64)
-        grouped_sgemm_kernel<MODE, 64><<<grid, NTHREADS, 0, st>>>(p);
+        grouped_sgemm_kernel<MODE, 64, 32><<<grid, NTHREADS, 0, st>>>(p);
     else
-        grouped_sgemm_kernel<MODE, 128><<<grid, NTHREADS, 0, st>>>(p);
+        grouped_sgemm_kernel<MODE, 128, 16><<<grid, NTHREADS, 0, st>>>(p);
     CMRL_CHECK_LAUNCH(name);
     return 0;
 }
