@@ -41,7 +41,7 @@ PROTOTYPES = {
     "cmrl_sample_scatter": [_P, _I, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P],
     "cmrl_select_sample": [_P, _P, _P, _I, _I, _I, _P, _P, _P],
     "cmrl_mopo_penalty": [_P, _I, _I, _I, _P, _P],
-    "cmrl_pack_layer_f16": [_P, _P, _P, _LL, _LL, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _P],
+    "cmrl_pack_layer_f16": [_P, _P, _P, _LL, _LL, _I, _I, _I, _I, _I, _I, _I, ctypes.c_float, _P, _LL, _P],
     "cmrl_mlp_rollout_f16": [_P, _LL, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P,
                              _I, _P, _P, _I, _P],
     "cmrl_env_step_tail": [_P, _P, _P, _P, _P, _F, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],

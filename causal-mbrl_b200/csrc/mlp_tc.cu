@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_rollout_f16_kernel(const R
 //   half index = (n/8)*(k_pad*8) + (k/8)*64 + (n%8)*8 + (k%8)
 __global__ void pack_layer_f16_kernel(const float* __restrict__ w, const float* __restrict__ b,
                                       const float* __restrict__ mask, long long m_sp, long long m_se, int E, int in,
-                                      int out, int k_pad, int n_pad, int interleave_d, __half* __restrict__ dst,
-                                      long long net_stride) {
+                                      int out, int k_pad, int n_pad, int interleave_d, float scale,
+                                      __half* __restrict__ dst, long long net_stride) {
     const int g = blockIdx.y;
     const long long total = (long long)n_pad * k_pad;
     const float* wg = w + (long long)g * in * out;
@@ -276,7 +276,7 @@ __global__ void pack_layer_f16_kernel(const float* __restrict__ w, const float* 
                 v = b[(long long)g * out + src];
             }
         }
-        v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+        v = fminf(fmaxf(v * scale, -65504.0f), 65504.0f);
         d[i] = __float2half_rn(v);
     }
 }
@@ -304,7 +304,7 @@ extern "C" void cmrl_debug_set_buffer(void* buf) { g_dbg_buffer = (long long*)bu
 
 extern "C" int cmrl_pack_layer_f16(const float* w, const float* b, const float* mask, long long m_sp, long long m_se,
                                    int P, int E, int in_size, int out_size, int k_pad, int n_pad, int interleave_d,
-                                   void* dst_half, long long net_stride_halfs, void* stream) {
+                                   float scale, void* dst_half, long long net_stride_halfs, void* stream) {
     CMRL_REQUIRE(w && dst_half, "pack_layer_f16: null pointer");
     CMRL_REQUIRE(k_pad % 16 == 0 && n_pad % 16 == 0 && k_pad >= in_size + 1 && n_pad >= out_size,
                  "pack_layer_f16: k_pad must be a multiple of 16 >= in+1, n_pad a multiple of 16 >= out");
@@ -315,7 +315,7 @@ extern "C" int cmrl_pack_layer_f16(const float* w, const float* b, const float* 
     if (bx > 1024) bx = 1024;
     dim3 grid(bx, P * E);
     tc::pack_layer_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, b, mask, m_sp, m_se, E, in_size, out_size, k_pad,
-                                                                    n_pad, interleave_d, (__half*)dst_half, net_stride_halfs);
+                                                                    n_pad, interleave_d, scale, (__half*)dst_half, net_stride_halfs);
     CMRL_CHECK_LAUNCH("pack_layer_f16");
     return 0;
 }

@@ -126,6 +126,11 @@ __device__ __forceinline__ uint32_t act_h2(uint32_t z) {
         asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(hz));
         asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(y) : "r"(hz), "r"(t));      // hz * t + hz
         return y;
+    } else if (ACT == CMRL_ACT_SILU_HALF) {
+        uint32_t t, y;
+        asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(z));
+        asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(y) : "r"(z), "r"(t));
+        return y;
     } else if (ACT == CMRL_ACT_RELU) {
         uint32_t y;
         asm("max.f16x2 %0, %1, %2;" : "=r"(y) : "r"(z), "r"(0u));
@@ -142,6 +147,11 @@ __device__ __forceinline__ uint32_t act_pack(float a, float b) {
         asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(ha));
         asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(hb));
         return pack_h2(fmaf(ha, ta, ha), fmaf(hb, tb, hb));
+    } else if (ACT == CMRL_ACT_SILU_HALF) {
+        float ta, tb;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(a));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(b));
+        return pack_h2(fmaf(a, ta, a), fmaf(b, tb, b));
     } else if (ACT == CMRL_ACT_RELU) {
         return pack_h2(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
     }
@@ -533,6 +543,7 @@ int launch_rollout_v2(const RolloutP& p, cudaStream_t st) {
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         attr_set = true;
     }
     int max_items = p.P * ((p.N + V2_TILE - 1) / V2_TILE + p.E);
@@ -541,6 +552,8 @@ int launch_rollout_v2(const RolloutP& p, cudaStream_t st) {
     if (clusters < 1) clusters = 1;
     if (p.act == CMRL_ACT_SILU)
         mlp_rollout_f16_v2_kernel<CMRL_ACT_SILU><<<clusters * 2, V2_THREADS, sm.total, st>>>(p, sm);
+    else if (p.act == CMRL_ACT_SILU_HALF)
+        mlp_rollout_f16_v2_kernel<CMRL_ACT_SILU_HALF><<<clusters * 2, V2_THREADS, sm.total, st>>>(p, sm);
     else if (p.act == CMRL_ACT_RELU)
         mlp_rollout_f16_v2_kernel<CMRL_ACT_RELU><<<clusters * 2, V2_THREADS, sm.total, st>>>(p, sm);
     else

@@ -546,6 +546,7 @@ int launch_rollout_v3(const RolloutP& p, cudaStream_t st) {
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         attr_set = true;
     }
     int max_items = p.P * ((p.N + V3_TILE - 1) / V3_TILE + p.E);
@@ -554,6 +555,8 @@ int launch_rollout_v3(const RolloutP& p, cudaStream_t st) {
     if (clusters < 1) clusters = 1;
     if (p.act == CMRL_ACT_SILU)
         mlp_rollout_f16_v3_kernel<CMRL_ACT_SILU><<<clusters * 2, V3_THREADS, sm.total, st>>>(p, sm);
+    else if (p.act == CMRL_ACT_SILU_HALF)
+        mlp_rollout_f16_v3_kernel<CMRL_ACT_SILU_HALF><<<clusters * 2, V3_THREADS, sm.total, st>>>(p, sm);
     else if (p.act == CMRL_ACT_RELU)
         mlp_rollout_f16_v3_kernel<CMRL_ACT_RELU><<<clusters * 2, V3_THREADS, sm.total, st>>>(p, sm);
     else

@@ -531,6 +531,7 @@ int launch_rollout_v5(const RolloutP& p, cudaStream_t st) {
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         attr_set = true;
     }
     int max_items = p.P * ((p.N + V5_TILE - 1) / V5_TILE + p.E);
@@ -539,6 +540,8 @@ int launch_rollout_v5(const RolloutP& p, cudaStream_t st) {
     if (clusters < 1) clusters = 1;
     if (p.act == CMRL_ACT_SILU)
         mlp_rollout_f16_v5_kernel<CMRL_ACT_SILU><<<clusters * 2, V5_THREADS, lay.total, st>>>(p, lay);
+    else if (p.act == CMRL_ACT_SILU_HALF)
+        mlp_rollout_f16_v5_kernel<CMRL_ACT_SILU_HALF><<<clusters * 2, V5_THREADS, lay.total, st>>>(p, lay);
     else if (p.act == CMRL_ACT_RELU)
         mlp_rollout_f16_v5_kernel<CMRL_ACT_RELU><<<clusters * 2, V5_THREADS, lay.total, st>>>(p, lay);
     else

@@ -150,6 +150,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 __device__ __forceinline__ float act_fast(float z, int act) {
     if (act == CMRL_ACT_RELU) return fmaxf(z, 0.0f);
     if (act == CMRL_ACT_SILU) return __fdividef(z, 1.0f + __expf(-z));
+    if (act == CMRL_ACT_SILU_HALF) return __fdividef(2.0f * z, 1.0f + __expf(-2.0f * z));  // z holds half the pre-activation
     return z;
 }
 
@@ -304,6 +305,11 @@ __device__ __forceinline__ uint32_t v3_act_pack(float a, float b) {
         asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(ha));
         asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(hb));
         return pack_h2(fmaf(ha, ta, ha), fmaf(hb, tb, hb));
+    } else if (ACT == CMRL_ACT_SILU_HALF) {  // a, b are already z/2 (weights packed with scale 0.5): no multiply
+        float ta, tb;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(a));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(b));
+        return pack_h2(fmaf(a, ta, a), fmaf(b, tb, b));
     } else if (ACT == CMRL_ACT_RELU) {
         return pack_h2(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
     }

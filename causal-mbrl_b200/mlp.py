@@ -325,7 +325,8 @@ class EnsembleMLP(nn.Module):
             mask_str = ops.mask_strides(mask, self._parallel_num(), E, -1) if mask is not None else (0, 0, 0)
             with torch.no_grad():
                 inter = self._head_dim if (self._head_layout == ops.HEAD_PLAIN and not self.deterministic) else 0
-                pack = ops.pack_mlp_f16(params[0:n_lin:2], params[1:n_lin:2], mask, mask_str, head_interleave_d=inter)
+                pack = ops.pack_mlp_f16(params[0:n_lin:2], params[1:n_lin:2], mask, mask_str, head_interleave_d=inter,
+                                        act_kind=self._act_kind)
             cached = (key, pack)
             self._packed["f16"] = cached
         return cached[1]

@@ -355,7 +355,10 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0), head_interleave_d=0):
+ACT_SILU_HALF = 3  # CMRL_ACT_SILU_HALF: SiLU on halved pre-activations (hidden layers packed with scale 0.5)
+
+
+def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0), head_interleave_d=0, act_kind=None):
     """Pack a mechanism's fp32 parameters into the private fp16 device layout of cmrl_mlp_rollout_f16.
     weights/biases: per layer [(P,)E,in,out] / [(P,)E,1,out] (hidden layers, then the head).
     Returns (blob half tensor [nets, blob_halfs], layer_off, layer_k, layer_n) -- never part of state_dict."""
@@ -387,10 +390,13 @@ def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0), head_interleave
         w, b = w.detach().contiguous(), b.detach().contiguous()
         m = mask if i == 0 else None
         inter = head_interleave_d if i == len(weights) - 1 else 0
+        # SiLU models: hidden layers are stored halved (exact), the kernels evaluate h + h*tanh(h) on h = z/2
+        scale = 0.5 if (act_kind == ACT_SILU and i < len(weights) - 1) else 1.0
         _lib.call("cmrl_pack_layer_f16", w.data_ptr(), b.data_ptr(), _ptr(m), mask_str[0], mask_str[1], P, E,
-                  w.shape[-2], w.shape[-1], layer_k[i], layer_n[i], inter, blob.data_ptr() + 2 * layer_off[i], off,
+                  w.shape[-2], w.shape[-1], layer_k[i], layer_n[i], inter, scale, blob.data_ptr() + 2 * layer_off[i], off,
                   _stream())  # fmt: skip
-    return [blob, layer_off, layer_k, layer_n]
+    # [blob, layer offsets, K, N, ctypes views (lazy), kernel variant (lazy), hidden layers halved?]
+    return [blob, layer_off, layer_k, layer_n, None, None, act_kind == ACT_SILU]
 
 
 # Kernel variant of the tensor-core tier.  None = first that accepts the shape: 5 (CTA pairs, two 256-row tiles in
@@ -410,14 +416,15 @@ def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, ga
     N, O = obs.shape
     A = act.shape[1]
     L = len(layer_k) - 1
-    if len(pack) < 5:  # ctypes views of the layer tables, built once per pack
+    if pack[4] is None:  # ctypes views of the layer tables, built once per pack
         arr = ctypes.c_int * (L + 1)
-        pack.append((arr(*layer_off), arr(*layer_k), arr(*layer_n)))
+        pack[4] = (arr(*layer_off), arr(*layer_k), arr(*layer_n))
     c_off, c_k, c_n = pack[4]
+    if pack[6]:
+        assert act_kind == ACT_SILU, "this pack stores halved hidden layers: it belongs to a SiLU model"
+        act_kind = ACT_SILU_HALF
     pred = torch.empty((N, head_dim), device=obs.device, dtype=torch.float32) if out is None else out
     bounds_n = 0 if min_logvar is None else min_logvar.numel()
-    if len(pack) < 6:  # variant chosen once per pack (argument validation happens before any launch)
-        pack.append(None)
     wide = L >= 1 and layer_n[0] == H  # un-widened (streamed-weights) packing
     candidates = [TC_VARIANT] if TC_VARIANT is not None else ([pack[5]] if pack[5] else ([6] if wide else [5, 4, 3, 1]))
     last = None

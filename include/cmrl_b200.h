@@ -32,7 +32,10 @@ extern "C" {
 
 #define CMRL_B200_ABI_VERSION 1
 
-enum cmrl_act { CMRL_ACT_IDENTITY = 0, CMRL_ACT_RELU = 1, CMRL_ACT_SILU = 2 };
+/* CMRL_ACT_SILU_HALF (fused tensor-core rollout only): SiLU evaluated on HALVED pre-activations, h + h*tanh(h) with
+ * h = z/2 -- the hidden layers must have been packed with scale 0.5 (cmrl_pack_layer_f16), which is exact in binary
+ * floating point and saves one multiply per activation in the epilogue. */
+enum cmrl_act { CMRL_ACT_IDENTITY = 0, CMRL_ACT_RELU = 1, CMRL_ACT_SILU = 2, CMRL_ACT_SILU_HALF = 3 };
 /* layout of the head's raw output (see cmrl_gaussian_head_fwd) */
 enum cmrl_head_layout { CMRL_HEAD_PLAIN = 0, CMRL_HEAD_PARALLEL = 1 };
 
@@ -210,10 +213,11 @@ int cmrl_env_step_tail(const float* next_obs, const float* reward, const float* 
  * (UMMA K-major core-matrix order, bias folded in as K row `in_size`, optional 0/1 input mask
  * mask[p*m_sp + e*m_se + i] folded into the rows: exact per SURVEY Appendix B).  dst: half*, net g's layer
  * blob at dst + g*net_stride_halfs, n_pad*k_pad halves.  interleave_d = D for the Gaussian PLAIN head layer
- * (output columns re-ordered to 2d = mean_d, 2d+1 = logvar_d), 0 otherwise.  Never visible in state_dict. */
+ * (output columns re-ordered to 2d = mean_d, 2d+1 = logvar_d), 0 otherwise.  scale multiplies weights and bias
+ * (1, or 0.5 for the hidden layers of a CMRL_ACT_SILU_HALF rollout).  Never visible in state_dict. */
 int cmrl_pack_layer_f16(const float* w, const float* b, const float* mask, long long m_sp, long long m_se, int P,
-                        int E, int in_size, int out_size, int k_pad, int n_pad, int interleave_d, void* dst_half,
-                        long long net_stride_halfs, void* stream);
+                        int E, int in_size, int out_size, int k_pad, int n_pad, int interleave_d, float scale,
+                        void* dst_half, long long net_stride_halfs, void* stream);
 
 /* Fused selected-member rollout of ONE mechanism (VecFakeEnv.get_dynamics_predict, fake_env.py:195-215, over
  * PlainTransition / ExternalMaskTransition / PlainRewardMech / PlainTerminationMech forward): for every
