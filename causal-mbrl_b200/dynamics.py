@@ -405,6 +405,9 @@ class _DeviceEpochRunner:
         model.flat_parameters()
         getattr(self.dyn, "{}_optimizer".format(self.mech)).prepare_graphable()
         n_full = self.N // self.B
+        if self.Bl >= 2048:  # split-K dw workspace (ops.ens_linear_bwd_dw) must exist before the step is captured
+            worst = max((p.numel() // p.shape[-2]) * (p.shape[-2] + 1) for p in model.parameters() if p.dim() >= 3 and p.shape[-2] > 1)
+            ops.splitk_workspace(self.obs.device, min(32 * worst, (256 << 20) // 4))
         if self.use_graph and self.graph is None and n_full > 0:
             if self.dyn.dp_group is not None:
                 self._step()  # one eager step first: NCCL sets its communicator up outside the capture
@@ -412,7 +415,7 @@ class _DeviceEpochRunner:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             l0 = _lib.launch_count()
-            with torch.cuda.graph(g):
+            with ops.graph_capture(g):
                 self._step()
             self.graph_launches = _lib.launch_count() - l0
             self.graph = g

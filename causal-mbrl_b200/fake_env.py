@@ -352,7 +352,7 @@ class VecFakeEnv(VecEnv):
                 with torch.cuda.stream(copy_stream):
                     host_next_buf.copy_(next_obs, non_blocking=True)
 
-            with torch.cuda.graph(g):
+            with ops.graph_capture(g):
                 out = self._predict_all(obs, act, need_all, early_copy if copy_stream is not None else None)
                 ops.counter_add(self._rng_base, self._draw_counter - c0)
                 if copy_stream is not None:
@@ -444,7 +444,7 @@ class VecFakeEnv(VecEnv):
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 l0 = _lib.launch_count()
-                with torch.cuda.graph(g):
+                with ops.graph_capture(g):
                     tail_and_readback()
                 tg = self._tail_graphs[key] = (g, _lib.launch_count() - l0)
             tg[0].replay()
@@ -541,7 +541,7 @@ class VecFakeEnv(VecEnv):
             g = torch.cuda.CUDAGraph()
             c0 = self._draw_counter
             l0 = _lib.launch_count()
-            with torch.cuda.graph(g):
+            with ops.graph_capture(g):
                 self._graph_out = self.step_device(b["act"])
                 ops.counter_add(self._rng_base, self._draw_counter - c0)
             self._step_graph_launches = _lib.launch_count() - l0

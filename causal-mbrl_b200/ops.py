@@ -3,10 +3,29 @@
 PyTorch is plumbing here (device memory, streams); every arithmetic op below is a kernel of
 libcmrl_b200.so launched on torch's current CUDA stream.
 """
+import contextlib
+import gc
+
 import torch
 
 from . import _lib
 from ._lib import ACT_IDENTITY, ACT_RELU, ACT_SILU, HEAD_PARALLEL, HEAD_PLAIN  # noqa: F401
+
+
+@contextlib.contextmanager
+def graph_capture(graph):
+    """`torch.cuda.graph(graph)` with the cyclic garbage collector paused: a collection that fires in the middle of a
+    capture can destroy an older CUDA graph / its memory pool (objects kept alive only by reference cycles), and the
+    resulting cudaFree invalidates the capture in progress (cudaErrorStreamCaptureInvalidated)."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph):
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 def _stream():
@@ -130,6 +149,24 @@ def ens_linear_bwd_dx(dz, w, z_prev, act_prev, tier=None):
     return dx
 
 
+_SPLITK_WS = {}
+
+
+def splitk_workspace(device, floats):
+    """Persistent per-device scratch for the split-K dw GEMMs (they run one after the other on one stream).  It is grown
+    outside CUDA-graph captures only: inside a capture a too small workspace means "no split" for that call (call
+    `splitk_workspace(device, n)` before capturing, as the device-resident epoch runner does)."""
+    device = torch.device(device)
+    cur = _SPLITK_WS.get(device)
+    if cur is not None and cur.numel() >= floats:
+        return cur
+    if torch.cuda.is_current_stream_capturing():
+        return cur
+    cur = torch.empty(floats, device=device, dtype=torch.float32)
+    _SPLITK_WS[device] = cur
+    return cur
+
+
 def ens_linear_bwd_dw(x, dz, w_shape, mask=None, mask_str=(0, 0, 0), dw=None, db=None, want_db=True, accumulate=False,
                       tier=None):
     """dw = (x*mask)^T @ dz, db = sum_b dz, written into dw/db when given (flat-arena views)."""
@@ -152,8 +189,8 @@ def ens_linear_bwd_dw(x, dz, w_shape, mask=None, mask_str=(0, 0, 0), dw=None, db
         per_slice = P * E * (in_size + 1) * out_size
         slices = min(32, (256 << 20) // (4 * per_slice))
         if slices >= 2:
-            ws = torch.empty(slices * per_slice, device=dz.device, dtype=torch.float32)
-            ws_floats = ws.numel()
+            ws = splitk_workspace(dz.device, slices * per_slice)
+            ws_floats = 0 if ws is None else ws.numel()
     _lib.call(
         "cmrl_ens_linear_bwd_dw", x.data_ptr(), x_sp, x_se, _ptr(mask), mask_str[0], mask_str[1], mask_str[2],
         dz.data_ptr(), dw.data_ptr(), _ptr(db), P, E, B, in_size, out_size, 1 if accumulate else 0, tier, _ptr(ws),
