@@ -286,7 +286,6 @@ __global__ void pack_layer_f16_kernel(const float* __restrict__ w, const float* 
 
 namespace cmrl {
 namespace tc {
-int launch_rollout_v2(const RolloutP& p, cudaStream_t st);
 int launch_rollout_v3(const RolloutP& p, cudaStream_t st);
 int launch_rollout_v4(const RolloutP& p, cudaStream_t st);
 int launch_rollout_v5(const RolloutP& p, cudaStream_t st);
@@ -376,8 +375,7 @@ extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, co
     if (variant == 5) return tc::launch_rollout_v5(p, (cudaStream_t)stream);
     if (variant == 4) return tc::launch_rollout_v4(p, (cudaStream_t)stream);
     if (variant == 3) return tc::launch_rollout_v3(p, (cudaStream_t)stream);
-    if (variant == 2) return tc::launch_rollout_v2(p, (cudaStream_t)stream);
-    CMRL_REQUIRE(variant == 1, "mlp_rollout_f16: variant must be 1 (streamed weights), 2 / 4 (weight-stationary CTA pairs, 256-row tiles), 3 (pairs, two 128-row tiles in flight), 5 (pairs, two 256-row tiles, A operand partly in TMEM) or 6 (pairs, streamed weights, wide hidden)");
+    CMRL_REQUIRE(variant == 1, "mlp_rollout_f16: variant must be 1 (streamed weights, single CTA), 4 (weight-stationary CTA pairs, 256-row tiles), 3 (pairs, two 128-row tiles in flight), 5 (pairs, two 256-row tiles, A operand partly in TMEM) or 6 (pairs, streamed weights, wide hidden)");
     size_t w_stage = 0;
     int kmax = 0;
     for (int l = 0; l <= num_layers; ++l) {

@@ -441,7 +441,7 @@ def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0), head_interleave
 # epilogue; head <= 32 columns), 3 (pairs, two 128-row tiles in flight; head <= 128 columns), 1 (single-CTA tiles,
 # per-layer streamed weights) -- these need the padded hidden width to fit shared memory (hidden <= 207) -- and, for wide
 # models (hidden a multiple of 16, 208 .. 512), 6 (CTA pairs, weights streamed in K chunks).  Other widths use
-# precision="fp32".  2 is the first pair kernel (kept for A/B).
+# precision="fp32".
 TC_VARIANT = None
 
 

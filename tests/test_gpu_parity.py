@@ -519,7 +519,7 @@ def _tc_case(cm, kind, N, H, seed):
     return env, m, obs, act, idx, noise
 
 
-@pytest.fixture(params=[None, 5, 4, 3, 2, 1], ids=["auto", "pair256x2", "pair256", "pingpong", "cta_pair", "single_cta"])
+@pytest.fixture(params=[None, 5, 4, 3, 1], ids=["auto", "pair256x2", "pair256", "pingpong", "single_cta"])
 def tc_variant(request, cm):
     old = cm.ops.TC_VARIANT
     cm.ops.TC_VARIANT = request.param
