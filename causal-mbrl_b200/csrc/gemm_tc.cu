@@ -58,6 +58,22 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// activation / derivative with the fast exp and divide intrinsics (a few ulp: far inside the 1e-5 tier; the precise
+// expf + IEEE divide of common.cuh cost ~30 instructions per element and a third of the tile time in this kernel)
+__device__ __forceinline__ float tg_act_fwd(float z, int act) {
+    if (act == CMRL_ACT_RELU) return fmaxf(z, 0.0f);
+    if (act == CMRL_ACT_SILU) return __fdividef(z, 1.0f + __expf(-z));
+    return z;
+}
+__device__ __forceinline__ float tg_act_grad(float z, int act) {
+    if (act == CMRL_ACT_RELU) return z > 0.0f ? 1.0f : 0.0f;
+    if (act == CMRL_ACT_SILU) {
+        const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+        return s * (1.0f + z * (1.0f - s));
+    }
+    return 1.0f;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tc_kernel(const GemmP p, const TgLay lay) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -284,9 +300,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tc_kernel(const GemmP p, c
                     if (MODE == MODE_FWD) {
                         if (p.bias) x += p.bias[g * p.N + gn];
                         if (p.C2) p.C2[off] = x;
-                        p.C[off] = act_fwd(x, p.act);
+                        p.C[off] = tg_act_fwd(x, p.act);
                     } else if (MODE == MODE_DX) {
-                        if (p.emul) x *= act_grad(p.emul[off], p.act);
+                        if (p.emul) x *= tg_act_grad(p.emul[off], p.act);
                         p.C[off] = x;
                     } else {
                         p.C[off] = p.accumulate ? p.C[off] + x : x;
