@@ -282,11 +282,48 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_tc_kernel(const GemmP p, c
             for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         __syncthreads();
+        // four columns per lane where the output rows allow 16-byte accesses (the scalar write-out -- one element, its 64-bit
+        // address arithmetic, bias load and two stores per iteration -- was 45 % of the kernel's samples)
+        const bool vec_ok = lay.ksplit == 1 && (p.N % 4 == 0) && (p.c_sm % 4 == 0) && (c_off % 4 == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (!p.C2 || (reinterpret_cast<uintptr_t>(p.C2) & 15) == 0) &&
+                            (!p.emul || (reinterpret_cast<uintptr_t>(p.emul) & 15) == 0) &&
+                            (!p.bias || (reinterpret_cast<uintptr_t>(p.bias + g * p.N) & 15) == 0);
         for (int row = warp; row < TG_BM; row += TG_THREADS / 32) {
             const int gm = m0 + row;
             const bool row_ok = gm < p.M;
             const bool row_db = ones_row && gm == p.M;
             if (!row_ok && !row_db) continue;
+            if (vec_ok && row_ok) {
+                for (int col = lane * 4; col < NT; col += 128) {
+                    const int gn = n0 + col;
+                    if (gn >= p.N) continue;  // N % 4 == 0: a group of four is entirely inside or outside
+                    float4 x = *reinterpret_cast<const float4*>(&otile[(size_t)row * ostride + col]);
+                    const long long off = c_off + (long long)gm * p.c_sm + gn;
+                    if (MODE == MODE_FWD) {
+                        if (p.bias) {
+                            const float4 bb = *reinterpret_cast<const float4*>(p.bias + g * p.N + gn);
+                            x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                        }
+                        if (p.C2) *reinterpret_cast<float4*>(p.C2 + off) = x;
+                        *reinterpret_cast<float4*>(p.C + off) =
+                            make_float4(tg_act_fwd(x.x, p.act), tg_act_fwd(x.y, p.act), tg_act_fwd(x.z, p.act), tg_act_fwd(x.w, p.act));
+                    } else if (MODE == MODE_DX) {
+                        if (p.emul) {
+                            const float4 zz = *reinterpret_cast<const float4*>(p.emul + off);
+                            x.x *= tg_act_grad(zz.x, p.act); x.y *= tg_act_grad(zz.y, p.act);
+                            x.z *= tg_act_grad(zz.z, p.act); x.w *= tg_act_grad(zz.w, p.act);
+                        }
+                        *reinterpret_cast<float4*>(p.C + off) = x;
+                    } else {
+                        if (p.accumulate) {
+                            const float4 cc = *reinterpret_cast<const float4*>(p.C + off);
+                            x.x += cc.x; x.y += cc.y; x.z += cc.z; x.w += cc.w;
+                        }
+                        *reinterpret_cast<float4*>(p.C + off) = x;
+                    }
+                }
+                continue;
+            }
             for (int col = lane; col < NT; col += 32) {
                 const int gn = n0 + col;
                 if (gn >= p.N) continue;
