@@ -76,6 +76,8 @@ class VecFakeEnv(VecEnv):
         self.overlap_prepare = True  # device rng_mode: reward / termination / reset draws + buckets on a side stream
         self._side_stream = None
         self._copy_stream = None
+        self._stream_cache = {}
+        self._shared_infos = None
         self._prep_reset = None
         self._tail_graphs = {}
         self._obs_flip = False
@@ -112,6 +114,8 @@ class VecFakeEnv(VecEnv):
         self._reset_by_buffer = self.replay_buffer is not None
 
         self.device = dynamics.device
+        idx = torch.device(self.device).index
+        self._device_index = torch.cuda.current_device() if idx is None else idx
         self.has_set_up = True
         self._alloc()
 
@@ -363,13 +367,24 @@ class VecFakeEnv(VecEnv):
         _lib.note_replayed(cached[3])
         return cached[2]
 
+    def _current_stream(self):
+        """torch.cuda.current_stream() costs ~30 us of Python per call (device-index lookups); the raw handle is one
+        C call, so the Stream objects are cached by handle."""
+        raw = torch._C._cuda_getCurrentRawStream(self._device_index)
+        st = self._stream_cache.get(raw)
+        if st is None:
+            if len(self._stream_cache) > 16:
+                self._stream_cache.clear()
+            st = self._stream_cache[raw] = torch.cuda.current_stream(self._device_index)
+        return st
+
     def step_wait(self):
         assert self.has_set_up, "fake-env has not set up"
         assert len(self._current_batch_action.shape) == 2  # batch, action_dim
         b = self._bufs
         N = self.num_envs
         obs = self._obs_dev
-        stream = torch.cuda.current_stream()
+        stream = self._current_stream()
         if self._current_batch_obs is None:  # device-resident steps ran in between
             self.sync_host_obs()
         b["act_pin"].numpy()[...] = self._current_batch_action
@@ -408,7 +423,7 @@ class VecFakeEnv(VecEnv):
                 reward.copy_(torch.from_numpy(np.ascontiguousarray(r.reshape(N, 1))), non_blocking=False)
             if not self.learned_termination:
                 t = np.asarray(self.termination_fn(host_next, host_obs, self._current_batch_action))
-                b["h_term_u8"].numpy()[...] = t.reshape(N) != 0
+                np.not_equal(t.reshape(N), 0, out=b["h_term_u8"].numpy().view(np.bool_))  # one pass, no temporary
                 terminal_u8 = b["term_u8"]  # uploaded by tail_and_readback()
 
         def tail_and_readback():
@@ -484,7 +499,11 @@ class VecFakeEnv(VecEnv):
         self._current_batch_obs = host_next
 
         infos = self._make_infos(batch_truncate, done_idx, terminal_rows)
-        return ret_obs, b["h_reward"].numpy().copy(), batch_done.copy(), infos
+        # return_views: the reward array is the pinned read-back buffer itself (valid until the next step -- SB3's
+        # collectors add it to their buffers before stepping again); `done` is always a copy (on-policy collectors keep
+        # it as `_last_episode_starts` across the next step)
+        host_reward = b["h_reward"].numpy()
+        return ret_obs, (host_reward if self.return_views else host_reward.copy()), batch_done.copy(), infos
 
     def step_device(self, actions: torch.Tensor, termination=None):
         """Device-resident step for rollout collectors that keep their buffers on the GPU: `actions` is a CUDA
@@ -626,10 +645,14 @@ class VecFakeEnv(VecEnv):
         """`terminal_rows[k]` = pre-reset next_obs of env `done_idx[k]` (fake_env.py:126-135)."""
         N = self.num_envs
         if self.infos_mode == "shared":
-            shared = {"TimeLimit.truncated": np.False_}
-            infos = [shared] * N
-            for i in np.nonzero(batch_truncate)[0]:
-                infos[i] = {"TimeLimit.truncated": np.True_}
+            # every truncated env is also done (done = terminal | truncated), so only the done rows get their own dict;
+            # a step without done envs hands out one cached list (building 100 000 references costs ~20 us)
+            base = self._shared_infos
+            if base is None or len(base) != N:
+                base = self._shared_infos = [{"TimeLimit.truncated": np.False_}] * N
+            if done_idx.size == 0:
+                return base
+            infos = list(base)
             for k, i in enumerate(done_idx):
                 infos[i] = {"TimeLimit.truncated": batch_truncate[i], "terminal_observation": terminal_rows[k]}
             return infos
