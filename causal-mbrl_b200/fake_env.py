@@ -255,11 +255,14 @@ class VecFakeEnv(VecEnv):
         mn, mx = model._bounds()
         return ops.sample_scatter(raw, model._head_layout, perm, N, D, obs if model._residual() else None, mn, mx, noise)
 
-    def _predict_all(self, obs, act, need_all, after_transition=None):
+    def _predict_all(self, obs, act, need_all, after_transition=None, before_transition=None):
         """transition (+ reward / termination mechs): the device part of a step before any host callback.
-        `after_transition(next_obs)` is called as soon as the transition prediction is enqueued."""
+        `after_transition(next_obs)` is called as soon as the transition prediction is enqueued, `before_transition()`
+        after the draws / buckets (which do not read `act`) and before the first kernel that does."""
         all_out = {} if need_all else None
         preps = self._prepare_all(need_all)
+        if before_transition is not None:
+            before_transition()
         next_obs = self._predict("transition", obs, act, all_out, prep=preps.get("transition"))
         if after_transition is not None:
             after_transition(next_obs)
@@ -309,22 +312,23 @@ class VecFakeEnv(VecEnv):
             torch.cuda.current_stream().wait_stream(self._side_stream)
             self._prep_forked = False
 
-    def _predict_all_graphed(self, obs, act, need_all, host_next_buf=None):
+    def _predict_all_graphed(self, obs, act, need_all, host_next_buf=None, act_pin=None):
         """Same, replayed from a CUDA graph in device rng_mode (the graph is re-captured when packed weights, elite
         sets or the precision changed).  host_next_buf: pinned [N,O] tensor that receives next_obs -- the copy is a
         node of the graph on a branch that starts right after the transition kernel, so it overlaps the reward /
-        termination mechanisms (one graph per destination buffer: the host side ping-pongs between two)."""
+        termination mechanisms (one graph per destination buffer: the host side ping-pongs between two).  With
+        host_next_buf, `act_pin` (pinned [N,A]) is uploaded into `act` by a node on the copy branch beside the draws."""
         graphs = getattr(self, "_predict_graphs", None)
         if graphs is None:
             graphs = self._predict_graphs = {}
         slot = 0 if host_next_buf is None else host_next_buf.data_ptr()
         self._predict_graph = graphs.get(slot)
         try:
-            return self._predict_all_graphed_one(obs, act, need_all, host_next_buf)
+            return self._predict_all_graphed_one(obs, act, need_all, host_next_buf, act_pin)
         finally:
             graphs[slot] = self._predict_graph
 
-    def _predict_all_graphed_one(self, obs, act, need_all, host_next_buf):
+    def _predict_all_graphed_one(self, obs, act, need_all, host_next_buf, act_pin=None):
         key = (self.precision, self.deterministic, need_all) + tuple(
             (id(getattr(self.dynamics, m)._packed.get("f16")), id(getattr(self.dynamics, m)._elite_members),
              getattr(self.dynamics, m)._flat.data_ptr() if getattr(self.dynamics, m)._flat is not None else 0)
@@ -351,20 +355,34 @@ class VecFakeEnv(VecEnv):
                     self._copy_stream = torch.cuda.Stream(device=self.device)
                 copy_stream = self._copy_stream
 
+            # an EXTERNAL event becomes an event-record node of the graph: the host waits for the next_obs copy alone and
+            # runs its callbacks while the reward / termination mechanisms are still executing
+            copied = torch.cuda.Event(external=True) if copy_stream is not None else None
+
             def early_copy(next_obs):
                 copy_stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(copy_stream):
                     host_next_buf.copy_(next_obs, non_blocking=True)
+                    copied.record(copy_stream)
+
+            def join_upload():
+                torch.cuda.current_stream().wait_stream(copy_stream)
 
             with ops.graph_capture(g):
-                out = self._predict_all(obs, act, need_all, early_copy if copy_stream is not None else None)
+                if copy_stream is not None:  # action upload on the copy branch, joined before the transition kernel
+                    copy_stream.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(copy_stream):
+                        act.copy_(act_pin, non_blocking=True)
+                out = self._predict_all(obs, act, need_all, early_copy if copy_stream is not None else None,
+                                        join_upload if copy_stream is not None else None)
                 ops.counter_add(self._rng_base, self._draw_counter - c0)
                 if copy_stream is not None:
                     torch.cuda.current_stream().wait_stream(copy_stream)
-            cached = (key, g, out, _lib.launch_count() - l0)
+            cached = (key, g, out, _lib.launch_count() - l0, copied)
             self._predict_graph = cached
         cached[1].replay()
         _lib.note_replayed(cached[3])
+        self._next_obs_copied = cached[4]
         return cached[2]
 
     def _current_stream(self):
@@ -389,7 +407,6 @@ class VecFakeEnv(VecEnv):
             self.sync_host_obs()
         b["act_pin"].numpy()[...] = self._current_batch_action
         act = b["act"]
-        act.copy_(b["act_pin"], non_blocking=True)
 
         need_all = self.penalty_coeff != 0
         device_rng = self.rng_mode == "device"
@@ -398,9 +415,14 @@ class VecFakeEnv(VecEnv):
         host_callbacks = not (self.learned_reward and self.learned_termination)
         copied_in_graph = False
         if device_rng and self.use_graph:
-            next_obs, reward, terminal_f, penalty = self._predict_all_graphed(obs, act, need_all, h_next if host_callbacks else None)
+            if host_callbacks:  # the action upload is a node of the predict graph (beside the draws and buckets)
+                next_obs, reward, terminal_f, penalty = self._predict_all_graphed(obs, act, need_all, h_next, b["act_pin"])
+            else:
+                act.copy_(b["act_pin"], non_blocking=True)
+                next_obs, reward, terminal_f, penalty = self._predict_all_graphed(obs, act, need_all, None)
             copied_in_graph = host_callbacks
         else:
+            act.copy_(b["act_pin"], non_blocking=True)
             next_obs, reward, terminal_f, penalty = self._predict_all(obs, act, need_all)
         if penalty is not None and self.logger is not None:
             self.logger.record_mean("rollout/penalty", penalty.mean().item())
@@ -414,7 +436,9 @@ class VecFakeEnv(VecEnv):
         if host_callbacks:
             if not copied_in_graph:
                 h_next.copy_(next_obs, non_blocking=True)
-            stream.synchronize()
+                stream.synchronize()
+            else:
+                self._next_obs_copied.synchronize()  # the copy node of the predict graph; the other mechs keep running
             host_next = h_next.numpy()
             host_obs = self._current_batch_obs
             if not self.learned_reward:
@@ -423,7 +447,11 @@ class VecFakeEnv(VecEnv):
                 reward.copy_(torch.from_numpy(np.ascontiguousarray(r.reshape(N, 1))), non_blocking=False)
             if not self.learned_termination:
                 t = np.asarray(self.termination_fn(host_next, host_obs, self._current_batch_action))
-                np.not_equal(t.reshape(N), 0, out=b["h_term_u8"].numpy().view(np.bool_))  # one pass, no temporary
+                flags = b["h_term_u8"].numpy().view(np.bool_)
+                if t.dtype == np.bool_:
+                    np.copyto(flags, t.reshape(N))  # 100 KB memcpy; the generic compare below casts through int64 (~60 us)
+                else:
+                    np.not_equal(t.reshape(N), 0, out=flags)
                 terminal_u8 = b["term_u8"]  # uploaded by tail_and_readback()
 
         def tail_and_readback():

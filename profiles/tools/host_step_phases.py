@@ -31,6 +31,7 @@ def wrap(cls, name, key):
     setattr(cls, name, f)
 wrap(torch.cuda.CUDAGraph, 'replay', 'replay')
 wrap(torch.cuda.Stream, 'synchronize', 'sync')
+wrap(torch.cuda.Event, 'synchronize', 'evsync')
 S = 200
 t0 = time.perf_counter()
 for _ in range(S): env.step(act)
