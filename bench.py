@@ -400,7 +400,7 @@ def time_train(cm, dyn_unused, dev, args, world, barrier, B=256, n_batches=200, 
            "ms_per_step": ms, "steps_per_epoch": steps, "epoch_mean_nll": loss,
            "config": "C4-shaped: PlainTransition E=7 4x200 SiLU O=5 A=1, bs %d per member per GPU, fp32-grade tier "
                      "(GEMM tier %s: %s), device-resident epoch (on-device bootstrap gather + CUDA-graph replay), %s"
-                     % (B, cm.ops.TRAIN_GEMM_TIER, "tcgen05 3xTF32 forward/dx, FFMA dw" if B >= cm.ops.TRAIN_GEMM_TC_MIN_ROWS
+                     % (B, cm.ops.TRAIN_GEMM_TIER, "tcgen05 3xTF32 forward/dx" + (", split-K dw" if B >= 2048 else ", FFMA dw") if B >= cm.ops.TRAIN_GEMM_TC_MIN_ROWS
                         else "FFMA: latency bound at this batch size",
                         "single GPU" if world == 1 else "data parallel over %d GPUs: global batch %d rows per member sharded by rows, "
                         "one NCCL all-reduce of the flat gradient arena per step" % (world, Bg))}  # fmt: skip
