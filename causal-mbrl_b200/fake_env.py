@@ -415,12 +415,10 @@ class VecFakeEnv(VecEnv):
         host_callbacks = not (self.learned_reward and self.learned_termination)
         copied_in_graph = False
         if device_rng and self.use_graph:
-            if host_callbacks:  # the action upload is a node of the predict graph (beside the draws and buckets)
-                next_obs, reward, terminal_f, penalty = self._predict_all_graphed(obs, act, need_all, h_next, b["act_pin"])
-            else:
-                act.copy_(b["act_pin"], non_blocking=True)
-                next_obs, reward, terminal_f, penalty = self._predict_all_graphed(obs, act, need_all, None)
-            copied_in_graph = host_callbacks
+            # the action upload and the next_obs read-back are nodes of the predict graph (beside the draws / buckets and
+            # beside the reward / termination mechanisms), with or without host callbacks
+            next_obs, reward, terminal_f, penalty = self._predict_all_graphed(obs, act, need_all, h_next, b["act_pin"])
+            copied_in_graph = True
         else:
             act.copy_(b["act_pin"], non_blocking=True)
             next_obs, reward, terminal_f, penalty = self._predict_all(obs, act, need_all)
@@ -454,6 +452,8 @@ class VecFakeEnv(VecEnv):
                     np.not_equal(t.reshape(N), 0, out=flags)
                 terminal_u8 = b["term_u8"]  # uploaded by tail_and_readback()
 
+        need_term_obs = host_next is None and not copied_in_graph
+
         def tail_and_readback():
             """reset-row draw, fused tail, device -> host copies of the SB3 return values (all asynchronous)"""
             if terminal_u8 is not None:
@@ -463,22 +463,22 @@ class VecFakeEnv(VecEnv):
                 reset_rows, reset_index = self._device_reset_source(tail=True)
             ops.env_step_tail(next_obs, reward, terminal_f, terminal_u8, penalty, self.penalty_coeff, self._env_len_dev,
                               self.max_episode_steps, reset_rows, reset_index, obs, b["reward_out"], b["done"], b["trunc"],
-                              b["term_obs"] if host_next is None else None, None)  # fmt: skip
-            if host_next is None:  # fully learned step: the pre-reset next_obs comes back now
+                              b["term_obs"] if need_term_obs else None, None)  # fmt: skip
+            if need_term_obs:  # fully learned eager step: the pre-reset next_obs comes back now
                 h_next.copy_(b["term_obs"], non_blocking=True)
             b["h_reward"].copy_(b["reward_out"], non_blocking=True)
             b["h_done"].copy_(b["done"], non_blocking=True)
             b["h_trunc"].copy_(b["trunc"], non_blocking=True)
 
-        if device_rng and self.use_graph and copied_in_graph == host_callbacks and (self.learned_reward or reward is b["reward"]):
+        if device_rng and self.use_graph and copied_in_graph and (self.learned_reward or reward is b["reward"]):
             # second half of the step as one graph replay (5-6 launches / copies otherwise issued one by one from Python);
             # every operand is a fixed buffer: the predict graph's outputs, the pinned mirrors, this step's h_next
             if self._pool_dev is None or (self._reset_by_buffer and self._pool_rows != self._upper_bound()):
                 c_keep = self._draw_counter
                 self._device_reset_source(tail=True)  # (re)builds the reset pool outside any capture
                 self._draw_counter = c_keep
-            key = (id(next_obs), id(reward), id(terminal_f), terminal_u8 is not None, id(penalty), host_next is None,
-                   h_next.data_ptr() if host_next is None else 0, self._pool_dev.data_ptr(), self._pool_rows,
+            key = (id(next_obs), id(reward), id(terminal_f), terminal_u8 is not None, id(penalty), need_term_obs,
+                   h_next.data_ptr() if need_term_obs else 0, self._pool_dev.data_ptr(), self._pool_rows,
                    self.penalty_coeff, self.max_episode_steps)
             tg = self._tail_graphs.get(key)
             if tg is None:

@@ -17,7 +17,7 @@ with torch.no_grad():  # a termination head that fires rarely (the reference's r
 dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw, learned_termination=True, termination_mech=tm)
 env = cm.VecFakeEnv(N, None, None)
 env.set_up(dyn, get_init_obs_fn=lambda n: rng.normal(size=(n, O)).astype(np.float32), max_episode_steps=1000)
-env.rng_mode, env.infos_mode, env.precision, env.deterministic = 'device', 'shared', 'f16', True
+env.rng_mode, env.infos_mode, env.precision, env.deterministic, env.return_views = 'device', 'shared', 'f16', True, True
 env.seed(0); env.reset()
 act_h = rng.uniform(-1, 1, size=(N, A)).astype(np.float32); act = torch.from_numpy(act_h).to(dev)
 flush = torch.empty(64 * 1024 * 1024, device=dev)

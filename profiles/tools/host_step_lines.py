@@ -3,18 +3,30 @@ import sys, time, linecache, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 import cmrl_b200 as cm
 import cmrl_b200.fake_env as fe
+ARGS = sys.argv[1:]
 sys.argv = ['bench.py']
 import bench
 dev = 'cuda:0'
-N = 100000
+C3 = 'c3' in ARGS  # fully learned step (transition + reward + termination mechs), 125 000 envs
+N = 125000 if C3 else 100000
 torch.manual_seed(0); np.random.seed(0)
-tr = cm.ExternalMaskTransition(5, 1, hid_size=200, activation_fn_cfg=bench.SILU, device=dev)
-tr.set_input_mask(torch.from_numpy(bench.make_mask()))
-rw = cm.PlainRewardMech(5, 1, hid_size=200, activation_fn_cfg=bench.SILU, device=dev)
-dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw)
 rng = np.random.default_rng(0)
 env = cm.VecFakeEnv(N, None, None)
-env.set_up(dyn, termination_fn=lambda n, o, a: np.zeros((n.shape[0], 1), dtype=bool), get_init_obs_fn=lambda n: rng.normal(size=(n, 5)).astype(np.float32))
+if C3:
+    tr = cm.PlainTransition(5, 1, hid_size=200, activation_fn_cfg=bench.SILU, device=dev)
+    rw = cm.PlainRewardMech(5, 1, hid_size=200, activation_fn_cfg=bench.SILU, device=dev)
+    tm = cm.PlainTerminationMech(5, 1, hid_size=200, activation_fn_cfg=bench.SILU, device=dev)
+    with torch.no_grad():
+        tm.mean_and_logvar.weight.zero_(); tm.mean_and_logvar.bias.zero_()
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw, learned_termination=True, termination_mech=tm)
+    env.set_up(dyn, get_init_obs_fn=lambda n: rng.normal(size=(n, 5)).astype(np.float32))
+    env.deterministic = True
+else:
+    tr = cm.ExternalMaskTransition(5, 1, hid_size=200, activation_fn_cfg=bench.SILU, device=dev)
+    tr.set_input_mask(torch.from_numpy(bench.make_mask()))
+    rw = cm.PlainRewardMech(5, 1, hid_size=200, activation_fn_cfg=bench.SILU, device=dev)
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw)
+    env.set_up(dyn, termination_fn=lambda n, o, a: np.zeros((n.shape[0], 1), dtype=bool), get_init_obs_fn=lambda n: rng.normal(size=(n, 5)).astype(np.float32))
 env.rng_mode = 'device'; env.infos_mode = 'shared'; env.precision = 'f16'; env.return_views = True
 env.reset()
 act = rng.uniform(-1, 1, size=(N, 1)).astype(np.float32)
