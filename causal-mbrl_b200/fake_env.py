@@ -78,6 +78,12 @@ class VecFakeEnv(VecEnv):
         self._copy_stream = None
         self._stream_cache = {}
         self._shared_infos = None
+        # graph-replayed steps draw and bucket the transition's members for the NEXT step beside this step's reward
+        # mech (~18 us of small launches off the critical path); see _prepare_next_transition
+        self.prep_ahead = True
+        self._ahead_bufs = None      # persistent (idx, noise) of the transition draw
+        self._ahead_family = None    # token of the graph family whose last replay filled them for the coming step
+        self._prep_event = None
         self._prep_reset = None
         self._tail_graphs = {}
         self._obs_flip = False
@@ -255,25 +261,74 @@ class VecFakeEnv(VecEnv):
         mn, mx = model._bounds()
         return ops.sample_scatter(raw, model._head_layout, perm, N, D, obs if model._residual() else None, mn, mx, noise)
 
-    def _predict_all(self, obs, act, need_all, after_transition=None, before_transition=None):
+    def _predict_all(self, obs, act, need_all, after_transition=None, before_transition=None, ahead=None):
         """transition (+ reward / termination mechs): the device part of a step before any host callback.
         `after_transition(next_obs)` is called as soon as the transition prediction is enqueued, `before_transition()`
         after the draws / buckets (which do not read `act`) and before the first kernel that does."""
         all_out = {} if need_all else None
-        preps = self._prepare_all(need_all)
+        preps = self._prepare_all(need_all, ahead=ahead)
         if before_transition is not None:
             before_transition()
         next_obs = self._predict("transition", obs, act, all_out, prep=preps.get("transition"))
         if after_transition is not None:
             after_transition(next_obs)
+        if ahead is not None:
+            self._prepare_next_transition(ahead)
         self._join_prepare()
         reward = self._predict("reward_mech", obs, act, prep=preps.get("reward_mech")) if self.learned_reward else None
         terminal_f = (self._predict("termination_mech", obs, act, prep=preps.get("termination_mech"))
                       if self.learned_termination else None)
         penalty = ops.mopo_penalty(all_out["mean"]) if need_all else None
+        if ahead is not None:
+            torch.cuda.current_stream().wait_stream(self._side_stream)  # the next step's draws / buckets
         return next_obs, reward, terminal_f, penalty
 
-    def _prepare_all(self, need_all, reset_source=False):
+    # ---- transition draws one step ahead (graph-replayed steps only) ---------------------------------------------
+    def _ahead_ok(self, need_all):
+        return (self.prep_ahead and self.overlap_prepare and self.rng_mode == "device"
+                and self._selected_path(self.dynamics.transition, need_all))
+
+    def _ahead_new(self, reset_source):
+        """Capture-time description of a pipelined step graph: the transition kernel reads persistent draw / bucket
+        buffers that the PREVIOUS replay filled (Philox stream id of this step's draw = t_id + device counter; the
+        draw for the next step uses t_id + n, n = draws per step, because the graph advances the counter by n)."""
+        tr = self.dynamics.transition
+        if self._ahead_bufs is None or self._ahead_bufs[0].numel() != self.num_envs or \
+                (self._ahead_bufs[1] is None) != bool(self.deterministic):
+            idx = torch.empty(self.num_envs, device=self.device, dtype=torch.uint8)
+            noise = None if self.deterministic else torch.empty((self.num_envs, tr._head_dim), device=self.device)
+            self._ahead_bufs = (idx, noise)
+            self._ahead_family = None
+        n = 1 + int(self.learned_reward) + int(self.learned_termination) + int(bool(reset_source))
+        return {"t_id": self._draw_counter + 1, "n": n}
+
+    def _ahead_draw(self, stream_id):
+        tr = self.dynamics.transition
+        b = self._bufs
+        ops.draw_member_noise(self._device_seed, stream_id, self.num_envs, self._elite_u8("transition"), tr._head_dim,
+                              want_noise=not self.deterministic, stream_base=self._rng_base, out=self._ahead_bufs)
+        ops.member_bucket(self._ahead_bufs[0], tr.ensemble_num, b["perm@transition"], b["offsets@transition"],
+                          b["counters@transition"])
+
+    def _prepare_next_transition(self, ahead):
+        """(inside a capture) after the transition kernel consumed the buffers: refill them for the next replay, on the
+        side stream, concurrent with the reward / termination mechs"""
+        side = self._side_stream
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._ahead_draw(ahead["t_id"] + ahead["n"])
+
+    def _ahead_before_replay(self, ahead):
+        """the buffers hold this step's draws only if the previous thing that advanced the device counter was a replay
+        of the same graph family; otherwise draw them now (first step, after a re-capture, another step flavour)"""
+        if ahead is None:
+            self._ahead_family = None
+            return
+        if self._ahead_family != ahead["family"]:
+            self._ahead_draw(ahead["t_id"])
+        self._ahead_family = ahead["family"]
+
+    def _prepare_all(self, need_all, reset_source=False, ahead=None):
         """device rng_mode: the draws and member buckets of every mechanism (and the reset-row draw) are independent of
         the transition network, so all but the transition's own run on a side stream while the fused transition kernel
         computes (~20 us of small launches per step off the critical path; fork / join through events, also under
@@ -282,7 +337,14 @@ class VecFakeEnv(VecEnv):
         self._prep_reset = None
         if self.rng_mode != "device":
             return {}
-        preps = {"transition": self._prepare("transition", need_all)}
+        if ahead is not None:  # drawn by the previous replay (or _ahead_before_replay); the stream id is consumed all the same
+            self._draw_counter += 1
+            assert self._draw_counter == ahead["t_id"]
+            b = self._bufs
+            preps = {"transition": self._ahead_bufs + ((b["perm@transition"], b["offsets@transition"]),)}
+        else:
+            self._ahead_family = None  # the transition's bucket buffers are rewritten
+            preps = {"transition": self._prepare("transition", need_all)}
         others = [m for m, on in (("reward_mech", self.learned_reward), ("termination_mech", self.learned_termination)) if on]
         if not self.overlap_prepare:
             for m in others:
@@ -304,12 +366,15 @@ class VecFakeEnv(VecEnv):
             if reset_source:
                 self._prep_reset = self._device_reset_source()
                 self._prep_reset[1].record_stream(main)
+            # joined through an event, not the stream: with `ahead` more work follows on the side stream
+            self._prep_event = torch.cuda.Event()
+            self._prep_event.record(side)
         self._prep_forked = True
         return preps
 
     def _join_prepare(self):
         if getattr(self, "_prep_forked", False):
-            torch.cuda.current_stream().wait_stream(self._side_stream)
+            torch.cuda.current_stream().wait_event(self._prep_event)
             self._prep_forked = False
 
     def _predict_all_graphed(self, obs, act, need_all, host_next_buf=None, act_pin=None):
@@ -349,6 +414,7 @@ class VecFakeEnv(VecEnv):
             g = torch.cuda.CUDAGraph()
             c0 = self._draw_counter
             l0 = _lib.launch_count()
+            ahead = self._ahead_new(False) if self._ahead_ok(need_all) else None
             copy_stream = None
             if host_next_buf is not None:
                 if self._copy_stream is None:
@@ -374,12 +440,19 @@ class VecFakeEnv(VecEnv):
                     with torch.cuda.stream(copy_stream):
                         act.copy_(act_pin, non_blocking=True)
                 out = self._predict_all(obs, act, need_all, early_copy if copy_stream is not None else None,
-                                        join_upload if copy_stream is not None else None)
+                                        join_upload if copy_stream is not None else None, ahead=ahead)
                 ops.counter_add(self._rng_base, self._draw_counter - c0)
                 if copy_stream is not None:
                     torch.cuda.current_stream().wait_stream(copy_stream)
-            cached = (key, g, out, _lib.launch_count() - l0, copied)
+            if ahead is not None:
+                assert self._draw_counter - c0 == ahead["n"]
+                ahead["family"] = ("predict", key, ahead["t_id"], ahead["n"])
+            # every predict graph (one per pinned destination buffer) bakes the same Philox stream ids; the device
+            # counter the graphs advance makes them unique per step
+            self._draw_counter = c0
+            cached = (key, g, out, _lib.launch_count() - l0, copied, ahead)
             self._predict_graph = cached
+        self._ahead_before_replay(cached[5])
         cached[1].replay()
         _lib.note_replayed(cached[3])
         self._next_obs_copied = cached[4]
@@ -487,8 +560,10 @@ class VecFakeEnv(VecEnv):
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 l0 = _lib.launch_count()
+                c_keep = self._draw_counter
                 with ops.graph_capture(g):
                     tail_and_readback()
+                self._draw_counter = c_keep  # as for the predict graphs: baked id + device counter
                 tg = self._tail_graphs[key] = (g, _lib.launch_count() - l0)
             tg[0].replay()
             _lib.note_replayed(tg[1])
@@ -533,7 +608,7 @@ class VecFakeEnv(VecEnv):
         host_reward = b["h_reward"].numpy()
         return ret_obs, (host_reward if self.return_views else host_reward.copy()), batch_done.copy(), infos
 
-    def step_device(self, actions: torch.Tensor, termination=None):
+    def step_device(self, actions: torch.Tensor, termination=None, _ahead=None):
         """Device-resident step for rollout collectors that keep their buffers on the GPU: `actions` is a CUDA
         tensor [N,A]; nothing is copied to the host and nothing synchronises.  Needs rng_mode == "device" and a
         learned reward mech; termination is the learned mech, or `termination(next_obs, obs, actions)` -> CUDA
@@ -546,8 +621,10 @@ class VecFakeEnv(VecEnv):
         obs = self._obs_dev
         need_all = self.penalty_coeff != 0
         all_out = {} if need_all else None
-        preps = self._prepare_all(need_all, reset_source=True)
+        preps = self._prepare_all(need_all, reset_source=True, ahead=_ahead)
         next_obs = self._predict("transition", obs, actions, all_out, prep=preps.get("transition"))
+        if _ahead is not None:
+            self._prepare_next_transition(_ahead)
         self._join_prepare()
         reward = self._predict("reward_mech", obs, actions, prep=preps.get("reward_mech"))
         terminal_f = terminal_u8 = None
@@ -560,6 +637,8 @@ class VecFakeEnv(VecEnv):
         ops.env_step_tail(next_obs, reward, terminal_f, terminal_u8, penalty, self.penalty_coeff, self._env_len_dev,
                           self.max_episode_steps, reset_rows, reset_index, obs, b["reward_out"], b["done"], b["trunc"],
                           b["term_obs"], None)  # fmt: skip
+        if _ahead is not None:
+            torch.cuda.current_stream().wait_stream(self._side_stream)  # the next step's draws / buckets
         self._current_batch_obs = None  # host mirror is stale now (refreshed lazily by step_wait / sync_host_obs)
         return obs, b["reward_out"], b["done"], b["trunc"], b["term_obs"]
 
@@ -588,13 +667,19 @@ class VecFakeEnv(VecEnv):
             g = torch.cuda.CUDAGraph()
             c0 = self._draw_counter
             l0 = _lib.launch_count()
+            ahead = self._ahead_new(True) if self._ahead_ok(self.penalty_coeff != 0) else None
             with ops.graph_capture(g):
-                self._graph_out = self.step_device(b["act"])
+                self._graph_out = self.step_device(b["act"], _ahead=ahead)
                 ops.counter_add(self._rng_base, self._draw_counter - c0)
+            if ahead is not None:
+                assert self._draw_counter - c0 == ahead["n"]
+                ahead["family"] = ("step", id(g), ahead["t_id"], ahead["n"])
+            self._step_graph_ahead = ahead
             self._step_graph_launches = _lib.launch_count() - l0
             self._step_graph = g
         else:
             b["act"].copy_(actions, non_blocking=True)
+        self._ahead_before_replay(self._step_graph_ahead)
         self._step_graph.replay()
         _lib.note_replayed(self._step_graph_launches)
         self._current_batch_obs = None
@@ -602,6 +687,7 @@ class VecFakeEnv(VecEnv):
 
     def invalidate_step_graph(self):
         self._step_graph = None
+        self._ahead_family = None
 
     def rollout_device(self, policy, n_steps: int, termination=None, out: Optional[Dict[str, torch.Tensor]] = None):
         """Device-resident multi-step rollout into SB3 `ReplayBuffer`-layout slabs: replaces the
@@ -741,6 +827,12 @@ class VecFakeEnv(VecEnv):
         self.generator = np.random.default_rng(seed=seed)
         self._device_seed = 0 if seed is None else int(seed)
         self._draw_counter = 0
+        # seed and stream ids are baked into captured graphs
+        self._step_graph = None
+        self._predict_graphs = None
+        self._predict_graph = None
+        self._tail_graphs = {}
+        self._ahead_family = None
 
     def close(self) -> None:
         pass

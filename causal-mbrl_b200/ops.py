@@ -311,10 +311,15 @@ def bootstrap_gather(obs, act, target, member_idx, order, start_dev, advance, B,
 
 
 # ----------------------------------------------------------------------------- rollout
-def draw_member_noise(seed, stream_id, N, elite_u8, D, want_noise=True, device=None, stream_base=None):
+def draw_member_noise(seed, stream_id, N, elite_u8, D, want_noise=True, device=None, stream_base=None, out=None):
+    """out: optional (idx [N] uint8, noise [N,D] float32 or None) to draw into"""
     device = elite_u8.device if device is None else device
-    idx = torch.empty(N, device=device, dtype=torch.uint8)
-    noise = torch.empty((N, D), device=device, dtype=torch.float32) if want_noise else None
+    if out is not None:
+        idx, noise = out
+        assert idx.numel() == N and (noise is None) == (not want_noise)
+    else:
+        idx = torch.empty(N, device=device, dtype=torch.uint8)
+        noise = torch.empty((N, D), device=device, dtype=torch.float32) if want_noise else None
     _lib.call("cmrl_draw_member_noise", int(seed), int(stream_id), _ptr(stream_base), N, elite_u8.data_ptr(),
               elite_u8.numel(), D, idx.data_ptr(), _ptr(noise), _stream())  # fmt: skip
     return idx, noise
