@@ -135,9 +135,11 @@ class VecFakeEnv(VecEnv):
         b["next_obs"] = torch.empty((N, O), device=dev, dtype=torch.float32)
         b["reward"] = torch.empty((N, 1), device=dev, dtype=torch.float32)
         b["terminal"] = torch.empty((N, 1), device=dev, dtype=torch.float32)
-        b["reward_out"] = torch.empty(N, device=dev, dtype=torch.float32)
-        b["done"] = torch.empty(N, device=dev, dtype=torch.uint8)
-        b["trunc"] = torch.empty(N, device=dev, dtype=torch.uint8)
+        # reward [N] f32 | done [N] u8 | truncated [N] u8 live in ONE buffer so that they come back in one copy
+        b["tail_out"] = torch.empty(6 * N, device=dev, dtype=torch.uint8)
+        b["reward_out"] = b["tail_out"][:4 * N].view(torch.float32)
+        b["done"] = b["tail_out"][4 * N:5 * N]
+        b["trunc"] = b["tail_out"][5 * N:]
         b["term_obs"] = torch.empty((N, O), device=dev, dtype=torch.float32)
         b["n_done"] = torch.zeros(1, device=dev, dtype=torch.int32)
         E = self.dynamics.ensemble_num
@@ -151,9 +153,10 @@ class VecFakeEnv(VecEnv):
         b["h_term_u8"] = torch.empty(N, dtype=torch.uint8).pin_memory()
         b["term_u8"] = torch.empty(N, device=dev, dtype=torch.uint8)
         b["h_term_obs"] = torch.empty((N, O), dtype=torch.float32).pin_memory()
-        b["h_reward"] = torch.empty(N, dtype=torch.float32).pin_memory()
-        b["h_done"] = torch.empty(N, dtype=torch.uint8).pin_memory()
-        b["h_trunc"] = torch.empty(N, dtype=torch.uint8).pin_memory()
+        b["h_tail_out"] = torch.empty(6 * N, dtype=torch.uint8).pin_memory()
+        b["h_reward"] = b["h_tail_out"][:4 * N].view(torch.float32)
+        b["h_done"] = b["h_tail_out"][4 * N:5 * N]
+        b["h_trunc"] = b["h_tail_out"][5 * N:]
         self._bufs = b
         self._obs_dev = torch.zeros((N, O), device=dev, dtype=torch.float32)
         self._env_len_dev = torch.zeros(N, device=dev, dtype=torch.int32)
@@ -539,9 +542,7 @@ class VecFakeEnv(VecEnv):
                               b["term_obs"] if need_term_obs else None, None)  # fmt: skip
             if need_term_obs:  # fully learned eager step: the pre-reset next_obs comes back now
                 h_next.copy_(b["term_obs"], non_blocking=True)
-            b["h_reward"].copy_(b["reward_out"], non_blocking=True)
-            b["h_done"].copy_(b["done"], non_blocking=True)
-            b["h_trunc"].copy_(b["trunc"], non_blocking=True)
+            b["h_tail_out"].copy_(b["tail_out"], non_blocking=True)  # reward, done, truncated
 
         if device_rng and self.use_graph and copied_in_graph and (self.learned_reward or reward is b["reward"]):
             # second half of the step as one graph replay (5-6 launches / copies otherwise issued one by one from Python);
