@@ -705,6 +705,51 @@ def test_rollout_device_slabs_equal_step_by_step(cm, precision):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
+def test_draws_one_step_ahead_same_numbers(cm, precision):
+    """`prep_ahead` (graph-replayed steps draw / bucket the transition's members for the NEXT step) only moves launches:
+    host-facing steps, device-resident graph steps, kernel-by-kernel steps and switches between them give bit-identical
+    trajectories with and without it."""
+    N = 500
+    act = np.random.default_rng(1).uniform(-1, 1, size=(N, 2)).astype(np.float32)
+    act_d = t(act)
+    runs = []
+    for ahead in (False, True):
+        env = _rollout_env(cm, N, 7)
+        env.precision, env.prep_ahead = precision, ahead
+        with torch.no_grad():  # a termination head that never fires ("non-zero => done"): episodes end by truncation, so
+            tm = env.dynamics.termination_mech  # the returned observations carry the transition's draws
+            tm.mean_and_logvar.weight.zero_()
+            tm.mean_and_logvar.bias.zero_()
+        tm.deterministic = True  # (its own sampling noise would make the output non-zero)
+        rec = []
+
+        def host_steps(n):
+            for _ in range(n):
+                o, r, d, _infos = env.step(act)
+                rec.extend([np.array(o), np.array(r), np.array(d)])
+
+        def graph_steps(n):
+            for _ in range(n):
+                o, r, d, _tr, to = env.step_device_graphed(act_d)
+                rec.extend([x.cpu().numpy().copy() for x in (o, r, d, to)])
+
+        host_steps(4)
+        graph_steps(3)
+        host_steps(3)
+        rec.extend([x.cpu().numpy().copy() for x in env.step_device(act_d)])  # kernel by kernel: rewrites the bucket buffers
+        graph_steps(2)
+        host_steps(2)
+        runs.append(rec)
+    assert len(runs[0]) == len(runs[1])
+    for k, (a, b) in enumerate(zip(*runs)):
+        assert np.array_equal(a, b), k
+    assert not np.array_equal(runs[0][1], runs[0][4])  # fresh draws every step
+    dones = [r for r in runs[0] if r.shape == (N,) and r.dtype in (np.bool_, np.uint8)]
+    assert not dones[0].any() and any(d.all() for d in dones)  # episodes end by truncation only (max_episode_steps = 7)
+
+
+@pytest.mark.gpu
 def test_extend_replay_buffer_wraps_like_sb3(cm):
     N, T, cap = 16, 10, 14
     env = _rollout_env(cm, N, 2)
