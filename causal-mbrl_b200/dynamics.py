@@ -41,6 +41,15 @@ def dp_row_slice(num_rows: int, world_size: int, rank: int) -> slice:
     return slice(start, start + base + (1 if rank < rem else 0))
 
 
+def dp_allreduce_member_sums(sums: torch.Tensor, group) -> torch.Tensor:
+    """[E] per-member sums over one rank's row shard -> the global sums, identical on every rank (sharded
+    evaluation; every rank then derives the same validation scores and the same elite set)."""
+    import torch.distributed as dist
+
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return sums
+
+
 def split_dict(old_dict: Dict, need_keys: List[str]):
     return dict([(key, old_dict[key]) for key in need_keys])
 
@@ -178,16 +187,20 @@ class BaseDynamics:
         data = dataset.transitions
         target_np = self._batch_variable(data, self._MECH_TO_VARIABLE[mech])
         sums = torch.zeros(self.ensemble_num, device=self.device, dtype=torch.float64)
-        n, d = len(data), 1
+        n, d = len(data), model._head_dim
+        # data parallel: every rank evaluates its contiguous share of the hold-out rows, one [E] all-reduce at the end
+        rows = dp_row_slice(n, self.dp_world, self.dp_rank) if self.dp_group is not None else slice(0, n)
         with torch.no_grad():
-            for s in range(0, n, chunk):
-                sl = slice(s, min(n, s + chunk))
+            for s in range(rows.start, rows.stop, chunk):
+                sl = slice(s, min(rows.stop, s + chunk))
                 obs = self.get_3d_tensor(data.batch_obs[sl], is_ensemble=False)
                 act = self.get_3d_tensor(data.batch_action[sl], is_ensemble=False)
                 target = self.get_3d_tensor(target_np[sl], is_ensemble=False)
                 mean, _ = model.forward(obs, act)
                 d = mean.shape[-1]
                 ops.mse_member_sums(mean, target, sums)
+        if self.dp_group is not None:
+            dp_allreduce_member_sums(sums, self.dp_group)
         return (sums / float(n * d)).to(torch.float32).cpu()
 
     def train_step(self, mech: str, obs: torch.Tensor, act: torch.Tensor, target: torch.Tensor,

@@ -21,7 +21,7 @@ def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     from oracle import cmrl_oracle as oc
     import cmrl_b200 as cm
-    from cmrl_b200.dynamics import dp_row_slice
+    from cmrl_b200.dynamics import dp_allreduce_member_sums, dp_row_slice
 
     g = load_golden("plain_train.npz")
     p = params_of(g, "p0.")
@@ -37,10 +37,21 @@ def _worker(rank, world, port, out):
     dyn = cm.PlainEnsembleDynamics(cm.PlainTransition(5, 1, hid_size=8), learned_reward=False)
     dyn.enable_data_parallel()
     ok = dyn.dp_world == world and dyn.dp_rank == rank
+    # sharded evaluation (evaluate_member_mse under data parallel): per-member squared-error sums of this rank's
+    # hold-out rows, one [E] all-reduce -> the full-set sums on every rank (ragged: 1001 rows over 2 ranks)
+    rng = np.random.default_rng(3)
+    pred, tgt = rng.normal(size=(7, 1001, 5)), rng.normal(size=(7, 1001, 5))
+    rows = dp_row_slice(1001, world, rank)
+    sums = torch.from_numpy(((pred[:, rows] - tgt[:, rows]) ** 2).sum(axis=(1, 2)))
+    dp_allreduce_member_sums(sums, dyn.dp_group)
+    eval_err = rel_err(sums.numpy(), ((pred - tgt) ** 2).sum(axis=(1, 2)))
+    gathered = [torch.zeros_like(sums) for _ in range(world)]
+    dist.all_gather(gathered, sums)
+    same_elites = all(np.array_equal(np.argsort(g.numpy()), np.argsort(sums.numpy())) for g in gathered)
     if rank == 0:
         _, full = oc.plain_nll_backward(p, obs, act, target)
         ref = torch.cat([torch.from_numpy(full[k]).reshape(-1) for k in sorted(full)])
-        out.put((rel_err(flat.numpy(), ref.numpy()), ok))
+        out.put((rel_err(flat.numpy(), ref.numpy()), ok and same_elites and eval_err < 1e-12))
     dist.barrier()
     dist.destroy_process_group()
 
