@@ -286,6 +286,27 @@ class BaseDynamics:
         self.dp_world = dist.get_world_size(self.dp_group)
         self.dp_rank = dist.get_rank(self.dp_group)
 
+    def broadcast_parameters(self, src: int = 0, group=None):
+        """Rollout replicas: envs are sharded over ranks with a full weight replica each and no per-step
+        collective, so after `learn` ran on one rank (or a checkpoint was loaded there) every mechanism's parameters
+        (one broadcast of the flat arena) and elite set are copied from global rank `src`.  Not needed after
+        data-parallel training, which leaves identical replicas."""
+        import torch.distributed as dist
+
+        if group is None:
+            group = self.dp_group if self.dp_group is not None else dist.group.WORLD
+        for mech in self.learn_mech:
+            model = getattr(self, mech)
+            try:
+                tensors = [model.flat_parameters()[0]]
+            except ops._lib.CmrlB200Error:  # parameters not on a CUDA device (host-logic tests): one broadcast each
+                tensors = [p.data for p in model.parameters()]
+            for x in tensors:
+                dist.broadcast(x, src=src, group=group)
+            elite = torch.tensor([int(e) for e in model.elite_members], dtype=torch.int64, device=tensors[0].device)
+            dist.broadcast(elite, src=src, group=group)
+            model.set_elite_members([int(e) for e in elite.tolist()])
+
     def _sync_grads(self, model):
         """Data-parallel gradient exchange: one NCCL all-reduce (sum) over the flat gradient arena."""
         if self.dp_group is not None:

@@ -48,10 +48,24 @@ def _worker(rank, world, port, out):
     gathered = [torch.zeros_like(sums) for _ in range(world)]
     dist.all_gather(gathered, sums)
     same_elites = all(np.array_equal(np.argsort(g.numpy()), np.argsort(sums.numpy())) for g in gathered)
+    # rollout replicas: parameters and elite set of rank 0 reach every rank
+    if rank != 0:
+        with torch.no_grad():
+            for q in dyn.transition.parameters():
+                q.fill_(float(rank))
+        dyn.transition.set_elite_members([6, 5, 4, 3, 2])
+    dyn.broadcast_parameters(src=0)
+    flat_w = torch.cat([q.detach().reshape(-1) for q in dyn.transition.parameters()])
+    all_w = [torch.zeros_like(flat_w) for _ in range(world)]
+    dist.all_gather(all_w, flat_w)
+    elites = [None] * world
+    dist.all_gather_object(elites, list(dyn.transition.elite_members))
+    same_replicas = all(torch.equal(w, all_w[0]) for w in all_w) and all(e == elites[0] for e in elites) and \
+        not bool((flat_w == 1.0).all())  # rank 0's initialisation, not rank 1's fill value
     if rank == 0:
         _, full = oc.plain_nll_backward(p, obs, act, target)
         ref = torch.cat([torch.from_numpy(full[k]).reshape(-1) for k in sorted(full)])
-        out.put((rel_err(flat.numpy(), ref.numpy()), ok and same_elites and eval_err < 1e-12))
+        out.put((rel_err(flat.numpy(), ref.numpy()), ok and same_elites and eval_err < 1e-12 and same_replicas))
     dist.barrier()
     dist.destroy_process_group()
 
