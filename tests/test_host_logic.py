@@ -224,6 +224,11 @@ def test_fake_env_host_side_contract():
     infos2 = env._make_infos(np.array([False, True] + [False] * 6), np.array([1, 3]), full[[1, 3]])
     assert [bool(i["TimeLimit.truncated"]) for i in infos2] == [False, True] + [False] * 6
     assert np.array_equal(infos2[3]["terminal_observation"], [6.0, 7.0]) and infos2[0] is infos2[2]
+    # shared mode: a step without done envs hands out one cached list; a step with done envs never writes into it
+    none_done = env._make_infos(np.zeros(8, bool), np.array([], dtype=np.int64), None)
+    assert none_done is env._make_infos(np.zeros(8, bool), np.array([], dtype=np.int64), None)
+    assert len(none_done) == 8 and all(not i["TimeLimit.truncated"] and "terminal_observation" not in i for i in none_done)
+    assert infos2 is not none_done and "terminal_observation" not in none_done[1]
 
 
 @pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted (GPU box)")
