@@ -66,6 +66,18 @@ __device__ __forceinline__ float soft_clamp_logvar(float raw, float mn, float mx
     return mn + softplusf_(lv1 - mn);
 }
 
+// cudaFuncSetAttribute applies to the CURRENT device only: one bit per device and call site, so that a process driving
+// several GPUs configures the kernels on each of them (a race between host threads only repeats the idempotent call)
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    bool pending(int* dev) {
+        *dev = 0;
+        cudaGetDevice(dev);
+        return ((mask >> (*dev & 63)) & 1ull) == 0;
+    }
+    void done(int dev) { mask |= 1ull << (dev & 63); }
+};
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {

@@ -404,12 +404,13 @@ int launch_gemm_tc(const GemmP& p, int passes, cudaStream_t st, const char* name
     const uint32_t otile = (uint32_t)TG_BM * (uint32_t)(NT + 4) * 4;  // epilogue staging tile re-uses the operand stages
     if (lay.total < otile) lay.total = otile;
     lay.tmem_cols = NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static cmrl::PerDeviceOnce attr_once;
+    int attr_dev = 0;
+    if (attr_once.pending(&attr_dev)) {
         CMRL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         CMRL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         CMRL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-        attr_set = true;
+        attr_once.done(attr_dev);
     }
     CMRL_REQUIRE(lay.total <= 232448 - 1024, "%s: tensor-core tile needs %u B of shared memory", name, lay.total);
     const int m_rows = p.M + ((MODE == MODE_DW && p.bsum) ? 1 : 0);

@@ -389,10 +389,11 @@ extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, co
     const size_t a_bytes = (size_t)p.a_chunks * tc::A_CHUNK_BYTES;
     const size_t smem = 2 * w_stage + a_bytes + 96 + sizeof(int) * (E + 1) + 16;
     CMRL_REQUIRE(smem <= 232448, "mlp_rollout_f16: hidden width %d needs %zu B of shared memory (> 227 KB)", H, smem);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static cmrl::PerDeviceOnce attr_once;
+    int attr_dev = 0;
+    if (attr_once.pending(&attr_dev)) {
         CMRL_CUDA(cudaFuncSetAttribute(tc::mlp_rollout_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        attr_set = true;
+        attr_once.done(attr_dev);
     }
     int items = P * ((N + tc::TILE_M - 1) / tc::TILE_M + E);
     int grid = num_sms();

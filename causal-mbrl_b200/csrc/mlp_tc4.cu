@@ -467,13 +467,14 @@ int launch_rollout_v4(const RolloutP& p, cudaStream_t st) {
     off += V4_BAR_COUNT * 8;
     sm.total = off;
     CMRL_REQUIRE(sm.total <= 232448 - 1024, "mlp_rollout_f16 v4: needs %u B of shared memory", sm.total);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static cmrl::PerDeviceOnce attr_once;
+    int attr_dev = 0;
+    if (attr_once.pending(&attr_dev)) {
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
         CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-        attr_set = true;
+        attr_once.done(attr_dev);
     }
     int max_items = p.P * ((p.N + V4_TILE - 1) / V4_TILE + p.E);
     int clusters = num_sms() / 2;
