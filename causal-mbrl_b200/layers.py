@@ -32,67 +32,62 @@ class _EnsLinearFn(torch.autograd.Function):
 
 
 def truncated_normal_init(m: nn.Module):
-    """Truncated-normal weights with std 1/(2*sqrt(in)), zero bias, member slice by member slice
-    (same RNG order as layers.py:8-28)."""
+    """Truncated-normal weights with std 1/(2*sqrt(fan)), zero bias; every [in,out] matrix of a grouped layer is drawn
+    on its own, net by net in row-major (sub-network, member) order -- the RNG order of layers.py:8-28."""
     if isinstance(m, nn.Linear):
-        # the reference reads shape[0] (= out_features) as the "input" dim here (quirk 6, kept)
-        stddev = 1 / (2 * np.sqrt(m.weight.data.shape[0]))
-        model_util.truncated_normal_(m.weight.data, std=stddev)
-        m.bias.data.fill_(0.0)
-    elif isinstance(m, EnsembleLinearLayer):
-        num_members, input_dim, _ = m.weight.data.shape
-        stddev = 1 / (2 * np.sqrt(input_dim))
-        for i in range(num_members):
-            model_util.truncated_normal_(m.weight.data[i], std=stddev)
-        m.bias.data.fill_(0.0)
-    elif isinstance(m, ParallelEnsembleLinearLayer):
-        num_parallel, num_members, input_dim, _ = m.weight.data.shape
-        stddev = 1 / (2 * np.sqrt(input_dim))
-        for i in range(num_parallel):
-            for j in range(num_members):
-                model_util.truncated_normal_(m.weight.data[i, j], std=stddev)
-        m.bias.data.fill_(0.0)
+        fan = m.weight.shape[0]  # the reference reads shape[0] (= out_features) as the "input" dim here (quirk 6, kept)
+        matrices = [m.weight.data]
+    elif isinstance(m, _GroupedLinear):
+        fan = m.in_size
+        matrices = m.weight.data.reshape((-1,) + tuple(m.weight.shape[-2:]))  # views of the parameter
+    else:
+        return
+    for w in matrices:
+        model_util.truncated_normal_(w, std=1 / (2 * np.sqrt(fan)))
+    m.bias.data.fill_(0.0)
 
 
-class EnsembleLinearLayer(nn.Module):
-    """An ensemble of linear layers: weight [E,in,out], bias [E,1,out]."""
+class _GroupedLinear(nn.Module):
+    """`group` = leading dims of the parameters: weight [*group, in, out], bias [*group, 1, out] (uniform(0,1) until
+    `truncated_normal_init` is applied, drawn weight first like the reference constructors)."""
 
-    def __init__(self, in_size: int, out_size: int, use_bias: bool = True, ensemble_num: int = 1):
-        super().__init__()
-        self.ensemble_num = ensemble_num
+    def _build(self, group, in_size: int, out_size: int, use_bias: bool):
         self.in_size = in_size
         self.out_size = out_size
-        self.weight = nn.Parameter(torch.rand(self.ensemble_num, self.in_size, self.out_size))
         self.use_bias = bool(use_bias)
-        if use_bias:
-            self.bias = nn.Parameter(torch.rand(self.ensemble_num, 1, self.out_size))
+        self.weight = nn.Parameter(torch.rand(*group, in_size, out_size))
+        if self.use_bias:
+            self.bias = nn.Parameter(torch.rand(*group, 1, out_size))
 
     def forward(self, x):
         return _EnsLinearFn.apply(x, self.weight, self.bias if self.use_bias else None)
 
+    def _describe(self, **group):
+        fields = dict(in_size=self.in_size, out_size=self.out_size, use_bias=self.use_bias, **group)
+        return ", ".join("%s=%s" % kv for kv in fields.items())
+
+
+class EnsembleLinearLayer(_GroupedLinear):
+    """An ensemble of linear layers: weight [E,in,out], bias [E,1,out] (layers.py:31-68)."""
+
+    def __init__(self, in_size: int, out_size: int, use_bias: bool = True, ensemble_num: int = 1):
+        super().__init__()
+        self.ensemble_num = ensemble_num
+        self._build((ensemble_num,), in_size, out_size, use_bias)
+
     def __repr__(self) -> str:
-        return "in_size=%d, out_size=%d, use_bias=%s, ensemble_num=%d" % (
-            self.in_size, self.out_size, self.use_bias, self.ensemble_num)  # fmt: skip
+        return self._describe(ensemble_num=self.ensemble_num)
 
 
-class ParallelEnsembleLinearLayer(nn.Module):
-    """P parallel sub-networks x E members: weight [P,E,in,out], bias [P,E,1,out]."""
+class ParallelEnsembleLinearLayer(_GroupedLinear):
+    """P parallel sub-networks x E members: weight [P,E,in,out], bias [P,E,1,out] (layers.py:71-117)."""
 
     def __init__(self, in_size: int, out_size: int, use_bias: bool = True, parallel_num: int = 1,
                  ensemble_num: int = 1):  # fmt: skip
         super().__init__()
         self.parallel_num = parallel_num
         self.ensemble_num = ensemble_num
-        self.in_size = in_size
-        self.out_size = out_size
-        self.weight = nn.Parameter(torch.rand(self.parallel_num, self.ensemble_num, self.in_size, self.out_size))
-        self.use_bias = bool(use_bias)
-        if use_bias:
-            self.bias = nn.Parameter(torch.rand(self.parallel_num, self.ensemble_num, 1, self.out_size))
-
-    def forward(self, x):
-        return _EnsLinearFn.apply(x, self.weight, self.bias if self.use_bias else None)
+        self._build((parallel_num, ensemble_num), in_size, out_size, use_bias)
 
     def __repr__(self) -> str:
-        return "in_size=%d, out_size=%d, use_bias=%s, parallel_num=%d, ensemble_num=%d" % (
-            self.in_size, self.out_size, self.use_bias, self.parallel_num, self.ensemble_num)  # fmt: skip
+        return self._describe(parallel_num=self.parallel_num, ensemble_num=self.ensemble_num)
