@@ -23,19 +23,15 @@ class TransitionConditionalMutualInformationTest(EnsembleMLP):
 
     def __init__(
         self,
-        # transition info
         obs_size: int,
         action_size: int,
-        # algorithm parameters
         ensemble_num: int = 7,
         elite_num: int = 5,
         residual: bool = True,
         learn_logvar_bounds: bool = False,
-        # network parameters
         num_layers: int = 4,
         hid_size: int = 200,
         activation_fn_cfg: Optional[Dict] = None,
-        # others
         device: Union[str, torch.device] = "cpu",
     ):
         super().__init__(ensemble_num=ensemble_num, elite_num=elite_num, device=device)
@@ -106,8 +102,8 @@ class TransitionConditionalMutualInformationTest(EnsembleMLP):
 
     def forward(
         self,
-        batch_obs: torch.Tensor,  # shape: (parallel_num, )ensemble_num, batch_size, obs_size
-        batch_action: torch.Tensor,  # shape: ensemble_num, batch_size, action_size
+        batch_obs: torch.Tensor,  # [(P,) E, B, obs_size]
+        batch_action: torch.Tensor,  # [E, B, action_size]
     ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         assert len(batch_action.shape) == 3 and batch_action.shape[-1] == self.action_size
         assert batch_obs.dim() in (3, 4) and batch_obs.shape[-1] == self.obs_size

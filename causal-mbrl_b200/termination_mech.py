@@ -28,19 +28,15 @@ class PlainTerminationMech(_ScalarHeadMixin, BaseTerminationMech):
 
     def __init__(
         self,
-        # transition info
         obs_size: int,
         action_size: int,
         deterministic: bool = False,
-        # algorithm parameters
         ensemble_num: int = 7,
         elite_num: int = 5,
         learn_logvar_bounds: bool = False,
-        # network parameters
         num_layers: int = 4,
         hid_size: int = 200,
         activation_fn_cfg: Optional[Dict] = None,
-        # others
         device: Union[str, torch.device] = "cpu",
     ):
         BaseTerminationMech.__init__(self, obs_size=obs_size, action_size=action_size, deterministic=deterministic,

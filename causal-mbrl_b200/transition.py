@@ -35,20 +35,16 @@ class PlainTransition(BaseTransition):
 
     def __init__(
         self,
-        # transition info
         obs_size: int,
         action_size: int,
         deterministic: bool = False,
-        # algorithm parameters
         ensemble_num: int = 7,
         elite_num: int = 5,
         residual: bool = True,
         learn_logvar_bounds: bool = False,
-        # network parameters
         num_layers: int = 4,
         hid_size: int = 200,
         activation_fn_cfg: Optional[Dict] = None,
-        # others
         device: Union[str, torch.device] = "cpu",
     ):
         super().__init__(obs_size=obs_size, action_size=action_size, deterministic=deterministic,
@@ -72,8 +68,8 @@ class PlainTransition(BaseTransition):
 
     def forward(
         self,
-        batch_obs: torch.Tensor,  # shape: ensemble_num, batch_size, obs_size
-        batch_action: torch.Tensor,  # shape: ensemble_num, batch_size, action_size
+        batch_obs: torch.Tensor,  # [E, B, obs_size]
+        batch_action: torch.Tensor,  # [E, B, action_size]
     ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         assert len(batch_obs.shape) == 3 and batch_obs.shape[-1] == self.obs_size
         assert len(batch_action.shape) == 3 and batch_action.shape[-1] == self.action_size
@@ -90,20 +86,16 @@ class ExternalMaskTransition(BaseTransition):
 
     def __init__(
         self,
-        # transition info
         obs_size: int,
         action_size: int,
         deterministic: bool = False,
-        # algorithm parameters
         ensemble_num: int = 7,
         elite_num: int = 5,
         residual: bool = True,
         learn_logvar_bounds: bool = False,
-        # network parameters
         num_layers: int = 4,
         hid_size: int = 200,
         activation_fn_cfg: Optional[Dict] = None,
-        # others
         device: Union[str, torch.device] = "cpu",
     ):
         super().__init__(obs_size=obs_size, action_size=action_size, deterministic=deterministic,
@@ -172,8 +164,8 @@ class ExternalMaskTransition(BaseTransition):
 
     def forward(
         self,
-        batch_obs: torch.Tensor,  # shape: ensemble_num, batch_size, obs_size
-        batch_action: torch.Tensor,  # shape: ensemble_num, batch_size, action_size
+        batch_obs: torch.Tensor,  # [E, B, obs_size]
+        batch_action: torch.Tensor,  # [E, B, action_size]
     ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         assert len(batch_obs.shape) == 3 and batch_obs.shape[-1] == self.obs_size
         assert len(batch_action.shape) == 3 and batch_action.shape[-1] == self.action_size
