@@ -152,7 +152,7 @@ def test_iterators_match_reference_bit_for_bit():
         for _ in range(2):  # two epochs: the shuffle consumes the generator identically
             for x, y in zip(a, b):
                 for u, v in zip(x.as_tuple(), y.as_tuple()):
-                    assert np.array_equal(u, v)
+                    assert np.array_equal(u, v) and u.dtype == v.dtype and u.shape == v.shape
 
 
 @pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted (GPU box)")
