@@ -126,6 +126,15 @@ class VecFakeEnv(VecEnv):
         self._alloc()
 
     def _alloc(self):
+        # a (repeated) set_up starts from scratch: captured graphs hold the addresses of the previous buffers
+        self._step_graph = None
+        self._predict_graphs = None
+        self._predict_graph = None
+        self._tail_graphs = {}
+        self._ahead_bufs = None
+        self._ahead_family = None
+        self._pool_dev = None
+        self._pool_rows = 0
         N, dev = self.num_envs, self.device
         tr = self.dynamics.transition
         O, A = tr.obs_size, tr.action_size
