@@ -238,3 +238,26 @@ def test_batched_reset_draws_equal_reference_per_env_draws():
     x = a.normal(size=(5, 4)).astype(np.float32)
     y = np.concatenate([b.normal(size=(1, 4)).astype(np.float32) for _ in range(5)])
     assert np.array_equal(x, y)
+
+
+def test_draw_ahead_buffers_are_trusted_only_after_a_replay_of_the_same_graph_family():
+    """VecFakeEnv._ahead_before_replay: the transition draws made one step ahead are reused only if the previous
+    counter-advancing event was a replay of the same graph family; anything else draws them before the replay."""
+    env = cm.VecFakeEnv(4, None, None)
+    drawn = []
+    env._ahead_draw = drawn.append  # the kernels are not under test here
+    predict = {"t_id": 5, "n": 3, "family": ("predict", "key", 5, 3)}
+    step = {"t_id": 5, "n": 4, "family": ("step", 1234, 5, 4)}
+    env._ahead_before_replay(predict)  # first replay: nothing prepared yet
+    env._ahead_before_replay(predict)  # steady state
+    env._ahead_before_replay(dict(predict))  # the second graph of the family (other pinned destination buffer)
+    assert drawn == [5]
+    env._ahead_before_replay(step)  # another step flavour advanced the counter by its own n
+    env._ahead_before_replay(predict)
+    assert drawn == [5, 5, 5]
+    env._ahead_before_replay(None)  # a graph without draw-ahead
+    env._ahead_before_replay(predict)
+    assert drawn == [5, 5, 5, 5]
+    env._ahead_family = None  # what an eager transition prepare / seed() / invalidate_step_graph() leave behind
+    env._ahead_before_replay(predict)
+    assert drawn == [5] * 5
