@@ -116,3 +116,45 @@ def test_reward_and_termination_mech_forward_loss_and_gradient(case, cls):
     assert rel_err(loss, loss_r) < TOL
     for k in grads_r:
         assert grads[k].shape == grads_r[k].shape and rel_err(grads[k], grads_r[k]) < 2e-4, k
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_adam_l2_steps_match_torch_adam_as_the_reference_constructs_it(seed):
+    """base_dynamics.py:58-63: torch.optim.Adam(lr, weight_decay (L2, coupled), eps) over a mech's parameters; several steps on
+    tensors of assorted shapes, against oc.adam_step."""
+    rng = np.random.default_rng(seed)
+    shapes = [(7, 6, 20), (7, 1, 20), (3, 4, 5, 2), (1,), (2, 1, 1, 1)]
+    lr, wd, eps = float(rng.choice([1e-4, 1e-3])), float(rng.choice([1e-5, 5e-4])), 1e-8
+    tensors = [torch.nn.Parameter(torch.from_numpy(rng.normal(size=s).astype(np.float32))) for s in shapes]
+    optim = torch.optim.Adam(tensors, lr=lr, weight_decay=wd, eps=eps)
+    params = {str(i): t.detach().numpy().copy() for i, t in enumerate(tensors)}
+    state = {}
+    for _ in range(5):
+        grads = {str(i): rng.normal(size=s).astype(np.float32) for i, s in enumerate(shapes)}
+        for i, t in enumerate(tensors):
+            t.grad = torch.from_numpy(grads[str(i)].copy())
+        optim.step()
+        oc.adam_step(params, grads, state, lr=lr, weight_decay=wd, eps=eps)
+    for i, t in enumerate(tensors):
+        assert rel_err(params[str(i)], t.detach().numpy()) < 1e-6, i
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_rollout_sampling_and_penalty_match_the_reference_fake_env(seed):
+    """fake_env.py:186-215: `get_dynamics_predict` (member draw + Gaussian sample from the env's generator) and `get_penalty`."""
+    ref = refshim.load_reference()
+    rng = np.random.default_rng(seed)
+    E, B, D = 7, 64, 5
+    mean = rng.normal(size=(E, B, D)).astype(np.float32)
+    logvar = rng.uniform(-6, 0.5, size=(E, B, D)).astype(np.float32)
+    env = ref.VecFakeEnv(B, None, None)
+    mlp = ref.EnsembleMLP(ensemble_num=E, elite_num=5)
+    mlp.set_elite_members([0, 2, 3, 5, 6])
+    env.dynamics = type("D", (), {"transition": mlp, "get_variable_by_mech": staticmethod(lambda mech: "batch_next_obs")})()
+    env.generator = np.random.default_rng(seed + 100)
+    out_ref = env.get_dynamics_predict({"batch_next_obs": {"mean": mean, "logvar": logvar}}, "transition")
+    gen = np.random.default_rng(seed + 100)  # same stream: member draw, then the noise
+    idx = mlp.get_random_index(B, gen)
+    noise = gen.normal(size=(B, D)).astype(np.float32)
+    assert rel_err(oc.dynamics_predict(mean, logvar, idx, noise), out_ref) < 1e-6
+    assert rel_err(oc.mopo_penalty(mean), env.get_penalty(mean)) < 1e-6
