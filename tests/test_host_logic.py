@@ -261,3 +261,35 @@ def test_draw_ahead_buffers_are_trusted_only_after_a_replay_of_the_same_graph_fa
     env._ahead_family = None  # what an eager transition prepare / seed() / invalidate_step_graph() leave behind
     env._ahead_before_replay(predict)
     assert drawn == [5] * 5
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("n,ratio,full", [(50, 0.2, True), (37, 0.33, True), (64, 0.0, True), (257, 0.2, False)])
+def test_dataset_split_and_elite_selection_match_the_reference(n, ratio, full):
+    """base_dynamics.py:123-156 (train / validation split of an SB3 buffer) and plain_dynamics.py:113-142 (best-weights
+    snapshot rule, elite set) against the live reference on the same inputs."""
+    ref = refshim.load_reference()
+    rng = np.random.default_rng(n)
+    buf = refshim.DuckReplayBuffer(rng.normal(size=(n, 3)).astype(np.float32), rng.normal(size=(n, 1)).astype(np.float32),
+                                   rng.normal(size=(n, 3)).astype(np.float32), rng.normal(size=n).astype(np.float32), rng.uniform(size=n) < 0.1)
+    if not full:  # a partly filled ring buffer: only the first `pos` rows count
+        buf.full, buf.pos = False, n - 40
+    torch.manual_seed(0)
+    mine = cm.PlainEnsembleDynamics(cm.PlainTransition(3, 1, hid_size=8), learned_reward=False)
+    theirs = ref.PlainEnsembleDynamics(ref.PlainTransition(3, 1, hid_size=8), learned_reward=False)
+    (a_tr, a_val), (b_tr, b_val) = mine.dataset_split(buf, ratio, 16), theirs.dataset_split(buf, ratio, 16)
+    assert (a_val is None) == (b_val is None) and a_tr.num_stored == b_tr.num_stored and len(a_tr) == len(b_tr)
+    for x, y in zip(a_tr.transitions.as_tuple(), b_tr.transitions.as_tuple()):
+        assert np.array_equal(x, y) and x.dtype == y.dtype
+    if a_val is not None:
+        assert len(a_val) == len(b_val)
+        for x, y in zip(a_val.transitions.as_tuple(), b_val.transitions.as_tuple()):
+            assert np.array_equal(x, y) and x.dtype == y.dtype
+    for _ in range(6):
+        best = torch.from_numpy(rng.uniform(0.1, 2.0, size=7).astype(np.float32))
+        val = best * torch.from_numpy(rng.uniform(0.97, 1.02, size=7).astype(np.float32))
+        assert (mine.maybe_get_best_weights(best, val, "transition", 0.01) is None) == \
+            (theirs.maybe_get_best_weights(best, val, "transition", 0.01) is None)
+        mine.maybe_set_best_weights_and_elite(None, val, "transition")
+        theirs.maybe_set_best_weights_and_elite(None, val, "transition")
+        assert [int(e) for e in mine.transition.elite_members] == [int(e) for e in theirs.transition.elite_members]
