@@ -457,6 +457,8 @@ class _DeviceEpochRunner:
             if self.graph is not None:
                 self.graph.replay()
                 _lib.note_replayed(self.graph_launches)
+                # the captured Adam step ran again (no Python inside a replay)
+                getattr(self.dyn, "{}_optimizer".format(self.mech))._mark_weights_changed()
             else:
                 self._step()
         total = (self.N // self.B) * self.B

@@ -94,6 +94,8 @@ class VecFakeEnv(VecEnv):
         self._env_len_dev = None
         self._rng_base = None  # device counter added to the Philox stream ids (advanced inside captured step graphs)
         self._step_graph = None
+        self._step_graph_key = None
+        self._step_graph_ahead = None
         self._pool_dev = None
         self._pool_rows = 0
         self._bufs = None
@@ -405,11 +407,20 @@ class VecFakeEnv(VecEnv):
         finally:
             graphs[slot] = self._predict_graph
 
+    def _graph_state_key(self, need_all):
+        """What a captured step graph bakes in besides the env's fixed buffers: the tier, the sampling mode and, per
+        mechanism, the weights (token: torch version counters + the fused optimiser's counter -- a graph captured
+        before a `learn()` must not be replayed after it: the fp16 copies it points at are stale), the packed copy, the
+        elite list and the parameter arena."""
+        parts = [self.precision, self.deterministic, need_all]
+        for m in self.dynamics.learn_mech:
+            model = getattr(self.dynamics, m)
+            parts.append((model.weights_token(), id(model._packed.get("f16")), id(model._elite_members),
+                          model._flat.data_ptr() if model._flat is not None else 0))
+        return tuple(parts)
+
     def _predict_all_graphed_one(self, obs, act, need_all, host_next_buf, act_pin=None):
-        key = (self.precision, self.deterministic, need_all) + tuple(
-            (id(getattr(self.dynamics, m)._packed.get("f16")), id(getattr(self.dynamics, m)._elite_members),
-             getattr(self.dynamics, m)._flat.data_ptr() if getattr(self.dynamics, m)._flat is not None else 0)
-            for m in self.dynamics.learn_mech)  # fmt: skip
+        key = self._graph_state_key(need_all)
         cached = getattr(self, "_predict_graph", None)
         if cached is None or cached[0] != key:
             if self._rng_base is None:
@@ -418,10 +429,7 @@ class VecFakeEnv(VecEnv):
                 self._elite_u8(mech)
                 if self.precision == "f16":
                     getattr(self.dynamics, mech).packed_f16()
-            key = (self.precision, self.deterministic, need_all) + tuple(
-                (id(getattr(self.dynamics, m)._packed.get("f16")), id(getattr(self.dynamics, m)._elite_members),
-                 getattr(self.dynamics, m)._flat.data_ptr() if getattr(self.dynamics, m)._flat is not None else 0)
-                for m in self.dynamics.learn_mech)  # fmt: skip
+            key = self._graph_state_key(need_all)  # again: packed_f16() may have rebuilt the fp16 copies
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             c0 = self._draw_counter
@@ -560,7 +568,10 @@ class VecFakeEnv(VecEnv):
                 c_keep = self._draw_counter
                 self._device_reset_source(tail=True)  # (re)builds the reset pool outside any capture
                 self._draw_counter = c_keep
-            key = (id(next_obs), id(reward), id(terminal_f), terminal_u8 is not None, id(penalty), need_term_obs,
+            # keyed by the ADDRESSES the graph bakes in (object ids are recycled once a re-captured predict graph's
+            # outputs are freed: a stale entry could match new tensors that live somewhere else)
+            ptr = lambda x: 0 if x is None else x.data_ptr()  # noqa: E731
+            key = (ptr(next_obs), ptr(reward), ptr(terminal_f), terminal_u8 is not None, ptr(penalty), need_term_obs,
                    h_next.data_ptr() if need_term_obs else 0, self._pool_dev.data_ptr(), self._pool_rows,
                    self.penalty_coeff, self.max_episode_steps)
             tg = self._tail_graphs.get(key)
@@ -657,10 +668,12 @@ class VecFakeEnv(VecEnv):
         The Philox stream ids baked into the graph are offset by a device-side counter that the graph itself advances,
         so every replay draws fresh members / noise / reset rows.  Weights, elite lists and the reset pool are read at
         replay time from the same device buffers; the graph is re-captured when the packed weights or the reset pool
-        were rebuilt (call `invalidate_step_graph()` after `set_elite_members`)."""
+        changed, after a `learn()` (the graph points at the fp16 copies of the weights), a new elite set or other step settings."""
         b = self._bufs
         if self._reset_by_buffer and self._pool_dev is not None and self._pool_rows != self._upper_bound():
             self._step_graph = None
+        if self._step_graph is not None and self._step_graph_key != self._step_graph_state():
+            self._step_graph = None  # weights (a `learn()` in between), elites, tier or step settings changed
         if self._step_graph is None:
             assert self.rng_mode == "device" and self.learned_reward
             if self._rng_base is None:
@@ -686,6 +699,7 @@ class VecFakeEnv(VecEnv):
                 ahead["family"] = ("step", id(g), ahead["t_id"], ahead["n"])
             self._step_graph_ahead = ahead
             self._step_graph_launches = _lib.launch_count() - l0
+            self._step_graph_key = self._step_graph_state()
             self._step_graph = g
         else:
             b["act"].copy_(actions, non_blocking=True)
@@ -694,6 +708,9 @@ class VecFakeEnv(VecEnv):
         _lib.note_replayed(self._step_graph_launches)
         self._current_batch_obs = None
         return self._graph_out
+
+    def _step_graph_state(self):
+        return self._graph_state_key(self.penalty_coeff != 0) + (self.penalty_coeff, self.max_episode_steps)
 
     def invalidate_step_graph(self):
         self._step_graph = None

@@ -175,6 +175,7 @@ class EnsembleMLP(nn.Module):
         self._flat = None  # flat parameter arena (device models only)
         self._flat_grad = None
         self._packed = {}  # private low-precision weight caches, keyed by kind -> (version, handle)
+        self._weights_epoch = 0  # bumped by writers that bypass torch's version counters (the fused Adam kernel)
 
     # ------------------------------------------------------------------ elite bookkeeping (mlp.py:31-44)
     def set_elite_members(self, elite_indices: Sequence[int]):
@@ -309,6 +310,19 @@ class EnsembleMLP(nn.Module):
         return cached[1]
 
     # ------------------------------------------------------------------ private fp16 weight cache (tcgen05 tier)
+    def weights_token(self) -> int:
+        """A number that grows whenever the parameters may have changed: in-place torch operations (`load_state_dict`,
+        `copy_`, ...) bump the tensors' `_version`, the fused Adam kernel writes through raw pointers and bumps
+        `_weights_epoch` (optim.py).  Caches derived from the weights (packed fp16 copies, captured step graphs that
+        bake their addresses) compare it before they are reused."""
+        plist = self.__dict__.get("_token_params")
+        if plist is None:  # the Parameter objects are fixed after construction (.to() / the arena only re-home their data)
+            plist = self.__dict__["_token_params"] = list(self.parameters())
+        token = getattr(self, "_weights_epoch", 0)
+        for p in plist:
+            token += p._version
+        return token
+
     def packed_f16(self):
         """Padded fp16 copy of the weights in the layout cmrl_mlp_rollout_f16 stages by TMA; rebuilt whenever a
         parameter (or the input mask) changed.  Private: never appears in state_dict / checkpoints."""
@@ -316,7 +330,7 @@ class EnsembleMLP(nn.Module):
         n_lin = len(params) - self._n_bound_params()
         mask = self._kernel_mask()
         key = tuple(p._version for p in params[:n_lin]) + tuple(p.data_ptr() for p in params[:n_lin]) + (
-            None if mask is None else (mask.data_ptr(), mask._version),)  # fmt: skip
+            None if mask is None else (mask.data_ptr(), mask._version), getattr(self, "_weights_epoch", 0))  # fmt: skip
         cached = self._packed.get("f16")
         if cached is None or cached[0] != key:
             E = self.ensemble_num

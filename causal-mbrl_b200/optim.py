@@ -40,7 +40,13 @@ class FusedAdamL2(torch.optim.Optimizer):
         self._step += 1
         ops.adam_l2_step(p, grad, self._exp_avg, self._exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
                          g["weight_decay"], self._step, grad_scale)  # fmt: skip
+        self._mark_weights_changed()
         return loss
+
+    def _mark_weights_changed(self):
+        """The kernel writes the arena through raw pointers: torch's version counters do not move, so the model's own
+        counter does (EnsembleMLP.weights_token; a replayed graph that contains the step calls this once per replay)."""
+        self.model._weights_epoch = getattr(self.model, "_weights_epoch", 0) + 1
 
     def prepare_graphable(self):
         """Allocate the moment buffers and the device step counter (must happen outside a graph capture)."""
@@ -56,6 +62,7 @@ class FusedAdamL2(torch.optim.Optimizer):
         p, grad = self._arena()
         ops.adam_l2_step_dev(p, grad, self._exp_avg, self._exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
                              g["weight_decay"], self._step_dev, grad_scale)  # fmt: skip
+        self._mark_weights_changed()
 
     @property
     def step_count(self):

@@ -293,3 +293,47 @@ def test_dataset_split_and_elite_selection_match_the_reference(n, ratio, full):
         mine.maybe_set_best_weights_and_elite(None, val, "transition")
         theirs.maybe_set_best_weights_and_elite(None, val, "transition")
         assert [int(e) for e in mine.transition.elite_members] == [int(e) for e in theirs.transition.elite_members]
+
+
+def test_weights_token_sees_torch_writes_and_fused_optimiser_steps(monkeypatch):
+    """Caches derived from the weights (packed fp16 copies, captured step graphs) are keyed by EnsembleMLP.weights_token():
+    it must move on in-place torch writes (version counters) AND on the fused Adam kernel, which writes through raw
+    pointers -- a rollout after `learn()` must never see the weights from before it."""
+    torch.manual_seed(0)
+    tr = cm.PlainTransition(3, 1, hid_size=8)
+    rw = cm.PlainRewardMech(3, 1, hid_size=8)
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw)
+    t0 = tr.weights_token()
+    assert tr.weights_token() == t0  # stable while nothing changes
+    tr.load_state_dict({k: v.clone() for k, v in tr.state_dict().items()})
+    t1 = tr.weights_token()
+    assert t1 > t0
+    with torch.no_grad():
+        next(tr.parameters()).mul_(1.0)
+    t2 = tr.weights_token()
+    assert t2 > t1
+    # the fused optimiser: kernels replaced by no-ops (no GPU here), the bookkeeping is what is under test
+    optim = dyn.transition_optimizer
+    flat = torch.zeros(4)
+    monkeypatch.setattr(optim, "_arena", lambda: (flat, flat))
+    monkeypatch.setattr(cm.ops, "adam_l2_step", lambda *a, **k: None)
+    monkeypatch.setattr(cm.ops, "adam_l2_step_dev", lambda *a, **k: None)
+    optim._exp_avg = optim._exp_avg_sq = flat
+    optim.step()
+    t3 = tr.weights_token()
+    assert t3 > t2
+    monkeypatch.setattr(optim, "prepare_graphable", lambda: None)
+    optim._step_dev = flat
+    optim.step_graphable()
+    assert tr.weights_token() > t3 and rw.weights_token() == rw.weights_token()
+    # the key the fake env compares before it replays a captured step graph
+    env = cm.VecFakeEnv(4, None, None)
+    env.dynamics, env.precision, env.deterministic, env.penalty_coeff, env.max_episode_steps = dyn, "f16", False, 0.0, 10
+    k0 = env._graph_state_key(False)
+    assert env._graph_state_key(False) == k0 and env._step_graph_state()[:len(k0)] == k0
+    optim._mark_weights_changed()  # what a replayed training graph reports per step
+    k1 = env._graph_state_key(False)
+    assert k1 != k0 and k1[4] == k0[4]  # the transition's entry moved, the reward mech's did not
+    tr.set_elite_members([0, 1, 2, 3, 4])
+    assert env._graph_state_key(False) != k1
+    assert env._graph_state_key(True) != env._graph_state_key(False)
