@@ -1007,3 +1007,64 @@ def test_tcgen05_wide_hidden_streamed_weights(cm, kind, O, A, H, N):
     out_m = env.predict_selected(m, env._obs_dev, act, idx, None)
     base = env._obs_dev if kind != "reward" else 0.0
     assert rel_err((out_m - base).cpu().numpy(), (ref_m - base).cpu().numpy()) < 6e-3  # raw head output alone
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# rollout -> optimiser step -> rollout: captured step graphs and the packed fp16 weights follow the parameters
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_rollouts_after_an_optimiser_step_use_the_new_weights(cm):
+    """The fused Adam kernel writes the parameter arena through raw pointers (no torch version bump).  The packed fp16
+    copies and the captured step graphs (which bake the copies' addresses) must follow all the same: after a step that
+    moves every weight by ~0.05 away from zero, the tcgen05 tier -- graph-replayed device steps and host-facing steps
+    alike -- agrees with the fp32 tier evaluated on the NEW weights, which is far away from what the old weights predict
+    (at this model's initialisation one such step changes next_obs by ~1.5e-2 relative, the second by ~9e-2)."""
+    N = 300
+    env = _rollout_env(cm, N, 3, max_steps=1000)
+    dyn = env.dynamics
+    tr, tm = dyn.transition, dyn.termination_mech
+    with torch.no_grad():  # a termination head that never fires: no resets, the returned observations are the predictions
+        tm.mean_and_logvar.weight.zero_()
+        tm.mean_and_logvar.bias.zero_()
+    tm.deterministic = True
+    for m in (tr, dyn.reward_mech, tm):
+        m.set_elite_members([1, 1, 1, 1, 1])  # every env draws member 1: predictions are a function of the weights alone
+    env.precision, env.deterministic = "f16", True
+    rng = np.random.default_rng(0)
+    act_h = rng.uniform(-1, 1, size=(N, 2)).astype(np.float32)
+    act = t(act_h)
+    idx = torch.ones(N, dtype=torch.uint8, device=DEV)
+
+    def fp32_prediction():
+        env.precision = "fp32"
+        ref = env.predict_selected(tr, env._obs_dev.clone(), act, idx, None).clone()
+        env.precision = "f16"
+        return ref.cpu().numpy()
+
+    def big_optimiser_step():
+        opt = dyn.transition_optimizer
+        opt.zero_grad()
+        # zero gradient + NEGATIVE L2: g = -p, so Adam moves every weight by ~lr away from zero (the network's output grows)
+        opt.param_groups[0].update(lr=0.05, weight_decay=-1.0)
+        opt.step()
+
+    # device-resident graph steps
+    ref = fp32_prediction()
+    term_obs = env.step_device_graphed(act)[4].cpu().numpy().copy()
+    assert rel_err(term_obs, ref) < TOL_TC
+    before = fp32_prediction()
+    big_optimiser_step()
+    after = fp32_prediction()
+    assert rel_err(after, before) > 5 * TOL_TC  # the step really changed what the model predicts
+    term_obs = env.step_device_graphed(act)[4].cpu().numpy().copy()
+    assert rel_err(term_obs, after) < 2 * TOL_TC
+    # host-facing steps (predict graph + tail graph)
+    ref = fp32_prediction()
+    obs_h = np.array(env.step(act_h)[0])
+    assert rel_err(obs_h, ref) < TOL_TC
+    before = fp32_prediction()
+    big_optimiser_step()
+    after = fp32_prediction()
+    assert rel_err(after, before) > 5 * TOL_TC
+    obs_h = np.array(env.step(act_h)[0])
+    assert rel_err(obs_h, after) < 2 * TOL_TC
