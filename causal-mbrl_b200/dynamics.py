@@ -509,19 +509,15 @@ class PlainEnsembleDynamics(BaseDynamics):
 
     def learn(
         self,
-        # data
         replay_buffer,
-        # dataset split
         validation_ratio: float = 0.2,
         batch_size: int = 256,
         shuffle_each_epoch: bool = True,
         bootstrap_permutes: bool = False,
-        # model learning
         longest_epoch: int = -1,
         improvement_threshold: float = 0.1,
         patience: int = 5,
         work_dir: Optional[Union[str, pathlib.Path]] = None,
-        # other
         **kwargs
     ):
         """Early-stopped training of every learned mechanism, then elite selection by best hold-out MSE
