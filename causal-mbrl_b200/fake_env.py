@@ -416,7 +416,7 @@ class VecFakeEnv(VecEnv):
         for m in self.dynamics.learn_mech:
             model = getattr(self.dynamics, m)
             parts.append((model.weights_token(), id(model._packed.get("f16")), id(model._elite_members),
-                          model._flat.data_ptr() if model._flat is not None else 0))
+                          model._flat.data_ptr() if model._flat is not None else 0, bool(model.deterministic)))
         return tuple(parts)
 
     def _predict_all_graphed_one(self, obs, act, need_all, host_next_buf, act_pin=None):

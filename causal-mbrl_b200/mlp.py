@@ -330,7 +330,8 @@ class EnsembleMLP(nn.Module):
         n_lin = len(params) - self._n_bound_params()
         mask = self._kernel_mask()
         key = tuple(p._version for p in params[:n_lin]) + tuple(p.data_ptr() for p in params[:n_lin]) + (
-            None if mask is None else (mask.data_ptr(), mask._version), getattr(self, "_weights_epoch", 0))  # fmt: skip
+            None if mask is None else (mask.data_ptr(), mask._version), getattr(self, "_weights_epoch", 0),
+            bool(self.deterministic))  # fmt: skip
         cached = self._packed.get("f16")
         if cached is None or cached[0] != key:
             E = self.ensemble_num
