@@ -46,7 +46,13 @@ class FusedAdamL2(torch.optim.Optimizer):
     def _mark_weights_changed(self):
         """The kernel writes the arena through raw pointers: torch's version counters do not move, so the model's own
         counter does (EnsembleMLP.weights_token; a replayed graph that contains the step calls this once per replay)."""
-        self.model._weights_epoch = getattr(self.model, "_weights_epoch", 0) + 1
+        holders = self.__dict__.get("_epoch_holders")
+        if holders is None:  # the model and any wrapped mechanism (ForwardEulerTransition holds its one-step model)
+            if not hasattr(self.model, "_weights_epoch"):
+                self.model._weights_epoch = 0
+            holders = self.__dict__["_epoch_holders"] = [m for m in self.model.modules() if hasattr(m, "_weights_epoch")]
+        for m in holders:
+            m._weights_epoch += 1
 
     def prepare_graphable(self):
         """Allocate the moment buffers and the device step counter (must happen outside a graph capture)."""
