@@ -50,10 +50,6 @@ def dp_allreduce_member_sums(sums: torch.Tensor, group) -> torch.Tensor:
     return sums
 
 
-def split_dict(old_dict: Dict, need_keys: List[str]):
-    return dict([(key, old_dict[key]) for key in need_keys])
-
-
 class BaseDynamics:
     _MECH_TO_VARIABLE = {
         "transition": "batch_next_obs",
@@ -211,8 +207,18 @@ class BaseDynamics:
         batch is one shard of a data-parallel step."""
         model = getattr(self, mech)
         optim = getattr(self, "{}_optimizer".format(mech))
-        if model.deterministic or any(p.requires_grad for p in model._bounds() if p is not None):
-            # uncommon configurations go through the autograd nodes (same kernels)
+        if obs.shape[1] == 0:
+            # data parallel, ragged last batch with fewer rows than ranks: this rank has no rows, but it still has to
+            # contribute (zero) gradients to the all-reduce and apply the same Adam update as every other rank
+            _, flat_grad = model.flat_parameters()
+            flat_grad.zero_()
+            self._sync_grads(model)
+            optim.step_graphable() if graphable else optim.step()
+            return torch.empty((obs.shape[0], 0, target.shape[-1]), device=obs.device, dtype=torch.float32) if want_loss else None
+        if (model.deterministic or any(p.requires_grad for p in model._bounds() if p is not None)
+                or not hasattr(model, "hidden_layers")):
+            # uncommon configurations (deterministic heads, learned logvar bounds, wrappers without a layer stack of
+            # their own such as ForwardEulerTransition) go through the autograd nodes (same kernels)
             loss = (model.get_mse_loss if model.deterministic else model.get_nll_loss)(
                 {"batch_obs": obs, "batch_action": act}, target)  # fmt: skip
             optim.zero_grad()
@@ -324,7 +330,7 @@ class BaseDynamics:
         assert isinstance(dataset, BootstrapIterator)
         model = getattr(self, mech)
         optim = getattr(self, "{}_optimizer".format(mech))
-        fast = (not model.deterministic and dataset._bootstrap_iter
+        fast = (not model.deterministic and dataset._bootstrap_iter and hasattr(model, "hidden_layers")
                 and not any(q.requires_grad for q in model._bounds()))  # fmt: skip
         if not fast:
             return float(self.train(dataset, mech=mech).mean().item())
@@ -422,8 +428,9 @@ class _DeviceEpochRunner:
 
     def _step(self):
         # `start` points at this rank's first row of the batch and advances by the global batch size
-        ops.bootstrap_gather(self.obs, self.act, self.target, self.member_idx, self.order, self.start, self.B, self.Bl,
-                             self.b_obs, self.b_act, self.b_tgt)  # fmt: skip
+        if self.Bl > 0:
+            ops.bootstrap_gather(self.obs, self.act, self.target, self.member_idx, self.order, self.start, self.B, self.Bl,
+                                 self.b_obs, self.b_act, self.b_tgt)  # fmt: skip
         loss = self.dyn.train_step(self.mech, self.b_obs, self.b_act, self.b_tgt, want_loss=True, graphable=True,
                                    grad_rows=self.B if self.dyn.dp_group is not None else None)  # fmt: skip
         self.loss_sum += loss.sum(dtype=torch.float64)

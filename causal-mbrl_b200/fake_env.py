@@ -137,6 +137,8 @@ class VecFakeEnv(VecEnv):
         self._ahead_family = None
         self._pool_dev = None
         self._pool_rows = 0
+        if self._rng_base is not None:
+            self._rng_base.zero_()
         N, dev = self.num_envs, self.device
         tr = self.dynamics.transition
         O, A = tr.obs_size, tr.action_size
@@ -642,6 +644,10 @@ class VecFakeEnv(VecEnv):
         obs = self._obs_dev
         need_all = self.penalty_coeff != 0
         all_out = {} if need_all else None
+        # Once a device-side stream base exists (graph-replayed steps advance it), an eager step advances the same base
+        # instead of the host counter, so that eager steps and replays never share a Philox stream id.
+        eager_base = self._rng_base is not None and not torch.cuda.is_current_stream_capturing()
+        c_start = self._draw_counter
         preps = self._prepare_all(need_all, reset_source=True, ahead=_ahead)
         next_obs = self._predict("transition", obs, actions, all_out, prep=preps.get("transition"))
         if _ahead is not None:
@@ -660,6 +666,10 @@ class VecFakeEnv(VecEnv):
                           b["term_obs"], None)  # fmt: skip
         if _ahead is not None:
             torch.cuda.current_stream().wait_stream(self._side_stream)  # the next step's draws / buckets
+        if eager_base:
+            ops.counter_add(self._rng_base, self._draw_counter - c_start)
+            self._draw_counter = c_start
+            self._ahead_family = None  # buffers drawn ahead by a replay belong to ids this step has just used
         self._current_batch_obs = None  # host mirror is stale now (refreshed lazily by step_wait / sync_host_obs)
         return obs, b["reward_out"], b["done"], b["trunc"], b["term_obs"]
 
@@ -854,6 +864,8 @@ class VecFakeEnv(VecEnv):
         self.generator = np.random.default_rng(seed=seed)
         self._device_seed = 0 if seed is None else int(seed)
         self._draw_counter = 0
+        if self._rng_base is not None:
+            self._rng_base.zero_()  # in place: same seed -> same draws again
         # seed and stream ids are baked into captured graphs
         self._step_graph = None
         self._predict_graphs = None

@@ -150,6 +150,7 @@ def ens_linear_bwd_dx(dz, w, z_prev, act_prev, tier=None):
 
 
 _SPLITK_WS = {}
+_SPLITK_WS_RETIRED = []
 
 
 def splitk_workspace(device, floats):
@@ -162,6 +163,8 @@ def splitk_workspace(device, floats):
         return cur
     if torch.cuda.is_current_stream_capturing():
         return cur
+    if cur is not None:
+        _SPLITK_WS_RETIRED.append(cur)  # a captured step graph may hold its address: never freed while the process lives
     cur = torch.empty(floats, device=device, dtype=torch.float32)
     _SPLITK_WS[device] = cur
     return cur

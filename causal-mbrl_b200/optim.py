@@ -34,12 +34,14 @@ class FusedAdamL2(torch.optim.Optimizer):
         loss = closure() if closure is not None else None
         g = self.param_groups[0]
         p, grad = self._arena()
-        if self._step_dev is not None:  # a graph replay advanced the device counter
+        if self._step_dev is not None:  # a graph replay may have advanced the device counter
             self._step = int(self._step_dev.item())
-            self._step_dev = None
         self._step += 1
         ops.adam_l2_step(p, grad, self._exp_avg, self._exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
                          g["weight_decay"], self._step, grad_scale)  # fmt: skip
+        if self._step_dev is not None:
+            # the device counter is never freed or replaced: captured step graphs hold its address
+            self._step_dev.fill_(self._step)
         self._mark_weights_changed()
         return loss
 
@@ -84,6 +86,8 @@ class FusedAdamL2(torch.optim.Optimizer):
 
     def load_state_dict(self, state):
         self._step = state["step"]
+        if self._step_dev is not None:
+            self._step_dev.fill_(self._step)
         self._exp_avg = None if state["exp_avg"] is None else state["exp_avg"].clone()
         self._exp_avg_sq = None if state["exp_avg_sq"] is None else state["exp_avg_sq"].clone()
         for g, s in zip(self.param_groups, state["param_groups"]):

@@ -210,3 +210,43 @@ class ForwardEulerTransition(BaseTransition):
         for _ in range(self.repeat_times):
             mean, logvar = self.one_step_transition.forward(mean, batch_action)
         return mean, logvar
+
+    # ------------------------------------------------------------------ the wrapper owns no layers of its own:
+    # parameters, arena, packed copies and kernel-facing attributes are the one-step model's.  Training goes through
+    # `get_nll_loss` -> `forward` (autograd over the k applications, BaseDynamics.train_step), rollouts re-apply the
+    # one-step kernels k times on the drawn member (VecFakeEnv.predict_selected).
+    def flat_parameters(self):
+        return self.one_step_transition.flat_parameters()
+
+    def _flatten_parameters(self):
+        return self.one_step_transition._flatten_parameters()
+
+    @property
+    def _n_trainable(self):
+        return self.one_step_transition._n_trainable
+
+    def weights_token(self) -> int:
+        return self.one_step_transition.weights_token()
+
+    def _bounds(self):
+        return self.one_step_transition._bounds()
+
+    def _kernel_mask(self):
+        return self.one_step_transition._kernel_mask()
+
+    def _parallel_num(self):
+        return self.one_step_transition._parallel_num()
+
+    def _residual(self):
+        return self.one_step_transition._residual()
+
+    @property
+    def _head_dim(self):
+        return self.one_step_transition._head_dim
+
+    @property
+    def _head_layout(self):
+        return self.one_step_transition._head_layout
+
+    def packed_f16(self):
+        return self.one_step_transition.packed_f16()

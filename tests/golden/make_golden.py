@@ -116,6 +116,75 @@ def cmi_fixtures():
     train_fixture("cmi_learnbounds_train.npz", m, rng, B=32, target_dim=O, steps=3)
 
 
+def euler_fixtures():
+    """ForwardEulerTransition (transition/multi_step/forward_euler.py:8-41): k-fold re-application of a one-step model.
+    Forward with input gradients (k = 3), three Adam steps through the wrapper (k = 2) and a VecFakeEnv trajectory."""
+    torch.manual_seed(21)
+    np.random.seed(21)
+    rng = np.random.default_rng(21)
+    O, A, E, B, H = 5, 1, 7, 28, 32
+    one = ref.PlainTransition(O, A, ensemble_num=E, elite_num=5, hid_size=H, activation_fn_cfg=SILU)
+    fe = ref.ForwardEulerTransition(one, repeat_times=3)
+    obs, act = make_inputs(rng, E, B, O, A, True)
+    target = (obs + 0.3 * rng.normal(size=(E, B, O))).astype(np.float32)
+    t_obs = torch.from_numpy(obs.copy()).requires_grad_(True)
+    t_act = torch.from_numpy(act.copy()).requires_grad_(True)
+    mean, logvar = fe.forward(t_obs, t_act)
+    nll = fe.get_nll_loss({"batch_obs": t_obs, "batch_action": t_act}, torch.from_numpy(target))
+    nll.mean().backward()
+    out = sd_np(one)
+    out.update(obs=obs, act=act, target=target, mean=mean.detach().numpy(), logvar=logvar.detach().numpy(),
+               nll=nll.detach().numpy(), g_obs=t_obs.grad.numpy().copy(), g_act=t_act.grad.numpy().copy(),
+               repeat_times=np.int64(3))
+    for k, p in one.named_parameters():
+        if p.grad is not None:
+            out["g." + k] = p.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "euler_forward.npz"), **out)
+    print("euler_forward", mean.shape)
+
+    one = ref.PlainTransition(O, A, ensemble_num=E, elite_num=5, hid_size=H, activation_fn_cfg=SILU)
+    fe = ref.ForwardEulerTransition(one, repeat_times=2)
+    train_fixture("euler_train.npz", fe, rng, B=24, target_dim=O, steps=3, extra={"repeat_times": np.int64(2)})
+
+    # VecFakeEnv trajectory with the wrapper as the transition (the wrapper keeps its OWN elite set: its
+    # set_elite_members forwards to the one-step model, get_random_index reads the wrapper's, forward_euler.py:29-30)
+    torch.manual_seed(22)
+    np.random.seed(22)
+    N, T = 40, 3
+    one = ref.PlainTransition(O, A, ensemble_num=E, elite_num=5, hid_size=H, activation_fn_cfg=SILU)
+    rw = ref.PlainRewardMech(O, A, ensemble_num=E, elite_num=5, hid_size=H, activation_fn_cfg=SILU)
+    with torch.no_grad():
+        for m in (one, rw):
+            m.mean_and_logvar.bias.add_(torch.from_numpy(rng.normal(size=tuple(m.mean_and_logvar.bias.shape)).astype(np.float32)) * 0.3)
+    fe = ref.ForwardEulerTransition(one, repeat_times=2)
+    dyn = ref.PlainEnsembleDynamics(fe, learned_reward=True, reward_mech=rw)
+    init_rng = np.random.default_rng(78)
+    env = ref.VecFakeEnv(N, None, None)
+    env.set_up(dyn, reward_fn=None, termination_fn=lambda n, o, a: np.abs(n[:, 0:1]) > 1.5,
+               get_init_obs_fn=lambda n: init_rng.normal(size=(n, O)).astype(np.float32))
+    env.seed(13)
+    out = sd_np(one, "tr.")
+    out.update(sd_np(rw, "rw."))
+    out["fe_elite"] = np.asarray(fe.elite_members, dtype=np.int64)
+    out["tr_elite"] = np.asarray(one.elite_members, dtype=np.int64)
+    out["rw_elite"] = np.asarray(rw.elite_members, dtype=np.int64)
+    out["reset_obs"] = env.reset()
+    actions = rng.uniform(-1, 1, size=(T, N, A)).astype(np.float32)
+    out["actions"] = actions
+    for t in range(T):
+        o, r, d, infos = env.step(actions[t])
+        out["obs%d" % t], out["rew%d" % t], out["done%d" % t] = o, r, d
+        term = np.zeros((N, O), np.float32)
+        for i, info in enumerate(infos):
+            if d[i]:
+                term[i] = info["terminal_observation"]
+        out["termobs%d" % t] = term
+    out["T"] = np.int64(T)
+    out["repeat_times"] = np.int64(2)
+    np.savez_compressed(os.path.join(HERE, "fake_env_euler.npz"), **out)
+    print("fake_env_euler done counts", [int(out["done%d" % t].sum()) for t in range(T)])
+
+
 def synth_dataset(rng, N, O, A):
     """SURVEY 8(d) synthetic transitions."""
     obs = rng.normal(size=(N, O)).astype(np.float32)
@@ -301,6 +370,9 @@ def main():
 if __name__ == "__main__":
     if "--only-cmi" in sys.argv:
         cmi_fixtures()
+    elif "--only-euler" in sys.argv:
+        euler_fixtures()
     else:
         main()
         cmi_fixtures()
+        euler_fixtures()
