@@ -44,6 +44,10 @@ PROTOTYPES = {
     "cmrl_pack_layer_f16": [_P, _P, _P, _LL, _LL, _I, _I, _I, _I, _I, _I, _I, ctypes.c_float, _P, _LL, _P],
     "cmrl_mlp_rollout_f16": [_P, _LL, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P,
                              _I, _P, _P, _I, _P],
+    "cmrl_train_pack_tf32": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _LL, _LL, _P, _P],
+    "cmrl_train_fused": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _P, _LL, _P, _LL, _I, _P, _P, _I, _F, _F,
+                         _P, _P, _P],
+    "cmrl_train_dw": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _LL, _LL, _P, _LL, _P],
     "cmrl_env_step_tail": [_P, _P, _P, _P, _P, _F, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
 }
 
@@ -68,6 +72,8 @@ def load():
     lib.cmrl_abi_version.restype = _I
     lib.cmrl_last_error.restype = _c.c_char_p
     lib.cmrl_launch_count.restype = _LL
+    lib.cmrl_train_fused_sizes.restype = _LL
+    lib.cmrl_train_fused_sizes.argtypes = [_I, _I, _I, _I, _I, _I, _I, _c.POINTER(_LL), _c.POINTER(_LL), _c.POINTER(_LL)]
     for name, argtypes in PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

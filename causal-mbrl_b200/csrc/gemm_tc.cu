@@ -43,21 +43,6 @@ struct TgLay {
     int m_tot;
 };
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// kind::tf32 instruction descriptor: D fp32, A/B tf32, both K-major, M x N
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 // activation / derivative with the fast exp and divide intrinsics (a few ulp: far inside the 1e-5 tier; the precise
 // expf + IEEE divide of common.cuh cost ~30 instructions per element and a third of the tile time in this kernel)
 __device__ __forceinline__ float tg_act_fwd(float z, int act) {

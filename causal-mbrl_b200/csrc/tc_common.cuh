@@ -317,5 +317,81 @@ __device__ __forceinline__ uint32_t v3_act_pack(float a, float b) {
 }
 
 
+// ---- kind::tf32 (cta_group::1) helpers shared by the training kernels (gemm_tc.cu, train_tc.cu) -----------------------
+// kind::tf32 instruction descriptor: D fp32, A/B tf32, both K-major, M x N
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// warp-uniform forms (all lanes execute, one elected lane issues; see v3_mma_uni)
+__device__ __forceinline__ void tf32_mma_ss_uni(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, p;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A operand in tensor memory: lane = row, one 32-bit column per k (8 columns per K step) -- profiles/r2_tf32_probe.txt
+__device__ __forceinline__ void tf32_mma_ts_uni(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, p;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_uni(uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr));
+}
+// activation / derivative with the fast exp and divide intrinsics (a few ulp: far inside the 1e-5 tier)
+__device__ __forceinline__ float act_fwd_fast(float z, int act) {
+    if (act == CMRL_ACT_RELU) return fmaxf(z, 0.0f);
+    if (act == CMRL_ACT_SILU) return __fdividef(z, 1.0f + __expf(-z));
+    return z;
+}
+__device__ __forceinline__ float act_grad_fast(float z, int act) {
+    if (act == CMRL_ACT_RELU) return z > 0.0f ? 1.0f : 0.0f;
+    if (act == CMRL_ACT_SILU) {
+        const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+        return s * (1.0f + z * (1.0f - s));
+    }
+    return 1.0f;
+}
+
 }  // namespace tc
 }  // namespace cmrl

@@ -228,6 +228,15 @@ class BaseDynamics:
             return loss.detach()
         E, B = obs.shape[0], obs.shape[1]
         flat, flat_grad = model.flat_parameters()
+        plan = ops.fused_train_plan(model, E, B) if obs.dim() == 3 else None
+        if plan is not None:
+            # forward, Gaussian head, NLL, dz chain and every weight gradient on tcgen05 (3xTF32): three launches
+            mn, mx = model._bounds()
+            rows = B if grad_rows is None else grad_rows
+            loss = plan.step(obs, act, target, mn, mx, model._nll_reg(), 1.0 / float(E * rows * model._head_dim), want_loss)
+            self._sync_grads(model)
+            optim.step_graphable() if graphable else optim.step()
+            return loss
         params = model._stack_params()
         L = model.num_layers
         kind = model._act_kind

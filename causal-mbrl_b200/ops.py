@@ -485,3 +485,94 @@ def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, ga
         except _lib.CmrlB200Error as e:  # shape not supported by this variant
             last = e
     raise _lib.CmrlB200Error("no tensor-core kernel variant supports this model (use precision='fp32'): %s" % last)
+
+
+# ----------------------------------------------------------------------------- fused tcgen05 training step
+# One optimiser step of a mechanism = pack + fused forward / loss / dz chain + all weight gradients (three launches of
+# train_tc.cu) instead of ~25 per-layer launches.  TRAIN_FUSED_PASSES: 3 = 3xTF32 (fp32-grade, the default), 1 = TF32.
+TRAIN_FUSED = True
+TRAIN_FUSED_PASSES = 3
+TRAIN_FUSED_SCRATCH_CAP = 24 << 30  # bytes of saved activations above which the per-layer path is used instead
+TRAIN_FUSED_DW_WS_CAP = 256 << 20   # bytes of batch-slice partial sums for the weight-gradient GEMMs
+
+
+class FusedTrainPlan:
+    """Device buffers and host pointer tables of the fused training step for one model and batch size."""
+
+    def __init__(self, model, E, B):
+        import ctypes
+
+        params = model._stack_params()
+        n_lin = len(params) - model._n_bound_params()
+        ws, bs = params[0:n_lin:2], params[1:n_lin:2]
+        self.L = len(ws) - 1
+        self.P, self.E, self.B = model._parallel_num(), E, B
+        self.in_size, self.hidden = ws[0].shape[-2], ws[0].shape[-1]
+        self.layout = model._head_layout
+        self.head_dim = model._head_dim
+        self.head_outputs = 1 if self.layout == HEAD_PARALLEL else self.head_dim
+        self.act = model._act_kind
+        self.residual = 1 if model._residual() else 0
+        blob, scratch, dw_ws = ctypes.c_longlong(0), ctypes.c_longlong(0), ctypes.c_longlong(0)
+        rc = _lib.load().cmrl_train_fused_sizes(self.L, self.in_size, self.hidden, self.head_outputs, self.P, E, B,
+                                                 ctypes.byref(blob), ctypes.byref(scratch), ctypes.byref(dw_ws))
+        self.ok = rc == 0 and scratch.value * 4 <= TRAIN_FUSED_SCRATCH_CAP
+        if not self.ok:
+            return
+        dev = ws[0].device
+        nets = self.P * E
+        self.packed = torch.empty(nets * blob.value, device=dev, dtype=torch.float32)
+        self.scratch = torch.empty(scratch.value, device=dev, dtype=torch.float32)
+        tiles = (B + 127) // 128
+        slices = min(64, tiles, TRAIN_FUSED_DW_WS_CAP // (4 * dw_ws.value)) if tiles > 1 else 0
+        self.dw_ws = torch.empty(slices * dw_ws.value, device=dev, dtype=torch.float32) if slices >= 2 else None
+        arr = ctypes.c_void_p * (self.L + 1)
+        self.w_ptrs = arr(*[w.data_ptr() for w in ws])
+        self.b_ptrs = arr(*[b.data_ptr() for b in bs])
+        self.dw_ptrs = arr(*[w.grad.data_ptr() for w in ws])
+        self.db_ptrs = arr(*[b.grad.data_ptr() for b in bs])
+        mask = model._kernel_mask()
+        self.mask = mask
+        self.mask_str = mask_strides(mask, self.P, E, -1)[:2] if mask is not None else (0, 0)
+        self.launches = 3 + (1 if self.dw_ws is not None else 0)
+
+    def step(self, obs, act, target, mn, mx, reg, g_scale, want_loss=True):
+        """pack -> fused forward / NLL / dz chain -> weight gradients, all on the current stream; returns the loss."""
+        E, B = self.E, self.B
+        obs, act, target = _rows_contig(_req(obs, "obs"), "obs"), _rows_contig(_req(act, "act"), "act"), _rows_contig(_req(target, "target"), "target")
+        loss = torch.empty((E, B, self.head_dim), device=obs.device, dtype=torch.float32) if want_loss else None
+        st = _stream()
+        m = self.mask
+        _lib.call("cmrl_train_pack_tf32", self.w_ptrs, self.b_ptrs, self.L, self.P, E, self.in_size, self.hidden,
+                  self.head_outputs, _ptr(m), self.mask_str[0], self.mask_str[1], self.packed.data_ptr(), st)  # fmt: skip
+        _lib.call("cmrl_train_fused", self.packed.data_ptr(), self.L, self.P, E, B, obs.shape[-1], act.shape[-1], self.hidden,
+                  self.head_dim, self.layout, self.act, self.residual, int(TRAIN_FUSED_PASSES), obs.data_ptr(),
+                  _lead_strides(obs)[1], act.data_ptr(), _lead_strides(act)[1], target.data_ptr(), _lead_strides(target)[1],
+                  target.shape[-1], mn.data_ptr(), mx.data_ptr(), mn.numel(), float(reg), float(g_scale), _ptr(loss),
+                  self.scratch.data_ptr(), st)  # fmt: skip
+        _lib.call("cmrl_train_dw", self.scratch.data_ptr(), self.L, self.P, E, B, self.in_size, self.hidden, self.head_outputs,
+                  self.dw_ptrs, self.db_ptrs, _ptr(m), self.mask_str[0], self.mask_str[1], _ptr(self.dw_ws),
+                  0 if self.dw_ws is None else self.dw_ws.numel(), st)  # fmt: skip
+        return loss
+
+
+def fused_train_plan(model, E, B):
+    """The model's FusedTrainPlan for batches of B rows per member, or None when the fused kernels do not take this model
+    (deterministic head, CMI-test layout, per-sample masks, wide hidden layers ...: the per-layer kernels run instead)."""
+    if not TRAIN_FUSED or model.deterministic or not hasattr(model, "hidden_layers"):
+        return None
+    P = model._parallel_num()
+    if not ((model._head_layout == HEAD_PLAIN and P == 1) or (model._head_layout == HEAD_PARALLEL and P == model._head_dim)):
+        return None
+    mask = model._kernel_mask()
+    if mask is not None and not (mask.dim() == 2 or (mask.dim() == 3 and mask.shape[1] == E)):
+        return None
+    flat, flat_grad = model.flat_parameters()
+    key = (E, B, flat.data_ptr(), flat_grad.data_ptr(), None if mask is None else (mask.data_ptr(), mask._version))
+    cached = model._packed.get("train_plan")
+    if cached is None or cached[0] != key:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.CmrlB200Error("the fused training plan must be built before the step is captured in a CUDA graph")
+        cached = (key, FusedTrainPlan(model, E, B))
+        model._packed["train_plan"] = cached
+    return cached[1] if cached[1].ok else None

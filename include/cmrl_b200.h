@@ -233,6 +233,40 @@ int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, const int* la
                          const int* offsets, int residual, const float* min_logvar, const float* max_logvar,
                          int bounds_n, const float* noise, float* pred, int variant, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused training step (BaseDynamics.train, base_dynamics.py:181-186: `loss = get_nll_loss(...); loss.mean().backward()`
+ * over PlainTransition / ExternalMaskTransition / PlainRewardMech / PlainTerminationMech) on tcgen05 kind::tf32 tensor
+ * cores.  passes = 3 -> 3xTF32 error compensation (fp32-grade, 1e-5 tier), passes = 1 -> plain TF32 (1e-3 tier).
+ * Three launches per step: pack (weights -> streamed tf32 hi/lo B operands), fused (forward, Gaussian head, NLL and its
+ * gradient, dz chain; one persistent CTA per (net, 128-row tile)), dw (every layer's weight / bias gradient).
+ * L = hidden layers (the head is layer L); in_size = O + A; head_outputs = outputs PER NET (PLAIN head: D; PARALLEL
+ * head: 1).  Limits: hidden <= 239, head_outputs <= 16, in_size <= hidden.  Returns <0 for unsupported shapes.
+ * ------------------------------------------------------------------------------------------ */
+/* sizes (floats) of the packed-weight blob per net, of the saved-activation scratch for a batch of B rows per net, and of
+ * ONE batch slice of the dw workspace (pass a multiple of it to cmrl_train_dw to let large batches split over CTAs) */
+long long cmrl_train_fused_sizes(int L, int in_size, int hidden, int head_outputs, int P, int E, int B,
+                                 long long* blob_floats, long long* scratch_floats, long long* dw_ws_floats);
+/* weights_host / biases_host: HOST arrays of L+1 device pointers ([P,E,in,out] / [P,E,1,out], layers.py:42-58,86-104).
+ * mask: NULL or the 0/1 input mask of the first layer addressed mask[p*m_sp + e*m_se + i] (folded into W1). */
+int cmrl_train_pack_tf32(const float* const* weights_host, const float* const* biases_host, int L, int P, int E,
+                         int in_size, int hidden, int head_outputs, const float* mask, long long m_sp, long long m_se,
+                         float* packed, void* stream);
+/* obs [E,B,O] / actn [E,B,A] / target [E,B,tgt_ld] with member strides *_se (floats).  loss [E,B,head_dim] (may be
+ * NULL) = gaussian_nll(reduce=False) + reg (util.py:14-37, mlp.py:72-76); the gradient is that of
+ * g_scale * sum(loss) (g_scale = 1 / (E * global_rows * head_dim) reproduces loss.mean().backward()).
+ * scratch: cmrl_train_fused_sizes floats; it carries the layer inputs and dz of every layer to cmrl_train_dw. */
+int cmrl_train_fused(const float* packed, int L, int P, int E, int B, int O, int A, int hidden, int head_dim,
+                     int layout, int act, int residual, int passes, const float* obs, long long obs_se,
+                     const float* actn, long long act_se, const float* target, long long tgt_se, int tgt_ld,
+                     const float* min_logvar, const float* max_logvar, int bounds_n, float reg, float g_scale,
+                     float* loss, float* scratch, void* stream);
+/* dw_host / db_host: HOST arrays of L+1 device pointers to the gradient tensors (overwritten, not accumulated).
+ * mask as in cmrl_train_pack_tf32 (gradient rows of masked inputs are zero, as in the reference's masked forward).
+ * workspace: optional device floats for deterministic batch-slice partial sums. */
+int cmrl_train_dw(const float* scratch, int L, int P, int E, int B, int in_size, int hidden, int head_outputs,
+                  float* const* dw_host, float* const* db_host, const float* mask, long long m_sp, long long m_se,
+                  float* workspace, long long workspace_floats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ def test_abi_exports_every_declared_symbol():
     assert lib.cmrl_abi_version() == 1
     for name in declared:
         assert hasattr(lib, name), "libcmrl_b200.so does not export %s" % name
-    bound = set(cm._lib.PROTOTYPES) | {"cmrl_abi_version", "cmrl_last_error", "cmrl_launch_count"}
+    bound = set(cm._lib.PROTOTYPES) | {"cmrl_abi_version", "cmrl_last_error", "cmrl_launch_count", "cmrl_train_fused_sizes"}
     assert declared == bound, declared ^ bound
     # argument validation happens before any CUDA call
     rc = lib.cmrl_ens_linear_fwd(None, 0, 0, None, None, None, None, 1, 1, 1, 1, 1, None, 0, 0, 0, None, 0, 0, None)
