@@ -35,6 +35,21 @@ constexpr uint32_t SMEM_LIMIT = 232448 - 1024;
 
 enum { PH_FWD = 0, PH_HEAD = 1, PH_DX = 2 };
 
+// Event trace of CTA (0,0) for profiles/tools/train_trace.py: compiled in only with -DCMRL_TRACE (a separate tool build of
+// this file; the shipped library carries none of it).  Stamps are clock64 values in [role][1024] slots.
+#ifdef CMRL_TRACE
+__device__ long long* g_trace_buf = nullptr;
+#define TRACE_DECL int trace_n = 0
+#define TRACE(role)                                                                                                   \
+    do {                                                                                                              \
+        if (g_trace_buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && trace_n < 1024) \
+            g_trace_buf[(role) * 1024 + trace_n++] = clock64();                                                       \
+    } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(role)
+#endif
+
 // Geometry shared by the three kernels (built on the host by make_geom)
 struct Geom {
     int L;            // hidden layers; layer L is the head
@@ -44,7 +59,7 @@ struct Geom {
     int ph_kind[TF_MAX_PH], ph_layer[TF_MAX_PH], ph_k[TF_MAX_PH], ph_n[TF_MAX_PH];
     long long ph_off[TF_MAX_PH];  // float offset of the phase's chunks inside a net blob
     long long blob_floats;
-    // saved tiles per (net, row tile), floats: x | z_l, a_l (l < L) | dz_l (l <= L)
+    // saved tiles per (net, row tile), floats: x | act'(z_l), a_l (l < L) | dz_l (l <= L)
     long long off_x, off_z[TF_MAX_LAYERS], off_a[TF_MAX_LAYERS], off_dz[TF_MAX_LAYERS + 1], item_floats;
 };
 
@@ -166,11 +181,15 @@ __device__ __forceinline__ void split_store_chunk(uint32_t a_hi_row, uint32_t a_
     for (int j = 0; j < 4; ++j) v3_sts128(a_hi_row + (uint32_t)(c * 4 + j) * TF_GROUP, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
     tmem_st16(a_lo_t + (uint32_t)c * 16, lo);
 }
-// saved tile layout = the operand layout: [col / 4][128 rows][4 floats]
-__device__ __forceinline__ void save_chunk(float* tile, int row, int c, const float* v) {
+// Saved tile layout: [row quarter q][col / 4][32 rows][4 floats].  Inside a quarter it is the K-major operand layout
+// (a 4-column group of 32 rows is 512 contiguous bytes, so a warp's store is one contiguous 512-byte run), and a
+// 32-row slice of any range of column groups is ONE contiguous block: the weight-gradient kernel fetches it with a single
+// TMA bulk copy (512-byte copies, one per group, cost ~180 cycles each and made that kernel 10x slower).
+__device__ __forceinline__ long long tile_off(int q, int lane, int ncg, int cg) { return ((long long)(q * ncg + cg) * 32 + lane) * 4; }
+__device__ __forceinline__ void save_chunk(float* tile, int q, int lane, int ncg, int c, const float* v) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<float4*>(tile + ((long long)(c * 4 + j) * TF_ROWS + row) * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        *reinterpret_cast<float4*>(tile + tile_off(q, lane, ncg, c * 4 + j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
 __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP p) {
@@ -209,6 +228,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
         // ===================== weight producer: one bulk copy per 16-deep K chunk (hi | lo) ================================
         if (lane == 0) {
             uint32_t n = 0;
+            TRACE_DECL;
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
                 const float* blob = p.packed + (long long)(item / p.tiles_per_net) * g.blob_floats;
                 for (int ph = 0; ph < g.n_ph; ++ph) {
@@ -218,6 +238,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
                     for (int c = 0; c < nch; ++c, ++n) {
                         const uint32_t s = n % (uint32_t)S;
                         if (n >= (uint32_t)S) mbar_wait_sleep(&bar_wempty[s], ((n / (uint32_t)S) - 1) & 1, 32);
+                        TRACE(0);
                         mbar_expect_tx(&bar_wfull[s], bytes);
                         tma_bulk_g2s(smem + p.a_bytes + s * p.stage_bytes, src + (long long)c * 32 * g.ph_n[ph], bytes, &bar_wfull[s]);
                     }
@@ -227,6 +248,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
     } else if (warp == TF_WARP_MMA) {
         // ===================== MMA issuer =====================================================================================
         uint32_t n = 0, n_a = 0;
+        TRACE_DECL;
         const uint32_t a_hi0 = smem_u32(smem);
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             for (int ph = 0; ph < g.n_ph; ++ph) {
@@ -236,13 +258,16 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
                 const uint32_t part = 64u * (uint32_t)N;  // bytes of one (hi or lo) part of a weight chunk: 4 groups x N x 16
                 const uint32_t b_lbo = 16u * (uint32_t)N;
                 const int nch = g.ph_k[ph] / 16;
+                TRACE(2);
                 mbar_wait(bar_aready, n_a & 1);
                 ++n_a;
                 tc_fence_after();
+                TRACE(2);
 #pragma unroll 1
                 for (int c = 0; c < nch; ++c, ++n) {
                     const uint32_t s = n % (uint32_t)S;
                     mbar_wait(&bar_wfull[s], (n / (uint32_t)S) & 1);
+                    if (c == 0 || c == nch - 1) TRACE(2);
                     const uint32_t w_hi = smem_u32(smem + p.a_bytes + s * p.stage_bytes), w_lo = w_hi + part;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
@@ -261,6 +286,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
                     umma_commit_uni(&bar_wempty[s]);
                 }
                 umma_commit_uni(bar_dfull);
+                TRACE(2);
             }
         }
     } else {
@@ -273,6 +299,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
         const int act = p.act;
         const int Dn = g.Dn;
         uint32_t n_d = 0;
+        TRACE_DECL;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int net = item / p.tiles_per_net, tile = item % p.tiles_per_net;
             const int pp = net / p.E, e = net % p.E;
@@ -296,7 +323,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
                         else if (k == g.in0) x = 1.0f;
                         v[i] = x;
                     }
-                    save_chunk(sc + g.off_x, row, c, v);
+                    save_chunk(sc + g.off_x, q, lane, g.K0P / 4, c, v);
                     split_store_chunk(a_hi_row, a_lo_t, c, v);
                 }
             }
@@ -309,9 +336,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
             for (int ph = 0; ph < g.n_ph; ++ph) {
                 const int kind = g.ph_kind[ph], l = g.ph_layer[ph];
                 // prefetch what the head needs before the accumulator is ready
+                if (warp == 0) TRACE(1);
                 mbar_wait(bar_dfull, n_d & 1);
                 ++n_d;
                 tc_fence_after();
+                if (warp == 0) TRACE(1);
                 if (kind == PH_FWD) {
                     float* zt = sc + g.off_z[l];
                     float* at = sc + g.off_a[l];
@@ -323,15 +352,25 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
                         __syncwarp();
                         v5_ld16_issue(tmem + lane_off + (uint32_t)c * 16, raw);
                         v3_ld_wait();
+                        float gz[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) z[i] = __uint_as_float(raw[i]);
-                        save_chunk(zt, row, c, z);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            z[i] = act_fwd_fast(z[i], act);
+                        for (int i = 0; i < 16; ++i) {  // activation and its derivative from one exp + one reciprocal
+                            const float zi = __uint_as_float(raw[i]);
+                            if (act == CMRL_ACT_SILU) {
+                                const float sg = __fdividef(1.0f, 1.0f + __expf(-zi));
+                                z[i] = zi * sg;
+                                gz[i] = sg * (1.0f + zi * (1.0f - sg));
+                            } else if (act == CMRL_ACT_RELU) {
+                                z[i] = fmaxf(zi, 0.0f);
+                                gz[i] = zi > 0.0f ? 1.0f : 0.0f;
+                            } else {
+                                z[i] = zi;
+                                gz[i] = 1.0f;
+                            }
                             if (c * 16 + i == g.H) z[i] = 1.0f;  // the next layer's bias input
                         }
-                        save_chunk(at, row, c, z);
+                        save_chunk(zt, q, lane, g.HP / 4, c, gz);  // act'(z): what the dz chain multiplies by
+                        save_chunk(at, q, lane, g.HP / 4, c, z);
                         split_store_chunk(a_hi_row, a_lo_t, c, z);
                     }
                 } else if (kind == PH_DX) {
@@ -346,13 +385,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
                         v5_ld16_issue(tmem + lane_off + (uint32_t)c * 16, raw);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float4 t4 = *reinterpret_cast<const float4*>(zt + ((long long)(c * 4 + j) * TF_ROWS + row) * 4);
+                            const float4 t4 = *reinterpret_cast<const float4*>(zt + tile_off(q, lane, g.HP / 4, c * 4 + j));
                             z[4 * j] = t4.x; z[4 * j + 1] = t4.y; z[4 * j + 2] = t4.z; z[4 * j + 3] = t4.w;
                         }
                         v3_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) z[i] = __uint_as_float(raw[i]) * act_grad_fast(z[i], act);
-                        save_chunk(dt, row, c, z);
+                        for (int i = 0; i < 16; ++i) z[i] *= __uint_as_float(raw[i]);  // dz = (dz_next . W^T) * act'(z)
+                        save_chunk(dt, q, lane, g.HP / 4, c, z);
                         if (l > 0) split_store_chunk(a_hi_row, a_lo_t, c, z);
                     }
                 } else if (cset == 0) {
@@ -386,12 +425,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
                             }
                         }
                         const int k = 2 * d;
-                        *reinterpret_cast<float2*>(dt + ((long long)(k / 4) * TF_ROWS + row) * 4 + (k & 3)) = make_float2(dm, dl);
+                        *reinterpret_cast<float2*>(dt + tile_off(q, lane, g.NH / 4, k / 4) + (k & 3)) = make_float2(dm, dl);
                         const uint32_t hm = __float_as_uint(dm) & 0xFFFFE000u, hl = __float_as_uint(dl) & 0xFFFFE000u;
                         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi_row + (uint32_t)(k / 4) * TF_GROUP + (uint32_t)(k & 3) * 4), "r"(hm), "r"(hl) : "memory");
                         tmem_st2(a_lo_t + (uint32_t)k, __float_as_uint(dm - __uint_as_float(hm)), __float_as_uint(dl - __uint_as_float(hl)));
                     }
                 }
+                if (warp == 0) TRACE(1);
                 if (ph + 1 < g.n_ph) {  // the last phase (dz of the first layer) feeds no further GEMM
                     v5_st_wait();
                     tc_fence_before();
@@ -510,31 +550,31 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
     const float* base = p.scratch + ((long long)net * p.tiles_per_net) * g.item_floats;
 
     if (warp == TF_WARP_W) {
-        // ===================== raw tile producer: 512-byte pieces (one 4-feature group x 32 rows) ===========================
+        // ===================== raw tile producer: one bulk copy per operand and 32-row slice ================================
+        TRACE_DECL;
         for (int i = 0; i < n_sub; ++i) {
             const int s = i & 1;
             const int t = t0 + i / 4, qr = i % 4;
             const float* item = base + (long long)t * g.item_floats;
             if (lane == 0) {
                 if (i >= 2) mbar_wait_sleep(&bar_rempty[s], ((i >> 1) - 1) & 1, 32);
+                TRACE(0);
                 mbar_expect_tx(&bar_rfull[s], (uint32_t)(ga + gb) * 512u);
-            }
-            __syncwarp();
-            uint8_t* dst = smem + s * DW_RAW;
-            for (int c = lane; c < ga + gb; c += 32) {
-                const bool isa = c < ga;
-                const int grp = isa ? mt * 32 + c : nt * (DW_NT / 4) + (c - ga);
-                const float* src = item + (isa ? a_off : z_off) + ((long long)grp * TF_ROWS + qr * DW_SUB) * 4;
-                tma_bulk_g2s(dst + (isa ? (uint32_t)c * 512u : DW_RAW_A + (uint32_t)(c - ga) * 512u), src, 512u, &bar_rfull[s]);
+                uint8_t* dst = smem + s * DW_RAW;
+                tma_bulk_g2s(dst, item + a_off + ((long long)(qr * (a_cols / 4) + mt * 32) * 32) * 4, (uint32_t)ga * 512u, &bar_rfull[s]);
+                tma_bulk_g2s(dst + DW_RAW_A, item + z_off + ((long long)(qr * (z_cols / 4) + nt * (DW_NT / 4)) * 32) * 4, (uint32_t)gb * 512u,
+                             &bar_rfull[s]);
             }
         }
     } else if (warp == TF_WARP_MMA) {
         // ===================== MMA issuer: A = features x rows, B = columns x rows, both K-major after the transpose =============
         const uint32_t idesc = umma_idesc_tf32(TF_ROWS, NT);
+        TRACE_DECL;
         for (int i = 0; i < n_sub; ++i) {
             const int s = i & 1;
             mbar_wait(&bar_ofull[s], (i >> 1) & 1);
             tc_fence_after();
+            TRACE(2);
             const uint32_t op = smem_u32(smem + DW_RAW_STAGES * DW_RAW + s * DW_OP);
             const uint32_t a_hi = op, a_lo = op + DW_OP_A, b_hi = op + 2 * DW_OP_A, b_lo = b_hi + DW_OP_B;
 #pragma unroll
@@ -553,10 +593,14 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
     } else {
         // ===================== transposers, then the epilogue ====================================================================
         const int tid = threadIdx.x;  // 0..511
+        TRACE_DECL;
         for (int i = 0; i < n_sub; ++i) {
             const int s = i & 1;
+            if (warp == 0) TRACE(1);
             mbar_wait(&bar_rfull[s], (i >> 1) & 1);
+            if (warp == 0) TRACE(1);
             if (i >= 2) mbar_wait(&bar_oempty[s], ((i >> 1) - 1) & 1);
+            if (warp == 0) TRACE(1);
             const uint8_t* raw = smem + s * DW_RAW;
             const uint32_t op = smem_u32(smem + DW_RAW_STAGES * DW_RAW + s * DW_OP);
             for (int idx = tid; idx < (ga + gb) * 32; idx += TF_EPI_WARPS * 32) {
@@ -581,10 +625,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
                 mbar_arrive(&bar_ofull[s]);
                 mbar_arrive(&bar_rempty[s]);
             }
+            if (warp == 0) TRACE(1);
         }
         // ---- epilogue: TMEM lane = feature row of this tile, columns = output features --------------------------------------
         mbar_wait(bar_acc, 0);
         tc_fence_after();
+        if (warp == 0) TRACE(1);
         const int q = warp & 3, cset = warp >> 2;
         const int i_row = mt * TF_ROWS + q * 32 + lane;
         float* wsp = p.ksplit > 1 ? p.ws + ((long long)slice * gridDim.y + net) * p.ext_total + p.ext_off[l] : nullptr;
@@ -636,6 +682,13 @@ __global__ void train_dw_reduce_kernel(const DwP p, int nets) {
 
 using namespace cmrl;
 using namespace cmrl::tr;
+
+#ifdef CMRL_TRACE
+extern "C" int cmrl_trace_set(long long* buf) {
+    CMRL_CUDA(cudaMemcpyToSymbol(cmrl::tr::g_trace_buf, &buf, sizeof(buf)));
+    return 0;
+}
+#endif
 
 extern "C" long long cmrl_train_fused_sizes(int L, int in_size, int hidden, int head_outputs, int P, int E, int B, long long* blob_floats,
                                             long long* scratch_floats, long long* dw_ws_floats) {

@@ -453,6 +453,10 @@ class _DeviceEpochRunner:
         model = getattr(self.dyn, self.mech)
         model._nll_reg()  # host-side constant, cached before any capture
         model.flat_parameters()
+        if self.Bl > 0:
+            plan = ops.fused_train_plan(model, self.E, self.Bl)  # buffers of the fused tcgen05 step: allocated before the capture
+            if plan is not None:
+                plan.pinned = True  # the captured graph bakes their addresses
         getattr(self.dyn, "{}_optimizer".format(self.mech)).prepare_graphable()
         n_full = self.N // self.B
         if self.Bl >= 2048:  # split-K dw workspace (ops.ens_linear_bwd_dw) must exist before the step is captured

@@ -568,11 +568,18 @@ def fused_train_plan(model, E, B):
     if mask is not None and not (mask.dim() == 2 or (mask.dim() == 3 and mask.shape[1] == E)):
         return None
     flat, flat_grad = model.flat_parameters()
-    key = (E, B, flat.data_ptr(), flat_grad.data_ptr(), None if mask is None else (mask.data_ptr(), mask._version))
-    cached = model._packed.get("train_plan")
-    if cached is None or cached[0] != key:
+    key = (E, flat.data_ptr(), flat_grad.data_ptr(), None if mask is None else (mask.data_ptr(), mask._version))
+    plans = model._packed.get("train_plans")
+    if plans is None or plans[0] != key:  # the arena or the mask moved: every plan points at stale memory
+        plans = model._packed["train_plans"] = (key, {})
+    plan = plans[1].get(B)
+    if plan is None:
         if torch.cuda.is_current_stream_capturing():
             raise _lib.CmrlB200Error("the fused training plan must be built before the step is captured in a CUDA graph")
-        cached = (key, FusedTrainPlan(model, E, B))
-        model._packed["train_plan"] = cached
-    return cached[1] if cached[1].ok else None
+        if len(plans[1]) >= 8:  # ragged batch sizes of a growing data set: keep the set of live plans small
+            for b_old, p_old in list(plans[1].items()):
+                if not getattr(p_old, "pinned", False):  # a captured step graph holds the buffers of a pinned plan
+                    del plans[1][b_old]
+                    break
+        plan = plans[1][B] = FusedTrainPlan(model, E, B)
+    return plan if plan.ok else None

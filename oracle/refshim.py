@@ -17,7 +17,28 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CMRL_REFERENCE_ROOT", "/root/reference")
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# The unmodified reference: the mounted tree in the build container, else the copy `__graft_entry__.build()` installed with
+# pip into the git-ignored baseline/_ref/ (it travels to the GPU box, where bench.py's reference arm times it).
+_INSTALLED = os.path.join(_REPO_ROOT, "baseline", "_ref")
+
+
+def _default_root():
+    env = os.environ.get("CMRL_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/cmrl"):
+        return "/root/reference"
+    return _INSTALLED
+
+
+REFERENCE_ROOT = _default_root()
+
+
+def mounted() -> bool:
+    """True only where the reference SOURCE TREE is mounted (the build container): live-reference tests and the golden
+    generator need it; the installed copy under baseline/_ref is for bench.py's timed reference arm."""
+    return os.path.isdir("/root/reference/cmrl")
 
 
 def available() -> bool:

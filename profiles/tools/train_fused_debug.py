@@ -20,8 +20,8 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-def tile_to_rows(flat, cols):
-    return flat.reshape(cols // 4, 128, 4).transpose(1, 0, 2).reshape(128, cols)
+def tile_to_rows(flat, cols):  # [row quarter][col / 4][32 rows][4]
+    return flat.reshape(4, cols // 4, 32, 4).transpose(0, 2, 1, 3).reshape(128, cols)
 
 
 def reference(model, obs, act, target, g_scale):
@@ -116,7 +116,10 @@ def check(name, model, B, seed=0):
             for l in range(L):
                 z = tile_to_rows(sc[base + off:base + off + HP * 128], HP); off += HP * 128
                 a = tile_to_rows(sc[base + off:base + off + HP * 128], HP); off += HP * 128
-                worst["z%d" % l] = max(worst.get("z%d" % l, 0), rel(z[:nr, :H], sel(ref["zs"][l])[r0:r0 + nr]))
+                zr = sel(ref["zs"][l])[r0:r0 + nr]
+                sg = 1.0 / (1.0 + np.exp(-zr))
+                gref = sg * (1 + zr * (1 - sg)) if model._act_kind == ops.ACT_SILU else (zr > 0).astype(np.float64)
+                worst["g%d" % l] = max(worst.get("g%d" % l, 0), rel(z[:nr, :H], gref))
                 worst["a%d" % l] = max(worst.get("a%d" % l, 0), rel(a[:nr, :H], sel(ref["hs"][l + 1])[r0:r0 + nr]))
                 assert np.all(a[:, H] == 1.0), "bias column of a%d" % l
             for l in range(L):
