@@ -102,11 +102,6 @@ __device__ __forceinline__ bool v3_iter_next(V3Iter& it, const RolloutP& p, cons
 // provably warp-uniform: ptxas then keeps them in uniform registers (UIADD3) instead of moving vector registers to
 // uniform ones (R2UR) in front of every UTCHMMA -- the issue path is a single thread's dependent instruction chain
 // and directly bounds the MMA rate (54-cycle MMAs).
-// optional event trace (profiling): p.dbg + 4096 holds [3 roles][512] clock64 stamps of CTA 0
-__device__ __forceinline__ void v3_trace(const RolloutP& p, int role, int& n, bool on) {
-    if (on && n < 512) p.dbg[4096 + role * 512 + n++] = clock64();
-}
-
 template <int SLOT>
 __device__ __forceinline__ void v3_mma_role(const RolloutP& p, const V3Smem& sm, uint8_t* smem, uint64_t* bars, const int* s_off,
                                             uint32_t tmem_base, uint32_t rank, int lane, int item_begin, int item_end,
@@ -123,10 +118,6 @@ __device__ __forceinline__ void v3_mma_role(const RolloutP& p, const V3Smem& sm,
             const uint32_t b_sbo0 = (uint32_t)(K0 / 8) * 128, b_sbo = (uint32_t)(HP / 8) * 128;
             const uint64_t ad_a = umma_desc(smem_u32(smem + sm.a_off[s]), V3_CHUNK, 128);
             const uint32_t a_hi = (uint32_t)(ad_a >> 32);
-            const bool timing = p.dbg != nullptr && lane == 0 && SLOT == 0;
-            const bool tracing = p.dbg != nullptr && lane == 0 && blockIdx.x == 0 && (p.dbg_flags & 16);
-            int n_tr = 0;
-            long long t_wa = 0, t_issue = 0, t_wx = 0, t_all = timing ? clock64() : 0, tt = 0;
             V3Pair pr;
             V3Iter it;
             v3_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
@@ -141,9 +132,7 @@ __device__ __forceinline__ void v3_mma_role(const RolloutP& p, const V3Smem& sm,
                 const int st = n_pair & 1;
                 // ---- layer 0 ------------------------------------------------------------------------------------------
                 {
-                    if (timing) tt = clock64();
                     mbar_wait(&bars[V3_X_READY + st * 2 + s], n_x[st] & 1);
-                    if (timing) t_wx += clock64() - tt;
                     ++n_x[st];
                     tc_fence_after();
                     const uint64_t ad0 = umma_desc(smem_u32(smem + sm.x_off[st][s]), V3_CHUNK, 128);
@@ -159,21 +148,13 @@ __device__ __forceinline__ void v3_mma_role(const RolloutP& p, const V3Smem& sm,
                 for (int l = 1; l <= L; ++l) {
                     const bool head = (l == L);
                     const uint64_t bd0 = umma_desc(smem_u32(smem + sm.w_off[l]), 128, b_sbo);
-                    if (timing) tt = clock64();
-                    v3_trace(p, 1 + SLOT, n_tr, tracing);  // wait start
                     mbar_wait(&bars[V3_A_READY + s], n_a & 1);
                     ++n_a;
                     if (head) {  // the head accumulator of this slot must have been drained by the head warps
                         mbar_wait(&bars[V3_DH_EMPTY + s], (n_h & 1) ^ 1);
                         ++n_h;
                     }
-                    if (timing) {
-                        long long t = clock64();
-                        t_wa += t - tt;
-                        tt = t;
-                    }
                     tc_fence_after();
-                    v3_trace(p, 1 + SLOT, n_tr, tracing);  // wait end / issue start
                     const uint32_t d_tmem = tmem_base + (head ? v3_dh_col(s) : v3_d_col(s));
                     const uint32_t idesc = head ? idesc_head : idesc_h;
                     uint32_t a_lo = (uint32_t)ad_a, b_lo = (uint32_t)bd0;
@@ -186,17 +167,7 @@ __device__ __forceinline__ void v3_mma_role(const RolloutP& p, const V3Smem& sm,
                         v3_mma_uni(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
                     }
                     v3_commit_uni(head ? &bars[V3_DH_FULL + s] : &bars[V3_D_FULL + s]);
-                    v3_trace(p, 1 + SLOT, n_tr, tracing);  // issue end
-                    if (timing) t_issue += clock64() - tt;
                 }
-            }
-            if (timing) {
-                long long* d = p.dbg + (long long)blockIdx.x * 16;
-                d[0] = clock64() - t_all;
-                d[1] = t_wx;
-                d[2] = t_wa;
-                d[3] = t_issue;
-                d[4] = item_end - item_begin;
             }
         }
 }
@@ -415,10 +386,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
         const bool owns_ones = ones_rel >= 0 && (ones_rel & 3) == 0 && (ones_rel >> 2) < my_n && ones_chunk < (h + 1) * n_chunks;
         const uint32_t ones_off = (uint32_t)(ones_rel * V3_CHUNK + (p.H & 7) * 2);
         uint32_t n_d0 = 0, n_d1 = 0;
-        const bool timing = p.dbg != nullptr && threadIdx.x == 0;
-        const bool tracing = p.dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && (p.dbg_flags & 16);
-        int n_tr = 0;
-        long long t_wd = 0, t_loop = 0, t_pub = 0, t0 = timing ? clock64() : 0, tt = 0;
         // A warp's chunks are processed in two halves (chunks {0,1} and {2,3}).  tcgen05.wait::ld waits for ALL of the
         // thread's outstanding loads, so the loads of the next half are issued right after the wait for the current
         // one and before its conversion: the TMEM load latency hides behind the SFU-bound conversion, also across the
@@ -453,9 +420,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
             for (int ts = 0; ts < n_steps; ++ts) {
                 const int s = (pr.n == 2) ? (ts & 1) : 0;
                 // ---- half 0 ---------------------------------------------------------------------------------------------
-                v3_trace(p, 0, n_tr, tracing);  // step start
                 if (!have0) {
-                    if (timing) tt = clock64();
                     if (s) {
                         mbar_wait(&bars[V3_D_FULL + 1], n_d1 & 1);
                         ++n_d1;
@@ -463,12 +428,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
                         mbar_wait(&bars[V3_D_FULL + 0], n_d0 & 1);
                         ++n_d0;
                     }
-                    if (timing) t_wd += clock64() - tt;
                     tc_fence_after();
                     issue_half(s, 0, r0);
                 }
-                if (timing) tt = clock64();
-                v3_trace(p, 0, n_tr, tracing);  // accumulator available
                 v3_ld_wait();
                 issue_half(s, 1, r1);
                 convert_half(s, 0, r0);
@@ -485,25 +447,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
                     }
                 }
                 convert_half(s, 1, r1);
-                if (timing) {
-                    long long t = clock64();
-                    t_loop += t - tt;
-                    tt = t;
-                }
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) v3_arrive_leader(&bars[V3_A_READY + s]);
-                v3_trace(p, 0, n_tr, tracing);  // published
-                if (timing) t_pub += clock64() - tt;
             }
-        }
-        if (timing) {
-            long long* d = p.dbg + (long long)blockIdx.x * 16;
-            d[8] = clock64() - t0;
-            d[9] = t_wd;
-            d[10] = t_loop;
-            d[14] = t_pub;
         }
     }
 

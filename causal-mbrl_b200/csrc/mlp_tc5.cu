@@ -96,11 +96,6 @@ __device__ __forceinline__ bool v5_iter_next(V5Iter& it, const RolloutP& p, cons
     return true;
 }
 
-// optional event trace (profiling, dbg_flags & 256): p.dbg + 4096 holds [3 roles][512] clock64 stamps of CTA 0
-__device__ __forceinline__ void v5_trace(const RolloutP& p, int role, int& n, bool on) {
-    if (on && n < 512) p.dbg[4096 + role * 512 + n++] = clock64();
-}
-
 // MMA issuer of tile slot SLOT (compile-time slot: every descriptor is provably warp-uniform, see mlp_tc3.cu)
 template <int SLOT>
 __device__ __forceinline__ void v5_mma_role(const RolloutP& p, const V5Lay& lay, uint8_t* smem, uint64_t* bars, const int* s_off,
@@ -113,7 +108,7 @@ __device__ __forceinline__ void v5_mma_role(const RolloutP& p, const V5Lay& lay,
     const int K0 = p.layer_k[0];
     const int NH = p.layer_n[L];
     const int n_ks = HP / 16, kt = lay.kt;
-    const uint32_t ns_mma = (p.dbg_flags & 16) ? 32u : 0u;
+    const uint32_t ns_mma = 0u;
     int cur_net = -1;
     uint32_t n_w = 0, n_a = 0, n_h = 0, n_x = 0;
     const uint32_t idesc_h = umma_idesc_f16(V5_TILE, HP), idesc_head = umma_idesc_f16(V5_TILE, NH);
@@ -121,12 +116,6 @@ __device__ __forceinline__ void v5_mma_role(const RolloutP& p, const V5Lay& lay,
     const uint64_t ad_a = umma_desc(smem_u32(smem + lay.a_off[s]), V5_CHUNK, 128);
     const uint32_t a_hi = (uint32_t)(ad_a >> 32);
     const uint32_t d_t = tmem_base + lay.d_col[s], dh_t = tmem_base + lay.dh_col[s], a_t = tmem_base + lay.at_col[s];
-    const bool timing = p.dbg != nullptr && lane == 0 && SLOT == 0;
-    const bool tracing = p.dbg != nullptr && lane == 0 && blockIdx.x == 0 && (p.dbg_flags & 256);
-    int n_tr = 0;
-    long long t_wa = 0, t_issue = 0, t_wx = 0, t_all = timing ? clock64() : 0, tt = 0;
-    unsigned long long g0 = 0;
-    if (timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     V5Pair pr;
     V5Iter it;
     v5_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
@@ -140,10 +129,8 @@ __device__ __forceinline__ void v5_mma_role(const RolloutP& p, const V5Lay& lay,
         if (s >= pr.n) continue;
         // ---- layer 0 ------------------------------------------------------------------------------------------------
         {
-            if (timing) tt = clock64();
             mbar_wait_sleep(&bars[V5_X_READY + s], n_x & 1, ns_mma);
             ++n_x;
-            if (timing) t_wx += clock64() - tt;
             tc_fence_after();
             const uint64_t ad0 = umma_desc(smem_u32(smem + lay.x_off[s]), V5_CHUNK, 128);
             const uint64_t bd0 = umma_desc(smem_u32(smem + lay.w_off[0]), 128, b_sbo0);
@@ -159,51 +146,25 @@ __device__ __forceinline__ void v5_mma_role(const RolloutP& p, const V5Lay& lay,
         for (int l = 1; l <= L; ++l) {
             const bool head = (l == L);
             const uint64_t bd0 = umma_desc(smem_u32(smem + lay.w_off[l]), 128, b_sbo);
-            if (timing) tt = clock64();
-            v5_trace(p, 1 + SLOT, n_tr, tracing);  // wait start
             mbar_wait_sleep(&bars[V5_A_READY + s], n_a & 1, ns_mma);
             ++n_a;
             if (head) {  // the head accumulator of this slot must have been drained by the head warps
                 mbar_wait_sleep(&bars[V5_DH_EMPTY + s], (n_h & 1) ^ 1, ns_mma);
                 ++n_h;
             }
-            if (timing) {
-                long long t = clock64();
-                t_wa += t - tt;
-                tt = t;
-            }
             tc_fence_after();
-            v5_trace(p, 1 + SLOT, n_tr, tracing);  // wait end / issue start
             const uint32_t d_tmem = head ? dh_t : d_t;
             const uint32_t idesc = head ? idesc_head : idesc_h;
             uint32_t a_lo = (uint32_t)ad_a, b_lo = (uint32_t)bd0, at = a_t;
             const uint32_t b_hi = (uint32_t)(bd0 >> 32);
             int ks = 0;
-            if (p.dbg_flags & 512) ks = n_ks;  // profiling experiment (results invalid): no MMAs at all for layers >= 1
-            if (p.dbg_flags & 4) {  // profiling experiment (results invalid): skip the MMAs that read A from tensor memory
-                ks = kt;
-                b_lo += 16 * kt;
-            }
             // rolled loops: the issue path has slack (105-cycle MMAs) and the kernel has to stay small (instruction caches)
 #pragma unroll 1
             for (; ks < kt; ++ks, at += 8, b_lo += 16) v5_mma_ts_uni(d_tmem, at, b_lo, b_hi, idesc, ks > 0);
 #pragma unroll 1
             for (; ks < n_ks; ++ks, a_lo += 2 * V5_CHUNK / 16, b_lo += 16) v3_mma_uni(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, ks > 0);
             v3_commit_uni(head ? &bars[V5_DH_FULL + s] : &bars[V5_D_FULL + s]);
-            v5_trace(p, 1 + SLOT, n_tr, tracing);  // issue end
-            if (timing) t_issue += clock64() - tt;
         }
-    }
-    if (timing) {
-        long long* d = p.dbg + (long long)blockIdx.x * 16;
-        d[0] = clock64() - t_all;
-        d[1] = t_wx;
-        d[2] = t_wa;
-        d[3] = t_issue;
-        d[4] = item_end - item_begin;
-        unsigned long long g1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
-        d[5] = (long long)(g1 - g0);  // ns: with d[0] gives the SM clock the kernel really ran at
     }
 }
 
@@ -221,13 +182,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
     const uint32_t rank = v3_ctarank();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t ns_slack = (p.dbg_flags & 8) ? 256u : 0u;  // poll interval of the roles with slack (head, weights, layer-0 loader)
+    const uint32_t ns_slack = 0u;  // poll interval of the roles with slack (head, weights, layer-0 loader)
 
-    if (p.dbg != nullptr && threadIdx.x == 0) {  // profiling: wall-clock (ns) at kernel entry / exit of every CTA
-        unsigned long long g;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-        p.dbg[(long long)blockIdx.x * 16 + 6] = (long long)g;
-    }
     for (int i = threadIdx.x; i <= p.E; i += blockDim.x) s_off[i] = p.offsets[i];
     if (threadIdx.x == 0) {
         mbar_init(&bars[V5_W_FULL], 1);
@@ -420,11 +376,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
         // (kt <= H / 16, see the launcher) so that it is one 16-bit store after the chunk that holds it
         const int ones_c = p.H >> 4;
         const uint32_t ones_off = (uint32_t)((2 * (ones_c - kt) + ((p.H >> 3) & 1)) * V5_CHUNK + (p.H & 7) * 2);
-        const int dflags = p.dbg_flags;  // profiling experiments only (results invalid): 1 skip TMEM stores, 2 skip smem stores
-        const bool timing = p.dbg != nullptr && warp == 0;
-        const long long t0 = timing ? clock64() : 0;
-        const bool tracing = p.dbg != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && (p.dbg_flags & 256);
-        int n_tr = 0;
         uint32_t dph = 0;  // phase parity of D_FULL[slot] in bit `slot`
 
         V5Pair pr;
@@ -435,11 +386,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
 #pragma unroll 1
             for (int ts = 0; ts < n_steps; ++ts) {
                 const int s = (pr.n == 2) ? (ts & 1) : 0;
-                v5_trace(p, 0, n_tr, tracing);  // tile-step start
                 mbar_wait(&bars[V5_D_FULL + s], (dph >> s) & 1);
                 dph ^= 1u << s;
                 tc_fence_after();
-                v5_trace(p, 0, n_tr, tracing);  // accumulator complete
                 const uint32_t d_addr = s ? d_addr1 : d_addr0, at_addr = s ? at_addr1 : at_addr0, as_addr = s ? as_addr1 : as_addr0;
 #pragma unroll 1
                 for (int c = cset; c < n_chunks; c += 4) {
@@ -450,8 +399,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) hh[j] = v3_act_pack<ACT>(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
                     if (c < kt) {
-                        if (!(dflags & 1)) v5_st8(at_addr + (uint32_t)c * 8, hh);
-                    } else if (!(dflags & 2)) {
+                        v5_st8(at_addr + (uint32_t)c * 8, hh);
+                    } else {
                         const uint32_t dst = as_addr + (uint32_t)((c - kt) * 2 * V5_CHUNK);
                         v3_sts128(dst, hh[0], hh[1], hh[2], hh[3]);
                         v3_sts128(dst + V5_CHUNK, hh[4], hh[5], hh[6], hh[7]);
@@ -463,12 +412,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) v3_arrive_leader(&bars[V5_A_READY + s]);
-                v5_trace(p, 0, n_tr, tracing);  // published
             }
-        }
-        if (timing && lane == 0) {
-            long long* d = p.dbg + (long long)blockIdx.x * 16;
-            d[8] = clock64() - t0;
         }
     }
 
@@ -479,28 +423,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
     if (warp == V5_WARP_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
-    if (p.dbg != nullptr && threadIdx.x == 0) {
-        unsigned long long g;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-        p.dbg[(long long)blockIdx.x * 16 + 7] = (long long)g;
-    }
 }
 
-int launch_rollout_v5(const RolloutP& p, cudaStream_t st) {
+// tensor-memory and shared-memory layout for this model; false when it does not fit (the caller then uses mlp_tc3.cu)
+static bool v5_layout(const RolloutP& p, V5Lay& lay) {
     const int L = p.num_layers;
     const int HP = p.layer_n[0];
     const int NH = p.layer_n[L];
-    CMRL_REQUIRE(HP % 16 == 0 && NH % 16 == 0 && 2 * HP + 2 * NH <= 512,
-                 "mlp_rollout_f16 v5: accumulators of two tiles (2 x %d + 2 x %d columns) do not fit tensor memory", HP, NH);
-    V5Lay lay{};
+    if (HP % 16 != 0 || NH % 16 != 0 || 2 * HP + 2 * NH > 512) return false;
     const int n_ks = HP / 16;
     // TMEM columns: [D slot 0 | D slot 1 | A (K steps 0..kt-1) slot 0 | slot 1 | head slot 0 | slot 1]
-    int d1 = HP;
-    if (p.dbg_flags & 1024) d1 = (HP + 31) / 32 * 32;  // profiling experiment: 32-column aligned second accumulator
+    const int d1 = HP;
     int kt = (512 - d1 - HP - 2 * NH) / 16;  // A-operand K steps per slot that fit the remaining TMEM columns
     if (kt > n_ks) kt = n_ks;
     if (kt > p.H / 16) kt = p.H / 16;  // the K step that holds the ones column (hidden unit H) stays in shared memory
-    CMRL_REQUIRE(kt >= 0, "mlp_rollout_f16 v5: tensor memory layout does not fit");
+    if (kt < 0) return false;
     lay.kt = kt;
     lay.d_col[0] = 0;
     lay.d_col[1] = (uint32_t)d1;
@@ -525,7 +462,18 @@ int launch_rollout_v5(const RolloutP& p, cudaStream_t st) {
     lay.bar_off = off;
     off += V5_BAR_COUNT * 8;
     lay.total = off;
-    CMRL_REQUIRE(lay.total <= 232448 - 1024, "mlp_rollout_f16 v5: needs %u B of shared memory (> 226 KB)", lay.total);
+    return lay.total <= 232448 - 1024;
+}
+
+bool rollout_v5_supports(const RolloutP& p) {
+    V5Lay lay{};
+    return v5_layout(p, lay);
+}
+
+int launch_rollout_v5(const RolloutP& p, cudaStream_t st) {
+    V5Lay lay{};
+    CMRL_REQUIRE(v5_layout(p, lay), "mlp_rollout_f16 v5: two 256-row tiles of this model (hidden %d, head %d columns) do not fit tensor / shared memory",
+                 p.layer_n[0], p.layer_n[p.num_layers]);
     static cmrl::PerDeviceOnce attr_once;
     int attr_dev = 0;
     if (attr_once.pending(&attr_dev)) {

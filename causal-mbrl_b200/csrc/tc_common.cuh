@@ -8,8 +8,6 @@ namespace cmrl {
 namespace tc {
 
 constexpr int TILE_M = 128;
-constexpr int NUM_THREADS = 192;
-constexpr int A_CHUNK_BYTES = TILE_M * 16;  // one 8-element K chunk for all 128 rows (core matrices of 8 rows x 16 B)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t HEAD_TMEM_COL = 256;
 constexpr unsigned long long SPIN_LIMIT = 1ull << 27;  // ~ seconds; a broken pipeline traps instead of hanging the GPU
@@ -36,10 +34,6 @@ struct RolloutP {
     int bounds_n;
     const float* noise;        // [N,D] env order or NULL
     float* pred;               // [N,D] env order
-    uint32_t w_stage_bytes;    // max over layers of n*k*2
-    int a_chunks;              // K chunks (of 8) the A buffer holds
-    int dbg_flags;             // profiling experiments only (results invalid): 1 skip A stores, 2 skip TMEM loads, 4 skip activation
-    long long* dbg;            // optional [gridDim.x][16] cycle counters (profiling builds of the caller), else NULL
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -377,6 +371,55 @@ __device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b)
 }
 __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr));
+}
+
+
+// cta_group::2 kind::tf32 (CTA pair, M = 256: 128 rows per CTA, the B operand split over the pair's shared memories)
+__device__ __forceinline__ void tf32_mma2_ss_uni(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, p;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// same, descriptors as (lo, hi) words: only the start-address field in the low word changes between MMAs, so the issue loop is
+// one 32-bit add per operand (computing a 64-bit descriptor per MMA in the issuing thread cost ~170 cycles per MMA and paced the
+// whole training kernel: profiles/r2_train_trace_*.txt)
+__device__ __forceinline__ void tf32_mma2_lohi_uni(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                   uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, p;\n"
+        ".reg .b64 da, db;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// multicast forms for 2-CTA clusters of independent (cta_group::1) tiles that share one weight stream
+__device__ __forceinline__ void tma_bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_uni(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
 }
 // activation / derivative with the fast exp and divide intrinsics (a few ulp: far inside the 1e-5 tier)
 __device__ __forceinline__ float act_fwd_fast(float z, int act) {

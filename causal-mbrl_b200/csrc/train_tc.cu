@@ -27,7 +27,7 @@ using namespace tc;
 constexpr int TF_ROWS = 128;
 constexpr int TF_EPI_WARPS = 16;
 constexpr int TF_WARP_W = 16, TF_WARP_MMA = 17;
-constexpr int TF_THREADS = 18 * 32;
+constexpr int TF_THREADS = 20 * 32;
 constexpr int TF_MAX_PH = 16;
 constexpr int TF_MAX_LAYERS = 8;  // hidden layers + head
 constexpr uint32_t TF_GROUP = TF_ROWS * 16;  // bytes of one 4-wide K group of a 128-row operand tile
@@ -39,15 +39,26 @@ enum { PH_FWD = 0, PH_HEAD = 1, PH_DX = 2 };
 // this file; the shipped library carries none of it).  Stamps are clock64 values in [role][1024] slots.
 #ifdef CMRL_TRACE
 __device__ long long* g_trace_buf = nullptr;
+// tool build only -- experiments that INVALIDATE the results, to attribute time: 1 no weight copies, 2 no MMAs, 4 no global
+// loads / stores in the epilogue, 8 no A-ring writes
+__device__ int g_trace_flags = 0;
+#define XFLAG(bit) (g_trace_flags & (bit))
 #define TRACE_DECL int trace_n = 0
+#define TRACE_FINE(on)                                                                                              \
+    do {                                                                                                              \
+        if ((on) && g_trace_buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && fine_n < 1024) \
+            g_trace_buf[3 * 1024 + fine_n++] = clock64();                                                             \
+    } while (0)
 #define TRACE(role)                                                                                                   \
     do {                                                                                                              \
         if (g_trace_buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && trace_n < 1024) \
             g_trace_buf[(role) * 1024 + trace_n++] = clock64();                                                       \
     } while (0)
 #else
+#define XFLAG(bit) 0
 #define TRACE_DECL
 #define TRACE(role)
+#define TRACE_FINE(on)
 #endif
 
 // Geometry shared by the three kernels (built on the host by make_geom)
@@ -59,8 +70,8 @@ struct Geom {
     int ph_kind[TF_MAX_PH], ph_layer[TF_MAX_PH], ph_k[TF_MAX_PH], ph_n[TF_MAX_PH];
     long long ph_off[TF_MAX_PH];  // float offset of the phase's chunks inside a net blob
     long long blob_floats;
-    // saved tiles per (net, row tile), floats: x | act'(z_l), a_l (l < L) | dz_l (l <= L)
-    long long off_x, off_z[TF_MAX_LAYERS], off_a[TF_MAX_LAYERS], off_dz[TF_MAX_LAYERS + 1], item_floats;
+    // saved tiles per (net, row tile), floats: x | z_l (l < L) | dz_l (l <= L)
+    long long off_x, off_z[TF_MAX_LAYERS], off_dz[TF_MAX_LAYERS + 1], item_floats;
 };
 
 static int make_geom(Geom& g, int L, int in0, int H, int Dn) {
@@ -86,7 +97,7 @@ static int make_geom(Geom& g, int L, int in0, int H, int Dn) {
     g.blob_floats = off;
     long long o = 0;
     g.off_x = o; o += (long long)g.K0P * TF_ROWS;
-    for (int l = 0; l < L; ++l) { g.off_z[l] = o; o += (long long)g.HP * TF_ROWS; g.off_a[l] = o; o += (long long)g.HP * TF_ROWS; }
+    for (int l = 0; l < L; ++l) { g.off_z[l] = o; o += (long long)g.HP * TF_ROWS; }
     for (int l = 0; l < L; ++l) { g.off_dz[l] = o; o += (long long)g.HP * TF_ROWS; }
     g.off_dz[L] = o; o += (long long)g.NH * TF_ROWS;
     g.item_floats = o;
@@ -139,17 +150,37 @@ __global__ void train_pack_kernel(const PackP p) {
             v[j] = x;
         }
         const int c = kg / 4, gi = kg % 4;
-        float* dst = blob + (long long)c * 32 * N + ((long long)gi * N + n) * 4;
+        // chunk = [CTA half of the output rows][hi | lo][4 K groups][N/2 rows][4 floats]: each CTA of a pair streams its half
+        const int half = n >= N / 2 ? 1 : 0, nl = n - half * (N / 2);
+        float* dst = blob + (long long)c * 32 * N + (long long)half * 16 * N + ((long long)gi * (N / 2) + nl) * 4;
         uint32_t h[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) h[j] = __float_as_uint(v[j]) & 0xFFFFE000u;
         *reinterpret_cast<float4*>(dst) = make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3]));
-        *reinterpret_cast<float4*>(dst + 16 * N) = make_float4(v[0] - __uint_as_float(h[0]), v[1] - __uint_as_float(h[1]),
+        *reinterpret_cast<float4*>(dst + 8 * N) = make_float4(v[0] - __uint_as_float(h[0]), v[1] - __uint_as_float(h[1]),
                                                                v[2] - __uint_as_float(h[2]), v[3] - __uint_as_float(h[3]));
     }
 }
 
 // ================================================= fused forward + dz chain ================================================
+// Shared memory: [A ring: R slots of one 16-deep K chunk x 128 rows, hi | lo][weight ring: S stages][barriers].
+// Tensor memory: two accumulators (phases alternate, so the epilogue of phase p reads one while the MMAs of phase p+1 --
+// which chase that epilogue chunk by chunk through the A ring -- fill the other) + the head accumulator.
+constexpr int TF_A_SLOTS = 9;
+constexpr uint32_t TF_A_PART = 4 * TF_GROUP;   // bytes of the hi (or lo) part of an A chunk: 4 K groups x 128 rows x 16 B
+constexpr uint32_t TF_A_SLOT = 2 * TF_A_PART;
+// SHARED-MEMORY BANDWIDTH bounds this kernel, not the tensor pipe (profiles/r2_train_trace_*.txt): a kind::tf32 MMA of
+// 128 x 208 x 8 reads 4 KB of A and 6.6 KB of B in its 104 cycles (102 B/clk of the ~128 an SM has), three of them per K step,
+// next to the weight stream landing and the epilogue writing the next A.  CTAs therefore run as cta_group::2 PAIRS on two row
+// tiles of the same net (M = 256): each CTA holds and streams only HALF of every weight chunk (the B operand is split over the
+// pair), which halves both the B reads and the weight-stream writes per SM.
+constexpr int TF_WARP_FWD = 18;                // reports landed weight stages to the leader CTA
+constexpr int TF_WARP_AW = 19;                 // leader: waits for A chunks on behalf of the MMA issuer
+// An mbarrier wait costs the waiting thread ~300 cycles even when the phase completed long ago.  Two of them per 16-deep K chunk
+// in the issuing thread (A chunk published, weight stage landed) paced the whole kernel at ~1.2k cycles per chunk against 624
+// cycles of MMAs (3xTF32) or 208 (TF32).  Two helper warps therefore do the mbarrier waits AHEAD of the issuer and publish plain
+// progress counters in shared memory; the issuer polls those with ordinary loads (~30 cycles).
+
 struct TrainP {
     Geom g;
     const float* packed;
@@ -163,129 +194,218 @@ struct TrainP {
     float* loss;  // [E,B,Dtot] or NULL
     int loss_ld;  // Dtot
     float* scratch;
-    int tiles_per_net;
+    int tiles_per_net;   // real row tiles per net
+    int pairs_per_net;   // cluster work items per net; tile slots in the scratch = 2 * pairs_per_net
     int stages;
-    uint32_t stage_bytes, a_bytes, bar_off;
+    uint32_t stage_bytes, w_off, bar_off;
 };
 
-// bars: [0,S) W_FULL, [S,2S) W_EMPTY, 2S A_READY, 2S+1 D_FULL
+// bars: [0,S) W_FULL (local, tx), [S,2S) W_EMPTY (both CTAs, commit), [2S,3S) W_READY (leader, both halves landed),
+//       [3S,3S+R) A_FULL (leader, 2 x 4 warps), [3S+R,3S+2R) A_EMPTY (both, commit), 3S+2R D_FULL (both, commit)
 
-__device__ __forceinline__ void split_store_chunk(uint32_t a_hi_row, uint32_t a_lo_t, int c, const float* v) {
-    uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        hi[i] = __float_as_uint(v[i]) & 0xFFFFE000u;
-        lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v3_sts128(a_hi_row + (uint32_t)(c * 4 + j) * TF_GROUP, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-    tmem_st16(a_lo_t + (uint32_t)c * 16, lo);
-}
 // Saved tile layout: [row quarter q][col / 4][32 rows][4 floats].  Inside a quarter it is the K-major operand layout
 // (a 4-column group of 32 rows is 512 contiguous bytes, so a warp's store is one contiguous 512-byte run), and a
 // 32-row slice of any range of column groups is ONE contiguous block: the weight-gradient kernel fetches it with a single
 // TMA bulk copy (512-byte copies, one per group, cost ~180 cycles each and made that kernel 10x slower).
 __device__ __forceinline__ long long tile_off(int q, int lane, int ncg, int cg) { return ((long long)(q * ncg + cg) * 32 + lane) * 4; }
 __device__ __forceinline__ void save_chunk(float* tile, int q, int lane, int ncg, int c, const float* v) {
+    if (XFLAG(4)) return;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         *reinterpret_cast<float4*>(tile + tile_off(q, lane, ncg, c * 4 + j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
-__global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP p) {
+// A-ring bookkeeping of an epilogue warp: chunk `seq` of the global chunk sequence lives in slot seq % R
+struct ARing {
+    uint32_t smem0;  // shared-memory address of slot 0 + this thread's row offset
+    uint64_t *full, *empty;
+};
+__device__ __forceinline__ uint32_t aring_acquire(const ARing& r, uint32_t seq) {
+    const uint32_t slot = seq % TF_A_SLOTS, k = seq / TF_A_SLOTS;
+    if (k >= 1) mbar_wait(&r.empty[slot], (k - 1) & 1);  // the MMAs that read the slot's previous chunk are complete
+    return r.smem0 + slot * TF_A_SLOT;
+}
+__device__ __forceinline__ void aring_publish(const ARing& r, uint32_t seq, int lane) {
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) v3_arrive_leader(&r.full[seq % TF_A_SLOTS]);  // the leader CTA issues the pair's MMAs
+}
+// 16 values of this thread's row = one K chunk of the next GEMM: tf32 hi and lo parts, four 16-byte groups each
+__device__ __forceinline__ void split_store_chunk(uint32_t dst, const float* v) {
+    if (XFLAG(8)) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            h[u] = __float_as_uint(v[4 * j + u]) & 0xFFFFE000u;
+            l[u] = __float_as_uint(v[4 * j + u] - __uint_as_float(h[u]));
+        }
+        v3_sts128(dst + (uint32_t)j * TF_GROUP, h[0], h[1], h[2], h[3]);
+        v3_sts128(dst + TF_A_PART + (uint32_t)j * TF_GROUP, l[0], l[1], l[2], l[3]);
+    }
+}
+
+// ACT is a template parameter: with a run-time activation switch the unrolled 16-element epilogue bodies compiled to a chain of
+// branches per ELEMENT and the epilogue (not the tensor pipe, not the weight stream) paced the kernel at ~12k cycles per phase
+// (profiles/r2_train_trace_attribution.txt).
+template <int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_slot;
+    __shared__ volatile uint32_t a_ready_seq, w_ready_n;  // leader: chunks whose A operand / weight stage are known to be ready
     const Geom& g = p.g;
     const int S = p.stages;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
     uint64_t* bar_wfull = bars;
     uint64_t* bar_wempty = bars + S;
-    uint64_t* bar_aready = bars + 2 * S;
-    uint64_t* bar_dfull = bars + 2 * S + 1;
+    uint64_t* bar_wready = bars + 2 * S;
+    uint64_t* bar_afull = bars + 3 * S;
+    uint64_t* bar_aempty = bars + 3 * S + TF_A_SLOTS;
+    uint64_t* bar_dfull = bars + 3 * S + 2 * TF_A_SLOTS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int items = p.P * p.E * p.tiles_per_net;
+    const uint32_t rank = v3_ctarank();
+    const int n_pairs = p.P * p.E * p.pairs_per_net;          // work items of a cluster: two row tiles of one net
+    const int pair0 = blockIdx.x / 2, pair_step = gridDim.x / 2;
 
     if (threadIdx.x == 0) {
+        a_ready_seq = 0;
+        w_ready_n = 0;
         for (int s = 0; s < S; ++s) {
             mbar_init(&bar_wfull[s], 1);
             mbar_init(&bar_wempty[s], 1);
+            mbar_init(&bar_wready[s], 2);  // both CTAs' halves of the stage have landed
         }
-        mbar_init(bar_aready, TF_EPI_WARPS);
+        for (int s = 0; s < TF_A_SLOTS; ++s) {
+            mbar_init(&bar_afull[s], 8);  // the four lane quarters of one column set, in both CTAs
+            mbar_init(&bar_aempty[s], 1);
+        }
         mbar_init(bar_dfull, 1);
         fence_barrier_init();
     }
     if (warp == TF_WARP_MMA) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    v3_cluster_sync();  // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t col_alo = (uint32_t)g.HP, col_head = (uint32_t)(2 * g.HP);
+    const uint32_t col_head = (uint32_t)(2 * g.HP);
+    const int hi_only = p.passes == 1;
 
     if (warp == TF_WARP_W) {
-        // ===================== weight producer: one bulk copy per 16-deep K chunk (hi | lo) ================================
+        // ===================== weight producer: this CTA's half (N/2 output rows, hi | lo) of every 16-deep K chunk =================
         if (lane == 0) {
             uint32_t n = 0;
             TRACE_DECL;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const float* blob = p.packed + (long long)(item / p.tiles_per_net) * g.blob_floats;
+            for (int pair = pair0; pair < n_pairs; pair += pair_step) {
+                const float* blob = p.packed + (long long)(pair / p.pairs_per_net) * g.blob_floats;
                 for (int ph = 0; ph < g.n_ph; ++ph) {
-                    const uint32_t bytes = 128u * (uint32_t)g.ph_n[ph];
+                    const uint32_t half = 64u * (uint32_t)g.ph_n[ph];          // bytes of one CTA's half of a chunk: hi | lo
+                    const uint32_t bytes = hi_only ? half / 2 : half;           // the lo part is not read by plain TF32
                     const float* src = blob + g.ph_off[ph];
                     const int nch = g.ph_k[ph] / 16;
                     for (int c = 0; c < nch; ++c, ++n) {
                         const uint32_t s = n % (uint32_t)S;
                         if (n >= (uint32_t)S) mbar_wait_sleep(&bar_wempty[s], ((n / (uint32_t)S) - 1) & 1, 32);
                         TRACE(0);
+                        if (XFLAG(1)) {
+                            mbar_arrive(&bar_wfull[s]);
+                            continue;
+                        }
                         mbar_expect_tx(&bar_wfull[s], bytes);
-                        tma_bulk_g2s(smem + p.a_bytes + s * p.stage_bytes, src + (long long)c * 32 * g.ph_n[ph], bytes, &bar_wfull[s]);
+                        tma_bulk_g2s(smem + p.w_off + s * p.stage_bytes,
+                                     reinterpret_cast<const uint8_t*>(src + (long long)c * 32 * g.ph_n[ph]) + rank * half, bytes, &bar_wfull[s]);
                     }
                 }
             }
         }
-    } else if (warp == TF_WARP_MMA) {
-        // ===================== MMA issuer =====================================================================================
-        uint32_t n = 0, n_a = 0;
-        TRACE_DECL;
-        const uint32_t a_hi0 = smem_u32(smem);
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            for (int ph = 0; ph < g.n_ph; ++ph) {
-                const int N = g.ph_n[ph];
-                const uint32_t idesc = umma_idesc_tf32(TF_ROWS, N);
-                const uint32_t d_t = tmem + (g.ph_kind[ph] == PH_HEAD ? col_head : 0u);
-                const uint32_t part = 64u * (uint32_t)N;  // bytes of one (hi or lo) part of a weight chunk: 4 groups x N x 16
-                const uint32_t b_lbo = 16u * (uint32_t)N;
-                const int nch = g.ph_k[ph] / 16;
-                TRACE(2);
-                mbar_wait(bar_aready, n_a & 1);
-                ++n_a;
-                tc_fence_after();
-                TRACE(2);
-#pragma unroll 1
-                for (int c = 0; c < nch; ++c, ++n) {
-                    const uint32_t s = n % (uint32_t)S;
-                    mbar_wait(&bar_wfull[s], (n / (uint32_t)S) & 1);
-                    if (c == 0 || c == nch - 1) TRACE(2);
-                    const uint32_t w_hi = smem_u32(smem + p.a_bytes + s * p.stage_bytes), w_lo = w_hi + part;
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint64_t ad = umma_desc(a_hi0 + (uint32_t)(c * 4 + ks * 2) * TF_GROUP, TF_GROUP, 128);
-                        const uint64_t bh = umma_desc(w_hi + (uint32_t)ks * 2 * b_lbo, b_lbo, 128);
-                        const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
-                        if (p.passes == 3) {  // small terms first
-                            const uint64_t bl = umma_desc(w_lo + (uint32_t)ks * 2 * b_lbo, b_lbo, 128);
-                            tf32_mma_ts_uni(d_t, tmem + col_alo + (uint32_t)(c * 16 + ks * 8), bh, idesc, first);
-                            tf32_mma_ss_uni(d_t, ad, bl, idesc, 1u);
-                            tf32_mma_ss_uni(d_t, ad, bh, idesc, 1u);
-                        } else {
-                            tf32_mma_ss_uni(d_t, ad, bh, idesc, first);
+    } else if (warp == TF_WARP_FWD) {
+        // ===================== forwarder: tells the leader CTA that this CTA's half of a weight stage has landed ===================
+        if (lane == 0) {
+            uint32_t n = 0;
+            for (int pair = pair0; pair < n_pairs; pair += pair_step)
+                for (int ph = 0; ph < g.n_ph; ++ph)
+                    for (int c = 0; c < g.ph_k[ph] / 16; ++c, ++n) {
+                        const uint32_t s = n % (uint32_t)S;
+                        mbar_wait(&bar_wfull[s], (n / (uint32_t)S) & 1);
+                        v3_arrive_leader(&bar_wready[s]);
+                        if (rank == 0) {  // both halves landed -> tell the issuer through the plain counter
+                            mbar_wait(&bar_wready[s], (n / (uint32_t)S) & 1);
+                            __threadfence_block();
+                            w_ready_n = n + 1;
                         }
                     }
-                    umma_commit_uni(&bar_wempty[s]);
+        }
+    } else if (warp == TF_WARP_AW) {
+        // ===================== A-chunk waiter (leader): all 8 producer warps of a chunk have published it ==========================
+        if (lane == 0 && rank == 0) {
+            uint32_t seq = 0;
+            for (int pair = pair0; pair < n_pairs; pair += pair_step)
+                for (int ph = 0; ph < g.n_ph; ++ph)
+                    for (int c = 0; c < g.ph_k[ph] / 16; ++c, ++seq) {
+                        mbar_wait(&bar_afull[seq % TF_A_SLOTS], (seq / TF_A_SLOTS) & 1);
+                        __threadfence_block();
+                        a_ready_seq = seq + 1;
+                    }
+        }
+    } else if (warp == TF_WARP_MMA) {
+        // ===================== MMA issuer: chases the epilogue through the A ring ================================================
+        uint32_t n = 0, seq = 0, n_phase = 0;
+        TRACE_DECL;
+        // Descriptors are kept as (lo, hi) words: hi = stride field | version, lo = start address | leading-dimension field; an MMA
+        // costs the issuing thread two 32-bit adds.
+        const uint32_t a0 = smem_u32(smem), w0 = smem_u32(smem + p.w_off);
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+        const uint32_t a_lbo = (TF_GROUP >> 4) << 16;
+        for (int pair = pair0; rank == 0 && pair < n_pairs; pair += pair_step) {  // the leader issues for the pair
+            for (int ph = 0; ph < g.n_ph; ++ph, ++n_phase) {
+                const int N = g.ph_n[ph];
+                const uint32_t idesc = umma_idesc_tf32(2 * TF_ROWS, N);
+                const uint32_t d_t = tmem + (g.ph_kind[ph] == PH_HEAD ? col_head : (n_phase & 1) ? (uint32_t)g.HP : 0u);
+                const uint32_t b_lbo = 8u * (uint32_t)N;                           // bytes between K groups of this CTA's N/2 rows
+                const uint32_t b_part = (4u * b_lbo) >> 4;                         // hi -> lo part of a half chunk (16-byte units)
+                const uint32_t b_ks = (2u * b_lbo) >> 4, b_lbo_f = (b_lbo >> 4) << 16;
+                const int nch = g.ph_k[ph] / 16;
+                TRACE(2);
+#pragma unroll 1
+                for (int c = 0; c < nch; ++c, ++n, ++seq) {
+                    const uint32_t s = n % (uint32_t)S, slot = seq % TF_A_SLOTS;
+                    {
+                        unsigned long long spins = 0;
+                        while (a_ready_seq <= seq)
+                            if (++spins > SPIN_LIMIT) __trap();
+                        if (c == 0) TRACE(2);
+                        while (w_ready_n <= n)
+                            if (++spins > SPIN_LIMIT) __trap();
+                    }
+                    if (c == 0) TRACE(2);
+                    if (c == nch - 1) TRACE(2);
+                    __threadfence_block();
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const uint32_t ah = ((a0 + slot * TF_A_SLOT) >> 4) | a_lbo, al = ah + (TF_A_PART >> 4);
+                    const uint32_t bh = ((w0 + s * p.stage_bytes) >> 4) | b_lbo_f, bl = bh + b_part;
+                    const uint32_t first = c == 0 ? 0u : 1u;
+                    if (!XFLAG(2)) {
+                        if (!hi_only) {  // 3xTF32, small terms first
+                            tf32_mma2_lohi_uni(d_t, al, desc_hi, bh, desc_hi, idesc, first);
+                            tf32_mma2_lohi_uni(d_t, ah, desc_hi, bl, desc_hi, idesc, 1u);
+                            tf32_mma2_lohi_uni(d_t, ah, desc_hi, bh, desc_hi, idesc, 1u);
+                            tf32_mma2_lohi_uni(d_t, al + (2 * TF_GROUP >> 4), desc_hi, bh + b_ks, desc_hi, idesc, 1u);
+                            tf32_mma2_lohi_uni(d_t, ah + (2 * TF_GROUP >> 4), desc_hi, bl + b_ks, desc_hi, idesc, 1u);
+                            tf32_mma2_lohi_uni(d_t, ah + (2 * TF_GROUP >> 4), desc_hi, bh + b_ks, desc_hi, idesc, 1u);
+                        } else {
+                            tf32_mma2_lohi_uni(d_t, ah, desc_hi, bh, desc_hi, idesc, first);
+                            tf32_mma2_lohi_uni(d_t, ah + (2 * TF_GROUP >> 4), desc_hi, bh + b_ks, desc_hi, idesc, 1u);
+                        }
+                    }
+                    v3_commit_uni(&bar_wempty[s]);  // cta_group::2 commits arrive in both CTAs of the pair
+                    v3_commit_uni(&bar_aempty[slot]);
                 }
-                umma_commit_uni(bar_dfull);
+                v3_commit_uni(bar_dfull);
                 TRACE(2);
             }
         }
@@ -294,25 +414,29 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
         const int q = warp & 3, cset = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const uint32_t a_hi_row = smem_u32(smem) + (uint32_t)row * 16;
-        const uint32_t a_lo_t = tmem + lane_off + col_alo;
-        const int act = p.act;
+        ARing ring{smem_u32(smem) + (uint32_t)row * 16, bar_afull, bar_aempty};
         const int Dn = g.Dn;
-        uint32_t n_d = 0;
+        // the next layer's bias input: hidden unit H is 1.0 -- patched into the chunk that holds it after the chunk is stored
+        const int ones_c = g.H >> 4;
+        const uint32_t ones_off = (uint32_t)((g.H & 15) >> 2) * TF_GROUP + (uint32_t)(g.H & 3) * 4;
+        uint32_t n_d = 0, seq_base = 0, n_phase = 0;
         TRACE_DECL;
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int net = item / p.tiles_per_net, tile = item % p.tiles_per_net;
+#ifdef CMRL_TRACE
+        int fine_n = 0;
+#endif
+        for (int pair = pair0; pair < n_pairs; pair += pair_step) {
+            const int net = pair / p.pairs_per_net, tile = (pair % p.pairs_per_net) * 2 + (int)rank;  // may be a padding tile: no valid row
             const int pp = net / p.E, e = net % p.E;
             const int grow = tile * TF_ROWS + row;
             const bool valid = grow < p.B;
             const long long rr = valid ? grow : 0;
-            float* sc = p.scratch + (long long)item * g.item_floats;
+            float* sc = p.scratch + ((long long)net * 2 * p.pairs_per_net + tile) * g.item_floats;
             // ---- layer-0 operand: [obs | action | 1 | 0...] -------------------------------------------------------------------
-            if (cset == 0) {
+            {
                 const float* po = p.obs + e * p.obs_se + rr * p.O;
                 const float* pa = p.actn + e * p.act_se + rr * p.A;
 #pragma unroll 1
-                for (int c = 0; c < g.K0P / 16; ++c) {
+                for (int c = cset; c < g.K0P / 16; c += 4) {
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -324,131 +448,156 @@ __global__ void __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP
                         v[i] = x;
                     }
                     save_chunk(sc + g.off_x, q, lane, g.K0P / 4, c, v);
-                    split_store_chunk(a_hi_row, a_lo_t, c, v);
+                    split_store_chunk(aring_acquire(ring, seq_base + c), v);
+                    aring_publish(ring, seq_base + c, lane);
                 }
+                seq_base += g.K0P / 16;
             }
-            v5_st_wait();
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_aready);
-
-            for (int ph = 0; ph < g.n_ph; ++ph) {
+            for (int ph = 0; ph < g.n_ph; ++ph, ++n_phase) {
                 const int kind = g.ph_kind[ph], l = g.ph_layer[ph];
-                // prefetch what the head needs before the accumulator is ready
+                const int out_chunks = ph + 1 < g.n_ph ? g.ph_k[ph + 1] / 16 : 0;  // A chunks this epilogue hands to the next GEMM
+                const bool has_work = kind == PH_HEAD ? cset == 0 : cset < g.HP / 16;
+                // Every warp waits for every phase, also one it has no chunk of: a parity wait is only meaningful when the
+                // previous phase is known to be complete (a warp that skipped the head's wait walked straight through the
+                // next one and read a stale accumulator).
                 if (warp == 0) TRACE(1);
                 mbar_wait(bar_dfull, n_d & 1);
                 ++n_d;
-                tc_fence_after();
-                if (warp == 0) TRACE(1);
-                if (kind == PH_FWD) {
-                    float* zt = sc + g.off_z[l];
-                    float* at = sc + g.off_a[l];
-                    const int nchunks = g.HP / 16;
-#pragma unroll 1
-                    for (int c = cset; c < nchunks; c += 4) {
+                if (has_work) {
+                    tc_fence_after();
+                    if (warp == 0) TRACE(1);
+                    const uint32_t acc_t = tmem + lane_off + ((n_phase & 1) ? (uint32_t)g.HP : 0u);
+                    if (kind == PH_FWD) {
+                        // All 16 warps reach this loop together, so an un-pipelined body runs the SM's resources one after the
+                        // other (TMEM read, global stores, MUFU, shared-memory stores: ~3.3k cycles per round of 4 chunks).  Order
+                        // per chunk: the NEXT chunk's TMEM load is in flight, the activations (MUFU) are issued BEFORE the global
+                        // stores of z so that both pipes work at the same time.
+                        float* zt = sc + g.off_z[l];
                         uint32_t raw[16];
-                        float z[16];
                         __syncwarp();
-                        v5_ld16_issue(tmem + lane_off + (uint32_t)c * 16, raw);
-                        v3_ld_wait();
-                        float gz[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {  // activation and its derivative from one exp + one reciprocal
-                            const float zi = __uint_as_float(raw[i]);
-                            if (act == CMRL_ACT_SILU) {
-                                const float sg = __fdividef(1.0f, 1.0f + __expf(-zi));
-                                z[i] = zi * sg;
-                                gz[i] = sg * (1.0f + zi * (1.0f - sg));
-                            } else if (act == CMRL_ACT_RELU) {
-                                z[i] = fmaxf(zi, 0.0f);
-                                gz[i] = zi > 0.0f ? 1.0f : 0.0f;
-                            } else {
-                                z[i] = zi;
-                                gz[i] = 1.0f;
-                            }
-                            if (c * 16 + i == g.H) z[i] = 1.0f;  // the next layer's bias input
-                        }
-                        save_chunk(zt, q, lane, g.HP / 4, c, gz);  // act'(z): what the dz chain multiplies by
-                        save_chunk(at, q, lane, g.HP / 4, c, z);
-                        split_store_chunk(a_hi_row, a_lo_t, c, z);
-                    }
-                } else if (kind == PH_DX) {
-                    const float* zt = sc + g.off_z[l];
-                    float* dt = sc + g.off_dz[l];
-                    const int nchunks = g.HP / 16;
+                        v5_ld16_issue(acc_t + (uint32_t)cset * 16, raw);
 #pragma unroll 1
-                    for (int c = cset; c < nchunks; c += 4) {
-                        uint32_t raw[16];
-                        float z[16];
-                        __syncwarp();
-                        v5_ld16_issue(tmem + lane_off + (uint32_t)c * 16, raw);
+                        for (int c = cset; c < g.HP / 16; c += 4) {
+                            float z[16], a[16];
+                            TRACE_FINE(warp == 0 && ph == 1);
+                            v3_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 t4 = *reinterpret_cast<const float4*>(zt + tile_off(q, lane, g.HP / 4, c * 4 + j));
-                            z[4 * j] = t4.x; z[4 * j + 1] = t4.y; z[4 * j + 2] = t4.z; z[4 * j + 3] = t4.w;
-                        }
-                        v3_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) z[i] *= __uint_as_float(raw[i]);  // dz = (dz_next . W^T) * act'(z)
-                        save_chunk(dt, q, lane, g.HP / 4, c, z);
-                        if (l > 0) split_store_chunk(a_hi_row, a_lo_t, c, z);
-                    }
-                } else if (cset == 0) {
-                    // ---- Gaussian head + NLL + their gradient, one output per iteration (columns 2d = mean_d, 2d+1 = logvar_d)
-                    float* dt = sc + g.off_dz[g.L];
-                    const uint32_t h_t = tmem + lane_off + col_head;
-#pragma unroll 1
-                    for (int d = 0; d < g.NH / 2; ++d) {
-                        float dm = 0.f, dl = 0.f;
-                        uint32_t r0, r1;
-                        __syncwarp();
-                        tmem_ld2(h_t + (uint32_t)(2 * d), r0, r1);
-                        v3_ld_wait();
-                        if (d < Dn) {
-                            const int od = p.layout == CMRL_HEAD_PARALLEL ? pp : d;
-                            const int bi = p.bounds_n == 1 ? 0 : od;
-                            float m = __uint_as_float(r0);
-                            const float r = __uint_as_float(r1);
-                            if (p.residual) m += p.obs[e * p.obs_se + rr * p.O + od];
-                            const float t = p.target[e * p.tgt_se + rr * p.tgt_ld + od];
-                            const float mn = p.min_logvar[bi], mx = p.max_logvar[bi];
-                            float lv1;
-                            const float lv = soft_clamp_logvar(r, mn, mx, &lv1);
-                            const float diff = m - t, iv = expf(-lv);
-                            if (valid) {
-                                if (p.loss) p.loss[((long long)e * p.B + grow) * p.loss_ld + od] = diff * diff * iv + lv + p.reg;
-                                const float s_lo = (lv1 - mn) > 20.0f ? 1.0f : sigmoidf_(lv1 - mn);
-                                const float s_hi = (mx - r) > 20.0f ? 1.0f : sigmoidf_(mx - r);
-                                dm = p.g_scale * 2.0f * diff * iv;
-                                dl = p.g_scale * (1.0f - diff * diff * iv) * s_lo * s_hi;
+                            for (int i = 0; i < 16; ++i) z[i] = __uint_as_float(raw[i]);
+                            if (c + 4 < g.HP / 16) {
+                                __syncwarp();
+                                v5_ld16_issue(acc_t + (uint32_t)(c + 4) * 16, raw);
                             }
+                            TRACE_FINE(warp == 0 && ph == 1);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) a[i] = act_fwd_fast(z[i], ACT);
+                            TRACE_FINE(warp == 0 && ph == 1);
+                            save_chunk(zt, q, lane, g.HP / 4, c, z);  // pre-activations: the dz chain and the dw kernel re-activate
+                            TRACE_FINE(warp == 0 && ph == 1);
+                            const uint32_t dst = aring_acquire(ring, seq_base + c);
+                            TRACE_FINE(warp == 0 && ph == 1);
+                            split_store_chunk(dst, a);
+                            TRACE_FINE(warp == 0 && ph == 1);
+                            if (c == ones_c && !XFLAG(8)) {  // hi part 1.0, lo part 0
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + ones_off), "r"(0x3F800000u) : "memory");
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + TF_A_PART + ones_off), "r"(0u) : "memory");
+                            }
+                            aring_publish(ring, seq_base + c, lane);
+                            TRACE_FINE(warp == 0 && ph == 1);
                         }
-                        const int k = 2 * d;
-                        *reinterpret_cast<float2*>(dt + tile_off(q, lane, g.NH / 4, k / 4) + (k & 3)) = make_float2(dm, dl);
-                        const uint32_t hm = __float_as_uint(dm) & 0xFFFFE000u, hl = __float_as_uint(dl) & 0xFFFFE000u;
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi_row + (uint32_t)(k / 4) * TF_GROUP + (uint32_t)(k & 3) * 4), "r"(hm), "r"(hl) : "memory");
-                        tmem_st2(a_lo_t + (uint32_t)k, __float_as_uint(dm - __uint_as_float(hm)), __float_as_uint(dl - __uint_as_float(hl)));
+                    } else if (kind == PH_DX) {
+                        // dz = (dz_next . W^T) * act'(z): act'(z) does not depend on the accumulator, so it is evaluated (MUFU) while
+                        // the TMEM load is in flight; the A chunk is published before dz is saved; the next chunk's z is fetched last.
+                        const float* zt = sc + g.off_z[l];
+                        float* dt = sc + g.off_dz[l];
+                        float z[16];
+                        auto load_z = [&](int c) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (XFLAG(4)) {
+                                    z[4 * j] = z[4 * j + 1] = z[4 * j + 2] = z[4 * j + 3] = 0.5f;
+                                    continue;
+                                }
+                                const float4 t4 = *reinterpret_cast<const float4*>(zt + tile_off(q, lane, g.HP / 4, c * 4 + j));
+                                z[4 * j] = t4.x; z[4 * j + 1] = t4.y; z[4 * j + 2] = t4.z; z[4 * j + 3] = t4.w;
+                            }
+                        };
+                        load_z(cset);
+#pragma unroll 1
+                        for (int c = cset; c < g.HP / 16; c += 4) {
+                            uint32_t raw[16];
+                            __syncwarp();
+                            v5_ld16_issue(acc_t + (uint32_t)c * 16, raw);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) z[i] = act_grad_fast(z[i], ACT);
+                            v3_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) z[i] *= __uint_as_float(raw[i]);
+                            if (out_chunks > 0) {
+                                split_store_chunk(aring_acquire(ring, seq_base + c), z);
+                                aring_publish(ring, seq_base + c, lane);
+                            }
+                            save_chunk(dt, q, lane, g.HP / 4, c, z);
+                            if (c + 4 < g.HP / 16) load_z(c + 4);
+                        }
+                    } else {
+                        // ---- Gaussian head + NLL + their gradient, one output per iteration (columns 2d = mean_d, 2d+1 = logvar_d);
+                        // the NH-wide dz of the head is chunk 0 (and 1) of the next GEMM
+                        float* dt = sc + g.off_dz[g.L];
+                        const uint32_t h_t = tmem + lane_off + col_head;
+                        uint32_t dst = 0;
+#pragma unroll 1
+                        for (int d = 0; d < g.NH / 2; ++d) {
+                            if ((d & 7) == 0) dst = aring_acquire(ring, seq_base + (d >> 3));
+                            float dm = 0.f, dl = 0.f;
+                            uint32_t r0, r1;
+                            __syncwarp();
+                            tmem_ld2(h_t + (uint32_t)(2 * d), r0, r1);
+                            v3_ld_wait();
+                            if (d < Dn) {
+                                const int od = p.layout == CMRL_HEAD_PARALLEL ? pp : d;
+                                const int bi = p.bounds_n == 1 ? 0 : od;
+                                float m = __uint_as_float(r0);
+                                const float r = __uint_as_float(r1);
+                                if (p.residual) m += p.obs[e * p.obs_se + rr * p.O + od];
+                                const float t = p.target[e * p.tgt_se + rr * p.tgt_ld + od];
+                                const float mn = p.min_logvar[bi], mx = p.max_logvar[bi];
+                                float lv1;
+                                const float lv = soft_clamp_logvar(r, mn, mx, &lv1);
+                                const float diff = m - t, iv = expf(-lv);
+                                if (valid) {
+                                    if (p.loss) p.loss[((long long)e * p.B + grow) * p.loss_ld + od] = diff * diff * iv + lv + p.reg;
+                                    const float s_lo = (lv1 - mn) > 20.0f ? 1.0f : sigmoidf_(lv1 - mn);
+                                    const float s_hi = (mx - r) > 20.0f ? 1.0f : sigmoidf_(mx - r);
+                                    dm = p.g_scale * 2.0f * diff * iv;
+                                    dl = p.g_scale * (1.0f - diff * diff * iv) * s_lo * s_hi;
+                                }
+                            }
+                            const int k = 2 * d;
+                            *reinterpret_cast<float2*>(dt + tile_off(q, lane, g.NH / 4, k / 4) + (k & 3)) = make_float2(dm, dl);
+                            const uint32_t hm = __float_as_uint(dm) & 0xFFFFE000u, hl = __float_as_uint(dl) & 0xFFFFE000u;
+                            const uint32_t at = dst + (uint32_t)((k & 15) / 4) * TF_GROUP + (uint32_t)(k & 3) * 4;
+                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(at), "r"(hm), "r"(hl) : "memory");
+                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(at + TF_A_PART), "r"(__float_as_uint(dm - __uint_as_float(hm))),
+                                         "r"(__float_as_uint(dl - __uint_as_float(hl)))
+                                         : "memory");
+                            if ((d & 7) == 7) aring_publish(ring, seq_base + (d >> 3), lane);
+                        }
                     }
+                    tc_fence_before();  // orders this warp's accumulator reads before the MMAs that overwrite it two phases on
+                    if (warp == 0) TRACE(1);
                 }
-                if (warp == 0) TRACE(1);
-                if (ph + 1 < g.n_ph) {  // the last phase (dz of the first layer) feeds no further GEMM
-                    v5_st_wait();
-                    tc_fence_before();
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_aready);
-                }
+                seq_base += out_chunks;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == TF_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    v3_cluster_sync();  // no CTA leaves while its peer may still arrive on its barriers or read its shared memory
+    if (warp == TF_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 // ================================================= weight gradients ========================================================
-constexpr int DW_THREADS = 18 * 32;
+constexpr int DW_THREADS = 18 * 32;  // (the dw kernel has no forwarder warp)
 constexpr int DW_NT = 112;          // output columns per CTA
 constexpr int DW_SUB = 32;          // rows (= K) per pipeline step
 constexpr uint32_t DW_KG = 144;     // bytes between K groups of 4 rows in the transposed operands (128 + 16: bank spread)
@@ -463,7 +612,7 @@ static_assert(DW_SMEM <= SMEM_LIMIT, "dw kernel shared memory");
 struct DwP {
     Geom g;
     const float* scratch;
-    int P, E, tiles_per_net;
+    int P, E, tiles_per_net, tile_slots, act;  // real row tiles / tile slots per net in the scratch (padded to cluster pairs)
     int in_l[TF_MAX_LAYERS], out_l[TF_MAX_LAYERS];
     float* dw[TF_MAX_LAYERS];
     float* db[TF_MAX_LAYERS];
@@ -496,6 +645,7 @@ __device__ __forceinline__ void dw_store(const DwP& p, int net, int l, int i, in
     }
 }
 
+template <int ACT>
 __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_slot;
@@ -515,15 +665,17 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
     while (w >= p.work_off[l + 1]) ++l;
     const int wi = w - p.work_off[l];
     const int mt = wi / p.n_tiles[l], nt = wi % p.n_tiles[l];
-    const int a_cols = l == 0 ? g.K0P : g.HP;            // saved input tile of layer l: x or a_{l-1}
+    const int a_cols = l == 0 ? g.K0P : g.HP;            // saved input tile of layer l: x, or z_{l-1} (re-activated here)
     const int z_cols = l == g.L ? g.NH : g.HP;           // dz_l
-    const long long a_off = l == 0 ? g.off_x : g.off_a[l - 1];
+    const long long a_off = l == 0 ? g.off_x : g.off_z[l - 1];
     const long long z_off = g.off_dz[l];
     const int ga = min(32, a_cols / 4 - mt * 32);         // 4-feature groups of this CTA's A rows
     const int NT = min(DW_NT, z_cols - nt * DW_NT);      // output columns of this CTA
     const int gb = NT / 4;
     const int t0 = slice * p.tiles_per_slice, t1 = min(p.tiles_per_net, t0 + p.tiles_per_slice);
     const int n_sub = max(0, t1 - t0) * (TF_ROWS / DW_SUB);
+    const bool activate = l > 0;  // layer 0 reads the saved inputs, the others re-activate saved pre-activations
+    const int ones_f = l == 0 ? -1 : g.H - mt * TF_ROWS;  // feature (local to this tile) that is the bias input of layer l
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -547,7 +699,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const float* base = p.scratch + ((long long)net * p.tiles_per_net) * g.item_floats;
+    const float* base = p.scratch + ((long long)net * p.tile_slots) * g.item_floats;
 
     if (warp == TF_WARP_W) {
         // ===================== raw tile producer: one bulk copy per operand and 32-row slice ================================
@@ -611,13 +763,20 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
                 const uint32_t hi_base = op + (isa ? 0u : 2 * DW_OP_A) + (uint32_t)(gl >> 1) * DW_MG + (uint32_t)(r >> 2) * DW_KG +
                                          (uint32_t)(gl & 1) * 64u + (uint32_t)(r & 3) * 4u;
                 const uint32_t lo_base = hi_base + (isa ? DW_OP_A : DW_OP_B);
-                const float e4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t h = __float_as_uint(e4[j]) & 0xFFFFE000u;
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(hi_base + (uint32_t)j * 16u), "r"(h) : "memory");
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(lo_base + (uint32_t)j * 16u), "r"(__float_as_uint(e4[j] - __uint_as_float(h))) : "memory");
+                float e0 = v.x, e1 = v.y, e2 = v.z, e3 = v.w;
+                if (isa && activate) {  // the layer input is the activation of the saved pre-activations (+ its bias column of ones)
+                    e0 = act_fwd_fast(e0, ACT); e1 = act_fwd_fast(e1, ACT); e2 = act_fwd_fast(e2, ACT); e3 = act_fwd_fast(e3, ACT);
+                    if ((ones_f >> 2) == gl) {
+                        const int oj = ones_f & 3;
+                        e0 = oj == 0 ? 1.0f : e0; e1 = oj == 1 ? 1.0f : e1; e2 = oj == 2 ? 1.0f : e2; e3 = oj == 3 ? 1.0f : e3;
+                    }
                 }
+                auto put = [&](uint32_t j, float x) {
+                    const uint32_t h = __float_as_uint(x) & 0xFFFFE000u;
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(hi_base + j * 16u), "r"(h) : "memory");
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(lo_base + j * 16u), "r"(__float_as_uint(x - __uint_as_float(h))) : "memory");
+                };
+                put(0, e0); put(1, e1); put(2, e2); put(3, e3);
             }
             fence_proxy_async();
             __syncwarp();
@@ -627,30 +786,40 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
             }
             if (warp == 0) TRACE(1);
         }
-        // ---- epilogue: TMEM lane = feature row of this tile, columns = output features --------------------------------------
+        // ---- epilogue: TMEM lane = feature row of this tile, columns = output features.  A thread owns one ROW; rows of the
+        // gradient are far apart in memory, so the tile goes through shared memory (the operand stages are free now) and is
+        // written out with the lanes along the columns.
         mbar_wait(bar_acc, 0);
         tc_fence_after();
         if (warp == 0) TRACE(1);
         const int q = warp & 3, cset = warp >> 2;
-        const int i_row = mt * TF_ROWS + q * 32 + lane;
-        float* wsp = p.ksplit > 1 ? p.ws + ((long long)slice * gridDim.y + net) * p.ext_total + p.ext_off[l] : nullptr;
-        const int zc = l == g.L ? g.NH : p.out_l[l];  // columns of the extended gradient in the workspace
+        float* otile = reinterpret_cast<float*>(smem + DW_RAW_STAGES * DW_RAW);
+        constexpr int OS = DW_NT + 4;  // floats per staged row (16-byte aligned, conflict-free for the float4 writes)
         for (int c = cset; c < NT / 16; c += 4) {
             uint32_t rawv[16];
             __syncwarp();
             v5_ld16_issue(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c * 16, rawv);
             v3_ld_wait();
-            if (n_sub == 0) {
+            float4* dst = reinterpret_cast<float4*>(otile + (q * 32 + lane) * OS + c * 16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) rawv[j] = 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = nt * DW_NT + c * 16 + j;
+            for (int j = 0; j < 4; ++j)
+                dst[j] = n_sub == 0 ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                    : make_float4(__uint_as_float(rawv[4 * j]), __uint_as_float(rawv[4 * j + 1]), __uint_as_float(rawv[4 * j + 2]),
+                                                  __uint_as_float(rawv[4 * j + 3]));
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(TF_EPI_WARPS * 32) : "memory");  // the 16 epilogue warps only
+        float* wsp = p.ksplit > 1 ? p.ws + ((long long)slice * gridDim.y + net) * p.ext_total + p.ext_off[l] : nullptr;
+        const int zc = l == g.L ? g.NH : p.out_l[l];  // columns of the extended gradient in the workspace
+        for (int r = warp; r < TF_ROWS; r += TF_EPI_WARPS) {
+            const int i_row = mt * TF_ROWS + r;
+            if (i_row > p.in_l[l]) break;
+            for (int cc = lane; cc < NT; cc += 32) {
+                const int n = nt * DW_NT + cc;
+                const float v = otile[r * OS + cc];
                 if (wsp) {
-                    if (i_row <= p.in_l[l] && n < zc) wsp[(long long)i_row * zc + n] = __uint_as_float(rawv[j]);
+                    if (n < zc) wsp[(long long)i_row * zc + n] = v;
                 } else {
-                    dw_store(p, net, l, i_row, n, __uint_as_float(rawv[j]));
+                    dw_store(p, net, l, i_row, n, v);
                 }
             }
         }
@@ -688,6 +857,10 @@ extern "C" int cmrl_trace_set(long long* buf) {
     CMRL_CUDA(cudaMemcpyToSymbol(cmrl::tr::g_trace_buf, &buf, sizeof(buf)));
     return 0;
 }
+extern "C" int cmrl_trace_flags(int flags) {
+    CMRL_CUDA(cudaMemcpyToSymbol(cmrl::tr::g_trace_flags, &flags, sizeof(flags)));
+    return 0;
+}
 #endif
 
 extern "C" long long cmrl_train_fused_sizes(int L, int in_size, int hidden, int head_outputs, int P, int E, int B, long long* blob_floats,
@@ -696,7 +869,7 @@ extern "C" long long cmrl_train_fused_sizes(int L, int in_size, int hidden, int 
     if (make_geom(g, L, in_size, hidden, head_outputs) != 0) return -1;
     const long long nets = (long long)P * E, tiles = (B + TF_ROWS - 1) / TF_ROWS;
     if (blob_floats) *blob_floats = g.blob_floats;
-    if (scratch_floats) *scratch_floats = nets * tiles * g.item_floats;
+    if (scratch_floats) *scratch_floats = nets * ((tiles + 1) / 2 * 2) * g.item_floats;  // tile slots padded to cluster pairs
     if (dw_ws_floats) {
         long long ext = 0;
         for (int l = 0; l <= L; ++l) ext += (long long)((l == 0 ? in_size : hidden) + 1) * (l == L ? g.NH : hidden);
@@ -743,37 +916,44 @@ extern "C" int cmrl_train_fused(const float* packed, int L, int P, int E, int B,
     p.min_logvar = min_logvar; p.max_logvar = max_logvar; p.bounds_n = bounds_n; p.reg = reg; p.g_scale = g_scale;
     p.loss = loss; p.loss_ld = head_dim; p.scratch = scratch;
     p.tiles_per_net = (B + TF_ROWS - 1) / TF_ROWS;
-    p.a_bytes = (uint32_t)(p.g.HP / 4) * TF_GROUP;
-    p.stage_bytes = 128u * (uint32_t)p.g.HP;
-    int stages = (int)((SMEM_LIMIT - 256 - p.a_bytes) / p.stage_bytes);
-    if (stages > 6) stages = 6;
+    p.pairs_per_net = (p.tiles_per_net + 1) / 2;
+    p.w_off = TF_A_SLOTS * TF_A_SLOT;
+    p.stage_bytes = 64u * (uint32_t)p.g.HP;  // one CTA's half (N/2 rows) of a 16-deep chunk, hi | lo
+    int stages = (int)((SMEM_LIMIT - 512 - p.w_off) / p.stage_bytes);
+    if (stages > 10) stages = 10;
     CMRL_REQUIRE(stages >= 2, "train_fused: hidden width %d leaves no room for a weight ring", hidden);
     p.stages = stages;
-    p.bar_off = p.a_bytes + (uint32_t)stages * p.stage_bytes;
-    const uint32_t smem_bytes = p.bar_off + (2 * stages + 2) * 8;
+    p.bar_off = p.w_off + (uint32_t)stages * p.stage_bytes;
+    const uint32_t smem_bytes = p.bar_off + (3 * stages + 2 * TF_A_SLOTS + 1) * 8;
     static cmrl::PerDeviceOnce attr_once;
     int attr_dev = 0;
     if (attr_once.pending(&attr_dev)) {
-        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_IDENTITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_once.done(attr_dev);
     }
-    const long long items = (long long)P * E * p.tiles_per_net;
-    CMRL_REQUIRE(items < (1ll << 30), "train_fused: too many row tiles");
-    int grid = (int)(items < num_sms() ? items : num_sms());
-    train_fused_kernel<<<grid, TF_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+    const long long pairs = (long long)P * E * p.pairs_per_net;
+    CMRL_REQUIRE(pairs < (1ll << 30), "train_fused: too many row tiles");
+    const int clusters = (int)(pairs < num_sms() / 2 ? pairs : num_sms() / 2);
+    if (act == CMRL_ACT_SILU) train_fused_kernel<CMRL_ACT_SILU><<<2 * clusters, TF_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+    else if (act == CMRL_ACT_RELU) train_fused_kernel<CMRL_ACT_RELU><<<2 * clusters, TF_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+    else train_fused_kernel<CMRL_ACT_IDENTITY><<<2 * clusters, TF_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
     CMRL_CHECK_LAUNCH("train_fused");
     return 0;
 }
 
-extern "C" int cmrl_train_dw(const float* scratch, int L, int P, int E, int B, int in_size, int hidden, int head_outputs,
+extern "C" int cmrl_train_dw(const float* scratch, int L, int P, int E, int B, int in_size, int hidden, int head_outputs, int act,
                              float* const* dw, float* const* db, const float* mask, long long m_sp, long long m_se, float* workspace,
                              long long workspace_floats, void* stream) {
     DwP p{};
     if (make_geom(p.g, L, in_size, hidden, head_outputs) != 0) return -1;
     CMRL_REQUIRE(scratch && dw && db, "train_dw: null pointer");
     const Geom& g = p.g;
-    p.scratch = scratch; p.P = P; p.E = E; p.mask = mask; p.m_sp = m_sp; p.m_se = m_se;
+    CMRL_REQUIRE(act == CMRL_ACT_IDENTITY || act == CMRL_ACT_RELU || act == CMRL_ACT_SILU, "train_dw: unsupported activation");
+    p.scratch = scratch; p.P = P; p.E = E; p.act = act; p.mask = mask; p.m_sp = m_sp; p.m_se = m_se;
     p.tiles_per_net = (B + TF_ROWS - 1) / TF_ROWS;
+    p.tile_slots = (p.tiles_per_net + 1) / 2 * 2;
     int work = 0;
     long long ext = 0;
     for (int l = 0; l <= L; ++l) {
@@ -794,15 +974,22 @@ extern "C" int cmrl_train_dw(const float* scratch, int L, int P, int E, int B, i
     const int nets = P * E;
     CMRL_REQUIRE(nets <= 65535, "train_dw: too many nets");
     // batch slices: enough CTAs for ~2 per SM, at least one row tile each, bounded by the workspace
+    // batch slices: the launch takes ceil(CTAs / SMs) waves of ceil(tiles / slices) row tiles each (one CTA per SM); slicing
+    // costs a reduction launch and workspace traffic, so it has to win by more than one tile time
     int ksplit = 1;
     if (p.tiles_per_net > 1 && workspace != nullptr) {
-        const long long ctas = (long long)work * nets;
-        long long want = (2LL * num_sms() + ctas - 1) / ctas;
-        if (want > p.tiles_per_net) want = p.tiles_per_net;
-        const long long fit = workspace_floats / (ext * nets);
-        if (want > fit) want = fit;
-        if (want > 64) want = 64;
-        if (want >= 2) ksplit = (int)want;
+        const long long ctas = (long long)work * nets, sms = num_sms();
+        long long fit = workspace_floats / (ext * nets);
+        if (fit > 64) fit = 64;
+        if (fit > p.tiles_per_net) fit = p.tiles_per_net;
+        long long best = ((ctas + sms - 1) / sms) * p.tiles_per_net;
+        for (long long ks = 2; ks <= fit; ++ks) {
+            const long long cost = ((ctas * ks + sms - 1) / sms) * ((p.tiles_per_net + ks - 1) / ks) + 1;
+            if (cost < best) {
+                best = cost;
+                ksplit = (int)ks;
+            }
+        }
     }
     p.tiles_per_slice = (p.tiles_per_net + ksplit - 1) / ksplit;
     ksplit = (p.tiles_per_net + p.tiles_per_slice - 1) / p.tiles_per_slice;
@@ -811,11 +998,15 @@ extern "C" int cmrl_train_dw(const float* scratch, int L, int P, int E, int B, i
     static cmrl::PerDeviceOnce attr_once;
     int attr_dev = 0;
     if (attr_once.pending(&attr_dev)) {
-        CMRL_CUDA(cudaFuncSetAttribute(train_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_dw_kernel<CMRL_ACT_IDENTITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_dw_kernel<CMRL_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_dw_kernel<CMRL_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_once.done(attr_dev);
     }
     dim3 grid(work * ksplit, nets);
-    train_dw_kernel<<<grid, DW_THREADS, DW_SMEM, (cudaStream_t)stream>>>(p);
+    if (act == CMRL_ACT_SILU) train_dw_kernel<CMRL_ACT_SILU><<<grid, DW_THREADS, DW_SMEM, (cudaStream_t)stream>>>(p);
+    else if (act == CMRL_ACT_RELU) train_dw_kernel<CMRL_ACT_RELU><<<grid, DW_THREADS, DW_SMEM, (cudaStream_t)stream>>>(p);
+    else train_dw_kernel<CMRL_ACT_IDENTITY><<<grid, DW_THREADS, DW_SMEM, (cudaStream_t)stream>>>(p);
     CMRL_CHECK_LAUNCH("train_dw");
     if (ksplit > 1) {
         const long long total = ext * nets;

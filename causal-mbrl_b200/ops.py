@@ -440,16 +440,14 @@ def pack_mlp_f16(weights, biases, mask=None, mask_str=(0, 0, 0), head_interleave
         _lib.call("cmrl_pack_layer_f16", w.data_ptr(), b.data_ptr(), _ptr(m), mask_str[0], mask_str[1], P, E,
                   w.shape[-2], w.shape[-1], layer_k[i], layer_n[i], inter, scale, blob.data_ptr() + 2 * layer_off[i], off,
                   _stream())  # fmt: skip
-    # [blob, layer offsets, K, N, ctypes views (lazy), kernel variant (lazy), hidden layers halved?]
+    # [blob, layer offsets, K, N, ctypes views (lazy), unused, hidden layers halved?]
     return [blob, layer_off, layer_k, layer_n, None, None, act_kind == ACT_SILU]
 
 
-# Kernel variant of the tensor-core tier.  None = first that accepts the shape: 5 (CTA pairs, two 256-row tiles in
-# flight, A operand partly in tensor memory; head <= 16 columns for hidden 200), 4 (CTA pairs, 256-row tiles, chased
-# epilogue; head <= 32 columns), 3 (pairs, two 128-row tiles in flight; head <= 128 columns), 1 (single-CTA tiles,
-# per-layer streamed weights) -- these need the padded hidden width to fit shared memory (hidden <= 207) -- and, for wide
-# models (hidden a multiple of 16, 208 .. 512), 6 (CTA pairs, weights streamed in K chunks).  Other widths use
-# precision="fp32".
+# Kernel variant of the tensor-core rollout tier.  None (default) = chosen by the library from the model's shape: 5 (CTA
+# pairs, two 256-row tiles in flight, A operand partly in tensor memory) where two tiles' accumulators and heads fit tensor
+# memory, 3 (pairs, two 128-row tiles in flight) for wider heads, 6 (pairs, weights streamed in K chunks) for hidden layers
+# that do not fit shared memory (a multiple of 16 from 208 to 512).  Other widths use precision="fp32".  Tests pin a variant.
 TC_VARIANT = None
 
 
@@ -470,21 +468,11 @@ def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, ga
         act_kind = ACT_SILU_HALF
     pred = torch.empty((N, head_dim), device=obs.device, dtype=torch.float32) if out is None else out
     bounds_n = 0 if min_logvar is None else min_logvar.numel()
-    wide = L >= 1 and layer_n[0] == H  # un-widened (streamed-weights) packing
-    candidates = [TC_VARIANT] if TC_VARIANT is not None else ([pack[5]] if pack[5] else ([6] if wide else [5, 4, 3, 1]))
-    last = None
-    for variant in candidates:
-        try:
-            _lib.call("cmrl_mlp_rollout_f16", blob.data_ptr(), blob.shape[1], c_off, c_k, c_n, L,
-                      P, E, N, O, A, H, head_dim, layout, 1 if gaussian else 0, act_kind, obs.data_ptr(), act.data_ptr(),
-                      perm.data_ptr(), offsets.data_ptr(), 1 if residual else 0, _ptr(min_logvar), _ptr(max_logvar),
-                      bounds_n, _ptr(noise), pred.data_ptr(), variant, _stream())  # fmt: skip
-            if TC_VARIANT is None:
-                pack[5] = variant
-            return pred
-        except _lib.CmrlB200Error as e:  # shape not supported by this variant
-            last = e
-    raise _lib.CmrlB200Error("no tensor-core kernel variant supports this model (use precision='fp32'): %s" % last)
+    _lib.call("cmrl_mlp_rollout_f16", blob.data_ptr(), blob.shape[1], c_off, c_k, c_n, L,
+              P, E, N, O, A, H, head_dim, layout, 1 if gaussian else 0, act_kind, obs.data_ptr(), act.data_ptr(),
+              perm.data_ptr(), offsets.data_ptr(), 1 if residual else 0, _ptr(min_logvar), _ptr(max_logvar),
+              bounds_n, _ptr(noise), pred.data_ptr(), 0 if TC_VARIANT is None else int(TC_VARIANT), _stream())  # fmt: skip
+    return pred
 
 
 # ----------------------------------------------------------------------------- fused tcgen05 training step
@@ -536,23 +524,32 @@ class FusedTrainPlan:
         self.mask_str = mask_strides(mask, self.P, E, -1)[:2] if mask is not None else (0, 0)
         self.launches = 3 + (1 if self.dw_ws is not None else 0)
 
-    def step(self, obs, act, target, mn, mx, reg, g_scale, want_loss=True):
-        """pack -> fused forward / NLL / dz chain -> weight gradients, all on the current stream; returns the loss."""
-        E, B = self.E, self.B
-        obs, act, target = _rows_contig(_req(obs, "obs"), "obs"), _rows_contig(_req(act, "act"), "act"), _rows_contig(_req(target, "target"), "target")
-        loss = torch.empty((E, B, self.head_dim), device=obs.device, dtype=torch.float32) if want_loss else None
-        st = _stream()
+    def run_pack(self):
         m = self.mask
-        _lib.call("cmrl_train_pack_tf32", self.w_ptrs, self.b_ptrs, self.L, self.P, E, self.in_size, self.hidden,
-                  self.head_outputs, _ptr(m), self.mask_str[0], self.mask_str[1], self.packed.data_ptr(), st)  # fmt: skip
+        _lib.call("cmrl_train_pack_tf32", self.w_ptrs, self.b_ptrs, self.L, self.P, self.E, self.in_size, self.hidden,
+                  self.head_outputs, _ptr(m), self.mask_str[0], self.mask_str[1], self.packed.data_ptr(), _stream())  # fmt: skip
+
+    def run_fused(self, obs, act, target, mn, mx, reg, g_scale, loss=None):
+        E, B = self.E, self.B
         _lib.call("cmrl_train_fused", self.packed.data_ptr(), self.L, self.P, E, B, obs.shape[-1], act.shape[-1], self.hidden,
                   self.head_dim, self.layout, self.act, self.residual, int(TRAIN_FUSED_PASSES), obs.data_ptr(),
                   _lead_strides(obs)[1], act.data_ptr(), _lead_strides(act)[1], target.data_ptr(), _lead_strides(target)[1],
                   target.shape[-1], mn.data_ptr(), mx.data_ptr(), mn.numel(), float(reg), float(g_scale), _ptr(loss),
-                  self.scratch.data_ptr(), st)  # fmt: skip
-        _lib.call("cmrl_train_dw", self.scratch.data_ptr(), self.L, self.P, E, B, self.in_size, self.hidden, self.head_outputs,
-                  self.dw_ptrs, self.db_ptrs, _ptr(m), self.mask_str[0], self.mask_str[1], _ptr(self.dw_ws),
-                  0 if self.dw_ws is None else self.dw_ws.numel(), st)  # fmt: skip
+                  self.scratch.data_ptr(), _stream())  # fmt: skip
+
+    def run_dw(self, *unused):
+        m = self.mask
+        _lib.call("cmrl_train_dw", self.scratch.data_ptr(), self.L, self.P, self.E, self.B, self.in_size, self.hidden,
+                  self.head_outputs, self.act, self.dw_ptrs, self.db_ptrs, _ptr(m), self.mask_str[0], self.mask_str[1],
+                  _ptr(self.dw_ws), 0 if self.dw_ws is None else self.dw_ws.numel(), _stream())  # fmt: skip
+
+    def step(self, obs, act, target, mn, mx, reg, g_scale, want_loss=True):
+        """pack -> fused forward / NLL / dz chain -> weight gradients, all on the current stream; returns the loss."""
+        obs, act, target = _rows_contig(_req(obs, "obs"), "obs"), _rows_contig(_req(act, "act"), "act"), _rows_contig(_req(target, "target"), "target")
+        loss = torch.empty((self.E, self.B, self.head_dim), device=obs.device, dtype=torch.float32) if want_loss else None
+        self.run_pack()
+        self.run_fused(obs, act, target, mn, mx, reg, g_scale, loss)
+        self.run_dw()
         return loss
 
 

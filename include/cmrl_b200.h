@@ -224,9 +224,10 @@ int cmrl_pack_layer_f16(const float* w, const float* b, const float* mask, long 
  * bucketed env row (perm/offsets from cmrl_member_bucket) run the drawn member's whole MLP on tcgen05 tensor
  * cores with TMA-staged packed weights and write pred[env,:] = mean (+obs) + sqrt(exp(logvar)) * noise[env,:].
  * layer_*: arrays of num_layers+1 entries (hidden layers, then the head).
- * variant: 3 = weight-stationary CTA pairs (cta_group::2, M=128) with two row tiles in flight (default),
- * 2 = CTA pairs with one 256-row tile and a pipelined epilogue (hidden <= 207), 1 = single-CTA tiles with
- * per-layer streamed weights. */
+ * variant: 0 = chosen from the shape (the default of the Python host): 5 = weight-stationary CTA pairs (cta_group::2,
+ * M=256) with two 256-row tiles in flight and part of the A operand in tensor memory, where two tiles' accumulators and heads
+ * fit tensor memory; 3 = pairs with two 128-row tiles in flight (wider heads); 6 = pairs with the weights streamed in K chunks
+ * (hidden layers too wide for shared memory, packed without widening: layer_n[0] == H). */
 int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, const int* layer_off_halfs, const int* layer_k,
                          const int* layer_n, int num_layers, int P, int E, int N, int O, int A, int H, int head_dim,
                          int layout, int gaussian, int act, const float* obs, const float* actn, const int* perm,
@@ -254,7 +255,8 @@ int cmrl_train_pack_tf32(const float* const* weights_host, const float* const* b
 /* obs [E,B,O] / actn [E,B,A] / target [E,B,tgt_ld] with member strides *_se (floats).  loss [E,B,head_dim] (may be
  * NULL) = gaussian_nll(reduce=False) + reg (util.py:14-37, mlp.py:72-76); the gradient is that of
  * g_scale * sum(loss) (g_scale = 1 / (E * global_rows * head_dim) reproduces loss.mean().backward()).
- * scratch: cmrl_train_fused_sizes floats; it carries the layer inputs and dz of every layer to cmrl_train_dw. */
+ * scratch: cmrl_train_fused_sizes floats; it carries the first layer's input, every hidden layer's pre-activations and
+ * every layer's dz to cmrl_train_dw (which re-applies `act` to the pre-activations). */
 int cmrl_train_fused(const float* packed, int L, int P, int E, int B, int O, int A, int hidden, int head_dim,
                      int layout, int act, int residual, int passes, const float* obs, long long obs_se,
                      const float* actn, long long act_se, const float* target, long long tgt_se, int tgt_ld,
@@ -263,7 +265,7 @@ int cmrl_train_fused(const float* packed, int L, int P, int E, int B, int O, int
 /* dw_host / db_host: HOST arrays of L+1 device pointers to the gradient tensors (overwritten, not accumulated).
  * mask as in cmrl_train_pack_tf32 (gradient rows of masked inputs are zero, as in the reference's masked forward).
  * workspace: optional device floats for deterministic batch-slice partial sums. */
-int cmrl_train_dw(const float* scratch, int L, int P, int E, int B, int in_size, int hidden, int head_outputs,
+int cmrl_train_dw(const float* scratch, int L, int P, int E, int B, int in_size, int hidden, int head_outputs, int act,
                   float* const* dw_host, float* const* db_host, const float* mask, long long m_sp, long long m_se,
                   float* workspace, long long workspace_floats, void* stream);
 

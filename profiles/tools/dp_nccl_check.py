@@ -99,6 +99,60 @@ if rank == 0:
           % (loss_dp, loss_1, float((w_dp - w_1).abs().max() / w_1.abs().max())))
 same_t = torch.tensor([1 if same else 0], device=dev); dist.all_reduce(same_t, op=dist.ReduceOp.MIN)
 assert int(same_t.item()) == 1
+
+# ---- ragged last batch with FEWER rows than ranks: the rank with an empty slice still joins the all-reduce and the Adam step --------
+dyn3 = build()
+dyn3.enable_data_parallel()
+rem = max(1, world - 1)  # rank world-1 gets no row
+obs_r = torch.from_numpy(rng.normal(size=(E, rem, O)).astype(np.float32)).to(dev)
+act_r = torch.from_numpy(rng.uniform(-1, 1, size=(E, rem, A)).astype(np.float32)).to(dev)
+tgt_r = obs_r + 0.1 * torch.tanh(obs_r)
+slr = dp_row_slice(rem, world, rank)
+dyn3.train_step("transition", obs_r[:, slr].contiguous(), act_r[:, slr].contiguous(), tgt_r[:, slr].contiguous(), grad_rows=rem)
+torch.cuda.synchronize()
+w3 = dyn3.transition.flat_parameters()[0].clone()
+ref3 = w3.clone(); dist.broadcast(ref3, 0)
+ok3 = torch.tensor([1 if torch.equal(ref3, w3) else 0], device=dev); dist.all_reduce(ok3, op=dist.ReduceOp.MIN)
+assert int(ok3.item()) == 1, "replicas diverged on a ragged batch with an empty shard"
+if rank == 0:
+    single3 = build()
+    single3.train_step("transition", obs_r, act_r, tgt_r)
+    w1 = single3.transition.flat_parameters()[0]
+    print("ragged batch of %d rows over %d ranks (one empty shard): replicas identical, weights vs single process rel %.2e"
+          % (rem, world, float((w3 - w1).abs().max() / w1.abs().max())))
+
+# ---- sharded hold-out evaluation + elite selection over NCCL, and broadcast_parameters ---------------------------
+from cmrl_b200.transition_iterator import TransitionIterator
+from cmrl_b200.types import InteractionBatch
+
+r4 = np.random.default_rng(9)
+nv = 1001  # ragged over the ranks
+o4 = r4.normal(size=(nv, O)).astype(np.float32); a4 = r4.uniform(-1, 1, size=(nv, A)).astype(np.float32)
+val = TransitionIterator(InteractionBatch(o4, a4, (o4 + 0.1 * np.tanh(o4)).astype(np.float32), np.zeros(nv, np.float32), np.zeros(nv, bool)), 256,
+                         shuffle_each_epoch=False)
+mse_dp = dyn3.evaluate_member_mse(val, "transition")
+dyn3.dp_group = None
+mse_1 = dyn3.evaluate_member_mse(val, "transition")
+dyn3.enable_data_parallel()
+err4 = float((mse_dp - mse_1).abs().max() / mse_1.abs().max())
+gath = [torch.zeros_like(mse_dp) for _ in range(world)]
+dist.all_gather_object(gath, mse_dp)
+assert all(torch.equal(g_, gath[0]) for g_ in gath), "ranks disagree on the hold-out scores"
+assert err4 < 1e-5, err4
+if rank != 0:
+    with torch.no_grad():
+        dyn3.transition.flat_parameters()[0].fill_(float(rank))
+    dyn3.transition.set_elite_members([6, 5, 4, 3, 2])
+dyn3.broadcast_parameters(src=0)
+w5 = dyn3.transition.flat_parameters()[0]
+ref5 = w5.clone(); dist.broadcast(ref5, 0)
+ok5 = torch.tensor([1 if (torch.equal(ref5, w5) and list(dyn3.transition.elite_members) == list(build().transition.elite_members) or rank == 0) else 0], device=dev)
+elites = [None] * world
+dist.all_gather_object(elites, [int(e) for e in dyn3.transition.elite_members])
+assert all(e == elites[0] for e in elites) and bool(torch.equal(ref5, w5)) and not bool((w5 == float(max(rank, 1))).all())
+if rank == 0:
+    print("sharded hold-out evaluation over NCCL: %d rows over %d ranks, [E] scores identical on every rank, vs single process rel %.2e; "
+          "broadcast_parameters: replicas and elite sets equal rank 0's" % (nv, world, err4))
 dist.barrier()
 torch.cuda.synchronize()
 mark('done')

@@ -35,7 +35,8 @@ mn, mx = model._bounds()
 plan.step(obs, act, target, mn, mx, 0.5, 1e-4)  # packs the weights (product library)
 torch.cuda.synchronize()
 st = ops._stream()
-trace = torch.zeros(3 * 1024, dtype=torch.int64, device=dev)
+fine = []
+trace = torch.zeros(4 * 1024, dtype=torch.int64, device=dev)
 
 
 def run(which, passes=3):
@@ -46,13 +47,15 @@ def run(which, passes=3):
                                   plan.residual, passes, obs.data_ptr(), obs.stride(0), act.data_ptr(), act.stride(0), target.data_ptr(),
                                   target.stride(0), 5, mn.data_ptr(), mx.data_ptr(), mn.numel(), 0.5, 1e-4, None, plan.scratch.data_ptr(), st)
     else:
-        rc = lib.cmrl_train_dw(plan.scratch.data_ptr(), plan.L, plan.P, E, B, plan.in_size, plan.hidden, plan.head_outputs, plan.dw_ptrs,
+        rc = lib.cmrl_train_dw(plan.scratch.data_ptr(), plan.L, plan.P, E, B, plan.in_size, plan.hidden, plan.head_outputs, plan.act, plan.dw_ptrs,
                                plan.db_ptrs, None, 0, 0, ops._ptr(plan.dw_ws), 0 if plan.dw_ws is None else plan.dw_ws.numel(), st)
     assert rc == 0, lib.cmrl_last_error()
     torch.cuda.synchronize()
-    t = trace.cpu().numpy().reshape(3, 1024)
+    t = trace.cpu().numpy().reshape(4, 1024)
     t0 = min(int(r[r > 0].min()) for r in t if (r > 0).any())
-    return [(r[r > 0] - t0) for r in t]
+    global fine
+    fine = t[3][t[3] > 0] - t0
+    return [(r[r > 0] - t0) for r in t[:3]]
 
 
 for passes in (3, 1):
@@ -62,12 +65,30 @@ for passes in (3, 1):
     n_ph = 2 * plan.L + 1
     # epilogue warp 0: per phase (wait start, accumulator ready, epilogue done); MMA: per phase (wait start, A ready, first W chunk
     # landed, last W chunk landed, all issued)
-    print(" phase | epi: wait-start  acc-ready  done | mma: wait-start  a-ready  w-first  w-last  issued")
+    print(" phase | epi: wait-start  acc-ready  done | mma: phase-start  a-first  w-first  w-last  issued")
     for ph in range(min(n_ph, len(epi) // 3)):
         e = epi[3 * ph:3 * ph + 3]
         m = mma[5 * ph:5 * ph + 5] if len(mma) >= 5 * ph + 5 else mma[5 * ph:]
         print("  %2d   | %10d %10d %10d | %s" % (ph, e[0], e[1], e[2], " ".join("%9d" % x for x in m)))
     print(" weight producer: chunk issue times (first 60):", " ".join(str(int(x)) for x in prod[:60]))
+    print(" epilogue warp 0, phase 1, per chunk: loop-top | +ldtm | +save z | +activation | +ring acquire | +split store | +publish")
+    for i in range(0, len(fine) - 6, 7):
+        f = fine[i:i + 7]
+        print("    top %7d: %s" % (f[0], " ".join("%5d" % (f[j] - f[j - 1]) for j in range(1, 7))))
+
+# attribution experiments (results invalid): which resource paces the fused kernel?
+lib.cmrl_trace_flags.argtypes = [ctypes.c_int]
+print("=== fused kernel, B=%d, experiments: cycles from the first to the last stamp of CTA 0" % B)
+for flags, what in ((0, "everything"), (1, "no weight copies"), (2, "no MMAs"), (4, "no global loads/stores in the epilogue"),
+                    (8, "no A-ring writes"), (1 | 4, "no weight copies, no global epilogue traffic"), (2 | 4, "no MMAs, no global epilogue traffic"),
+                    (1 | 2, "no weight copies, no MMAs"), (1 | 2 | 4 | 8, "barriers + TMEM loads + activation math only")):
+    assert lib.cmrl_trace_flags(flags) == 0
+    for passes in (3, 1):
+        for _ in range(2):
+            prod, epi, mma = run("fused", passes)
+        last = max(int(r.max()) for r in (prod, epi, mma) if len(r))
+        print("  flags %2d passes %d: %7d cycles   (%s)" % (flags, passes, last, what))
+assert lib.cmrl_trace_flags(0) == 0
 
 for _ in range(2):
     prod, tr, mma = run("dw")
