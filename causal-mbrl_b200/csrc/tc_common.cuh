@@ -404,6 +404,21 @@ __device__ __forceinline__ void tf32_mma2_lohi_uni(uint32_t d_tmem, uint32_t a_l
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand in tensor memory (each CTA of the pair supplies its own 128 rows), B descriptor as (lo, hi) words
+__device__ __forceinline__ void tf32_mma2_ts_lohi_uni(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                      uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, p;\n"
+        ".reg .b64 db;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "@pe tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // multicast forms for 2-CTA clusters of independent (cta_group::1) tiles that share one weight stream
 __device__ __forceinline__ void tma_bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
     asm volatile(

@@ -166,7 +166,7 @@ __global__ void train_pack_kernel(const PackP p) {
 // Shared memory: [A ring: R slots of one 16-deep K chunk x 128 rows, hi | lo][weight ring: S stages][barriers].
 // Tensor memory: two accumulators (phases alternate, so the epilogue of phase p reads one while the MMAs of phase p+1 --
 // which chase that epilogue chunk by chunk through the A ring -- fill the other) + the head accumulator.
-constexpr int TF_A_SLOTS = 9;
+constexpr int TF_A_SLOTS = 5;
 constexpr uint32_t TF_A_PART = 4 * TF_GROUP;   // bytes of the hi (or lo) part of an A chunk: 4 K groups x 128 rows x 16 B
 constexpr uint32_t TF_A_SLOT = 2 * TF_A_PART;
 // SHARED-MEMORY BANDWIDTH bounds this kernel, not the tensor pipe (profiles/r2_train_trace_*.txt): a kind::tf32 MMA of
@@ -197,6 +197,7 @@ struct TrainP {
     int tiles_per_net;   // real row tiles per net
     int pairs_per_net;   // cluster work items per net; tile slots in the scratch = 2 * pairs_per_net
     int stages;
+    int lo_tmem;  // the lo parts of the A chunks live in tensor memory (columns left over by the accumulators) instead of shared memory
     uint32_t stage_bytes, w_off, bar_off;
 };
 
@@ -218,38 +219,60 @@ __device__ __forceinline__ void save_chunk(float* tile, int q, int lane, int ncg
 // A-ring bookkeeping of an epilogue warp: chunk `seq` of the global chunk sequence lives in slot seq % R
 struct ARing {
     uint32_t smem0;  // shared-memory address of slot 0 + this thread's row offset
+    uint32_t tmem0;  // tensor-memory address (this thread's lane) of the lo ring, 16 columns per slot
     uint64_t *full, *empty;
 };
+// returns the slot index of chunk `seq` once the MMAs that read the slot's previous chunk are complete
 __device__ __forceinline__ uint32_t aring_acquire(const ARing& r, uint32_t seq) {
     const uint32_t slot = seq % TF_A_SLOTS, k = seq / TF_A_SLOTS;
-    if (k >= 1) mbar_wait(&r.empty[slot], (k - 1) & 1);  // the MMAs that read the slot's previous chunk are complete
-    return r.smem0 + slot * TF_A_SLOT;
+    if (k >= 1) mbar_wait(&r.empty[slot], (k - 1) & 1);
+    return slot;
 }
+template <bool LO_TMEM>
 __device__ __forceinline__ void aring_publish(const ARing& r, uint32_t seq, int lane) {
+    if (LO_TMEM) {
+        v5_st_wait();
+        tc_fence_before();
+    }
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) v3_arrive_leader(&r.full[seq % TF_A_SLOTS]);  // the leader CTA issues the pair's MMAs
 }
-// 16 values of this thread's row = one K chunk of the next GEMM: tf32 hi and lo parts, four 16-byte groups each
-__device__ __forceinline__ void split_store_chunk(uint32_t dst, const float* v) {
+// 16 values of this thread's row = one K chunk of the next GEMM: tf32 hi parts in shared memory (four 16-byte groups), lo parts in
+// tensor memory (16 columns of this thread's lane) or, where the accumulators leave no columns, in shared memory as well
+template <bool LO_TMEM>
+__device__ __forceinline__ void split_store_chunk(const ARing& r, uint32_t slot, const float* v) {
     if (XFLAG(8)) return;
+    const uint32_t dst = r.smem0 + slot * TF_A_SLOT;
+    uint32_t lo[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        uint32_t h[4], l[4];
+        uint32_t h[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             h[u] = __float_as_uint(v[4 * j + u]) & 0xFFFFE000u;
-            l[u] = __float_as_uint(v[4 * j + u] - __uint_as_float(h[u]));
+            lo[4 * j + u] = __float_as_uint(v[4 * j + u] - __uint_as_float(h[u]));
         }
         v3_sts128(dst + (uint32_t)j * TF_GROUP, h[0], h[1], h[2], h[3]);
-        v3_sts128(dst + TF_A_PART + (uint32_t)j * TF_GROUP, l[0], l[1], l[2], l[3]);
+        if (!LO_TMEM) v3_sts128(dst + TF_A_PART + (uint32_t)j * TF_GROUP, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
     }
+    if (LO_TMEM) tmem_st16(r.tmem0 + slot * 16, lo);
+}
+// one element pair (k, k + 1) of a chunk (the head writes its dz two values at a time)
+template <bool LO_TMEM>
+__device__ __forceinline__ void split_store_pair(const ARing& r, uint32_t slot, int k, float x, float y) {
+    const uint32_t hx = __float_as_uint(x) & 0xFFFFE000u, hy = __float_as_uint(y) & 0xFFFFE000u;
+    const uint32_t lx = __float_as_uint(x - __uint_as_float(hx)), ly = __float_as_uint(y - __uint_as_float(hy));
+    const uint32_t at = r.smem0 + slot * TF_A_SLOT + (uint32_t)((k & 15) / 4) * TF_GROUP + (uint32_t)(k & 3) * 4;
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(at), "r"(hx), "r"(hy) : "memory");
+    if (LO_TMEM) tmem_st2(r.tmem0 + slot * 16 + (uint32_t)(k & 15), lx, ly);
+    else asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(at + TF_A_PART), "r"(lx), "r"(ly) : "memory");
 }
 
 // ACT is a template parameter: with a run-time activation switch the unrolled 16-element epilogue bodies compiled to a chain of
 // branches per ELEMENT and the epilogue (not the tensor pipe, not the weight stream) paced the kernel at ~12k cycles per phase
 // (profiles/r2_train_trace_attribution.txt).
-template <int ACT>
+template <int ACT, bool LO_TMEM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_slot;
@@ -292,7 +315,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
     v3_cluster_sync();  // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t col_head = (uint32_t)(2 * g.HP);
+    const uint32_t col_head = (uint32_t)(2 * g.HP), col_alo = (uint32_t)(2 * g.HP + g.NH);
     const int hi_only = p.passes == 1;
 
     if (warp == TF_WARP_W) {
@@ -391,10 +414,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
                     const uint32_t first = c == 0 ? 0u : 1u;
                     if (!XFLAG(2)) {
                         if (!hi_only) {  // 3xTF32, small terms first
-                            tf32_mma2_lohi_uni(d_t, al, desc_hi, bh, desc_hi, idesc, first);
+                            const uint32_t alt = tmem + col_alo + slot * 16;  // lo part of the A chunk in tensor memory
+                            if (LO_TMEM) tf32_mma2_ts_lohi_uni(d_t, alt, bh, desc_hi, idesc, first);
+                            else tf32_mma2_lohi_uni(d_t, al, desc_hi, bh, desc_hi, idesc, first);
                             tf32_mma2_lohi_uni(d_t, ah, desc_hi, bl, desc_hi, idesc, 1u);
                             tf32_mma2_lohi_uni(d_t, ah, desc_hi, bh, desc_hi, idesc, 1u);
-                            tf32_mma2_lohi_uni(d_t, al + (2 * TF_GROUP >> 4), desc_hi, bh + b_ks, desc_hi, idesc, 1u);
+                            if (LO_TMEM) tf32_mma2_ts_lohi_uni(d_t, alt + 8, bh + b_ks, desc_hi, idesc, 1u);
+                            else tf32_mma2_lohi_uni(d_t, al + (2 * TF_GROUP >> 4), desc_hi, bh + b_ks, desc_hi, idesc, 1u);
                             tf32_mma2_lohi_uni(d_t, ah + (2 * TF_GROUP >> 4), desc_hi, bl + b_ks, desc_hi, idesc, 1u);
                             tf32_mma2_lohi_uni(d_t, ah + (2 * TF_GROUP >> 4), desc_hi, bh + b_ks, desc_hi, idesc, 1u);
                         } else {
@@ -414,11 +440,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
         const int q = warp & 3, cset = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        ARing ring{smem_u32(smem) + (uint32_t)row * 16, bar_afull, bar_aempty};
+        ARing ring{smem_u32(smem) + (uint32_t)row * 16, tmem + lane_off + col_alo, bar_afull, bar_aempty};
         const int Dn = g.Dn;
         // the next layer's bias input: hidden unit H is 1.0 -- patched into the chunk that holds it after the chunk is stored
-        const int ones_c = g.H >> 4;
-        const uint32_t ones_off = (uint32_t)((g.H & 15) >> 2) * TF_GROUP + (uint32_t)(g.H & 3) * 4;
+        const int ones_c = g.H >> 4, ones_i = g.H & 15;
         uint32_t n_d = 0, seq_base = 0, n_phase = 0;
         TRACE_DECL;
 #ifdef CMRL_TRACE
@@ -448,8 +473,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
                         v[i] = x;
                     }
                     save_chunk(sc + g.off_x, q, lane, g.K0P / 4, c, v);
-                    split_store_chunk(aring_acquire(ring, seq_base + c), v);
-                    aring_publish(ring, seq_base + c, lane);
+                    split_store_chunk<LO_TMEM>(ring, aring_acquire(ring, seq_base + c), v);
+                    aring_publish<LO_TMEM>(ring, seq_base + c, lane);
                 }
                 seq_base += g.K0P / 16;
             }
@@ -493,15 +518,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
                             TRACE_FINE(warp == 0 && ph == 1);
                             save_chunk(zt, q, lane, g.HP / 4, c, z);  // pre-activations: the dz chain and the dw kernel re-activate
                             TRACE_FINE(warp == 0 && ph == 1);
-                            const uint32_t dst = aring_acquire(ring, seq_base + c);
-                            TRACE_FINE(warp == 0 && ph == 1);
-                            split_store_chunk(dst, a);
-                            TRACE_FINE(warp == 0 && ph == 1);
-                            if (c == ones_c && !XFLAG(8)) {  // hi part 1.0, lo part 0
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + ones_off), "r"(0x3F800000u) : "memory");
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + TF_A_PART + ones_off), "r"(0u) : "memory");
+                            if (c == ones_c) {  // the next layer's bias input: hidden unit H is 1.0 (a warp-uniform patch of one element)
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (i == ones_i) a[i] = 1.0f;
                             }
-                            aring_publish(ring, seq_base + c, lane);
+                            const uint32_t slot = aring_acquire(ring, seq_base + c);
+                            TRACE_FINE(warp == 0 && ph == 1);
+                            split_store_chunk<LO_TMEM>(ring, slot, a);
+                            TRACE_FINE(warp == 0 && ph == 1);
+                            aring_publish<LO_TMEM>(ring, seq_base + c, lane);
                             TRACE_FINE(warp == 0 && ph == 1);
                         }
                     } else if (kind == PH_DX) {
@@ -533,8 +559,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
 #pragma unroll
                             for (int i = 0; i < 16; ++i) z[i] *= __uint_as_float(raw[i]);
                             if (out_chunks > 0) {
-                                split_store_chunk(aring_acquire(ring, seq_base + c), z);
-                                aring_publish(ring, seq_base + c, lane);
+                                split_store_chunk<LO_TMEM>(ring, aring_acquire(ring, seq_base + c), z);
+                                aring_publish<LO_TMEM>(ring, seq_base + c, lane);
                             }
                             save_chunk(dt, q, lane, g.HP / 4, c, z);
                             if (c + 4 < g.HP / 16) load_z(c + 4);
@@ -544,10 +570,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
                         // the NH-wide dz of the head is chunk 0 (and 1) of the next GEMM
                         float* dt = sc + g.off_dz[g.L];
                         const uint32_t h_t = tmem + lane_off + col_head;
-                        uint32_t dst = 0;
+                        uint32_t slot = 0;
 #pragma unroll 1
                         for (int d = 0; d < g.NH / 2; ++d) {
-                            if ((d & 7) == 0) dst = aring_acquire(ring, seq_base + (d >> 3));
+                            if ((d & 7) == 0) slot = aring_acquire(ring, seq_base + (d >> 3));
                             float dm = 0.f, dl = 0.f;
                             uint32_t r0, r1;
                             __syncwarp();
@@ -574,13 +600,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
                             }
                             const int k = 2 * d;
                             *reinterpret_cast<float2*>(dt + tile_off(q, lane, g.NH / 4, k / 4) + (k & 3)) = make_float2(dm, dl);
-                            const uint32_t hm = __float_as_uint(dm) & 0xFFFFE000u, hl = __float_as_uint(dl) & 0xFFFFE000u;
-                            const uint32_t at = dst + (uint32_t)((k & 15) / 4) * TF_GROUP + (uint32_t)(k & 3) * 4;
-                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(at), "r"(hm), "r"(hl) : "memory");
-                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(at + TF_A_PART), "r"(__float_as_uint(dm - __uint_as_float(hm))),
-                                         "r"(__float_as_uint(dl - __uint_as_float(hl)))
-                                         : "memory");
-                            if ((d & 7) == 7) aring_publish(ring, seq_base + (d >> 3), lane);
+                            split_store_pair<LO_TMEM>(ring, slot, k, dm, dl);
+                            if ((d & 7) == 7) aring_publish<LO_TMEM>(ring, seq_base + (d >> 3), lane);
                         }
                     }
                     tc_fence_before();  // orders this warp's accumulator reads before the MMAs that overwrite it two phases on
@@ -928,17 +949,28 @@ extern "C" int cmrl_train_fused(const float* packed, int L, int P, int E, int B,
     static cmrl::PerDeviceOnce attr_once;
     int attr_dev = 0;
     if (attr_once.pending(&attr_dev)) {
-        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_IDENTITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_IDENTITY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_RELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_SILU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_IDENTITY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_RELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_SILU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_once.done(attr_dev);
     }
+    // tensor-memory columns: two accumulators, the head accumulator, then (if they fit) the lo parts of the A-chunk ring
+    p.lo_tmem = 2 * p.g.HP + p.g.NH + 16 * TF_A_SLOTS <= 512 ? 1 : 0;
     const long long pairs = (long long)P * E * p.pairs_per_net;
     CMRL_REQUIRE(pairs < (1ll << 30), "train_fused: too many row tiles");
     const int clusters = (int)(pairs < num_sms() / 2 ? pairs : num_sms() / 2);
-    if (act == CMRL_ACT_SILU) train_fused_kernel<CMRL_ACT_SILU><<<2 * clusters, TF_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
-    else if (act == CMRL_ACT_RELU) train_fused_kernel<CMRL_ACT_RELU><<<2 * clusters, TF_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
-    else train_fused_kernel<CMRL_ACT_IDENTITY><<<2 * clusters, TF_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+#define CMRL_TF_LAUNCH(A)                                                                                              \
+    do {                                                                                                               \
+        if (p.lo_tmem) train_fused_kernel<A, true><<<2 * clusters, TF_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);  \
+        else train_fused_kernel<A, false><<<2 * clusters, TF_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);          \
+    } while (0)
+    if (act == CMRL_ACT_SILU) CMRL_TF_LAUNCH(CMRL_ACT_SILU);
+    else if (act == CMRL_ACT_RELU) CMRL_TF_LAUNCH(CMRL_ACT_RELU);
+    else CMRL_TF_LAUNCH(CMRL_ACT_IDENTITY);
+#undef CMRL_TF_LAUNCH
     CMRL_CHECK_LAUNCH("train_fused");
     return 0;
 }

@@ -259,6 +259,15 @@ class VecFakeEnv(VecEnv):
         b = self._bufs
         N, D, E = obs.shape[0], model._head_dim, model.ensemble_num
         perm, offsets = bucket if bucket is not None else ops.member_bucket(idx, E, b["perm"], b["offsets"], b["counters"])
+        repeat = getattr(model, "repeat_times", None)
+        if repeat is not None:
+            # ForwardEulerTransition (forward_euler.py:32-41): the drawn member's one-step MEAN is re-applied k times, the last
+            # application supplies the log-variance the sample is drawn with
+            cur = obs
+            for k in range(int(repeat)):
+                cur = self.predict_selected(model.one_step_transition, cur, act, idx, noise if k == repeat - 1 else None,
+                                            bucket=(perm, offsets))
+            return cur
         if self.precision == "f16":
             mn, mx = model._bounds()
             return ops.mlp_rollout_f16(model.packed_f16(), model._parallel_num(), E, obs, act, perm, offsets,
