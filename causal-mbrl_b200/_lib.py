@@ -49,6 +49,12 @@ PROTOTYPES = {
                          _P, _P, _P],
     "cmrl_train_dw": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _LL, _LL, _P, _LL, _P],
     "cmrl_env_step_tail": [_P, _P, _P, _P, _P, _F, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "cmrl_dp_comm_create": [_I, _I, _LL, _c.POINTER(_P), _c.c_char_p],
+    "cmrl_dp_comm_connect": [_P, _c.c_char_p],
+    "cmrl_dp_comm_error": [_P, _c.POINTER(_I)],
+    "cmrl_dp_comm_destroy": [_P],
+    "cmrl_allreduce_grads": [_P, _P, _LL, _P],
+    "cmrl_allreduce_grads_adam": [_P, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _P, _P],
 }
 
 _lib = None

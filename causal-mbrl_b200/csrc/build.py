@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libcmrl_b200.so")
 STAMP = os.path.join(PKG, ".libcmrl_b200.stamp")
-SOURCES = ["api.cu", "ens_linear.cu", "head_loss.cu", "rollout.cu", "mlp_tc.cu", "mlp_tc3.cu", "mlp_tc5.cu", "mlp_tc6.cu", "gemm_tc.cu", "train_tc.cu"]
+SOURCES = ["api.cu", "ens_linear.cu", "head_loss.cu", "rollout.cu", "mlp_tc.cu", "mlp_tc3.cu", "mlp_tc5.cu", "mlp_tc6.cu", "gemm_tc.cu", "train_tc.cu", "dp_sync.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",

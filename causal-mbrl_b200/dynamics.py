@@ -12,6 +12,7 @@ the arithmetic runs on libcmrl_b200 kernels:
 Deliberate differences from the reference: a learned termination mech trains on `batch_done`
 (the reference raises KeyError 'batch_terminal').
 """
+import os
 import abc
 import collections
 import copy
@@ -212,8 +213,7 @@ class BaseDynamics:
             # contribute (zero) gradients to the all-reduce and apply the same Adam update as every other rank
             _, flat_grad = model.flat_parameters()
             flat_grad.zero_()
-            self._sync_grads(model)
-            optim.step_graphable() if graphable else optim.step()
+            self._sync_and_step(model, optim, graphable)
             return torch.empty((obs.shape[0], 0, target.shape[-1]), device=obs.device, dtype=torch.float32) if want_loss else None
         if (model.deterministic or any(p.requires_grad for p in model._bounds() if p is not None)
                 or not hasattr(model, "hidden_layers")):
@@ -234,8 +234,7 @@ class BaseDynamics:
             mn, mx = model._bounds()
             rows = B if grad_rows is None else grad_rows
             loss = plan.step(obs, act, target, mn, mx, model._nll_reg(), 1.0 / float(E * rows * model._head_dim), want_loss)
-            self._sync_grads(model)
-            optim.step_graphable() if graphable else optim.step()
+            self._sync_and_step(model, optim, graphable)
             return loss
         params = model._stack_params()
         L = model.num_layers
@@ -284,22 +283,38 @@ class BaseDynamics:
         if side is not None:
             main.wait_stream(side)
         del keep
-        self._sync_grads(model)
-        if graphable:
-            optim.step_graphable()
-        else:
-            optim.step()
+        self._sync_and_step(model, optim, graphable)
         return loss
 
-    def enable_data_parallel(self, group=None):
+    def enable_data_parallel(self, group=None, sync: str = "auto"):
         """Shard every ensemble batch's rows over the ranks of `group` (default: the world group) in `train`;
-        gradients are summed with one all-reduce over the flat arena and the loss scale uses the global row count,
-        so every rank applies the identical Adam update."""
+        gradients are summed over the flat arena and the loss scale uses the global row count, so every rank applies
+        the identical Adam update.  sync="peer": ONE kernel per step exchanges the gradients over NVLink
+        peer memory and applies Adam (`cmrl_allreduce_grads_adam`, csrc/dp_sync.cu); sync="nccl": one
+        `torch.distributed.all_reduce` followed by the Adam kernel; "auto" = peer for CUDA models on an NCCL group of
+        more than one rank (every rank must make this call: the peer set-up is collective)."""
         import torch.distributed as dist
 
+        assert sync in ("auto", "peer", "nccl")
         self.dp_group = group if group is not None else dist.group.WORLD
         self.dp_world = dist.get_world_size(self.dp_group)
         self.dp_rank = dist.get_rank(self.dp_group)
+        self._peer_sync = None
+        on_cuda = torch.device(self.device).type == "cuda"
+        if sync == "auto" and os.environ.get("CMRL_DP_SYNC") in ("peer", "nccl"):  # operator override (A/B timing)
+            sync = os.environ["CMRL_DP_SYNC"]
+        if sync == "auto":
+            sync = "peer" if (on_cuda and self.dp_world > 1 and dist.get_backend(self.dp_group) == "nccl") else "nccl"
+        if sync == "peer":
+            from .peer_sync import PeerGradSync
+
+            assert on_cuda, "the peer-memory gradient exchange needs the models on a CUDA device"
+            largest = 1
+            for mech in self.learn_mech:
+                model = getattr(self, mech)
+                model.flat_parameters()
+                largest = max(largest, int(model._n_trainable))
+            self._peer_sync = PeerGradSync(self.dp_group, largest, self.device)
 
     def broadcast_parameters(self, src: int = 0, group=None):
         """Rollout replicas: envs are sharded over ranks with a full weight replica each and no per-step
@@ -323,12 +338,29 @@ class BaseDynamics:
             model.set_elite_members([int(e) for e in elite.tolist()])
 
     def _sync_grads(self, model):
-        """Data-parallel gradient exchange: one NCCL all-reduce (sum) over the flat gradient arena."""
+        """Data-parallel gradient exchange alone (autograd paths): the peer-memory kernel or one NCCL all-reduce (sum)
+        over the flat gradient arena."""
         if self.dp_group is not None:
+            _, flat_grad = model.flat_parameters()
+            peer = getattr(self, "_peer_sync", None)
+            if peer is not None:
+                peer.allreduce(flat_grad[: model._n_trainable])
+                return
             import torch.distributed as dist
 
-            _, flat_grad = model.flat_parameters()
             dist.all_reduce(flat_grad[: model._n_trainable], op=dist.ReduceOp.SUM, group=self.dp_group)
+
+    def _sync_and_step(self, model, optim, graphable):
+        """Gradient exchange + optimiser step: fused into one launch on the peer-memory path."""
+        peer = getattr(self, "_peer_sync", None) if self.dp_group is not None else None
+        if peer is not None:
+            optim.step_synced(peer)
+            return
+        self._sync_grads(model)
+        if graphable:
+            optim.step_graphable()
+        else:
+            optim.step()
 
     def train_epoch_device(self, dataset: BootstrapIterator, mech: str = "transition", use_graph: bool = True):
         """One pass over the bootstrap iterator with the training set, the bootstrap index table and the epoch order
@@ -434,6 +466,16 @@ class _DeviceEpochRunner:
         self.b_tgt = torch.empty((E, Bl, self.target.shape[1]), device=dev)
         self.loss_sum = torch.zeros((), device=dev, dtype=torch.float64)
         self.graph = None
+        self._order_pinned = [torch.empty(self.N, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._order_flip = 0
+        self._staged_order = None  # (the int64 permutation object, its int32 copy in pinned memory)
+
+    def _stage_order(self, order):
+        """int32 copy of an epoch order in one of two pinned buffers (the other may still be in flight to the device)."""
+        buf = self._order_pinned[self._order_flip]
+        self._order_flip ^= 1
+        buf.numpy()[:] = order
+        return buf
 
     def _step(self):
         # `start` points at this rank's first row of the batch and advances by the global batch size
@@ -447,7 +489,11 @@ class _DeviceEpochRunner:
     def run_epoch(self):
         ds = self.dataset
         iter(ds)  # reshuffles exactly like the reference iterator (one rng.permutation per epoch)
-        self.order.copy_(torch.from_numpy(np.ascontiguousarray(ds._order, dtype=np.int32)), non_blocking=True)
+        staged = self._staged_order
+        if staged is None or staged[0] is not ds._order:
+            staged = (ds._order, self._stage_order(ds._order))
+        self._staged_order = None
+        self.order.copy_(staged[1], non_blocking=True)
         self.start.fill_(self.row_slice.start)
         self.loss_sum.zero_()
         model = getattr(self.dyn, self.mech)
@@ -463,7 +509,7 @@ class _DeviceEpochRunner:
             worst = max((p.numel() // p.shape[-2]) * (p.shape[-2] + 1) for p in model.parameters() if p.dim() >= 3 and p.shape[-2] > 1)
             ops.splitk_workspace(self.obs.device, min(32 * worst, (256 << 20) // 4))
         if self.use_graph and self.graph is None and n_full > 0:
-            if self.dyn.dp_group is not None:
+            if self.dyn.dp_group is not None and getattr(self.dyn, "_peer_sync", None) is None:
                 self._step()  # one eager step first: NCCL sets its communicator up outside the capture
                 n_full -= 1
             g = torch.cuda.CUDAGraph()
@@ -492,10 +538,16 @@ class _DeviceEpochRunner:
                                        graphable=True, grad_rows=rem if dp else None)  # fmt: skip
             self.loss_sum += loss.sum(dtype=torch.float64)
         ds._current_batch = len(ds)  # the iterator is exhausted, like after a `for batch in dataset` loop
+        # the GPU is still executing this epoch: draw and stage the next epoch's permutation meanwhile
+        nxt = ds.prefetch_order()
+        if nxt is not None:
+            self._staged_order = (nxt, self._stage_order(nxt))
         if self.dyn.dp_group is not None:
             import torch.distributed as dist
 
             dist.all_reduce(self.loss_sum, op=dist.ReduceOp.SUM, group=self.dyn.dp_group)
+            if getattr(self.dyn, "_peer_sync", None) is not None:
+                self.dyn._peer_sync.check()
         denom = float(self.E * self.N * self.b_tgt.shape[-1])
         return float(self.loss_sum.item()) / denom
 

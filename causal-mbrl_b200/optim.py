@@ -72,6 +72,17 @@ class FusedAdamL2(torch.optim.Optimizer):
                              g["weight_decay"], self._step_dev, grad_scale)  # fmt: skip
         self._mark_weights_changed()
 
+    @torch.no_grad()
+    def step_synced(self, peer, grad_scale: float = 1.0):
+        """Data-parallel step: the gradient exchange over NVLink peer memory and this update in ONE launch
+        (`cmrl_allreduce_grads_adam`); step counter on the device, so the call is graph-capturable."""
+        g = self.param_groups[0]
+        self.prepare_graphable()
+        p, grad = self._arena()
+        peer.allreduce_adam(p, grad, self._exp_avg, self._exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                            g["weight_decay"], self._step_dev, grad_scale)  # fmt: skip
+        self._mark_weights_changed()
+
     @property
     def step_count(self):
         return self._step if self._step_dev is None else int(self._step_dev.item())

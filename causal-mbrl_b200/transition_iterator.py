@@ -37,8 +37,10 @@ class TransitionIterator:
         self.batch_size = batch_size
         self.num_stored = len(transitions)
         self._shuffle_each_epoch = shuffle_each_epoch
+        self._owns_rng = rng is None  # a private generator: nobody else draws from it between two passes
         self._rng = np.random.default_rng() if rng is None else rng
         self._order: np.ndarray = np.arange(self.num_stored)  # row visited at each position of the pass
+        self._next_order: Optional[np.ndarray] = None  # the next pass's permutation, drawn ahead of time
         self._current_batch = 0
 
     def __len__(self):
@@ -59,9 +61,21 @@ class TransitionIterator:
 
     def __iter__(self):
         if self._shuffle_each_epoch:
-            self._order = self._rng.permutation(self.num_stored)
+            if self._next_order is not None:
+                self._order, self._next_order = self._next_order, None
+            else:
+                self._order = self._rng.permutation(self.num_stored)
         self._current_batch = 0
         return self
+
+    def prefetch_order(self) -> Optional[np.ndarray]:
+        """Draw the NEXT pass's permutation now (the device-resident epoch calls this while the GPU executes the current
+        pass: at 10 ns per row the shuffle of a large set otherwise sits between two epochs).  The generator is consumed
+        in the same order as without the call -- the next `__iter__` uses exactly this draw -- but only a private
+        generator is touched early: with a caller-supplied one another consumer could sit between the two draws."""
+        if self._shuffle_each_epoch and self._owns_rng and self._next_order is None:
+            self._next_order = self._rng.permutation(self.num_stored)
+        return self._next_order
 
     def __next__(self):
         return self[self._get_indices_next_batch()]

@@ -269,6 +269,28 @@ int cmrl_train_dw(const float* scratch, int L, int P, int E, int B, int in_size,
                   float* const* dw_host, float* const* db_host, const float* mask, long long m_sp, long long m_se,
                   float* workspace, long long workspace_floats, void* stream);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory (SURVEY 8b item 6 `allreduce_grads`, 8e row 2) ----------
+ * The reference trains on one device (base_dynamics.py:173-188: loss.mean().backward(); optimizer.step()); with the
+ * rows of every ensemble batch sharded over W ranks, the per-rank gradients of the flat arena are summed between
+ * backward() and step().  The opaque handle is this library's own communicator: a cudaMalloc'ed exchange buffer per rank
+ * that every peer maps through CUDA IPC (handles are exchanged by the caller, e.g. with torch.distributed.all_gather).
+ *
+ * cmrl_dp_comm_create: allocates the buffer for arenas of up to max_floats floats on the current device and writes its
+ *   64-byte cudaIpcMemHandle_t to ipc_handle_out.  cmrl_dp_comm_connect: all_handles = world x 64 bytes in rank order.
+ * cmrl_allreduce_grads: grad[0..n) <- sum over ranks, in rank order, bit-identical on every rank; ONE launch.
+ * cmrl_allreduce_grads_adam: the same exchange fused with cmrl_adam_l2_step_dev (identical arithmetic); *step_dev is
+ *   incremented by the call.  Both are stream-ordered and CUDA-graph replayable (epochs live in device memory); every
+ *   rank must make the same sequence of calls with the same n.  A peer that does not arrive within ~20 s raises the
+ *   communicator's error word (cmrl_dp_comm_error, synchronises) instead of hanging the device. */
+int cmrl_dp_comm_create(int rank, int world, long long max_floats, void** comm_out, unsigned char* ipc_handle_out);
+int cmrl_dp_comm_connect(void* comm, const unsigned char* all_handles);
+int cmrl_dp_comm_error(void* comm, int* err_out);
+int cmrl_dp_comm_destroy(void* comm);
+int cmrl_allreduce_grads(void* comm, float* grad, long long n, void* stream);
+int cmrl_allreduce_grads_adam(void* comm, float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, float grad_scale, int* step_dev,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,6 +140,28 @@ def test_iterators_shapes_and_coverage():
     assert next(iter(bp)).batch_obs.shape == (32, 3)
 
 
+def test_prefetched_epoch_order_is_the_order_the_next_pass_would_have_drawn():
+    """The device-resident epoch draws the next pass's permutation while the GPU runs the current one: the sequence of
+    passes must not change, and a caller-supplied generator (other consumers may sit between two draws) is left alone."""
+    data = _data(57, np.random.default_rng(0))
+    a = cm.TransitionIterator(data, 16, shuffle_each_epoch=True)
+    b = cm.TransitionIterator(data, 16, shuffle_each_epoch=True)
+    a._rng, b._rng = np.random.default_rng(11), np.random.default_rng(11)
+    orders_a, orders_b = [], []
+    for k in range(4):
+        iter(a)
+        orders_a.append(a._order.copy())
+        if k % 2 == 0:
+            nxt = a.prefetch_order()
+            assert nxt is not None and a.prefetch_order() is nxt  # drawn once
+        iter(b)
+        orders_b.append(b._order.copy())
+    assert all(np.array_equal(x, y) for x, y in zip(orders_a, orders_b))
+    shared = cm.TransitionIterator(data, 16, shuffle_each_epoch=True, rng=np.random.default_rng(3))
+    assert shared.prefetch_order() is None
+    assert cm.TransitionIterator(data, 16, shuffle_each_epoch=False).prefetch_order() is None
+
+
 @pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted (GPU box)")
 def test_iterators_match_reference_bit_for_bit():
     ref = refshim.load_reference()
