@@ -32,6 +32,7 @@ PROTOTYPES = {
     "cmrl_mse_member_sums": [_P, _P, _LL, _I, _LL, _P, _P],
     "cmrl_adam_l2_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _I, _P],
     "cmrl_adam_l2_step_dev": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _P, _P],
+    "cmrl_sum_acc_f64": [_P, _LL, _P, _P, _P],
     "cmrl_bootstrap_gather": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "cmrl_draw_member_noise": [_ULL, _ULL, _P, _I, _P, _I, _I, _P, _P, _P],
     "cmrl_draw_uniform_index": [_ULL, _ULL, _P, _I, _I, _P, _P],

@@ -66,6 +66,22 @@ __device__ __forceinline__ float soft_clamp_logvar(float raw, float mn, float mx
     return mn + softplusf_(lv1 - mn);
 }
 
+// "Last block out" counter update: after EVERY block of the grid has reached this call, the last one to arrive adds `delta`
+// to counter[0].  counter[1] is the arrival ticket (zero between launches).  Blocks read counter[0] when they start, so a
+// kernel can consume a device-side counter and advance it without a trailing one-thread launch (CUDA-graph replayable).
+__device__ __forceinline__ void last_block_add(int* counter, int delta) {
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+        __threadfence();
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(reinterpret_cast<unsigned*>(counter + 1), 1u) == total - 1) {
+            counter[1] = 0;
+            counter[0] += delta;
+            __threadfence();
+        }
+    }
+}
+
 // cudaFuncSetAttribute applies to the CURRENT device only: one bit per device and call site, so that a process driving
 // several GPUs configures the kernels on each of them (a race between host threads only repeats the idempotent call)
 struct PerDeviceOnce {

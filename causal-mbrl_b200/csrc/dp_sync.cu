@@ -67,7 +67,7 @@ struct KParams {
     uint8_t* peer[MAX_WORLD];
     float *param, *grad, *m, *v;  // param == nullptr: exchange only
     float lr, beta1, beta2, eps, wd, gscale;
-    const int* step_dev;
+    int* step_dev;  // [0] steps taken, [1] arrival ticket of the last-block update
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) allreduce_adam_kernel(const KPa
     const uint32_t epoch = *ep + 1;
     __shared__ AdamC s_c;
     if (ADAM && tid == 0) {
-        const double t = (double)(*p.step_dev + 1);
+        const double t = (double)(p.step_dev[0] + 1);
         s_c.lr_over_bc1 = (float)((double)p.lr / (1.0 - pow((double)p.beta1, t)));
         s_c.sqrt_bc2 = (float)sqrt(1.0 - pow((double)p.beta2, t));
     }
@@ -257,9 +257,8 @@ __global__ void __launch_bounds__(DP_THREADS, 1) allreduce_adam_kernel(const KPa
         }
     }
     if (tid == 0) *ep = epoch;
+    if (ADAM) last_block_add(p.step_dev, 1);
 }
-
-__global__ void dp_bump_counter_kernel(int* c) { *c += 1; }
 
 static int launch(Comm* c, float* param, float* grad, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float wd, float gscale, int* step_dev, cudaStream_t st) {
@@ -289,10 +288,6 @@ static int launch(Comm* c, float* param, float* grad, float* m, float* v, long l
     if (param) allreduce_adam_kernel<true><<<c->ctas, DP_THREADS, 0, st>>>(p);
     else allreduce_adam_kernel<false><<<c->ctas, DP_THREADS, 0, st>>>(p);
     CMRL_CHECK_LAUNCH("allreduce_grads");
-    if (param) {
-        dp_bump_counter_kernel<<<1, 1, 0, st>>>(step_dev);
-        CMRL_CHECK_LAUNCH("allreduce_grads.bump");
-    }
     return 0;
 }
 

@@ -140,53 +140,90 @@ __global__ void mse_member_sums_kernel(const float* __restrict__ mean, const flo
     }
 }
 
-__global__ void adam_l2_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                               float* __restrict__ v, long long n, float lr_over_bc1, float beta1, float beta2,
-                               float eps, float wd, float gscale, float sqrt_bc2) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float pi = p[i];
-        float gi = fmaf(wd, pi, g[i] * gscale);
-        float mi = m[i];
-        mi = fmaf(1.0f - beta1, gi - mi, mi);                 // exp_avg.lerp_(grad, 1 - beta1)
-        float vi = fmaf((1.0f - beta2) * gi, gi, beta2 * v[i]);  // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+// Adam with the step counter in device memory (CUDA-graph replayable): t = step_dev[0] + 1; the last block to finish
+// advances the counter (step_dev[1] is its arrival ticket).  16-byte accesses when the four arrays are aligned.
+__device__ __forceinline__ float adam_l2_one(float pi, float g, float& mi, float& vi, float lr_over_bc1, float sqrt_bc2, float beta1,
+                                             float beta2, float eps, float wd, float gscale) {
+    const float gi = fmaf(wd, pi, g * gscale);
+    mi = fmaf(1.0f - beta1, gi - mi, mi);
+    vi = fmaf((1.0f - beta2) * gi, gi, beta2 * vi);
+    return pi - lr_over_bc1 * (mi / (sqrtf(vi) / sqrt_bc2 + eps));
+}
+__device__ __forceinline__ void adam_l2_range(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, long long n, int vec, float lr_over_bc1, float sqrt_bc2,
+                                              float beta1, float beta2, float eps, float wd, float gscale) {
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    const long long n4 = vec ? n / 4 : 0;
+    for (long long i = tid; i < n4; i += nth) {
+        const float4 pi = reinterpret_cast<const float4*>(p)[i], gi = reinterpret_cast<const float4*>(g)[i];
+        float4 mi = reinterpret_cast<const float4*>(m)[i], vi = reinterpret_cast<const float4*>(v)[i], o;
+        o.x = adam_l2_one(pi.x, gi.x, mi.x, vi.x, lr_over_bc1, sqrt_bc2, beta1, beta2, eps, wd, gscale);
+        o.y = adam_l2_one(pi.y, gi.y, mi.y, vi.y, lr_over_bc1, sqrt_bc2, beta1, beta2, eps, wd, gscale);
+        o.z = adam_l2_one(pi.z, gi.z, mi.z, vi.z, lr_over_bc1, sqrt_bc2, beta1, beta2, eps, wd, gscale);
+        o.w = adam_l2_one(pi.w, gi.w, mi.w, vi.w, lr_over_bc1, sqrt_bc2, beta1, beta2, eps, wd, gscale);
+        reinterpret_cast<float4*>(m)[i] = mi;
+        reinterpret_cast<float4*>(v)[i] = vi;
+        reinterpret_cast<float4*>(p)[i] = o;
+    }
+    for (long long i = 4 * n4 + tid; i < n; i += nth) {
+        float mi = m[i], vi = v[i];
+        p[i] = adam_l2_one(p[i], g[i], mi, vi, lr_over_bc1, sqrt_bc2, beta1, beta2, eps, wd, gscale);
         m[i] = mi;
         v[i] = vi;
-        float denom = sqrtf(vi) / sqrt_bc2 + eps;
-        p[i] = pi - lr_over_bc1 * (mi / denom);
     }
 }
-
-// Adam with the step counter in device memory (CUDA-graph replayable): t = *step_dev + 1; a trailing one-thread
-// kernel bumps the counter.
+__global__ void adam_l2_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                               long long n, float lr_over_bc1, float beta1, float beta2, float eps, float wd, float gscale,
+                               float sqrt_bc2, int vec) {
+    adam_l2_range(p, g, m, v, n, vec, lr_over_bc1, sqrt_bc2, beta1, beta2, eps, wd, gscale);
+}
 __global__ void adam_l2_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                    float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
-                                   float wd, float gscale, const int* __restrict__ step_dev) {
+                                   float wd, float gscale, int* step_dev, int vec) {
     __shared__ float s_lr_over_bc1, s_sqrt_bc2;
     if (threadIdx.x == 0) {
-        const double t = (double)(*step_dev + 1);
+        const double t = (double)(step_dev[0] + 1);
         s_lr_over_bc1 = (float)((double)lr / (1.0 - pow((double)beta1, t)));
         s_sqrt_bc2 = (float)sqrt(1.0 - pow((double)beta2, t));
     }
     __syncthreads();
-    const float lr_over_bc1 = s_lr_over_bc1, sqrt_bc2 = s_sqrt_bc2;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float pi = p[i];
-        float gi = fmaf(wd, pi, g[i] * gscale);
-        float mi = m[i];
-        mi = fmaf(1.0f - beta1, gi - mi, mi);
-        float vi = fmaf((1.0f - beta2) * gi, gi, beta2 * v[i]);
-        m[i] = mi;
-        v[i] = vi;
-        p[i] = pi - lr_over_bc1 * (mi / (sqrtf(vi) / sqrt_bc2 + eps));
+    adam_l2_range(p, g, m, v, n, vec, s_lr_over_bc1, s_sqrt_bc2, beta1, beta2, eps, wd, gscale);
+    last_block_add(step_dev, 1);
+}
+
+// acc[0] += sum(x[0..n)) in fp64, deterministic: per-block partial sums (fixed strided assignment), the last block to finish
+// adds them up in block order.  ws: [blocks] doubles then two ints (unused, arrival ticket), zero-initialised by the caller once.
+constexpr int SUM_BLOCKS = 64, SUM_THREADS = 512;
+__global__ void sum_acc_f64_kernel(const float* __restrict__ x, long long n, double* __restrict__ acc, double* __restrict__ ws) {
+    __shared__ double sh[SUM_THREADS / 32];
+    __shared__ bool last;
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += (double)x[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    int* ticket = reinterpret_cast<int*>(ws + SUM_BLOCKS);
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < SUM_THREADS / 32; ++w) t += sh[w];
+        ws[blockIdx.x] = t;
+        __threadfence();
+        last = atomicAdd(reinterpret_cast<unsigned*>(ticket + 1), 1u) == gridDim.x - 1;
+        if (last) {
+            __threadfence();
+            double tot = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) tot += reinterpret_cast<volatile double*>(ws)[b];
+            acc[0] += tot;
+            ticket[1] = 0;
+        }
     }
 }
-__global__ void bump_counter_kernel(int* c, int delta) { *c += delta; }
 
 // Bootstrap batch assembly on the device (BootstrapIterator.__next__ + _consolidate_batches,
 // cmrl/util/transition_iterator.py:14-28,131-139): row b of member e = transitions[member_idx[e, order[start + b]]]
 __global__ void bootstrap_gather_kernel(const float* __restrict__ obs, const float* __restrict__ act,
                                         const float* __restrict__ target, const int* __restrict__ member_idx,
-                                        const int* __restrict__ order, const int* __restrict__ start_dev, int B, int N,
+                                        const int* __restrict__ order, int* start_dev, int advance, int B, int N,
                                         int O, int A, int D, float* __restrict__ o_obs, float* __restrict__ o_act,
                                         float* __restrict__ o_target) {
     const int W = O + A + D;
@@ -201,6 +238,7 @@ __global__ void bootstrap_gather_kernel(const float* __restrict__ obs, const flo
         else if (c < O + A) o_act[row * A + (c - O)] = act[src * A + (c - O)];
         else o_target[row * D + (c - O - A)] = target[src * D + (c - O - A)];
     }
+    if (advance) last_block_add(start_dev, advance);
 }
 
 }  // namespace cmrl
@@ -212,11 +250,20 @@ extern "C" int cmrl_adam_l2_step_dev(float* param, const float* grad, float* exp
                                      float grad_scale, int* step_dev, void* stream) {
     CMRL_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev, "adam_l2_step_dev: null pointer");
     if (n == 0) return 0;
-    adam_l2_dev_kernel<<<ew_blocks(n), EW_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
-                                                                            beta2, eps, weight_decay, grad_scale, step_dev);
+    const int vec = ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0) ? 1 : 0;
+    adam_l2_dev_kernel<<<ew_blocks(n, 4), EW_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                               beta2, eps, weight_decay, grad_scale, step_dev, vec);
     CMRL_CHECK_LAUNCH("adam_l2_step_dev");
-    bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, 1);
-    CMRL_CHECK_LAUNCH("adam_l2_step_dev.bump");
+    return 0;
+}
+
+extern "C" int cmrl_sum_acc_f64(const float* x, long long n, double* acc, double* workspace, void* stream) {
+    CMRL_REQUIRE(x && acc && workspace && n >= 0, "sum_acc_f64: null pointer");
+    if (n == 0) return 0;
+    long long blocks = (n + SUM_THREADS * 8 - 1) / (SUM_THREADS * 8);
+    if (blocks > SUM_BLOCKS) blocks = SUM_BLOCKS;
+    sum_acc_f64_kernel<<<(int)blocks, SUM_THREADS, 0, (cudaStream_t)stream>>>(x, n, acc, workspace);
+    CMRL_CHECK_LAUNCH("sum_acc_f64");
     return 0;
 }
 
@@ -229,13 +276,9 @@ extern "C" int cmrl_bootstrap_gather(const float* obs, const float* act, const f
     int bx = (B * (O + A + D) + 255) / 256;
     if (bx > 64) bx = 64;
     dim3 grid(bx, E);
-    bootstrap_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(obs, act, target, member_idx, order, start_dev, B, N, O, A,
-                                                                  D, out_obs, out_act, out_target);
+    bootstrap_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(obs, act, target, member_idx, order, start_dev, advance, B, N,
+                                                                  O, A, D, out_obs, out_act, out_target);
     CMRL_CHECK_LAUNCH("bootstrap_gather");
-    if (advance) {
-        bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(start_dev, advance);
-        CMRL_CHECK_LAUNCH("bootstrap_gather.advance");
-    }
     return 0;
 }
 
@@ -327,9 +370,10 @@ extern "C" int cmrl_adam_l2_step(float* param, const float* grad, float* exp_avg
     if (n == 0) return 0;
     double bc1 = 1.0 - pow((double)beta1, (double)step);
     double bc2 = 1.0 - pow((double)beta2, (double)step);
-    adam_l2_kernel<<<ew_blocks(n), EW_THREADS, 0, (cudaStream_t)stream>>>(
+    const int vec = ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0) ? 1 : 0;
+    adam_l2_kernel<<<ew_blocks(n, 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
         param, grad, exp_avg, exp_avg_sq, n, (float)((double)lr / bc1), beta1, beta2, eps, weight_decay, grad_scale,
-        (float)sqrt(bc2));
+        (float)sqrt(bc2), vec);
     CMRL_CHECK_LAUNCH("adam_l2_step");
     return 0;
 }

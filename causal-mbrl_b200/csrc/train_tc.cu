@@ -621,6 +621,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
 constexpr int DW_THREADS = 18 * 32;  // (the dw kernel has no forwarder warp)
 constexpr int DW_NT = 112;          // output columns per CTA
 constexpr int DW_SUB = 32;          // rows (= K) per pipeline step
+constexpr int DW_DRAIN = 4;         // pipeline steps accumulated in tensor memory before the sum moves to registers (128 rows, 48 MMAs)
 constexpr uint32_t DW_KG = 144;     // bytes between K groups of 4 rows in the transposed operands (128 + 16: bank spread)
 constexpr uint32_t DW_MG = 8 * DW_KG;  // bytes between groups of 8 features
 constexpr uint32_t DW_RAW_A = 32 * 512, DW_RAW_B = (DW_NT / 4) * 512, DW_RAW = DW_RAW_A + DW_RAW_B;
@@ -676,7 +677,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
     uint64_t* bar_rempty = bars + 2;                 // [2] 16 warps
     uint64_t* bar_ofull = bars + 4;                  // [2] 16 warps
     uint64_t* bar_oempty = bars + 6;                 // [2] commit
-    uint64_t* bar_acc = bars + 8;
+    uint64_t* bar_accfull = bars + 8;                // [2] commit: the MMAs of an accumulation chunk are complete
+    uint64_t* bar_accempty = bars + 10;              // [2] 16 warps: the chunk was added to the register sums
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int net = blockIdx.y;
     // ---- which (layer, feature tile, column tile, batch slice) ------------------------------------------------------------
@@ -705,11 +707,14 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
             mbar_init(&bar_ofull[s], TF_EPI_WARPS);
             mbar_init(&bar_oempty[s], 1);
         }
-        mbar_init(bar_acc, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bar_accfull[s], 1);
+            mbar_init(&bar_accempty[s], TF_EPI_WARPS);
+        }
         fence_barrier_init();
     }
     if (warp == TF_WARP_MMA) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // rows of the transposed operands that no feature group fills must not hold NaN patterns: zero the operand stages once
@@ -745,27 +750,63 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
         TRACE_DECL;
         for (int i = 0; i < n_sub; ++i) {
             const int s = i & 1;
+            const int ch = i / DW_DRAIN, cb = ch & 1;  // accumulation chunk and its tensor-memory buffer
+            if (i % DW_DRAIN == 0 && ch >= 2) mbar_wait(&bar_accempty[cb], ((ch >> 1) - 1) & 1);
             mbar_wait(&bar_ofull[s], (i >> 1) & 1);
             tc_fence_after();
             TRACE(2);
             const uint32_t op = smem_u32(smem + DW_RAW_STAGES * DW_RAW + s * DW_OP);
             const uint32_t a_hi = op, a_lo = op + DW_OP_A, b_hi = op + 2 * DW_OP_A, b_lo = b_hi + DW_OP_B;
+            const uint32_t d_t = tmem + (uint32_t)cb * 128u;
 #pragma unroll
             for (int ks = 0; ks < DW_SUB / 8; ++ks) {
                 const uint32_t ko = (uint32_t)ks * 2 * DW_KG;
                 const uint64_t ah = umma_desc(a_hi + ko, DW_KG, DW_MG), bh = umma_desc(b_hi + ko, DW_KG, DW_MG);
-                const uint32_t first = (i == 0 && ks == 0) ? 0u : 1u;
+                const uint32_t first = (i % DW_DRAIN == 0 && ks == 0) ? 0u : 1u;
                 const uint64_t al = umma_desc(a_lo + ko, DW_KG, DW_MG), bl = umma_desc(b_lo + ko, DW_KG, DW_MG);
-                tf32_mma_ss_uni(tmem, al, bh, idesc, first);
-                tf32_mma_ss_uni(tmem, ah, bl, idesc, 1u);
-                tf32_mma_ss_uni(tmem, ah, bh, idesc, 1u);
+                tf32_mma_ss_uni(d_t, al, bh, idesc, first);
+                tf32_mma_ss_uni(d_t, ah, bl, idesc, 1u);
+                tf32_mma_ss_uni(d_t, ah, bh, idesc, 1u);
             }
             umma_commit_uni(&bar_oempty[s]);
+            if (i % DW_DRAIN == DW_DRAIN - 1 || i == n_sub - 1) umma_commit_uni(&bar_accfull[cb]);
         }
-        umma_commit_uni(bar_acc);
     } else {
         // ===================== transposers, then the epilogue ====================================================================
         const int tid = threadIdx.x;  // 0..511
+        // Running sums of this thread's part of the tile (TMEM lane = feature row q*32+lane, 16-column chunks cset and cset+4).
+        // The tensor cores accumulate with truncation: the error of one accumulator grows LINEARLY with the number of MMAs
+        // chained into it (measured 9e-6 relative after 256 rows, 4.8e-5 after 2 048), so a chunk of DW_DRAIN sub-steps is
+        // accumulated in tensor memory and then added, rounded to nearest, to fp32 registers -- two accumulators alternate,
+        // and a chunk is fetched two sub-steps after its last MMA was issued, so nothing waits.
+        const int q = warp & 3, cset = warp >> 2;
+        float sum[2][16];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[k][j] = 0.f;
+        const int n_chunks = (n_sub + DW_DRAIN - 1) / DW_DRAIN;
+        int drained = 0;
+        auto drain = [&](int ch) {
+            const int cb = ch & 1;
+            mbar_wait(&bar_accfull[cb], (ch >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int c = cset + 4 * k;
+                if (c < NT / 16) {
+                    uint32_t rawv[16];
+                    __syncwarp();
+                    v5_ld16_issue(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cb * 128u + (uint32_t)c * 16, rawv);
+                    v3_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[k][j] += __uint_as_float(rawv[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_accempty[cb]);
+        };
         TRACE_DECL;
         for (int i = 0; i < n_sub; ++i) {
             const int s = i & 1;
@@ -806,27 +847,24 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
                 mbar_arrive(&bar_rempty[s]);
             }
             if (warp == 0) TRACE(1);
+            if (i >= 1 && drained < (i - 1) / DW_DRAIN) drain(drained++);
         }
-        // ---- epilogue: TMEM lane = feature row of this tile, columns = output features.  A thread owns one ROW; rows of the
-        // gradient are far apart in memory, so the tile goes through shared memory (the operand stages are free now) and is
-        // written out with the lanes along the columns.
-        mbar_wait(bar_acc, 0);
-        tc_fence_after();
+        while (drained < n_chunks) drain(drained++);
+        // ---- epilogue: this thread's sums = feature row q*32+lane of the tile.  Rows of the gradient are far apart in memory, so
+        // the tile goes through shared memory and is written out with the lanes along the columns.  The operand stages are
+        // reused for it: the last chunk's accumulator-full barrier says every MMA that read them is complete.
         if (warp == 0) TRACE(1);
-        const int q = warp & 3, cset = warp >> 2;
+        asm volatile("bar.sync 1, %0;" ::"r"(TF_EPI_WARPS * 32) : "memory");  // every epilogue warp has seen that barrier
         float* otile = reinterpret_cast<float*>(smem + DW_RAW_STAGES * DW_RAW);
         constexpr int OS = DW_NT + 4;  // floats per staged row (16-byte aligned, conflict-free for the float4 writes)
-        for (int c = cset; c < NT / 16; c += 4) {
-            uint32_t rawv[16];
-            __syncwarp();
-            v5_ld16_issue(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c * 16, rawv);
-            v3_ld_wait();
-            float4* dst = reinterpret_cast<float4*>(otile + (q * 32 + lane) * OS + c * 16);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                dst[j] = n_sub == 0 ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                    : make_float4(__uint_as_float(rawv[4 * j]), __uint_as_float(rawv[4 * j + 1]), __uint_as_float(rawv[4 * j + 2]),
-                                                  __uint_as_float(rawv[4 * j + 3]));
+        for (int k = 0; k < 2; ++k) {
+            const int c = cset + 4 * k;
+            if (c < NT / 16) {
+                float4* dst = reinterpret_cast<float4*>(otile + (q * 32 + lane) * OS + c * 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_float4(sum[k][4 * j], sum[k][4 * j + 1], sum[k][4 * j + 2], sum[k][4 * j + 3]);
+            }
         }
         asm volatile("bar.sync 1, %0;" ::"r"(TF_EPI_WARPS * 32) : "memory");  // the 16 epilogue warps only
         float* wsp = p.ksplit > 1 ? p.ws + ((long long)slice * gridDim.y + net) * p.ext_total + p.ext_off[l] : nullptr;
@@ -847,7 +885,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) train_dw_kernel(const DwP p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == TF_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+    if (warp == TF_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
 // sums the batch-slice partials in slice order (deterministic) and scatters them to the gradient tensors
@@ -1005,18 +1043,21 @@ extern "C" int cmrl_train_dw(const float* scratch, int L, int P, int E, int B, i
     p.ext_total = ext;
     const int nets = P * E;
     CMRL_REQUIRE(nets <= 65535, "train_dw: too many nets");
-    // batch slices: enough CTAs for ~2 per SM, at least one row tile each, bounded by the workspace
-    // batch slices: the launch takes ceil(CTAs / SMs) waves of ceil(tiles / slices) row tiles each (one CTA per SM); slicing
-    // costs a reduction launch and workspace traffic, so it has to win by more than one tile time
+    // Batch slices.  The launch takes ceil(CTAs / SMs) waves (one CTA per SM); a CTA costs its row tiles plus a fixed part
+    // (set-up, pipeline fill, staging and writing its 128 x 112 tile: ~0.8 of a row tile, measured with the event trace), and
+    // slicing adds the reduction launch and ks x (workspace write + read).  The first version of this model charged slicing
+    // one tile time in total: at 4096 rows per member it cut the batch into 32 slices, 3 584 CTAs of one row tile each plus
+    // 400 MB of workspace traffic -- 0.28 ms where one wave of 112 CTAs takes 0.12 ms.
     int ksplit = 1;
     if (p.tiles_per_net > 1 && workspace != nullptr) {
         const long long ctas = (long long)work * nets, sms = num_sms();
         long long fit = workspace_floats / (ext * nets);
         if (fit > 64) fit = 64;
         if (fit > p.tiles_per_net) fit = p.tiles_per_net;
-        long long best = ((ctas + sms - 1) / sms) * p.tiles_per_net;
+        const double fixed = 0.8, reduce_launch = 1.0, reduce_per_slice = 0.35;
+        double best = (double)((ctas + sms - 1) / sms) * (p.tiles_per_net + fixed);
         for (long long ks = 2; ks <= fit; ++ks) {
-            const long long cost = ((ctas * ks + sms - 1) / sms) * ((p.tiles_per_net + ks - 1) / ks) + 1;
+            const double cost = (double)((ctas * ks + sms - 1) / sms) * ((p.tiles_per_net + ks - 1) / ks + fixed) + reduce_launch + reduce_per_slice * ks;
             if (cost < best) {
                 best = cost;
                 ksplit = (int)ks;

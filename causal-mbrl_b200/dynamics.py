@@ -201,13 +201,21 @@ class BaseDynamics:
         return (sums / float(n * d)).to(torch.float32).cpu()
 
     def train_step(self, mech: str, obs: torch.Tensor, act: torch.Tensor, target: torch.Tensor,
-                   want_loss: bool = True, grad_rows: Optional[int] = None, graphable: bool = False):  # fmt: skip
+                   want_loss: bool = True, grad_rows: Optional[int] = None, graphable: bool = False,
+                   data_ready=None):  # fmt: skip
         """One optimiser step on an ensemble batch (obs/act/target: [E,B,*] device tensors), equivalent to
         `loss = get_nll_loss(...); zero_grad(); loss.mean().backward(); step()` (base_dynamics.py:181-186).
         Returns the un-reduced loss [E,B,D] (None if not wanted).  grad_rows: global rows per member when the
-        batch is one shard of a data-parallel step."""
+        batch is one shard of a data-parallel step.  data_ready: called (once) right before the first kernel that reads
+        the batch -- the device-resident epoch assembles the batch on a side stream next to the weight packing and joins
+        the streams there."""
         model = getattr(self, mech)
         optim = getattr(self, "{}_optimizer".format(mech))
+        if data_ready is not None and ((model.deterministic or any(p.requires_grad for p in model._bounds() if p is not None)
+                                        or not hasattr(model, "hidden_layers")) or obs.shape[1] == 0 or obs.dim() != 3
+                                       or ops.fused_train_plan(model, obs.shape[0], obs.shape[1]) is None):
+            data_ready()  # only the fused plan has work (the packing) that does not depend on the batch
+            data_ready = None
         if obs.shape[1] == 0:
             # data parallel, ragged last batch with fewer rows than ranks: this rank has no rows, but it still has to
             # contribute (zero) gradients to the all-reduce and apply the same Adam update as every other rank
@@ -233,7 +241,8 @@ class BaseDynamics:
             # forward, Gaussian head, NLL, dz chain and every weight gradient on tcgen05 (3xTF32): three launches
             mn, mx = model._bounds()
             rows = B if grad_rows is None else grad_rows
-            loss = plan.step(obs, act, target, mn, mx, model._nll_reg(), 1.0 / float(E * rows * model._head_dim), want_loss)
+            loss = plan.step(obs, act, target, mn, mx, model._nll_reg(), 1.0 / float(E * rows * model._head_dim), want_loss,
+                             after_pack=data_ready)
             self._sync_and_step(model, optim, graphable)
             return loss
         params = model._stack_params()
@@ -454,7 +463,7 @@ class _DeviceEpochRunner:
         self.N = self.obs.shape[0]
         self.member_idx = torch.from_numpy(np.ascontiguousarray(dataset.member_indices, dtype=np.int32)).to(dev)
         self.order = torch.zeros(self.N, dtype=torch.int32, device=dev)
-        self.start = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.start = torch.zeros(2, dtype=torch.int32, device=dev)  # [first row of the next batch, the gather kernel's arrival ticket]
         E, B = dataset.ensemble_size, dataset.batch_size
         self.E, self.B = E, B
         # data parallel (every rank holds the same set and epoch order): this rank gathers and trains only its row slice
@@ -465,6 +474,8 @@ class _DeviceEpochRunner:
         self.b_act = torch.empty((E, Bl, self.act.shape[1]), device=dev)
         self.b_tgt = torch.empty((E, Bl, self.target.shape[1]), device=dev)
         self.loss_sum = torch.zeros((), device=dev, dtype=torch.float64)
+        self.sum_ws = torch.zeros(66, device=dev, dtype=torch.float64)
+        self.side = torch.cuda.Stream(device=dev)
         self.graph = None
         self._order_pinned = [torch.empty(self.N, dtype=torch.int32).pin_memory() for _ in range(2)]
         self._order_flip = 0
@@ -479,12 +490,18 @@ class _DeviceEpochRunner:
 
     def _step(self):
         # `start` points at this rank's first row of the batch and advances by the global batch size
+        # the batch is assembled on a side stream while the main stream packs the weights (fork / join: also under capture)
+        main = torch.cuda.current_stream()
+        join = None
         if self.Bl > 0:
-            ops.bootstrap_gather(self.obs, self.act, self.target, self.member_idx, self.order, self.start, self.B, self.Bl,
-                                 self.b_obs, self.b_act, self.b_tgt)  # fmt: skip
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                ops.bootstrap_gather(self.obs, self.act, self.target, self.member_idx, self.order, self.start, self.B, self.Bl,
+                                     self.b_obs, self.b_act, self.b_tgt)  # fmt: skip
+            join = lambda: main.wait_stream(self.side)  # noqa: E731
         loss = self.dyn.train_step(self.mech, self.b_obs, self.b_act, self.b_tgt, want_loss=True, graphable=True,
-                                   grad_rows=self.B if self.dyn.dp_group is not None else None)  # fmt: skip
-        self.loss_sum += loss.sum(dtype=torch.float64)
+                                   grad_rows=self.B if self.dyn.dp_group is not None else None, data_ready=join)  # fmt: skip
+        ops.sum_acc_f64(loss, self.loss_sum, self.sum_ws)
 
     def run_epoch(self):
         ds = self.dataset
@@ -494,7 +511,7 @@ class _DeviceEpochRunner:
             staged = (ds._order, self._stage_order(ds._order))
         self._staged_order = None
         self.order.copy_(staged[1], non_blocking=True)
-        self.start.fill_(self.row_slice.start)
+        self.start[:1].fill_(self.row_slice.start)
         self.loss_sum.zero_()
         model = getattr(self.dyn, self.mech)
         model._nll_reg()  # host-side constant, cached before any capture
@@ -536,7 +553,8 @@ class _DeviceEpochRunner:
             rows = self.member_idx.long()[:, idx]  # [E, local rem]
             loss = self.dyn.train_step(self.mech, self.obs[rows], self.act[rows], self.target[rows], want_loss=True,
                                        graphable=True, grad_rows=rem if dp else None)  # fmt: skip
-            self.loss_sum += loss.sum(dtype=torch.float64)
+            if loss.numel() > 0:
+                ops.sum_acc_f64(loss.contiguous(), self.loss_sum, self.sum_ws)
         ds._current_batch = len(ds)  # the iterator is exhausted, like after a `for batch in dataset` loop
         # the GPU is still executing this epoch: draw and stage the next epoch's permutation meanwhile
         nxt = ds.prefetch_order()

@@ -306,6 +306,11 @@ def adam_l2_step_dev(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, we
               step_dev.data_ptr(), _stream())  # fmt: skip
 
 
+def sum_acc_f64(x, acc, workspace):
+    """acc (float64 scalar tensor) += x.sum() on the device, deterministic; workspace: 66 zero-initialised doubles."""
+    _lib.call("cmrl_sum_acc_f64", x.data_ptr(), x.numel(), acc.data_ptr(), workspace.data_ptr(), _stream())
+
+
 def bootstrap_gather(obs, act, target, member_idx, order, start_dev, advance, B, out_obs, out_act, out_target):
     E, N = member_idx.shape
     _lib.call("cmrl_bootstrap_gather", obs.data_ptr(), act.data_ptr(), target.data_ptr(), member_idx.data_ptr(),
@@ -543,11 +548,14 @@ class FusedTrainPlan:
                   self.head_outputs, self.act, self.dw_ptrs, self.db_ptrs, _ptr(m), self.mask_str[0], self.mask_str[1],
                   _ptr(self.dw_ws), 0 if self.dw_ws is None else self.dw_ws.numel(), _stream())  # fmt: skip
 
-    def step(self, obs, act, target, mn, mx, reg, g_scale, want_loss=True):
-        """pack -> fused forward / NLL / dz chain -> weight gradients, all on the current stream; returns the loss."""
+    def step(self, obs, act, target, mn, mx, reg, g_scale, want_loss=True, after_pack=None):
+        """pack -> fused forward / NLL / dz chain -> weight gradients, all on the current stream; returns the loss.
+        after_pack: called between the packing (which reads only the weights) and the first kernel that reads the batch."""
         obs, act, target = _rows_contig(_req(obs, "obs"), "obs"), _rows_contig(_req(act, "act"), "act"), _rows_contig(_req(target, "target"), "target")
         loss = torch.empty((self.E, self.B, self.head_dim), device=obs.device, dtype=torch.float32) if want_loss else None
         self.run_pack()
+        if after_pack is not None:
+            after_pack()
         self.run_fused(obs, act, target, mn, mx, reg, g_scale, loss)
         self.run_dw()
         return loss

@@ -35,13 +35,13 @@ class FusedAdamL2(torch.optim.Optimizer):
         g = self.param_groups[0]
         p, grad = self._arena()
         if self._step_dev is not None:  # a graph replay may have advanced the device counter
-            self._step = int(self._step_dev.item())
+            self._step = int(self._step_dev[0].item())
         self._step += 1
         ops.adam_l2_step(p, grad, self._exp_avg, self._exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
                          g["weight_decay"], self._step, grad_scale)  # fmt: skip
         if self._step_dev is not None:
             # the device counter is never freed or replaced: captured step graphs hold its address
-            self._step_dev.fill_(self._step)
+            self._step_dev[:1].fill_(self._step)
         self._mark_weights_changed()
         return loss
 
@@ -59,8 +59,8 @@ class FusedAdamL2(torch.optim.Optimizer):
     def prepare_graphable(self):
         """Allocate the moment buffers and the device step counter (must happen outside a graph capture)."""
         p, _ = self._arena()
-        if self._step_dev is None:
-            self._step_dev = torch.tensor([self._step], dtype=torch.int32, device=p.device)
+        if self._step_dev is None:  # [steps taken, arrival ticket of the kernel's last-block update]
+            self._step_dev = torch.tensor([self._step, 0], dtype=torch.int32, device=p.device)
 
     @torch.no_grad()
     def step_graphable(self, grad_scale: float = 1.0):
@@ -85,7 +85,7 @@ class FusedAdamL2(torch.optim.Optimizer):
 
     @property
     def step_count(self):
-        return self._step if self._step_dev is None else int(self._step_dev.item())
+        return self._step if self._step_dev is None else int(self._step_dev[0].item())
 
     def state_dict(self):
         return {
@@ -98,7 +98,7 @@ class FusedAdamL2(torch.optim.Optimizer):
     def load_state_dict(self, state):
         self._step = state["step"]
         if self._step_dev is not None:
-            self._step_dev.fill_(self._step)
+            self._step_dev[:1].fill_(self._step)
         self._exp_avg = None if state["exp_avg"] is None else state["exp_avg"].clone()
         self._exp_avg_sq = None if state["exp_avg_sq"] is None else state["exp_avg_sq"].clone()
         for g, s in zip(self.param_groups, state["param_groups"]):

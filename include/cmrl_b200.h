@@ -131,17 +131,24 @@ int cmrl_adam_l2_step(float* param, const float* grad, float* exp_avg, float* ex
                       float beta1, float beta2, float eps, float weight_decay, float grad_scale, int step,
                       void* stream);
 
-/* Same update with the 1-based step counter kept in device memory (*step_dev is the number of steps already
- * taken; incremented by the call), so a captured CUDA graph can be replayed step after step. */
+/* Same update with the step counter kept in device memory, so a captured CUDA graph can be replayed step after step.
+ * step_dev points at TWO ints: [0] = steps already taken (the call increments it: the last block of the kernel to finish
+ * does, there is no trailing launch), [1] = that block's arrival ticket, zero between calls. */
 int cmrl_adam_l2_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                           float beta1, float beta2, float eps, float weight_decay, float grad_scale, int* step_dev,
                           void* stream);
+
+/* acc[0] += sum of x[0..n) in fp64, deterministic (fixed assignment of elements to blocks, partial sums added in block
+ * order by the last block to finish): the running epoch loss of BaseDynamics.train (`loss.mean()` of every batch,
+ * base_dynamics.py:181-187) without a host round trip.  workspace: 66 doubles, zeroed once by the caller. */
+int cmrl_sum_acc_f64(const float* x, long long n, double* acc, double* workspace, void* stream);
 
 /* Device-side bootstrap batch assembly (BootstrapIterator.__next__ + _consolidate_batches,
  * cmrl/util/transition_iterator.py:14-28,131-139): for member e and row b < B
  *   src = member_idx[e, order[min(*start_dev + b, N-1)]];  out_*[e,b,:] = {obs, act, target}[src,:]
  * obs [N,O], act [N,A], target [N,D] are the device-resident training set; member_idx int32 [E,N], order int32 [N].
- * advance != 0 adds it to *start_dev after the gather (graph-replayable epoch loop). */
+ * start_dev points at TWO ints: [0] = first row, [1] = arrival ticket (zero between calls); advance != 0 is added to
+ * start_dev[0] by the last block of the gather to finish (graph-replayable epoch loop, no trailing launch). */
 int cmrl_bootstrap_gather(const float* obs, const float* act, const float* target, const int* member_idx,
                           const int* order, int* start_dev, int advance, int E, int B, int N, int O, int A, int D,
                           float* out_obs, float* out_act, float* out_target, void* stream);
@@ -278,8 +285,8 @@ int cmrl_train_dw(const float* scratch, int L, int P, int E, int B, int in_size,
  * cmrl_dp_comm_create: allocates the buffer for arenas of up to max_floats floats on the current device and writes its
  *   64-byte cudaIpcMemHandle_t to ipc_handle_out.  cmrl_dp_comm_connect: all_handles = world x 64 bytes in rank order.
  * cmrl_allreduce_grads: grad[0..n) <- sum over ranks, in rank order, bit-identical on every rank; ONE launch.
- * cmrl_allreduce_grads_adam: the same exchange fused with cmrl_adam_l2_step_dev (identical arithmetic); *step_dev is
- *   incremented by the call.  Both are stream-ordered and CUDA-graph replayable (epochs live in device memory); every
+ * cmrl_allreduce_grads_adam: the same exchange fused with cmrl_adam_l2_step_dev (identical arithmetic; step_dev as there:
+ *   two ints).  Both are stream-ordered and CUDA-graph replayable (epochs live in device memory); every
  *   rank must make the same sequence of calls with the same n.  A peer that does not arrive within ~20 s raises the
  *   communicator's error word (cmrl_dp_comm_error, synchronises) instead of hanging the device. */
 int cmrl_dp_comm_create(int rank, int world, long long max_floats, void** comm_out, unsigned char* ipc_handle_out);

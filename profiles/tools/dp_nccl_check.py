@@ -162,7 +162,7 @@ n_arena = int(dyn.transition._n_trainable)
 peer = dyn._peer_sync if dyn._peer_sync is not None else PeerGradSync(dist.group.WORLD, n_arena, dev)
 g_buf = torch.randn(n_arena, device=dev) * 1e-3
 p_buf, m_buf, v_buf = torch.randn(n_arena, device=dev), torch.zeros(n_arena, device=dev), torch.zeros(n_arena, device=dev)
-step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+step_dev = torch.zeros(2, dtype=torch.int32, device=dev)  # [steps taken, arrival ticket]
 # correctness of the bare exchange against NCCL on the same data
 g_ref = g_buf.clone(); dist.all_reduce(g_ref)
 g_mine = g_buf.clone(); peer.allreduce(g_mine); torch.cuda.synchronize(); peer.check()

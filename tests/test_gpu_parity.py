@@ -1117,10 +1117,12 @@ def _fused_vs_oracle(cm, H, B, act_cfg_, seed):
             assert record_max(tag + " weights after Adam", rel_err(v.cpu().numpy(), p0[k])) < TOL, k
 
 
-@pytest.mark.parametrize("H,B,cfg", [(200, 256, SILU), (200, 300, SILU), (200, 1500, SILU), (64, 130, None), (24, 1, SILU), (239, 257, SILU)])
+@pytest.mark.parametrize("H,B,cfg", [(200, 256, SILU), (200, 300, SILU), (200, 1500, SILU), (64, 130, None), (24, 1, SILU), (239, 257, SILU),
+                                     (200, 12000, SILU)])
 def test_fused_tcgen05_train_step_vs_oracle(cm, H, B, cfg):
-    """The reference batch size and shape (C1: 4 x 200, 256 rows per member), a ragged batch, a batch that splits the
-    weight-gradient GEMMs over batch slices, ReLU, a single row and the widest supported hidden layer."""
+    """The reference batch size and shape (C1: 4 x 200, 256 rows per member), a ragged batch, a batch of several row tiles,
+    ReLU, a single row, the widest supported hidden layer, and a batch large enough (94 row tiles) for the weight-gradient
+    GEMMs to split it into slices whose partial sums a second launch adds up."""
     _fused_vs_oracle(cm, H, B, cfg, seed=H + B)
 
 
