@@ -671,8 +671,15 @@ def other_configs(cm, ctx, args, dyn_c2, act_host_c2):
     v, ms, _ = time_device_steps(cm, ctx, env32, torch.from_numpy(act_host_c2).to(dev), 5, 3)
     ev, ems = time_host_steps(ctx, env32, act_host_c2, 5, 3)
     out["C2_fp32_tier"] = {"workload": WORKLOAD % N, "value": v, "ms_per_step": ms, "e2e": ev, "e2e_ms_per_step": ems, "unit": "transitions/s",
-                           "precision": "fp32 (1e-5 parity tier of the rollout)"}  # fmt: skip
+                           "precision": "fp32 (the VecFakeEnv default, 1e-5 parity tier): train_fused_kernel in rollout mode, tcgen05 kind::tf32 "
+                                        "with hi/lo split operands (3xTF32)",
+                           "tflops_algorithmic": FLOP_PER_TRANSITION_SELECTED * v / 1e12}  # fmt: skip
     del env32
+    envff, _ = make_env(cm, ctx, dyn_c2, N, O, "ffma")
+    v, ms, _ = time_device_steps(cm, ctx, envff, torch.from_numpy(act_host_c2).to(dev), 3, 2)
+    out["C2_ffma_tier"] = {"workload": WORKLOAD % N, "value": v, "ms_per_step": ms, "unit": "transitions/s",
+                           "precision": "ffma (CUDA-core fp32 kernels, bit-identical to the all-member query path)"}  # fmt: skip
+    del envff
     for prec in ("f16", "fp32"):
         envd, _ = make_env(cm, ctx, dyn_c2, N, O, prec, throughput_knobs=False)
         ev, ems = time_host_steps(ctx, envd, act_host_c2, 3, 2)

@@ -199,7 +199,30 @@ struct TrainP {
     int stages;
     int lo_tmem;  // the lo parts of the A chunks live in tensor memory (columns left over by the accumulators) instead of shared memory
     uint32_t stage_bytes, w_off, bar_off;
+    // inference (rollout) mode: rows of member e are the envs perm[row_off[e] .. row_off[e+1]) (cmrl_member_bucket); only the
+    // forward phases run, nothing is saved, the head writes pred[env, :] = mean (+ obs) + sqrt(exp(logvar)) * noise[env, :]
+    const int *perm, *row_off;
+    const float* noise;
+    float* pred;
+    int D;
 };
+constexpr int TF_MAX_E = 64;
+// pair (cluster work item) -> (sub-net pp, member e, index of the tile pair inside the member's rows); pref = prefix sums of the
+// members' pair counts (uniform in training, by bucket size in rollouts)
+struct PairInfo {
+    int pp, e, tp;
+};
+__device__ __forceinline__ PairInfo pair_info(const int* pref, int E, int pair) {
+    const int per = pref[E];
+    PairInfo r;
+    r.pp = pair / per;
+    const int rem = pair - r.pp * per;
+    int e = 0;
+    while (pref[e + 1] <= rem) ++e;
+    r.e = e;
+    r.tp = rem - pref[e];
+    return r;
+}
 
 // bars: [0,S) W_FULL (local, tx), [S,2S) W_EMPTY (both CTAs, commit), [2S,3S) W_READY (leader, both halves landed),
 //       [3S,3S+R) A_FULL (leader, 2 x 4 warps), [3S+R,3S+2R) A_EMPTY (both, commit), 3S+2R D_FULL (both, commit)
@@ -272,11 +295,12 @@ __device__ __forceinline__ void split_store_pair(const ARing& r, uint32_t slot, 
 // ACT is a template parameter: with a run-time activation switch the unrolled 16-element epilogue bodies compiled to a chain of
 // branches per ELEMENT and the epilogue (not the tensor pipe, not the weight stream) paced the kernel at ~12k cycles per phase
 // (profiles/r2_train_trace_attribution.txt).
-template <int ACT, bool LO_TMEM>
+template <int ACT, bool LO_TMEM, bool INFER>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train_fused_kernel(const TrainP p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ volatile uint32_t a_ready_seq, w_ready_n;  // leader: chunks whose A operand / weight stage are known to be ready
+    __shared__ int s_pref[TF_MAX_E + 1], s_rowoff[TF_MAX_E + 1];
     const Geom& g = p.g;
     const int S = p.stages;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
@@ -288,10 +312,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
     uint64_t* bar_dfull = bars + 3 * S + 2 * TF_A_SLOTS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = v3_ctarank();
-    const int n_pairs = p.P * p.E * p.pairs_per_net;          // work items of a cluster: two row tiles of one net
     const int pair0 = blockIdx.x / 2, pair_step = gridDim.x / 2;
 
+    if (INFER) {
+        if ((int)threadIdx.x <= p.E) s_rowoff[threadIdx.x] = p.row_off[threadIdx.x];
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
+        s_pref[0] = 0;
+        for (int e = 0; e < p.E; ++e) {
+            const int tiles = INFER ? (s_rowoff[e + 1] - s_rowoff[e] + TF_ROWS - 1) / TF_ROWS : 0;
+            s_pref[e + 1] = s_pref[e] + (INFER ? (tiles + 1) / 2 : p.pairs_per_net);
+        }
         a_ready_seq = 0;
         w_ready_n = 0;
         for (int s = 0; s < S; ++s) {
@@ -317,6 +349,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
     const uint32_t tmem = tmem_slot;
     const uint32_t col_head = (uint32_t)(2 * g.HP), col_alo = (uint32_t)(2 * g.HP + g.NH);
     const int hi_only = p.passes == 1;
+    const int n_pairs = p.P * s_pref[p.E];  // work items of a cluster: two row tiles of one net
 
     if (warp == TF_WARP_W) {
         // ===================== weight producer: this CTA's half (N/2 output rows, hi | lo) of every 16-deep K chunk =================
@@ -324,7 +357,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
             uint32_t n = 0;
             TRACE_DECL;
             for (int pair = pair0; pair < n_pairs; pair += pair_step) {
-                const float* blob = p.packed + (long long)(pair / p.pairs_per_net) * g.blob_floats;
+                const PairInfo pi = pair_info(s_pref, p.E, pair);
+                const float* blob = p.packed + (long long)(pi.pp * p.E + pi.e) * g.blob_floats;
                 for (int ph = 0; ph < g.n_ph; ++ph) {
                     const uint32_t half = 64u * (uint32_t)g.ph_n[ph];          // bytes of one CTA's half of a chunk: hi | lo
                     const uint32_t bytes = hi_only ? half / 2 : half;           // the lo part is not read by plain TF32
@@ -450,16 +484,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
         int fine_n = 0;
 #endif
         for (int pair = pair0; pair < n_pairs; pair += pair_step) {
-            const int net = pair / p.pairs_per_net, tile = (pair % p.pairs_per_net) * 2 + (int)rank;  // may be a padding tile: no valid row
-            const int pp = net / p.E, e = net % p.E;
+            const PairInfo pi = pair_info(s_pref, p.E, pair);
+            const int pp = pi.pp, e = pi.e, net = pp * p.E + e;
+            const int tile = pi.tp * 2 + (int)rank;  // may be a padding tile: no valid row
             const int grow = tile * TF_ROWS + row;
-            const bool valid = grow < p.B;
-            const long long rr = valid ? grow : 0;
-            float* sc = p.scratch + ((long long)net * 2 * p.pairs_per_net + tile) * g.item_floats;
+            const bool valid = grow < (INFER ? s_rowoff[e + 1] - s_rowoff[e] : p.B);
+            // training: row grow of member e's dense batch; rollout: the env this bucketed row stands for
+            const long long rr = !valid ? 0 : INFER ? (long long)p.perm[s_rowoff[e] + grow] : grow;
+            float* sc = INFER ? nullptr : p.scratch + ((long long)net * 2 * p.pairs_per_net + tile) * g.item_floats;
             // ---- layer-0 operand: [obs | action | 1 | 0...] -------------------------------------------------------------------
             {
-                const float* po = p.obs + e * p.obs_se + rr * p.O;
-                const float* pa = p.actn + e * p.act_se + rr * p.A;
+                const float* po = p.obs + (INFER ? 0 : e * p.obs_se) + rr * p.O;
+                const float* pa = p.actn + (INFER ? 0 : e * p.act_se) + rr * p.A;
 #pragma unroll 1
                 for (int c = cset; c < g.K0P / 16; c += 4) {
                     float v[16];
@@ -472,7 +508,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
                         else if (k == g.in0) x = 1.0f;
                         v[i] = x;
                     }
-                    save_chunk(sc + g.off_x, q, lane, g.K0P / 4, c, v);
+                    if (!INFER) save_chunk(sc + g.off_x, q, lane, g.K0P / 4, c, v);
                     split_store_chunk<LO_TMEM>(ring, aring_acquire(ring, seq_base + c), v);
                     aring_publish<LO_TMEM>(ring, seq_base + c, lane);
                 }
@@ -497,7 +533,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
                         // other (TMEM read, global stores, MUFU, shared-memory stores: ~3.3k cycles per round of 4 chunks).  Order
                         // per chunk: the NEXT chunk's TMEM load is in flight, the activations (MUFU) are issued BEFORE the global
                         // stores of z so that both pipes work at the same time.
-                        float* zt = sc + g.off_z[l];
+                        float* zt = INFER ? nullptr : sc + g.off_z[l];
                         uint32_t raw[16];
                         __syncwarp();
                         v5_ld16_issue(acc_t + (uint32_t)cset * 16, raw);
@@ -516,7 +552,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
 #pragma unroll
                             for (int i = 0; i < 16; ++i) a[i] = act_fwd_fast(z[i], ACT);
                             TRACE_FINE(warp == 0 && ph == 1);
-                            save_chunk(zt, q, lane, g.HP / 4, c, z);  // pre-activations: the dz chain and the dw kernel re-activate
+                            if (!INFER) save_chunk(zt, q, lane, g.HP / 4, c, z);  // pre-activations: the dz chain and the dw kernel re-activate
                             TRACE_FINE(warp == 0 && ph == 1);
                             if (c == ones_c) {  // the next layer's bias input: hidden unit H is 1.0 (a warp-uniform patch of one element)
 #pragma unroll
@@ -529,6 +565,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
                             TRACE_FINE(warp == 0 && ph == 1);
                             aring_publish<LO_TMEM>(ring, seq_base + c, lane);
                             TRACE_FINE(warp == 0 && ph == 1);
+                        }
+                    } else if (INFER) {
+                        // ---- rollout head: mean (+ residual) + sqrt(exp(soft-clamped logvar)) * noise, scattered to the env's row
+                        // (fake_env.py:205-215 over plain_transition.py:111-120); columns 2d = mean_d, 2d+1 = logvar_d
+                        const uint32_t h_t = tmem + lane_off + col_head;
+#pragma unroll 1
+                        for (int d = 0; d < Dn; ++d) {
+                            uint32_t r0, r1;
+                            __syncwarp();
+                            tmem_ld2(h_t + (uint32_t)(2 * d), r0, r1);
+                            v3_ld_wait();
+                            if (valid) {
+                                const int od = p.layout == CMRL_HEAD_PARALLEL ? pp : d;
+                                float m = __uint_as_float(r0);
+                                if (p.residual) m += p.obs[rr * p.O + od];
+                                if (p.noise) {
+                                    const int bi = p.bounds_n == 1 ? 0 : od;
+                                    const float lv = soft_clamp_logvar(__uint_as_float(r1), p.min_logvar[bi], p.max_logvar[bi]);
+                                    m += sqrtf(expf(lv)) * p.noise[rr * p.D + od];
+                                }
+                                p.pred[rr * p.D + od] = m;
+                            }
                         }
                     } else if (kind == PH_DX) {
                         // dz = (dz_next . W^T) * act'(z): act'(z) does not depend on the accumulator, so it is evaluated (MUFU) while
@@ -956,6 +1014,48 @@ extern "C" int cmrl_train_pack_tf32(const float* const* weights, const float* co
     return 0;
 }
 
+// shared-memory plan, kernel attributes and launch of train_fused_kernel (training step or rollout mode)
+template <bool INFER>
+static int launch_fused_t(TrainP& p, int act, int clusters, uint32_t smem_bytes, cudaStream_t st) {
+#define CMRL_TF_LAUNCH(A)                                                                              \
+    do {                                                                                               \
+        if (p.lo_tmem) train_fused_kernel<A, true, INFER><<<2 * clusters, TF_THREADS, smem_bytes, st>>>(p); \
+        else train_fused_kernel<A, false, INFER><<<2 * clusters, TF_THREADS, smem_bytes, st>>>(p);          \
+    } while (0)
+    static cmrl::PerDeviceOnce attr_once;
+    int attr_dev = 0;
+    if (attr_once.pending(&attr_dev)) {
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_IDENTITY, false, INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_RELU, false, INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_SILU, false, INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_IDENTITY, true, INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_RELU, true, INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_SILU, true, INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr_once.done(attr_dev);
+    }
+    if (act == CMRL_ACT_SILU) CMRL_TF_LAUNCH(CMRL_ACT_SILU);
+    else if (act == CMRL_ACT_RELU) CMRL_TF_LAUNCH(CMRL_ACT_RELU);
+    else CMRL_TF_LAUNCH(CMRL_ACT_IDENTITY);
+#undef CMRL_TF_LAUNCH
+    CMRL_CHECK_LAUNCH(INFER ? "mlp_rollout_tf32" : "train_fused");
+    return 0;
+}
+static int launch_fused(TrainP& p, int act, long long max_pairs, bool infer, cudaStream_t st) {
+    p.w_off = TF_A_SLOTS * TF_A_SLOT;
+    p.stage_bytes = 64u * (uint32_t)p.g.HP;  // one CTA's half (N/2 rows) of a 16-deep chunk, hi | lo
+    int stages = (int)((SMEM_LIMIT - 512 - p.w_off) / p.stage_bytes);
+    if (stages > 10) stages = 10;
+    CMRL_REQUIRE(stages >= 2, "train_fused: hidden width %d leaves no room for a weight ring", p.g.H);
+    p.stages = stages;
+    p.bar_off = p.w_off + (uint32_t)stages * p.stage_bytes;
+    const uint32_t smem_bytes = p.bar_off + (3 * stages + 2 * TF_A_SLOTS + 1) * 8;
+    // tensor-memory columns: two accumulators, the head accumulator, then (if they fit) the lo parts of the A-chunk ring
+    p.lo_tmem = 2 * p.g.HP + p.g.NH + 16 * TF_A_SLOTS <= 512 ? 1 : 0;
+    CMRL_REQUIRE(max_pairs < (1ll << 30), "train_fused: too many row tiles");
+    const int clusters = (int)(max_pairs < num_sms() / 2 ? (max_pairs < 1 ? 1 : max_pairs) : num_sms() / 2);
+    return infer ? launch_fused_t<true>(p, act, clusters, smem_bytes, st) : launch_fused_t<false>(p, act, clusters, smem_bytes, st);
+}
+
 extern "C" int cmrl_train_fused(const float* packed, int L, int P, int E, int B, int O, int A, int hidden, int head_dim, int layout, int act,
                                 int residual, int passes, const float* obs, long long obs_se, const float* actn, long long act_se,
                                 const float* target, long long tgt_se, int tgt_ld, const float* min_logvar, const float* max_logvar,
@@ -968,6 +1068,7 @@ extern "C" int cmrl_train_fused(const float* packed, int L, int P, int E, int B,
     CMRL_REQUIRE(layout == CMRL_HEAD_PLAIN ? P == 1 : P == head_dim, "train_fused: P must be 1 (plain head) or head_dim (parallel head)");
     CMRL_REQUIRE(passes == 1 || passes == 3, "train_fused: passes must be 1 (TF32) or 3 (3xTF32)");
     CMRL_REQUIRE(B >= 1 && E >= 1, "train_fused: empty batch");
+    CMRL_REQUIRE(E <= TF_MAX_E, "train_fused: at most %d members", TF_MAX_E);
     CMRL_REQUIRE(bounds_n == 1 || bounds_n == head_dim, "train_fused: logvar bounds must have 1 or head_dim entries");
     CMRL_REQUIRE(act == CMRL_ACT_IDENTITY || act == CMRL_ACT_RELU || act == CMRL_ACT_SILU, "train_fused: unsupported activation");
     p.packed = packed; p.P = P; p.E = E; p.B = B; p.O = O; p.A = A; p.layout = layout; p.act = act; p.residual = residual; p.passes = passes;
@@ -976,41 +1077,31 @@ extern "C" int cmrl_train_fused(const float* packed, int L, int P, int E, int B,
     p.loss = loss; p.loss_ld = head_dim; p.scratch = scratch;
     p.tiles_per_net = (B + TF_ROWS - 1) / TF_ROWS;
     p.pairs_per_net = (p.tiles_per_net + 1) / 2;
-    p.w_off = TF_A_SLOTS * TF_A_SLOT;
-    p.stage_bytes = 64u * (uint32_t)p.g.HP;  // one CTA's half (N/2 rows) of a 16-deep chunk, hi | lo
-    int stages = (int)((SMEM_LIMIT - 512 - p.w_off) / p.stage_bytes);
-    if (stages > 10) stages = 10;
-    CMRL_REQUIRE(stages >= 2, "train_fused: hidden width %d leaves no room for a weight ring", hidden);
-    p.stages = stages;
-    p.bar_off = p.w_off + (uint32_t)stages * p.stage_bytes;
-    const uint32_t smem_bytes = p.bar_off + (3 * stages + 2 * TF_A_SLOTS + 1) * 8;
-    static cmrl::PerDeviceOnce attr_once;
-    int attr_dev = 0;
-    if (attr_once.pending(&attr_dev)) {
-        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_IDENTITY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_RELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_SILU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_IDENTITY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_RELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        CMRL_CUDA(cudaFuncSetAttribute(train_fused_kernel<CMRL_ACT_SILU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        attr_once.done(attr_dev);
-    }
-    // tensor-memory columns: two accumulators, the head accumulator, then (if they fit) the lo parts of the A-chunk ring
-    p.lo_tmem = 2 * p.g.HP + p.g.NH + 16 * TF_A_SLOTS <= 512 ? 1 : 0;
-    const long long pairs = (long long)P * E * p.pairs_per_net;
-    CMRL_REQUIRE(pairs < (1ll << 30), "train_fused: too many row tiles");
-    const int clusters = (int)(pairs < num_sms() / 2 ? pairs : num_sms() / 2);
-#define CMRL_TF_LAUNCH(A)                                                                                              \
-    do {                                                                                                               \
-        if (p.lo_tmem) train_fused_kernel<A, true><<<2 * clusters, TF_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);  \
-        else train_fused_kernel<A, false><<<2 * clusters, TF_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);          \
-    } while (0)
-    if (act == CMRL_ACT_SILU) CMRL_TF_LAUNCH(CMRL_ACT_SILU);
-    else if (act == CMRL_ACT_RELU) CMRL_TF_LAUNCH(CMRL_ACT_RELU);
-    else CMRL_TF_LAUNCH(CMRL_ACT_IDENTITY);
-#undef CMRL_TF_LAUNCH
-    CMRL_CHECK_LAUNCH("train_fused");
-    return 0;
+    return launch_fused(p, act, (long long)P * E * p.pairs_per_net, false, (cudaStream_t)stream);
+}
+
+/* Rollout (inference) mode of the same kernel: the fp32-grade tier of VecFakeEnv.get_dynamics_predict on tensor cores. */
+extern "C" int cmrl_mlp_rollout_tf32(const float* packed, int L, int P, int E, int N, int O, int A, int hidden, int head_dim, int layout,
+                                     int act, int residual, const float* obs, const float* actn, const int* perm, const int* offsets,
+                                     const float* min_logvar, const float* max_logvar, int bounds_n, const float* noise, float* pred,
+                                     void* stream) {
+    TrainP p{};
+    const int Dn = layout == CMRL_HEAD_PARALLEL ? 1 : head_dim;
+    if (make_geom(p.g, L, O + A, hidden, Dn) != 0) return -1;
+    p.g.n_ph = L + 1;  // forward phases only; the blob keeps the training layout (the backward operands are not read)
+    CMRL_REQUIRE(packed && obs && actn && perm && offsets && pred, "mlp_rollout_tf32: null pointer");
+    CMRL_REQUIRE(layout == CMRL_HEAD_PLAIN || layout == CMRL_HEAD_PARALLEL, "mlp_rollout_tf32: bad head layout");
+    CMRL_REQUIRE(layout == CMRL_HEAD_PLAIN ? P == 1 : P == head_dim, "mlp_rollout_tf32: P must be 1 (plain head) or head_dim (parallel head)");
+    CMRL_REQUIRE(E >= 1 && E <= TF_MAX_E && N >= 0, "mlp_rollout_tf32: 1..%d members", TF_MAX_E);
+    CMRL_REQUIRE(!noise || (min_logvar && max_logvar && (bounds_n == 1 || bounds_n == head_dim)),
+                 "mlp_rollout_tf32: sampling needs logvar bounds with 1 or head_dim entries");
+    CMRL_REQUIRE(act == CMRL_ACT_IDENTITY || act == CMRL_ACT_RELU || act == CMRL_ACT_SILU, "mlp_rollout_tf32: unsupported activation");
+    if (N == 0) return 0;
+    p.packed = packed; p.P = P; p.E = E; p.B = 0; p.O = O; p.A = A; p.layout = layout; p.act = act; p.residual = residual; p.passes = 3;
+    p.obs = obs; p.actn = actn; p.min_logvar = min_logvar; p.max_logvar = max_logvar; p.bounds_n = bounds_n;
+    p.perm = perm; p.row_off = offsets; p.noise = noise; p.pred = pred; p.D = head_dim;
+    // every member's rows round up to whole tile pairs: at most N / 256 + E pairs per sub-net
+    return launch_fused(p, act, (long long)P * (N / (2 * TF_ROWS) + E), true, (cudaStream_t)stream);
 }
 
 extern "C" int cmrl_train_dw(const float* scratch, int L, int P, int E, int B, int in_size, int hidden, int head_outputs, int act,

@@ -13,8 +13,11 @@ Extra (non-reference) attributes, all optional:
     rng_mode     "numpy"  (default): member choice and noise drawn by `self.generator` in the reference's order --
                            bit-exact member choice / done flags against the reference for the same seed;
                  "device": Philox draws on the GPU (statistically equivalent, no host RNG work).
-    precision    "fp32"   (default): CUDA-core FFMA kernels, 1e-5 relative parity with the reference;
-                 "f16":   the fused tcgen05 kernel (fp16 operands, fp32 accumulation), 1e-3 relative parity.
+    precision    "fp32"   (default): 1e-5 relative parity with the reference -- the fused tcgen05 kernel with kind::tf32
+                           operands split into hi + lo parts (3xTF32, fp32 accumulation) for Gaussian models it takes
+                           (hidden width up to ~240), the CUDA-core FFMA kernels otherwise;
+                 "ffma":  always the CUDA-core kernels (fp32 FMA in ascending-k order: bit-identical to `query`);
+                 "f16":   the fused tcgen05 kernel with fp16 operands (fp32 accumulation), 1e-3 relative parity.
     infos_mode   "dicts"  (default): one fresh dict per env like the reference;
                  "shared": envs that are neither done nor truncated share one read-only dict (O(#done) host work).
 """
@@ -70,7 +73,7 @@ class VecFakeEnv(VecEnv):
         # B200-side knobs and state
         self.rng_mode = "numpy"
         self.infos_mode = "dicts"
-        self.precision = "fp32"  # "fp32": CUDA-core tier (1e-5 parity); "f16": tcgen05 tier (1e-3 parity)
+        self.precision = "fp32"  # "fp32" / "ffma": 1e-5 parity tiers (3xTF32 tensor cores / CUDA cores); "f16": tcgen05 tier (1e-3 parity)
         self.use_graph = True   # device rng_mode: replay the per-step launches from a CUDA graph
         self.return_views = False    # step(): hand out the pinned observation buffer itself instead of a copy (opt-in)
         self.overlap_prepare = True  # device rng_mode: reward / termination / reset draws + buckets on a side stream
@@ -254,6 +257,14 @@ class VecFakeEnv(VecEnv):
             return ops.select_sample(mean, logvar, idx, noise)
         return self.predict_selected(model, obs, act, idx, noise)
 
+    def _prebuild_pack(self, model):
+        """The packed operand copies of the active precision tier, built outside a graph capture (they allocate and launch)."""
+        model = getattr(model, "one_step_transition", model)  # ForwardEulerTransition rolls its one-step model out
+        if self.precision == "f16":
+            model.packed_f16()
+        elif self.precision == "fp32" and hasattr(model, "packed_tf32"):
+            model.packed_tf32()
+
     def predict_selected(self, model, obs, act, idx, noise, bucket=None):
         """Selected-member evaluation: bucket envs by drawn member, run the MLP on each member's rows only."""
         b = self._bufs
@@ -273,7 +284,13 @@ class VecFakeEnv(VecEnv):
             return ops.mlp_rollout_f16(model.packed_f16(), model._parallel_num(), E, obs, act, perm, offsets,
                                        model.hid_size, D, model._head_layout, not model.deterministic, model._act_kind,
                                        model._residual(), mn, mx, noise)  # fmt: skip
-        assert self.precision == "fp32", "precision must be 'fp32' or 'f16'"
+        assert self.precision in ("fp32", "ffma"), "precision must be 'fp32', 'ffma' or 'f16'"
+        if self.precision == "fp32":
+            # fp32-grade on tensor cores: kind::tf32 with hi/lo split operands (3xTF32) where the fused kernel takes the model
+            pack = model.packed_tf32()
+            if pack is not None and pack.ok:
+                mn, mx = model._bounds()
+                return ops.mlp_rollout_tf32(pack, obs, act, perm, offsets, model._act_kind, model._residual(), mn, mx, noise)
         h = ops.gather_inputs(obs, act, perm)
         params = model._stack_params()
         L = model.num_layers
@@ -426,7 +443,7 @@ class VecFakeEnv(VecEnv):
         parts = [self.precision, self.deterministic, need_all]
         for m in self.dynamics.learn_mech:
             model = getattr(self.dynamics, m)
-            parts.append((model.weights_token(), id(model._packed.get("f16")), id(model._elite_members),
+            parts.append((model.weights_token(), id(model._packed.get("f16")), id(model._packed.get("tf32")), id(model._elite_members),
                           model._flat.data_ptr() if model._flat is not None else 0, bool(model.deterministic)))
         return tuple(parts)
 
@@ -438,9 +455,8 @@ class VecFakeEnv(VecEnv):
                 self._rng_base = torch.zeros(1, dtype=torch.int64, device=self.device)
             for mech in self.dynamics.learn_mech:
                 self._elite_u8(mech)
-                if self.precision == "f16":
-                    getattr(self.dynamics, mech).packed_f16()
-            key = self._graph_state_key(need_all)  # again: packed_f16() may have rebuilt the fp16 copies
+                self._prebuild_pack(getattr(self.dynamics, mech))
+            key = self._graph_state_key(need_all)  # again: the packed copies may have been rebuilt
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             c0 = self._draw_counter
@@ -699,8 +715,7 @@ class VecFakeEnv(VecEnv):
                 self._rng_base = torch.zeros(1, dtype=torch.int64, device=self.device)
             for mech in self.dynamics.learn_mech:  # everything that allocates or syncs happens before the capture
                 self._elite_u8(mech)
-                if self.precision == "f16":
-                    getattr(self.dynamics, mech).packed_f16()
+                self._prebuild_pack(getattr(self.dynamics, mech))
             c_keep = self._draw_counter
             self._device_reset_source()  # builds the reset pool; its draw is discarded so that the graph-replayed
             self._draw_counter = c_keep  # steps use the same Philox streams as kernel-by-kernel `step_device` calls

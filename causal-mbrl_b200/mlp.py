@@ -346,6 +346,25 @@ class EnsembleMLP(nn.Module):
             self._packed["f16"] = cached
         return cached[1]
 
+    def packed_tf32(self):
+        """3xTF32 operand blob for the fp32-grade tensor-core rollout (ops.Tf32RolloutPack; `.ok` False when the fused tf32
+        kernel does not take this model); rebuilt whenever a parameter or the input mask changed."""
+        params = self._stack_params()
+        n_lin = len(params) - self._n_bound_params()
+        mask = self._kernel_mask()
+        key = tuple(p._version for p in params[:n_lin]) + tuple(p.data_ptr() for p in params[:n_lin]) + (
+            None if mask is None else (mask.data_ptr(), mask._version), getattr(self, "_weights_epoch", 0),
+            bool(self.deterministic))  # fmt: skip
+        cached = self._packed.get("tf32")
+        if cached is None or cached[0] != key:
+            E = self.ensemble_num
+            per_sample = mask is not None and (mask.dim() == 4 or (mask.dim() == 3 and mask.shape[1] != E))
+            with torch.no_grad():
+                pack = ops.Tf32RolloutPack(self) if not per_sample else None
+            cached = (key, pack)
+            self._packed["tf32"] = cached
+        return cached[1]
+
     # ------------------------------------------------------------------ flat parameter arena
     def _flatten_parameters(self):
         """Re-home every parameter as a view of one contiguous fp32 buffer (16-byte aligned slots).

@@ -480,6 +480,46 @@ def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, ga
     return pred
 
 
+class Tf32RolloutPack:
+    """3xTF32 operand blob of a model for cmrl_mlp_rollout_tf32 (the layout cmrl_train_pack_tf32 writes), or ok == False
+    when the fused tf32 kernel does not take the model (deterministic head, wide hidden layers, more than 16 head outputs)."""
+
+    def __init__(self, model):
+        import ctypes
+
+        params = model._stack_params()
+        n_lin = len(params) - model._n_bound_params()
+        ws, bs = params[0:n_lin:2], params[1:n_lin:2]
+        self.L = len(ws) - 1
+        self.P, self.E = model._parallel_num(), model.ensemble_num
+        self.in_size, self.hidden = ws[0].shape[-2], ws[0].shape[-1]
+        self.layout, self.head_dim = model._head_layout, model._head_dim
+        head_outputs = 1 if self.layout == HEAD_PARALLEL else self.head_dim
+        blob = ctypes.c_longlong(0)
+        self.ok = (not model.deterministic and self.E <= 64
+                   and ((self.layout == HEAD_PLAIN and self.P == 1) or (self.layout == HEAD_PARALLEL and self.P == self.head_dim))
+                   and _lib.load().cmrl_train_fused_sizes(self.L, self.in_size, self.hidden, head_outputs, self.P, self.E, 1,
+                                                          ctypes.byref(blob), None, None) == 0)
+        if not self.ok:
+            return
+        self.packed = torch.empty(self.P * self.E * blob.value, device=ws[0].device, dtype=torch.float32)
+        arr = ctypes.c_void_p * (self.L + 1)
+        mask = model._kernel_mask()
+        m_str = mask_strides(mask, self.P, self.E, -1)[:2] if mask is not None else (0, 0)
+        _lib.call("cmrl_train_pack_tf32", arr(*[w.data_ptr() for w in ws]), arr(*[b.data_ptr() for b in bs]), self.L, self.P, self.E,
+                  self.in_size, self.hidden, head_outputs, _ptr(mask), m_str[0], m_str[1], self.packed.data_ptr(), _stream())
+
+
+def mlp_rollout_tf32(pack, obs, act, perm, offsets, act_kind, residual, min_logvar, max_logvar, noise, out=None):
+    """Fused selected-member rollout on tcgen05 kind::tf32 with hi/lo split operands (fp32-grade): see cmrl_mlp_rollout_tf32."""
+    N, O = obs.shape
+    pred = torch.empty((N, pack.head_dim), device=obs.device, dtype=torch.float32) if out is None else out
+    _lib.call("cmrl_mlp_rollout_tf32", pack.packed.data_ptr(), pack.L, pack.P, pack.E, N, O, act.shape[1], pack.hidden, pack.head_dim,
+              pack.layout, act_kind, 1 if residual else 0, obs.data_ptr(), act.data_ptr(), perm.data_ptr(), offsets.data_ptr(),
+              _ptr(min_logvar), _ptr(max_logvar), 0 if min_logvar is None else min_logvar.numel(), _ptr(noise), pred.data_ptr(), _stream())
+    return pred
+
+
 # ----------------------------------------------------------------------------- fused tcgen05 training step
 # One optimiser step of a mechanism = pack + fused forward / loss / dz chain + all weight gradients (three launches of
 # train_tc.cu) instead of ~25 per-layer launches.  TRAIN_FUSED_PASSES: 3 = 3xTF32 (fp32-grade, the default), 1 = TF32.

@@ -269,6 +269,14 @@ int cmrl_train_fused(const float* packed, int L, int P, int E, int B, int O, int
                      const float* actn, long long act_se, const float* target, long long tgt_se, int tgt_ld,
                      const float* min_logvar, const float* max_logvar, int bounds_n, float reg, float g_scale,
                      float* loss, float* scratch, void* stream);
+/* Rollout mode of the same kernel -- the fp32-grade (3xTF32) tier of the fused selected-member rollout: same contract as
+ * cmrl_mlp_rollout_f16 (fake_env.py:195-215: perm / offsets from cmrl_member_bucket, pred[env,:] = mean (+obs) +
+ * sqrt(exp(logvar)) * noise[env,:], noise == NULL: the mean) for Gaussian heads, with the weights packed by
+ * cmrl_train_pack_tf32 (the backward operands of that blob are not read).  Only the forward phases run and nothing is saved. */
+int cmrl_mlp_rollout_tf32(const float* packed, int L, int P, int E, int N, int O, int A, int hidden, int head_dim, int layout,
+                          int act, int residual, const float* obs, const float* actn, const int* perm, const int* offsets,
+                          const float* min_logvar, const float* max_logvar, int bounds_n, const float* noise, float* pred,
+                          void* stream);
 /* dw_host / db_host: HOST arrays of L+1 device pointers to the gradient tensors (overwritten, not accumulated).
  * mask as in cmrl_train_pack_tf32 (gradient rows of masked inputs are zero, as in the reference's masked forward).
  * workspace: optional device floats for deterministic batch-slice partial sums. */

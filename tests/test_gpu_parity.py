@@ -373,6 +373,7 @@ def test_selected_member_path_equals_all_member_path(cm):
         act = t(rng.uniform(-1, 1, size=(N, 1)).astype(np.float32))
         idx = t(rng.choice(np.asarray(model.elite_members), size=N).astype(np.uint8))
         noise = t(rng.normal(size=(N, D)).astype(np.float32))
+        env.precision = "ffma"  # the CUDA-core tier: same kernels and summation order as the all-member path
         sel = env.predict_selected(model, obs, act, idx, noise)
         with torch.no_grad():
             mean, logvar = model.forward(obs.unsqueeze(0), act.unsqueeze(0))
@@ -380,6 +381,15 @@ def test_selected_member_path_equals_all_member_path(cm):
         assert torch.equal(sel, allm)
         ref = oc.dynamics_predict(mean.cpu().numpy(), logvar.cpu().numpy(), idx.cpu().numpy().astype(np.int64), noise.cpu().numpy())
         assert rel_err(sel.cpu().numpy(), ref) < TOL
+        # the default tier: the fused tcgen05 kernel with hi/lo split tf32 operands (3xTF32) -- fp32-grade, elementwise too
+        env.precision = "fp32"
+        assert model.packed_tf32().ok
+        sel3 = env.predict_selected(model, obs, act, idx, noise)
+        assert record_max("3xTF32 rollout vs all-member %s" % mech, rel_err(sel3.cpu().numpy(), ref)) < TOL
+        assert record_max("3xTF32 rollout vs all-member %s elem" % mech, elem_err(sel3.cpu().numpy(), ref)) < 5 * TOL
+        mean_only = env.predict_selected(model, obs, act, idx, None)  # deterministic envs: no sampling
+        ref_m = np.take_along_axis(mean.cpu().numpy(), idx.cpu().numpy().astype(np.int64)[None, :, None], axis=0)[0]
+        assert rel_err(mean_only.cpu().numpy(), ref_m) < TOL
 
 
 def test_query_and_get_dynamics_predict(cm):
@@ -487,14 +497,22 @@ def test_large_rollout_properties(cm):
     act = t(rng.uniform(-1, 1, size=(N, 1)).astype(np.float32))
     idx = t(rng.choice(np.asarray(tr.elite_members), size=N).astype(np.uint8))
     noise = t(rng.normal(size=(N, 5)).astype(np.float32))
-    a = env.predict_selected(tr, obs, act, idx, noise)
-    b = env.predict_selected(tr, obs, act, idx, noise)
-    assert torch.equal(a, b)
     sub = torch.arange(0, N, 97, device=DEV)
     with torch.no_grad():
         mean, logvar = tr.forward(obs[sub].unsqueeze(0), act[sub].unsqueeze(0))
     ref = cm.ops.select_sample(mean, logvar, idx[sub].contiguous(), noise[sub].contiguous())
+    env.precision = "ffma"  # CUDA-core tier: bit-identical to the all-member path
+    a = env.predict_selected(tr, obs, act, idx, noise)
+    b = env.predict_selected(tr, obs, act, idx, noise)
+    assert torch.equal(a, b)
     assert torch.equal(a[sub], ref)
+    env.precision = "fp32"  # default tier, 3xTF32 on tcgen05: deterministic, fp32-grade
+    a3 = env.predict_selected(tr, obs, act, idx, noise)
+    assert torch.equal(a3, env.predict_selected(tr, obs, act, idx, noise))
+    assert record_max("3xTF32 rollout C2 100k envs vs all-member", rel_err(a3[sub].cpu().numpy(), ref.cpu().numpy())) < TOL
+    # elementwise over all 500 000 outputs, floor 1e-3 of the largest: an output near zero (observation + delta cancel) carries the
+    # absolute fp32 rounding of its O(1) terms, ~1e-7 of the output scale, i.e. up to ~1e-4 in this metric for either tier
+    assert record_max("3xTF32 rollout C2 100k envs vs ffma tier elem", elem_err(a3.cpu().numpy(), a.cpu().numpy())) < 5e-4
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 tier
