@@ -32,16 +32,22 @@ __device__ __forceinline__ float u32_to_unit_open(uint32_t x) {  // (0,1]
     return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
 }
 
+// Box-Muller with the fast intrinsics: the draws are statistical (rng_mode="device"), an absolute error of ~1e-6 in a
+// standard normal is far below anything a rollout can see, and the accurate logf / sincospif made this kernel spend four times
+// the instructions of its two Philox blocks.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float* n0, float* n1) {
-    float u = u32_to_unit_open(a), v = u32_to_unit_open(b);
-    float r = sqrtf(-2.0f * logf(u));
+    const float u = u32_to_unit_open(a), v = u32_to_unit_open(b);
+    const float r = sqrtf(-2.0f * __logf(u));
     float s, c;
-    sincospif(2.0f * v, &s, &c);
+    __sincosf(6.283185307179586f * v - 3.141592653589793f, &s, &c);  // argument in (-pi, pi]: the intrinsic's accurate range
     *n0 = r * c;
     *n1 = r * s;
 }
 
-// one thread per env: block 0 of the counter space draws the member, blocks 1.. draw 4 normals each
+// One thread per env.  Counter block 0 of an env's Philox stream: word x draws the member, y/z and w/(block 1).x feed the first
+// two Box-Muller pairs; every further block feeds two more pairs.  D = 5 takes two blocks (three with one block per four
+// normals and a separate member block).  The kernel is bound by integer issue slots (Philox4x32-10: ~90 instructions per block),
+// not by the 1 + 4 D bytes it writes per env.
 __global__ void draw_member_noise_kernel(unsigned long long seed, unsigned long long stream_id,
                                          const unsigned long long* __restrict__ stream_base, int N,
                                          const uint8_t* __restrict__ elite, int n_elite, int D,
@@ -54,12 +60,31 @@ __global__ void draw_member_noise_kernel(unsigned long long seed, unsigned long 
     uint4 r = philox4x32_10(make_uint4((uint32_t)n, 0u, s_lo, s_hi), key);
     if (member_idx) member_idx[n] = elite[(uint32_t)(((unsigned long long)r.x * (unsigned long long)n_elite) >> 32)];
     if (noise) {
-        for (int d0 = 0; d0 < D; d0 += 4) {
-            uint4 q = philox4x32_10(make_uint4((uint32_t)n, 1u + (uint32_t)(d0 >> 2), s_lo, s_hi), key);
-            float z[4];
-            box_muller(q.x, q.y, &z[0], &z[1]);
-            box_muller(q.z, q.w, &z[2], &z[3]);
-            for (int j = 0; j < 4 && d0 + j < D; ++j) noise[(long long)n * D + d0 + j] = z[j];
+        // word queue: r.y r.z r.w | next block x y z w | ...
+        uint32_t w[3] = {r.y, r.z, r.w};
+        int have = 3, blk = 1;
+        float* dst = noise + (long long)n * D;
+        for (int d0 = 0; d0 < D; d0 += 2) {
+            if (have < 2) {
+                const uint4 q = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)blk++, s_lo, s_hi), key);
+                if (have == 1) {  // one word left over: pair it with q.x, keep q.y q.z q.w
+                    float z0, z1;
+                    box_muller(w[0], q.x, &z0, &z1);
+                    dst[d0] = z0;
+                    if (d0 + 1 < D) dst[d0 + 1] = z1;
+                    w[0] = q.y; w[1] = q.z; w[2] = q.w;
+                    have = 3;
+                    continue;
+                }
+                w[0] = q.x; w[1] = q.y; w[2] = q.z;  // (have == 0; q.w is dropped: keeps the queue at three words)
+                have = 3;
+            }
+            float z0, z1;
+            box_muller(w[0], w[1], &z0, &z1);
+            dst[d0] = z0;
+            if (d0 + 1 < D) dst[d0 + 1] = z1;
+            w[0] = w[2];
+            have -= 2;
         }
     }
 }
@@ -279,44 +304,63 @@ __global__ void mopo_penalty_kernel(const float* __restrict__ mean, int E, int N
     penalty[n] = best;
 }
 
-// TPE = threads per env (1 for small O, 32 for wide observations)
-template <int TPE>
-__global__ void env_step_tail_kernel(const float* __restrict__ next_obs, const float* __restrict__ reward,
-                                     const float* __restrict__ terminal, const uint8_t* __restrict__ terminal_u8,
-                                     const float* __restrict__ penalty, float penalty_coeff, int* __restrict__ env_len,
-                                     int max_steps, const float* __restrict__ reset_obs,
-                                     const int* __restrict__ reset_index, int N, int O, float* __restrict__ obs_out,
-                                     float* __restrict__ reward_out, uint8_t* __restrict__ done_out,
-                                     uint8_t* __restrict__ trunc_out, float* __restrict__ terminal_obs,
-                                     int* __restrict__ n_done) {
-    const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long n = gt / TPE;
-    const int sub = (int)(gt % TPE);
+// A block takes TAIL_ENVS consecutive envs.  Phase 1, one thread per env: the episode bookkeeping and the per-env outputs
+// (4-byte and 1-byte arrays, coalesced), and where the env's next observation comes from (itself, or a reset row) into shared
+// memory.  Phase 2, all threads over the block's FLAT range of TAIL_ENVS x O floats: next_obs is read once with 16-byte
+// accesses and written to terminal_obs and (patched at reset envs) obs_out the same way -- the first version walked each
+// env's O floats with one thread (stride-O scalar accesses: 5 wavefronts per instruction at O = 5, 0.47 of the copy bandwidth).
+constexpr int TAIL_ENVS = 256;
+__global__ void __launch_bounds__(TAIL_ENVS) env_step_tail_kernel(
+    const float* __restrict__ next_obs, const float* __restrict__ reward, const float* __restrict__ terminal,
+    const uint8_t* __restrict__ terminal_u8, const float* __restrict__ penalty, float penalty_coeff, int* __restrict__ env_len,
+    int max_steps, const float* __restrict__ reset_obs, const int* __restrict__ reset_index, int N, int O,
+    float* __restrict__ obs_out, float* __restrict__ reward_out, uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
+    float* __restrict__ terminal_obs, int* __restrict__ n_done, int vec) {
+    __shared__ int s_src[TAIL_ENVS];  // -1: the env keeps its next observation; otherwise the row of reset_obs it restarts from
+    const int n0 = blockIdx.x * TAIL_ENVS;
+    const int n = n0 + threadIdx.x;
     bool done = false;
     if (n < N) {
-        int len = env_len[n] + 1;
-        bool trunc = len >= max_steps;
-        bool term = (terminal && terminal[n] != 0.0f) || (terminal_u8 && terminal_u8[n] != 0);
+        const int len = env_len[n] + 1;
+        const bool trunc = len >= max_steps;
+        const bool term = (terminal && terminal[n] != 0.0f) || (terminal_u8 && terminal_u8[n] != 0);
         done = term || trunc;
-        if (TPE > 1) __syncwarp();
-        if (sub == 0) {
-            float r = reward[n];
-            if (penalty) r -= penalty[n] * penalty_coeff;
-            reward_out[n] = r;
-            done_out[n] = done ? 1 : 0;
-            trunc_out[n] = trunc ? 1 : 0;
-            env_len[n] = done ? 0 : len;
-        }
-        const long long rs = reset_index ? (long long)reset_index[n] : n;
-        for (int o = sub; o < O; o += TPE) {
-            float v = next_obs[n * O + o];
-            if (terminal_obs) terminal_obs[n * O + o] = v;
-            obs_out[n * O + o] = (done && reset_obs) ? reset_obs[rs * O + o] : v;
-        }
+        float r = reward[n];
+        if (penalty) r -= penalty[n] * penalty_coeff;
+        reward_out[n] = r;
+        done_out[n] = done ? 1 : 0;
+        trunc_out[n] = trunc ? 1 : 0;
+        env_len[n] = done ? 0 : len;
+        s_src[threadIdx.x] = (done && reset_obs) ? (reset_index ? reset_index[n] : n) : -1;
     }
-    if (n_done) {
-        unsigned ballot = __ballot_sync(0xffffffffu, done && sub == 0);
-        if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(n_done, __popc(ballot));
+    const int n_done_blk = __syncthreads_count(done);
+    if (n_done && threadIdx.x == 0 && n_done_blk) atomicAdd(n_done, n_done_blk);
+    const int cnt = min(TAIL_ENVS, N - n0);
+    const int total = cnt * O;                      // floats of this block's flat range
+    const long long base = (long long)n0 * O;       // a multiple of 4 floats from the arrays' start (TAIL_ENVS = 256)
+    const int nv = vec ? total / 4 : 0;
+    for (int i = threadIdx.x; i < nv; i += TAIL_ENVS) {
+        float4 v = *reinterpret_cast<const float4*>(next_obs + base + 4 * i);
+        if (terminal_obs) *reinterpret_cast<float4*>(terminal_obs + base + 4 * i) = v;
+        int e = (4 * i) / O, o = 4 * i - e * O;
+        float c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int src = s_src[e];
+            if (src >= 0) c[j] = reset_obs[(long long)src * O + o];
+            if (++o == O) {
+                o = 0;
+                ++e;
+            }
+        }
+        *reinterpret_cast<float4*>(obs_out + base + 4 * i) = make_float4(c[0], c[1], c[2], c[3]);
+    }
+    for (int i = 4 * nv + threadIdx.x; i < total; i += TAIL_ENVS) {
+        const int e = i / O, o = i - e * O;
+        const float v = next_obs[base + i];
+        if (terminal_obs) terminal_obs[base + i] = v;
+        const int src = s_src[e];
+        obs_out[base + i] = src >= 0 ? reset_obs[(long long)src * O + o] : v;
     }
 }
 
@@ -433,16 +477,10 @@ extern "C" int cmrl_env_step_tail(const float* next_obs, const float* reward, co
                  "env_step_tail: null pointer");
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (O <= 16) {
-        env_step_tail_kernel<1><<<blocks_for(N), RT, 0, st>>>(next_obs, reward, terminal, terminal_u8, penalty,
-                                                              penalty_coeff, env_len, max_episode_steps, reset_obs,
-                                                              reset_index, N, O, obs_out, reward_out, done, truncated,
-                                                              terminal_obs, n_done);
-    } else {
-        env_step_tail_kernel<32><<<blocks_for((long long)N * 32), RT, 0, st>>>(
-            next_obs, reward, terminal, terminal_u8, penalty, penalty_coeff, env_len, max_episode_steps, reset_obs,
-            reset_index, N, O, obs_out, reward_out, done, truncated, terminal_obs, n_done);
-    }
+    const int vec = ((((uintptr_t)next_obs | (uintptr_t)obs_out | (uintptr_t)terminal_obs) & 15) == 0) ? 1 : 0;
+    env_step_tail_kernel<<<blocks_for(N, TAIL_ENVS), TAIL_ENVS, 0, st>>>(next_obs, reward, terminal, terminal_u8, penalty, penalty_coeff, env_len,
+                                                                          max_episode_steps, reset_obs, reset_index, N, O, obs_out, reward_out,
+                                                                          done, truncated, terminal_obs, n_done, vec);
     CMRL_CHECK_LAUNCH("env_step_tail");
     return 0;
 }
