@@ -387,6 +387,8 @@ def run_native(args):
         train["bs4096"]["roofline"] = train_kernel_roofline(cm, ctx, 4096)
         if not args.quick:
             train["c4"] = time_train_c4(cm, ctx, args)
+            if not args.skip_c5:
+                train["c5"] = time_train_c5(cm, ctx)
 
     # ---- the other configs of BASELINE.json + tiers / contracts -----------------------------------------------------------
     configs = {}
@@ -623,6 +625,51 @@ def time_train_c4(cm, ctx, args):
             "first_epoch_s_incl_upload_and_capture": first, "host_dataset_build_s": t_host, "holdout_eval_s": t_val,
             "epoch_mean_nll": loss, "holdout_mse_per_member": [float(x) for x in val.tolist()],
             "resident_bytes": int(train_it.num_stored * (2 * O + A) * 4 + E * train_it.num_stored * 4)}  # fmt: skip
+
+
+def time_train_c5(cm, ctx, B=256, steps=4):
+    """C5 training (BASELINE config 5: O = P = 100, A = 20, E = 16, H = 512, per-member masks: 1 600 nets, 1.36 G parameters).
+    N > 1: NET SHARDING -- every rank trains its contiguous share of the 100 sub-networks on the whole batch, with no exchange
+    at all during training (the sub-networks are independent); the same step is cut N ways, i.e. strong scaling."""
+    torch = ctx.torch
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    O5, A5, E5, H5 = 100, 20, 16, 512
+    p0, p1 = cm.net_shard_range(O5, world, rank)
+    t0 = time.perf_counter()
+    torch.manual_seed(5)
+    rng5 = np.random.default_rng(0)
+    m = cm.ExternalMaskTransition(O5, A5, ensemble_num=E5, elite_num=12, hid_size=H5, activation_fn_cfg=SILU, device=dev,
+                                  subnet_range=(p0, p1) if world > 1 else None)  # fmt: skip
+    mask = (rng5.uniform(size=(O5, E5, O5 + A5)) < 0.3).astype(np.float32)
+    mask[np.arange(O5), :, np.arange(O5)] = 1.0
+    m.set_input_mask(torch.from_numpy(mask))
+    dyn = cm.PlainEnsembleDynamics(m, learned_reward=False)
+    if world > 1:
+        dyn.enable_net_sharding()
+    obs = torch.randn(E5, B, O5, device=dev)
+    act = torch.rand(E5, B, A5, device=dev) * 2 - 1
+    tgt = m.target_columns(obs + 0.1 * torch.tanh(obs)).contiguous()
+    for _ in range(2):
+        dyn.train_step("transition", obs, act, tgt, want_loss=False)
+    ctx.barrier()
+    l0 = cm._lib.launch_count()
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        dyn.train_step("transition", obs, act, tgt, want_loss=False)
+    c.record()
+    ctx.barrier()
+    ms = ctx.max_over_ranks(a.elapsed_time(c)) / steps
+    flop = 3 * 2 * ((O5 + A5) * H5 + 3 * H5 * H5 + H5 * 2) * O5 * E5 * B
+    out = {"workload": "ExternalMaskTransition O=P=100 A=20 E=16 H=512 per-member 3-D mask: one optimiser step, %d rows per member" % B,
+           "value": E5 * B / (ms * 1e-3), "unit": "member-samples/s", "ms_per_step": ms, "tflops_algorithmic": flop / (ms * 1e-3) / 1e12,
+           "gpu_launches_per_step": (cm._lib.launch_count() - l0) / steps, "train_gemm_tier": str(cm.ops.TRAIN_GEMM_TIER),
+           "parallelism": "single GPU, all 100 sub-networks" if world == 1 else
+                          "net sharding over %d GPUs (rank 0: sub-networks %d..%d), no gradient traffic; scaling: strong" % (world, p0, p1 - 1),
+           "build_s": time.perf_counter() - t0}  # fmt: skip
+    del dyn, m, obs, act, tgt
+    torch.cuda.empty_cache()
+    return out
 
 
 def other_configs(cm, ctx, args, dyn_c2, act_host_c2):

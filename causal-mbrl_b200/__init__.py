@@ -6,7 +6,7 @@ signatures, attributes, state_dict keys and checkpoint files; the arithmetic run
 """
 from . import _lib, ops  # noqa: F401
 from .cmi_test import TransitionConditionalMutualInformationTest  # noqa: F401
-from .dynamics import BaseDynamics, ConstraintBasedDynamics, PlainEnsembleDynamics  # noqa: F401
+from .dynamics import BaseDynamics, ConstraintBasedDynamics, PlainEnsembleDynamics, net_shard_range  # noqa: F401
 from .fake_env import VecFakeEnv  # noqa: F401
 from .layers import EnsembleLinearLayer, ParallelEnsembleLinearLayer, truncated_normal_init  # noqa: F401
 from .mlp import EnsembleMLP, ExternalMaskEnsembleMLP  # noqa: F401

@@ -42,6 +42,13 @@ def dp_row_slice(num_rows: int, world_size: int, rank: int) -> slice:
     return slice(start, start + base + (1 if rank < rem else 0))
 
 
+def net_shard_range(num_subnets: int, world_size: int, rank: int):
+    """Output dimensions (sub-networks) of rank `rank` when `num_subnets` are dealt to `world_size` ranks in contiguous,
+    near-equal shares (the first `num_subnets % world_size` ranks take one more)."""
+    sl = dp_row_slice(num_subnets, world_size, rank)
+    return sl.start, sl.stop
+
+
 def dp_allreduce_member_sums(sums: torch.Tensor, group) -> torch.Tensor:
     """[E] per-member sums over one rank's row shard -> the global sums, identical on every rank (sharded
     evaluation; every rank then derives the same validation scores and the same elite set)."""
@@ -132,6 +139,10 @@ class BaseDynamics:
             return batch.batch_done
         return getattr(batch, variable)
 
+    def _mech_target(self, batch: InteractionBatch, mech: str):
+        """The variable `mech` is trained on (base_dynamics.py:27-28); a net-sharded transition takes its own columns."""
+        return getattr(self, mech).target_columns(self._batch_variable(batch, self._MECH_TO_VARIABLE[mech]))
+
     def get_mech_loss(self, batch: InteractionBatch, mech: str = "transition", loss_type: str = "default",
                       is_ensemble: bool = False):  # fmt: skip
         model = getattr(self, mech)
@@ -141,7 +152,7 @@ class BaseDynamics:
         }
         if loss_type == "default":
             loss_type = "mse" if model.deterministic else "nll"
-        target = self.get_3d_tensor(self._batch_variable(batch, self._MECH_TO_VARIABLE[mech]), is_ensemble=is_ensemble)
+        target = self.get_3d_tensor(self._mech_target(batch, mech), is_ensemble=is_ensemble)
         get_loss = getattr(model, "get_{}_loss".format(loss_type))
         return get_loss(model_in, target)
 
@@ -182,7 +193,7 @@ class BaseDynamics:
         assert not isinstance(dataset, BootstrapIterator)
         model = getattr(self, mech)
         data = dataset.transitions
-        target_np = self._batch_variable(data, self._MECH_TO_VARIABLE[mech])
+        target_np = self._mech_target(data, mech)
         sums = torch.zeros(self.ensemble_num, device=self.device, dtype=torch.float64)
         n, d = len(data), model._head_dim
         # data parallel: every rank evaluates its contiguous share of the hold-out rows, one [E] all-reduce at the end
@@ -198,6 +209,11 @@ class BaseDynamics:
                 ops.mse_member_sums(mean, target, sums)
         if self.dp_group is not None:
             dp_allreduce_member_sums(sums, self.dp_group)
+        ns_group = getattr(self, "ns_group", None)
+        if ns_group is not None and getattr(model, "is_net_shard", False):
+            # net sharding: every rank scored its own output dimensions; the [E] sums of all shards make the mechanism's score
+            dp_allreduce_member_sums(sums, ns_group)
+            d = model._grad_dims()
         return (sums / float(n * d)).to(torch.float32).cpu()
 
     def train_step(self, mech: str, obs: torch.Tensor, act: torch.Tensor, target: torch.Tensor,
@@ -230,7 +246,7 @@ class BaseDynamics:
             loss = (model.get_mse_loss if model.deterministic else model.get_nll_loss)(
                 {"batch_obs": obs, "batch_action": act}, target)  # fmt: skip
             optim.zero_grad()
-            loss.mean().backward()
+            (loss.mean() * (model._head_dim / float(model._grad_dims()))).backward()
             self._sync_grads(model)
             optim.step()
             return loss.detach()
@@ -261,11 +277,10 @@ class BaseDynamics:
         raw = ops.ens_linear_fwd(h, params[2 * L], params[2 * L + 1], ops.ACT_IDENTITY)
         mn, mx = model._bounds()
         D = model._head_dim
-        mean, logvar = ops.gaussian_head_fwd(raw, model._head_layout, E, B, D, obs_c if model._residual() else None,
-                                             mn, mx)  # fmt: skip
+        mean, logvar = model._head_fwd(raw, obs_c if model._residual() else None, E, B)
         loss = ops.nll_loss_fwd(mean, logvar, target, model._nll_reg()) if want_loss else None
         rows = B if grad_rows is None else grad_rows
-        g_mean, g_logvar = ops.nll_loss_bwd(mean, logvar, target, g_scalar=1.0 / float(E * rows * D))
+        g_mean, g_logvar = ops.nll_loss_bwd(mean, logvar, target, g_scalar=1.0 / float(E * rows * model._grad_dims()))
         dz = ops.gaussian_head_bwd(raw, model._head_layout, E, B, D, mn, mx, g_mean, g_logvar)
         # Backward: dW_i and dx_i both need only dz_i, so the weight-gradient GEMMs run on a side stream next to the
         # dz chain (at the reference batch size every GEMM is a latency-bound ~17 us launch on < 148 CTAs: the critical
@@ -324,6 +339,24 @@ class BaseDynamics:
                 model.flat_parameters()
                 largest = max(largest, int(model._n_trainable))
             self._peer_sync = PeerGradSync(self.dp_group, largest, self.device)
+
+    def enable_net_sharding(self, group=None):
+        """The transition of this dynamics is one rank's NET SHARD of an ExternalMaskTransition (`subnet_range=`, see
+        `net_shard_range`): training needs no exchange at all -- the sub-networks are independent -- and the hold-out score
+        that drives early stopping and elite selection is the sum of every shard's [E] sums (one all-reduce per evaluation),
+        so all ranks stop at the same epoch and pick the same elites.  `gather_net_shards()` then assembles the full model."""
+        import torch.distributed as dist
+
+        assert getattr(self.transition, "is_net_shard", False), "build the transition with subnet_range=net_shard_range(...)"
+        self.ns_group = group if group is not None else dist.group.WORLD
+
+    def gather_net_shards(self):
+        """Replace the shard by the full transition (collective), e.g. before rolling it out in a VecFakeEnv."""
+        full = self.transition.gather_from_shards(self.ns_group)
+        self.transition = full
+        self.ns_group = None
+        self.transition_optimizer = self._make_optimizer(full)
+        return full
 
     def broadcast_parameters(self, src: int = 0, group=None):
         """Rollout replicas: envs are sharded over ranks with a full weight replica each and no per-step
@@ -453,7 +486,7 @@ class _DeviceEpochRunner:
         self.dyn, self.mech, self.dataset, self.use_graph = dyn, mech, dataset, use_graph
         dev = dyn.device
         data = dataset.transitions
-        target = dyn._batch_variable(data, dyn._MECH_TO_VARIABLE[mech])
+        target = dyn._mech_target(data, mech)
 
         def dev_f32(a):
             a = np.ascontiguousarray(a, dtype=np.float32)

@@ -254,6 +254,13 @@ class EnsembleMLP(nn.Module):
     def _residual(self):
         return False
 
+    def _grad_dims(self) -> int:
+        """Output dimensions `loss.mean()` averages over (net shards of a transition average over the full model's)."""
+        return self._head_dim
+
+    def target_columns(self, target):
+        return target
+
     def _n_bound_params(self):
         return 0 if self.deterministic else 2
 
@@ -334,6 +341,8 @@ class EnsembleMLP(nn.Module):
             bool(self.deterministic))  # fmt: skip
         cached = self._packed.get("f16")
         if cached is None or cached[0] != key:
+            if getattr(self, "is_net_shard", False):
+                raise ops._lib.CmrlB200Error("a net shard has no rollout kernels: gather the full model first (gather_from_shards)")
             E = self.ensemble_num
             if mask is not None and (mask.dim() == 4 or (mask.dim() == 3 and mask.shape[1] != E)):
                 raise ops._lib.CmrlB200Error("per-sample input masks cannot be folded into packed weights; use precision='fp32'")
@@ -360,7 +369,7 @@ class EnsembleMLP(nn.Module):
             E = self.ensemble_num
             per_sample = mask is not None and (mask.dim() == 4 or (mask.dim() == 3 and mask.shape[1] != E))
             with torch.no_grad():
-                pack = ops.Tf32RolloutPack(self) if not per_sample else None
+                pack = ops.Tf32RolloutPack(self) if not (per_sample or getattr(self, "is_net_shard", False)) else None
             cached = (key, pack)
             self._packed["tf32"] = cached
         return cached[1]

@@ -604,8 +604,8 @@ class FusedTrainPlan:
 def fused_train_plan(model, E, B):
     """The model's FusedTrainPlan for batches of B rows per member, or None when the fused kernels do not take this model
     (deterministic head, CMI-test layout, per-sample masks, wide hidden layers ...: the per-layer kernels run instead)."""
-    if not TRAIN_FUSED or model.deterministic or not hasattr(model, "hidden_layers"):
-        return None
+    if not TRAIN_FUSED or model.deterministic or not hasattr(model, "hidden_layers") or getattr(model, "is_net_shard", False):
+        return None  # (a net shard's outputs are not dimensions 0..P-1 of the observation: the per-layer kernels run)
     P = model._parallel_num()
     if not ((model._head_layout == HEAD_PLAIN and P == 1) or (model._head_layout == HEAD_PARALLEL and P == model._head_dim)):
         return None

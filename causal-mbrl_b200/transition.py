@@ -97,7 +97,12 @@ class ExternalMaskTransition(BaseTransition):
         hid_size: int = 200,
         activation_fn_cfg: Optional[Dict] = None,
         device: Union[str, torch.device] = "cpu",
+        subnet_range: Optional[Tuple[int, int]] = None,
     ):
+        """subnet_range=(p0, p1) (not in the reference) builds a NET SHARD: only the sub-networks of output dimensions
+        p0..p1-1 exist (parameters [p1-p0, E, ...]); `forward` still takes the full observation and returns
+        [E, B, p1-p0].  The sub-networks never exchange anything, so ranks can train disjoint shards with no gradient
+        traffic and assemble the full model afterwards with `gather_from_shards`."""
         super().__init__(obs_size=obs_size, action_size=action_size, deterministic=deterministic,
                          ensemble_num=ensemble_num, elite_num=elite_num, device=device)  # fmt: skip
         self.residual = residual
@@ -105,19 +110,79 @@ class ExternalMaskTransition(BaseTransition):
         self.num_layers = num_layers
         self.hid_size = hid_size
         self.activation_fn_cfg = activation_fn_cfg
+        self._sub0, self._sub1 = (0, obs_size) if subnet_range is None else (int(subnet_range[0]), int(subnet_range[1]))
+        assert 0 <= self._sub0 < self._sub1 <= obs_size, "subnet_range must be a non-empty range of output dimensions"
+        # learned bounds couple the shards through the regulariser 0.01 * (sum(max_logvar) - sum(min_logvar)) over ALL sub-networks
+        assert subnet_range is None or not learn_logvar_bounds, "net shards do not support learn_logvar_bounds"
+        n_sub = self._sub1 - self._sub0
 
         self._input_mask: Optional[torch.Tensor] = torch.ones((obs_size, obs_size + action_size)).to(device)
         self.add_save_attr("input_mask")
 
         self._build_stack(obs_size + action_size, hid_size, num_layers, 1 if deterministic else 2, activation_fn_cfg)
         if not deterministic:
-            self.min_logvar = nn.Parameter(-10 * torch.ones(obs_size, 1, 1, 1), requires_grad=learn_logvar_bounds)
-            self.max_logvar = nn.Parameter(0.5 * torch.ones(obs_size, 1, 1, 1), requires_grad=learn_logvar_bounds)
-        self._head_dim = obs_size
+            self.min_logvar = nn.Parameter(-10 * torch.ones(n_sub, 1, 1, 1), requires_grad=learn_logvar_bounds)
+            self.max_logvar = nn.Parameter(0.5 * torch.ones(n_sub, 1, 1, 1), requires_grad=learn_logvar_bounds)
+        self._head_dim = n_sub
         self._finish_init()
 
     def create_linear_layer(self, l_in, l_out):
-        return ParallelEnsembleLinearLayer(l_in, l_out, parallel_num=self.obs_size, ensemble_num=self.ensemble_num)
+        return ParallelEnsembleLinearLayer(l_in, l_out, parallel_num=self._sub1 - self._sub0, ensemble_num=self.ensemble_num)
+
+    @property
+    def is_net_shard(self) -> bool:
+        return self._sub1 - self._sub0 != self.obs_size
+
+    @property
+    def subnet_range(self) -> Tuple[int, int]:
+        return self._sub0, self._sub1
+
+    def _grad_dims(self) -> int:
+        """Output dimensions the reference's `loss.mean()` averages over: all of them, also for a shard (so that a shard's
+        gradients equal the corresponding slices of the full model's)."""
+        return self.obs_size
+
+    def _nll_reg(self) -> float:
+        """The loss constant of the FULL model (mlp.py:72-76 sums the bounds of all sub-networks): the bounds are fixed and
+        equal across sub-networks (not learned in a shard), so it is this shard's sum scaled up."""
+        reg = super()._nll_reg()
+        return reg * (self.obs_size / float(self._sub1 - self._sub0)) if self.is_net_shard else reg
+
+    def _head_fwd(self, raw, res_obs, E, B):
+        if res_obs is not None and self.is_net_shard:  # residual: this shard's columns of the observation
+            res_obs = res_obs[..., self._sub0:self._sub1].contiguous()
+        return super()._head_fwd(raw, res_obs, E, B)
+
+    def target_columns(self, target):
+        """The columns of a [.., obs_size] training / hold-out target this model predicts."""
+        return target[..., self._sub0:self._sub1] if self.is_net_shard else target
+
+    def gather_from_shards(self, group=None) -> "ExternalMaskTransition":
+        """Collective over `group`, whose ranks hold consecutive shards covering all output dimensions in rank order:
+        returns the full model (every parameter all-gathered along the sub-network axis, mask and elite set of this rank)."""
+        import torch.distributed as dist
+
+        world = dist.get_world_size(group)
+        full = ExternalMaskTransition(self.obs_size, self.action_size, deterministic=self.deterministic, ensemble_num=self.ensemble_num,
+                                      elite_num=self.elite_num, residual=self.residual, learn_logvar_bounds=self.learn_logvar_bounds,
+                                      num_layers=self.num_layers, hid_size=self.hid_size, activation_fn_cfg=self.activation_fn_cfg,
+                                      device=self.device)  # fmt: skip
+        sizes = [torch.zeros(1, dtype=torch.int64, device=self.min_logvar.device if not self.deterministic else self.device) for _ in range(world)]
+        mine = torch.tensor([self._sub1 - self._sub0], dtype=torch.int64, device=sizes[0].device)
+        dist.all_gather(sizes, mine, group=group)
+        sizes = [int(x.item()) for x in sizes]
+        assert sum(sizes) == self.obs_size, "the shards of the group do not cover the output dimensions exactly once"
+        biggest = max(sizes)
+        with torch.no_grad():
+            for p_full, p_loc in zip(full.parameters(), self.parameters()):
+                pad = torch.zeros((biggest,) + tuple(p_loc.shape[1:]), dtype=p_loc.dtype, device=p_loc.device)
+                pad[: p_loc.shape[0]].copy_(p_loc)
+                parts = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad, group=group)
+                p_full.copy_(torch.cat([part[:n] for part, n in zip(parts, sizes)], dim=0))
+        full.set_input_mask(self._input_mask)
+        full.set_elite_members(list(self.elite_members))
+        return full
 
     def set_input_mask(self, mask):
         self._input_mask = to_tensor(mask).to(self.device)
@@ -139,7 +204,8 @@ class ExternalMaskTransition(BaseTransition):
         if m is None or m.device != self.mean_and_logvar.weight.device:
             assert self._input_mask is not None
             assert 2 <= self._input_mask.ndim <= 4
-            m = self._input_mask.to(device=self.mean_and_logvar.weight.device, dtype=torch.float32).contiguous()
+            m = self._input_mask.to(device=self.mean_and_logvar.weight.device, dtype=torch.float32)
+            m = m[self._sub0:self._sub1].contiguous()  # (all rows unless this is a net shard)
             self._mask_f32 = m
         return m
 

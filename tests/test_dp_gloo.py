@@ -84,6 +84,55 @@ def test_dp_gradient_allreduce_matches_full_batch():
     assert ok and err < 1e-5
 
 
+def _shard_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import cmrl_b200 as cm
+
+    P = 5  # dealt 3 + 2 over two ranks
+    p0, p1 = cm.net_shard_range(P, world, rank)
+    torch.manual_seed(100 + rank)
+    shard = cm.ExternalMaskTransition(P, 1, hid_size=8, subnet_range=(p0, p1))
+    mask = (np.arange(P * (P + 1)).reshape(P, P + 1) % 3 != 0).astype(np.float32)
+    shard.set_input_mask(torch.from_numpy(mask))
+    shard.set_elite_members([4, 2, 0, 1, 3])
+    dyn = cm.PlainEnsembleDynamics(shard, learned_reward=False)
+    dyn.enable_net_sharding()
+    ok = shard.is_net_shard and tuple(shard._kernel_mask().shape) == (p1 - p0, P + 1) and np.array_equal(shard._kernel_mask().numpy(), mask[p0:p1])
+    ok = ok and shard._grad_dims() == P and shard._head_dim == p1 - p0
+    mine = {k: v.clone() for k, v in shard.state_dict().items()}
+    full = dyn.gather_net_shards()
+    ok = ok and not full.is_net_shard and dyn.transition is full and list(full.elite_members) == [4, 2, 0, 1, 3]
+    ok = ok and np.array_equal(full.input_mask.numpy(), mask)
+    for k, v in full.state_dict().items():  # this rank's slice of every tensor came through unchanged
+        ok = ok and v.shape[0] == P and torch.equal(v[p0:p1], mine[k])
+    flat = torch.cat([v.reshape(-1) for v in full.state_dict().values()])
+    both = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(both, flat)
+    ok = ok and all(torch.equal(b, both[0]) for b in both)
+    if rank == 0:
+        out.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_net_shards_gather_into_the_full_transition():
+    """Net sharding: ranks hold disjoint sub-network ranges of an ExternalMaskTransition; the gather
+    assembles identical full models everywhere (host logic on gloo; the arithmetic of shards is a GPU test)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
+
+
 def test_dp_row_slices_cover_ragged_batches():
     from cmrl_b200.dynamics import dp_row_slice
 

@@ -1292,3 +1292,66 @@ def test_forward_euler_fake_env_golden(cm, precision):
             assert rel_err(term, g["termobs%d" % s]) < tol
         else:  # a 1e-3 perturbation moved an env across the termination threshold: later steps are not comparable
             break
+
+
+def test_net_shards_train_like_the_full_model(cm):
+    """SURVEY 8e row 2 (net sharding): the sub-networks of an ExternalMaskTransition are independent, so shards holding
+    dimensions [0,3) and [3,5) -- trained separately, no exchange -- reproduce the full model's slices (same kernels per net;
+    the loss scale uses the FULL dimension count), and the shards' hold-out sums add up to the full model's score."""
+    torch.manual_seed(5)
+    rng = np.random.default_rng(5)
+    P, A, E, B, H = 5, 1, 7, 96, 48
+    mask = (rng.uniform(size=(P, P + A)) < 0.6).astype(np.float32)
+    mask[np.arange(P), np.arange(P)] = 1
+    full = cm.ExternalMaskTransition(P, A, hid_size=H, activation_fn_cfg=SILU, device=DEV)
+    full.set_input_mask(torch.from_numpy(mask))
+    shards = []
+    for p0, p1 in ((0, 3), (3, 5)):
+        sh = cm.ExternalMaskTransition(P, A, hid_size=H, activation_fn_cfg=SILU, device=DEV, subnet_range=(p0, p1))
+        sh.set_input_mask(torch.from_numpy(mask))
+        with torch.no_grad():
+            for q_full, q_sh in zip(full.parameters(), sh.parameters()):
+                q_sh.copy_(q_full[p0:p1])
+        shards.append(sh)
+    dyn_full = cm.PlainEnsembleDynamics(full, learned_reward=False, optim_lr=1e-3)
+    dyn_sh = [cm.PlainEnsembleDynamics(sh, learned_reward=False, optim_lr=1e-3) for sh in shards]
+    cm.ops.TRAIN_FUSED, keep = False, cm.ops.TRAIN_FUSED  # the full model on the per-layer kernels too: same arithmetic per net
+    try:
+        for step in range(3):
+            obs = t(rng.normal(size=(E, B, P)).astype(np.float32))
+            act = t(rng.uniform(-1, 1, size=(E, B, A)).astype(np.float32))
+            tgt = obs + 0.1 * torch.tanh(obs)
+            loss_full = dyn_full.train_step("transition", obs, act, tgt)
+            for sh, d in zip(shards, dyn_sh):
+                loss_sh = d.train_step("transition", obs, act, sh.target_columns(tgt).contiguous())
+                p0, p1 = sh.subnet_range
+                assert rel_err(loss_sh.cpu().numpy(), loss_full[..., p0:p1].cpu().numpy()) < TOL
+    finally:
+        cm.ops.TRAIN_FUSED = keep
+    for sh in shards:
+        p0, p1 = sh.subnet_range
+        for (name, q_full), (_, q_sh) in zip(full.named_parameters(), sh.named_parameters()):
+            assert record_max("net shard vs full model weights", rel_err(q_sh.detach().cpu().numpy(), q_full[p0:p1].detach().cpu().numpy())) < 1e-6, name
+    # forward of a shard = its columns of the full forward (residual included)
+    obs, act = t(rng.normal(size=(E, 33, P)).astype(np.float32)), t(rng.uniform(-1, 1, size=(E, 33, A)).astype(np.float32))
+    with torch.no_grad():
+        m_full, lv_full = full.forward(obs, act)
+        for sh in shards:
+            p0, p1 = sh.subnet_range
+            m_sh, lv_sh = sh.forward(obs, act)
+            assert rel_err(m_sh.cpu().numpy(), m_full[..., p0:p1].cpu().numpy()) < 1e-6
+            assert rel_err(lv_sh.cpu().numpy(), lv_full[..., p0:p1].cpu().numpy()) < 1e-6
+    # hold-out score: the shards' [E] sums over their dimensions add up to the full model's
+    from cmrl_b200.transition_iterator import TransitionIterator
+    from cmrl_b200.types import InteractionBatch
+
+    n = 300
+    o = rng.normal(size=(n, P)).astype(np.float32)
+    a = rng.uniform(-1, 1, size=(n, A)).astype(np.float32)
+    val = TransitionIterator(InteractionBatch(o, a, (o + 0.1 * np.tanh(o)).astype(np.float32), np.zeros(n, np.float32), np.zeros(n, bool)), 128)
+    score_full = dyn_full.evaluate_member_mse(val, "transition").numpy().astype(np.float64)
+    parts = [d.evaluate_member_mse(val, "transition").numpy().astype(np.float64) * (sh.subnet_range[1] - sh.subnet_range[0])
+             for sh, d in zip(shards, dyn_sh)]
+    assert rel_err(sum(parts) / P, score_full) < TOL
+    with pytest.raises(cm._lib.CmrlB200Error):
+        shards[0].packed_f16()
