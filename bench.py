@@ -383,7 +383,7 @@ def run_native(args):
     if not args.no_train:
         train = time_train(cm, ctx, args, B=256, n_batches=200)
         train["roofline"] = train_kernel_roofline(cm, ctx, 256)
-        train["bs4096"] = time_train(cm, ctx, args, B=4096, n_batches=12)
+        train["bs4096"] = time_train(cm, ctx, args, B=4096, n_batches=24)
         train["bs4096"]["roofline"] = train_kernel_roofline(cm, ctx, 4096)
         if not args.quick:
             train["c4"] = time_train_c4(cm, ctx, args)

@@ -514,6 +514,9 @@ class _DeviceEpochRunner:
         self._order_flip = 0
         self._staged_order = None  # (the int64 permutation object, its int32 copy in pinned memory)
 
+    def _stage_next(self, order):
+        self._staged_order = (order, self._stage_order(order))
+
     def _stage_order(self, order):
         """int32 copy of an epoch order in one of two pinned buffers (the other may still be in flight to the device)."""
         buf = self._order_pinned[self._order_flip]
@@ -538,12 +541,14 @@ class _DeviceEpochRunner:
 
     def run_epoch(self):
         ds = self.dataset
-        iter(ds)  # reshuffles exactly like the reference iterator (one rng.permutation per epoch)
+        iter(ds)  # reshuffles exactly like the reference iterator (one rng.permutation per epoch); joins a background draw
         staged = self._staged_order
         if staged is None or staged[0] is not ds._order:
             staged = (ds._order, self._stage_order(ds._order))
         self._staged_order = None
         self.order.copy_(staged[1], non_blocking=True)
+        # the NEXT epoch's permutation is drawn and staged on a helper thread while this epoch is launched and executed
+        ds.prefetch_order(background=True, then=self._stage_next)
         self.start[:1].fill_(self.row_slice.start)
         self.loss_sum.zero_()
         model = getattr(self.dyn, self.mech)
@@ -589,10 +594,6 @@ class _DeviceEpochRunner:
             if loss.numel() > 0:
                 ops.sum_acc_f64(loss.contiguous(), self.loss_sum, self.sum_ws)
         ds._current_batch = len(ds)  # the iterator is exhausted, like after a `for batch in dataset` loop
-        # the GPU is still executing this epoch: draw and stage the next epoch's permutation meanwhile
-        nxt = ds.prefetch_order()
-        if nxt is not None:
-            self._staged_order = (nxt, self._stage_order(nxt))
         if self.dyn.dp_group is not None:
             import torch.distributed as dist
 

@@ -157,6 +157,11 @@ def test_prefetched_epoch_order_is_the_order_the_next_pass_would_have_drawn():
         iter(b)
         orders_b.append(b._order.copy())
     assert all(np.array_equal(x, y) for x, y in zip(orders_a, orders_b))
+    # drawn on the helper thread: the next pass joins it and takes that draw; the callback saw the same array
+    seen = []
+    assert a.prefetch_order(background=True, then=seen.append) is None
+    iter(a), iter(b)
+    assert np.array_equal(a._order, b._order) and len(seen) == 1 and seen[0] is a._order
     shared = cm.TransitionIterator(data, 16, shuffle_each_epoch=True, rng=np.random.default_rng(3))
     assert shared.prefetch_order() is None
     assert cm.TransitionIterator(data, 16, shuffle_each_epoch=False).prefetch_order() is None
