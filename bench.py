@@ -385,10 +385,10 @@ def run_native(args):
         train["roofline"] = train_kernel_roofline(cm, ctx, 256)
         train["bs4096"] = time_train(cm, ctx, args, B=4096, n_batches=24)
         train["bs4096"]["roofline"] = train_kernel_roofline(cm, ctx, 4096)
-        if not args.quick:
+        if not args.quick or args.c4:
             train["c4"] = time_train_c4(cm, ctx, args)
-            if not args.skip_c5:
-                train["c5"] = time_train_c5(cm, ctx)
+        if not args.quick and not args.skip_c5:
+            train["c5"] = time_train_c5(cm, ctx)
 
     # ---- the other configs of BASELINE.json + tiers / contracts -----------------------------------------------------------
     configs = {}
@@ -785,6 +785,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training half of the metric")
     ap.add_argument("--quick", action="store_true", help="headline + short training legs only (no C1/C3/C4/C5 sub-records)")
     ap.add_argument("--skip-c5", action="store_true")
+    ap.add_argument("--c4", action="store_true", help="with --quick: still run the 10 M-row C4 training epoch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

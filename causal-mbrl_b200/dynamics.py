@@ -218,13 +218,14 @@ class BaseDynamics:
 
     def train_step(self, mech: str, obs: torch.Tensor, act: torch.Tensor, target: torch.Tensor,
                    want_loss: bool = True, grad_rows: Optional[int] = None, graphable: bool = False,
-                   data_ready=None):  # fmt: skip
+                   data_ready=None, loss_ready=None):  # fmt: skip
         """One optimiser step on an ensemble batch (obs/act/target: [E,B,*] device tensors), equivalent to
         `loss = get_nll_loss(...); zero_grad(); loss.mean().backward(); step()` (base_dynamics.py:181-186).
         Returns the un-reduced loss [E,B,D] (None if not wanted).  grad_rows: global rows per member when the
         batch is one shard of a data-parallel step.  data_ready: called (once) right before the first kernel that reads
         the batch -- the device-resident epoch assembles the batch on a side stream next to the weight packing and joins
-        the streams there."""
+        the streams there.  loss_ready(loss): called by the fused step as soon as the loss is enqueued (the epoch's loss
+        bookkeeping then runs on a side stream under the weight-gradient kernel); returns True there, else it is not called."""
         model = getattr(self, mech)
         optim = getattr(self, "{}_optimizer".format(mech))
         if data_ready is not None and ((model.deterministic or any(p.requires_grad for p in model._bounds() if p is not None)
@@ -258,7 +259,7 @@ class BaseDynamics:
             mn, mx = model._bounds()
             rows = B if grad_rows is None else grad_rows
             loss = plan.step(obs, act, target, mn, mx, model._nll_reg(), 1.0 / float(E * rows * model._head_dim), want_loss,
-                             after_pack=data_ready)
+                             after_pack=data_ready, after_fused=loss_ready)
             self._sync_and_step(model, optim, graphable)
             return loss
         params = model._stack_params()
@@ -535,9 +536,21 @@ class _DeviceEpochRunner:
                 ops.bootstrap_gather(self.obs, self.act, self.target, self.member_idx, self.order, self.start, self.B, self.Bl,
                                      self.b_obs, self.b_act, self.b_tgt)  # fmt: skip
             join = lambda: main.wait_stream(self.side)  # noqa: E731
+        summed = []
+
+        def sum_on_side(loss):  # the running epoch loss, under the weight-gradient kernel
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                ops.sum_acc_f64(loss, self.loss_sum, self.sum_ws)
+            summed.append(True)
+
         loss = self.dyn.train_step(self.mech, self.b_obs, self.b_act, self.b_tgt, want_loss=True, graphable=True,
-                                   grad_rows=self.B if self.dyn.dp_group is not None else None, data_ready=join)  # fmt: skip
-        ops.sum_acc_f64(loss, self.loss_sum, self.sum_ws)
+                                   grad_rows=self.B if self.dyn.dp_group is not None else None, data_ready=join,
+                                   loss_ready=sum_on_side)  # fmt: skip
+        if summed:
+            main.wait_stream(self.side)
+        elif loss.numel() > 0:
+            ops.sum_acc_f64(loss, self.loss_sum, self.sum_ws)
 
     def run_epoch(self):
         ds = self.dataset

@@ -588,15 +588,18 @@ class FusedTrainPlan:
                   self.head_outputs, self.act, self.dw_ptrs, self.db_ptrs, _ptr(m), self.mask_str[0], self.mask_str[1],
                   _ptr(self.dw_ws), 0 if self.dw_ws is None else self.dw_ws.numel(), _stream())  # fmt: skip
 
-    def step(self, obs, act, target, mn, mx, reg, g_scale, want_loss=True, after_pack=None):
+    def step(self, obs, act, target, mn, mx, reg, g_scale, want_loss=True, after_pack=None, after_fused=None):
         """pack -> fused forward / NLL / dz chain -> weight gradients, all on the current stream; returns the loss.
-        after_pack: called between the packing (which reads only the weights) and the first kernel that reads the batch."""
+        after_pack: called between the packing (which reads only the weights) and the first kernel that reads the batch;
+        after_fused(loss): called once the loss is enqueued, before the weight-gradient kernel (bookkeeping on a side stream)."""
         obs, act, target = _rows_contig(_req(obs, "obs"), "obs"), _rows_contig(_req(act, "act"), "act"), _rows_contig(_req(target, "target"), "target")
         loss = torch.empty((self.E, self.B, self.head_dim), device=obs.device, dtype=torch.float32) if want_loss else None
         self.run_pack()
         if after_pack is not None:
             after_pack()
         self.run_fused(obs, act, target, mn, mx, reg, g_scale, loss)
+        if after_fused is not None:
+            after_fused(loss)
         self.run_dw()
         return loss
 
