@@ -312,7 +312,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
     uint64_t* bar_dfull = bars + 3 * S + 2 * TF_A_SLOTS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = v3_ctarank();
-    const int pair0 = blockIdx.x / 2, pair_step = gridDim.x / 2;
 
     if (INFER) {
         if ((int)threadIdx.x <= p.E) s_rowoff[threadIdx.x] = p.row_off[threadIdx.x];
@@ -350,13 +349,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
     const uint32_t col_head = (uint32_t)(2 * g.HP), col_alo = (uint32_t)(2 * g.HP + g.NH);
     const int hi_only = p.passes == 1;
     const int n_pairs = p.P * s_pref[p.E];  // work items of a cluster: two row tiles of one net
+    // A cluster takes a contiguous range of the work list (net-major), like the f16 rollout kernel: neighbouring clusters work on
+    // different nets.  (Measured neutral against a strided assignment: the weight stream is not what paces the kernel -- with the
+    // weight copies disabled the event trace of a 4 096-row step is unchanged, profiles/r2_train_trace_4096.txt.)
+    const int n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
+    const int pair0 = (int)((long long)cid * n_pairs / n_clusters), pair_end = (int)((long long)(cid + 1) * n_pairs / n_clusters);
+    constexpr int pair_step = 1;
 
     if (warp == TF_WARP_W) {
         // ===================== weight producer: this CTA's half (N/2 output rows, hi | lo) of every 16-deep K chunk =================
         if (lane == 0) {
             uint32_t n = 0;
             TRACE_DECL;
-            for (int pair = pair0; pair < n_pairs; pair += pair_step) {
+            for (int pair = pair0; pair < pair_end; pair += pair_step) {
                 const PairInfo pi = pair_info(s_pref, p.E, pair);
                 const float* blob = p.packed + (long long)(pi.pp * p.E + pi.e) * g.blob_floats;
                 for (int ph = 0; ph < g.n_ph; ++ph) {
@@ -383,7 +388,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
         // ===================== forwarder: tells the leader CTA that this CTA's half of a weight stage has landed ===================
         if (lane == 0) {
             uint32_t n = 0;
-            for (int pair = pair0; pair < n_pairs; pair += pair_step)
+            for (int pair = pair0; pair < pair_end; pair += pair_step)
                 for (int ph = 0; ph < g.n_ph; ++ph)
                     for (int c = 0; c < g.ph_k[ph] / 16; ++c, ++n) {
                         const uint32_t s = n % (uint32_t)S;
@@ -400,7 +405,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
         // ===================== A-chunk waiter (leader): all 8 producer warps of a chunk have published it ==========================
         if (lane == 0 && rank == 0) {
             uint32_t seq = 0;
-            for (int pair = pair0; pair < n_pairs; pair += pair_step)
+            for (int pair = pair0; pair < pair_end; pair += pair_step)
                 for (int ph = 0; ph < g.n_ph; ++ph)
                     for (int c = 0; c < g.ph_k[ph] / 16; ++c, ++seq) {
                         mbar_wait(&bar_afull[seq % TF_A_SLOTS], (seq / TF_A_SLOTS) & 1);
@@ -417,7 +422,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
         const uint32_t a0 = smem_u32(smem), w0 = smem_u32(smem + p.w_off);
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
         const uint32_t a_lbo = (TF_GROUP >> 4) << 16;
-        for (int pair = pair0; rank == 0 && pair < n_pairs; pair += pair_step) {  // the leader issues for the pair
+        for (int pair = pair0; rank == 0 && pair < pair_end; pair += pair_step) {  // the leader issues for the pair
             for (int ph = 0; ph < g.n_ph; ++ph, ++n_phase) {
                 const int N = g.ph_n[ph];
                 const uint32_t idesc = umma_idesc_tf32(2 * TF_ROWS, N);
@@ -483,7 +488,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
 #ifdef CMRL_TRACE
         int fine_n = 0;
 #endif
-        for (int pair = pair0; pair < n_pairs; pair += pair_step) {
+        for (int pair = pair0; pair < pair_end; pair += pair_step) {
             const PairInfo pi = pair_info(s_pref, p.E, pair);
             const int pp = pi.pp, e = pi.e, net = pp * p.E + e;
             const int tile = pi.tp * 2 + (int)rank;  // may be a padding tile: no valid row
