@@ -326,9 +326,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
         a_ready_seq = 0;
         w_ready_n = 0;
         for (int s = 0; s < S; ++s) {
-            mbar_init(&bar_wfull[s], 1);
+            // the leader's "stage landed" barrier also counts the peer's report that ITS half landed: one wait per chunk tells
+            // the leader's forwarder that the whole stage is there (a separate both-halves barrier meant two waits in a row;
+            // measured neutral -- the forwarder is not what paces the kernel -- but one barrier less per stage)
+            mbar_init(&bar_wfull[s], rank == 0 ? 2 : 1);
             mbar_init(&bar_wempty[s], 1);
-            mbar_init(&bar_wready[s], 2);  // both CTAs' halves of the stage have landed
+            mbar_init(&bar_wready[s], 2);  // (unused since round 2)
         }
         for (int s = 0; s < TF_A_SLOTS; ++s) {
             mbar_init(&bar_afull[s], 8);  // the four lane quarters of one column set, in both CTAs
@@ -393,9 +396,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
                     for (int c = 0; c < g.ph_k[ph] / 16; ++c, ++n) {
                         const uint32_t s = n % (uint32_t)S;
                         mbar_wait(&bar_wfull[s], (n / (uint32_t)S) & 1);
-                        v3_arrive_leader(&bar_wready[s]);
-                        if (rank == 0) {  // both halves landed -> tell the issuer through the plain counter
-                            mbar_wait(&bar_wready[s], (n / (uint32_t)S) & 1);
+                        if (rank != 0) {
+                            v3_arrive_leader(&bar_wfull[s]);  // the second arrival of the leader's barrier for this stage
+                        } else {  // own bytes and the peer's report are in -> tell the issuer through the plain counter
                             __threadfence_block();
                             w_ready_n = n + 1;
                         }
