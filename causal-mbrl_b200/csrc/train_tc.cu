@@ -54,11 +54,18 @@ __device__ int g_trace_flags = 0;
         if (g_trace_buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && trace_n < 1024) \
             g_trace_buf[(role) * 1024 + trace_n++] = clock64();                                                       \
     } while (0)
+// per-chunk stamps of the MMA issuer (row 4), phase 1 of the first work item
+#define TRACE_MMA(on)                                                                                                 \
+    do {                                                                                                              \
+        if ((on) && g_trace_buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && mma_n < 1024) \
+            g_trace_buf[4 * 1024 + mma_n++] = clock64();                                                              \
+    } while (0)
 #else
 #define XFLAG(bit) 0
 #define TRACE_DECL
 #define TRACE(role)
 #define TRACE_FINE(on)
+#define TRACE_MMA(on)
 #endif
 
 // Geometry shared by the three kernels (built on the host by make_geom)
@@ -420,6 +427,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
         // ===================== MMA issuer: chases the epilogue through the A ring ================================================
         uint32_t n = 0, seq = 0, n_phase = 0;
         TRACE_DECL;
+#ifdef CMRL_TRACE
+        int mma_n = 0;
+#endif
         // Descriptors are kept as (lo, hi) words: hi = stride field | version, lo = start address | leading-dimension field; an MMA
         // costs the issuing thread two 32-bit adds.
         const uint32_t a0 = smem_u32(smem), w0 = smem_u32(smem + p.w_off);
@@ -438,19 +448,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
 #pragma unroll 1
                 for (int c = 0; c < nch; ++c, ++n, ++seq) {
                     const uint32_t s = n % (uint32_t)S, slot = seq % TF_A_SLOTS;
+                    TRACE_MMA(n_phase == 1);
                     {
                         unsigned long long spins = 0;
                         while (a_ready_seq <= seq)
                             if (++spins > SPIN_LIMIT) __trap();
                         if (c == 0) TRACE(2);
+                        TRACE_MMA(n_phase == 1);
                         while (w_ready_n <= n)
                             if (++spins > SPIN_LIMIT) __trap();
                     }
                     if (c == 0) TRACE(2);
                     if (c == nch - 1) TRACE(2);
+                    TRACE_MMA(n_phase == 1);
                     __threadfence_block();
-                    fence_proxy_async();
+                    fence_proxy_async();  // (measured free: dropping it changes nothing)
                     tc_fence_after();
+                    TRACE_MMA(n_phase == 1);
                     const uint32_t ah = ((a0 + slot * TF_A_SLOT) >> 4) | a_lbo, al = ah + (TF_A_PART >> 4);
                     const uint32_t bh = ((w0 + s * p.stage_bytes) >> 4) | b_lbo_f, bl = bh + b_part;
                     const uint32_t first = c == 0 ? 0u : 1u;
@@ -470,8 +484,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
                             tf32_mma2_lohi_uni(d_t, ah + (2 * TF_GROUP >> 4), desc_hi, bh + b_ks, desc_hi, idesc, 1u);
                         }
                     }
+                    TRACE_MMA(n_phase == 1);
                     v3_commit_uni(&bar_wempty[s]);  // cta_group::2 commits arrive in both CTAs of the pair
                     v3_commit_uni(&bar_aempty[slot]);
+                    TRACE_MMA(n_phase == 1);
                 }
                 v3_commit_uni(bar_dfull);
                 TRACE(2);

@@ -36,7 +36,8 @@ plan.step(obs, act, target, mn, mx, 0.5, 1e-4)  # packs the weights (product lib
 torch.cuda.synchronize()
 st = ops._stream()
 fine = []
-trace = torch.zeros(4 * 1024, dtype=torch.int64, device=dev)
+mma_fine = []
+trace = torch.zeros(5 * 1024, dtype=torch.int64, device=dev)
 
 
 def run(which, passes=3):
@@ -51,10 +52,11 @@ def run(which, passes=3):
                                plan.db_ptrs, None, 0, 0, ops._ptr(plan.dw_ws), 0 if plan.dw_ws is None else plan.dw_ws.numel(), st)
     assert rc == 0, lib.cmrl_last_error()
     torch.cuda.synchronize()
-    t = trace.cpu().numpy().reshape(4, 1024)
+    t = trace.cpu().numpy().reshape(5, 1024)
     t0 = min(int(r[r > 0].min()) for r in t if (r > 0).any())
-    global fine
+    global fine, mma_fine
     fine = t[3][t[3] > 0] - t0
+    mma_fine = t[4][t[4] > 0] - t0
     return [(r[r > 0] - t0) for r in t[:3]]
 
 
@@ -75,6 +77,11 @@ for passes in (3, 1):
     for i in range(0, len(fine) - 6, 7):
         f = fine[i:i + 7]
         print("    top %7d: %s" % (f[0], " ".join("%5d" % (f[j] - f[j - 1]) for j in range(1, 7))))
+
+    print(" MMA issuer, phase 1, per chunk: loop-top | +A chunk ready | +weights ready | +fences | +MMAs issued | +commits")
+    for i in range(0, len(mma_fine) - 5, 6):
+        f = mma_fine[i:i + 6]
+        print("    top %7d: %s" % (f[0], " ".join("%5d" % (f[j] - f[j - 1]) for j in range(1, 6))))
 
 # attribution experiments (results invalid): which resource paces the fused kernel?
 lib.cmrl_trace_flags.argtypes = [ctypes.c_int]
