@@ -577,10 +577,14 @@ def train_kernel_roofline(cm, ctx, B):
     ach = f_fused / (out["fused"] * 1e-3) / 1e12
     return {
         "kernel": "train_fused_kernel (forward + Gaussian head + NLL + dz chain, tcgen05 kind::tf32, 3xTF32)", "bound": "tensor",
-        "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+        "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+        # dram__bytes_read + dram__bytes_write per launch from the committed `ncu --set full` capture (profiles/r2_ncu_kernels.csv)
+        "traffic": {256: 15.2e6, 4096: 180.8e6}.get(B), "traffic_unit": "bytes per launch (ncu --set full, profiles/r2_ncu_kernels.csv)",
+        "tensor_pipe_active_pct_ncu": {256: 40.9, 4096: 40.4}.get(B),
         "peak_source": src + " bf16 burst", "flops_per_launch": f_fused, "ms_per_launch": out["fused"],
         "dw_kernel": {"kernel": "train_dw_kernel (all layers' weight / bias gradients)", "flops_per_launch": f_dw, "ms_per_launch": out["dw"],
-                      "achieved": f_dw / (out["dw"] * 1e-3) / 1e12, "frac": f_dw / (out["dw"] * 1e-3) / 1e12 / pk["bf16_tflops"]},
+                      "achieved": f_dw / (out["dw"] * 1e-3) / 1e12, "frac": f_dw / (out["dw"] * 1e-3) / 1e12 / pk["bf16_tflops"],
+                      "traffic": {256: 12.2e6, 4096: 198.0e6}.get(B), "tensor_pipe_active_pct_ncu": {256: 15.7, 4096: 27.8}.get(B)},
         "note": "algorithmic FLOPs (2*MAC, padding not counted); 3xTF32 issues three kind::tf32 MMAs per product, each at half the "
                 "bf16 rate, so 1/6 of the bf16 peak (%.0f TFLOP/s) is this tier's tensor-pipe ceiling" % (pk["bf16_tflops"] / 6),
     }  # fmt: skip

@@ -1355,3 +1355,53 @@ def test_net_shards_train_like_the_full_model(cm):
     assert rel_err(sum(parts) / P, score_full) < TOL
     with pytest.raises(cm._lib.CmrlB200Error):
         shards[0].packed_f16()
+
+
+def test_small_training_kernels_round2(cm):
+    """Deterministic fp64 loss accumulation (one block and many), Adam on sizes / offsets that leave the 16-byte path (tail of
+    1-3 elements, unaligned arenas) with the step counter advanced by the kernel's last block, and the gradient exchange of a
+    single-rank communicator (plain Adam through the exchange kernel)."""
+    import ctypes
+
+    rng = np.random.default_rng(11)
+    for n in (1, 1000, 8960, 300_001):
+        x = rng.normal(size=n).astype(np.float32)
+        acc = torch.full((), 2.5, device=DEV, dtype=torch.float64)
+        ws = torch.zeros(66, device=DEV, dtype=torch.float64)
+        for _ in range(3):  # the arrival ticket of the workspace resets itself
+            cm.ops.sum_acc_f64(t(x), acc, ws)
+        ref = 2.5 + 3 * float(np.sum(x.astype(np.float64)))
+        assert abs(float(acc.item()) - ref) <= 1e-12 * max(1.0, abs(ref)) * n ** 0.5 + 1e-12
+    for n, off in ((7, 0), (1026, 0), (4099, 1), (65_537, 3)):
+        base = [torch.zeros(n + 8, device=DEV) for _ in range(4)]
+        p_, g_, m_, v_ = (b[off:off + n] for b in base)
+        p0, g0 = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)
+        p_.copy_(t(p0)), g_.copy_(t(g0))
+        step = torch.tensor([4, 0], dtype=torch.int32, device=DEV)
+        cm.ops.adam_l2_step_dev(p_, g_, m_, v_, 1e-3, 0.9, 0.999, 1e-8, 1e-5, step, 0.5)
+        # closed form of one Adam step from zero moments at step t = 5 (torch.optim.Adam, L2-coupled decay)
+        gi = 0.5 * g0.astype(np.float64) + 1e-5 * p0.astype(np.float64)
+        m1, v1 = 0.1 * gi, 0.001 * gi * gi
+        upd = (1e-3 / (1 - 0.9 ** 5)) * m1 / (np.sqrt(v1) / np.sqrt(1 - 0.999 ** 5) + 1e-8)
+        assert rel_err(p_.cpu().numpy(), p0 - upd) < 1e-6
+        assert step.cpu().tolist() == [5, 0]
+        assert float(base[0][:off].abs().sum()) == 0.0 and float(base[0][off + n:].abs().sum()) == 0.0  # nothing outside the arena
+    # single-rank communicator: the exchange kernel degenerates to Adam + counter update
+    comm, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+    n = 10_003
+    cm._lib.call("cmrl_dp_comm_create", 0, 1, n, ctypes.byref(comm), handle)
+    try:
+        p_, g_, m_, v_ = t(rng.normal(size=n).astype(np.float32)), t(rng.normal(size=n).astype(np.float32)), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        q_, mq, vq = p_.clone(), m_.clone(), v_.clone()
+        s1, s2 = torch.tensor([2, 0], dtype=torch.int32, device=DEV), torch.tensor([2, 0], dtype=torch.int32, device=DEV)
+        g_keep = g_.clone()
+        cm._lib.call("cmrl_allreduce_grads_adam", comm, p_.data_ptr(), g_.data_ptr(), m_.data_ptr(), v_.data_ptr(), n, 1e-3, 0.9, 0.999,
+                     1e-8, 1e-5, 1.0, s1.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        cm.ops.adam_l2_step_dev(q_, g_keep, mq, vq, 1e-3, 0.9, 0.999, 1e-8, 1e-5, s2, 1.0)
+        assert torch.equal(p_, q_) and torch.equal(m_, mq) and torch.equal(v_, vq) and torch.equal(g_, g_keep)
+        assert s1.cpu().tolist() == [3, 0] == s2.cpu().tolist()
+        err = ctypes.c_int(7)
+        cm._lib.call("cmrl_dp_comm_error", comm, ctypes.byref(err))
+        assert err.value == 0
+    finally:
+        cm._lib.call("cmrl_dp_comm_destroy", comm)
