@@ -44,11 +44,11 @@ PROTOTYPES = {
     "cmrl_mopo_penalty": [_P, _I, _I, _I, _P, _P],
     "cmrl_pack_layer_f16": [_P, _P, _P, _LL, _LL, _I, _I, _I, _I, _I, _I, _I, ctypes.c_float, _P, _LL, _P],
     "cmrl_mlp_rollout_f16": [_P, _LL, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P,
-                             _I, _P, _P, _I, _P],
+                             _I, _P, _P, _LL, _I, _P],
     "cmrl_train_pack_tf32": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _LL, _LL, _P, _P],
     "cmrl_train_fused": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _P, _LL, _P, _LL, _I, _P, _P, _I, _F, _F,
                          _P, _P, _P],
-    "cmrl_mlp_rollout_tf32": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
+    "cmrl_mlp_rollout_tf32": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _LL, _P],
     "cmrl_train_dw": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _LL, _LL, _P, _LL, _P],
     "cmrl_env_step_tail": [_P, _P, _P, _P, _P, _F, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "cmrl_dp_comm_create": [_I, _I, _LL, _c.POINTER(_P), _c.c_char_p],

@@ -92,7 +92,7 @@ extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, co
                                     int A, int H, int head_dim, int layout, int gaussian, int act, const float* obs,
                                     const float* actn, const int* perm, const int* offsets, int residual,
                                     const float* min_logvar, const float* max_logvar, int bounds_n, const float* noise,
-                                    float* pred, int variant, void* stream) {
+                                    float* pred, long long pred_member_stride, int variant, void* stream) {
     CMRL_REQUIRE(packed && obs && perm && offsets && pred, "mlp_rollout_f16: null pointer");
     CMRL_REQUIRE(num_layers >= 1 && num_layers <= 7, "mlp_rollout_f16: 1..7 hidden layers supported");
     CMRL_REQUIRE(E >= 1 && E <= 64, "mlp_rollout_f16: E must be <= 64");
@@ -137,6 +137,7 @@ extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, co
     p.bounds_n = bounds_n;
     p.noise = noise;
     p.pred = pred;
+    p.pred_se = pred_member_stride;
     // variant 0: chosen by shape -- un-widened packing (hidden layers too wide for the weight-stationary kernels) -> 6; two tiles'
     // accumulators and heads fit tensor memory and the operands fit shared memory -> 5; otherwise 3
     if (variant == 0) variant = layer_n[0] == H ? 6 : (tc::rollout_v5_supports(p) ? 5 : 3);

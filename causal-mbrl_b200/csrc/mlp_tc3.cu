@@ -330,7 +330,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
                                 const float lv = soft_clamp_logvar(__uint_as_float(raw[1]), p.min_logvar[bi], p.max_logvar[bi]);
                                 out += sqrtf(expf(lv)) * p.noise[env * D + pr.pp];
                             }
-                            p.pred[env * D + pr.pp] = out;
+                            p.pred[(long long)(pr.net % p.E) * p.pred_se + env * D + pr.pp] = out;
                         }
                     } else if (p.gaussian) {
 #pragma unroll
@@ -344,7 +344,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
                                     const float lv = soft_clamp_logvar(__uint_as_float(raw[j + 1]), p.min_logvar[bi], p.max_logvar[bi]);
                                     m += sqrtf(expf(lv)) * p.noise[env * D + d];
                                 }
-                                p.pred[env * D + d] = m;
+                                p.pred[(long long)(pr.net % p.E) * p.pred_se + env * D + d] = m;
                             }
                         }
                     } else {
@@ -354,7 +354,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)
                             if (d < D) {
                                 float m = __uint_as_float(raw[j]);
                                 if (p.residual) m += p.obs[env * p.O + d];
-                                p.pred[env * D + d] = m;
+                                p.pred[(long long)(pr.net % p.E) * p.pred_se + env * D + d] = m;
                             }
                         }
                     }

@@ -343,7 +343,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
                             const float lv = soft_clamp_logvar(__uint_as_float(r1), p.min_logvar[bi], p.max_logvar[bi]);
                             m += sqrtf(expf(lv)) * (p.layout == CMRL_HEAD_PARALLEL ? nz0 : p.noise[env * D + d]);
                         }
-                        p.pred[env * D + od] = m;
+                        p.pred[(long long)(pr.net % p.E) * p.pred_se + env * D + od] = m;
                     }
                 }
                 tc_fence_before();

@@ -295,7 +295,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V6_THREADS, 1)
                             const float lv = soft_clamp_logvar(__uint_as_float(r1), p.min_logvar[bi], p.max_logvar[bi]);
                             m += sqrtf(expf(lv)) * p.noise[env * D + od];
                         }
-                        p.pred[env * D + od] = m;
+                        p.pred[(long long)(tl.net % p.E) * p.pred_se + env * D + od] = m;
                     }
                 }
             }

@@ -34,6 +34,7 @@ struct RolloutP {
     int bounds_n;
     const float* noise;        // [N,D] env order or NULL
     float* pred;               // [N,D] env order
+    long long pred_se;         // floats between the outputs of consecutive MEMBERS (0: one [N,D] array; E*N all-member rows: N*D)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -211,6 +211,7 @@ struct TrainP {
     const int *perm, *row_off;
     const float* noise;
     float* pred;
+    long long pred_se;  // floats between the outputs of consecutive members (0: one [N,D] array)
     int D;
 };
 constexpr int TF_MAX_E = 64;
@@ -609,7 +610,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1) train
                                     const float lv = soft_clamp_logvar(__uint_as_float(r1), p.min_logvar[bi], p.max_logvar[bi]);
                                     m += sqrtf(expf(lv)) * p.noise[rr * p.D + od];
                                 }
-                                p.pred[rr * p.D + od] = m;
+                                p.pred[(long long)e * p.pred_se + rr * p.D + od] = m;
                             }
                         }
                     } else if (kind == PH_DX) {
@@ -1108,7 +1109,7 @@ extern "C" int cmrl_train_fused(const float* packed, int L, int P, int E, int B,
 extern "C" int cmrl_mlp_rollout_tf32(const float* packed, int L, int P, int E, int N, int O, int A, int hidden, int head_dim, int layout,
                                      int act, int residual, const float* obs, const float* actn, const int* perm, const int* offsets,
                                      const float* min_logvar, const float* max_logvar, int bounds_n, const float* noise, float* pred,
-                                     void* stream) {
+                                     long long pred_member_stride, void* stream) {
     TrainP p{};
     const int Dn = layout == CMRL_HEAD_PARALLEL ? 1 : head_dim;
     if (make_geom(p.g, L, O + A, hidden, Dn) != 0) return -1;
@@ -1123,7 +1124,7 @@ extern "C" int cmrl_mlp_rollout_tf32(const float* packed, int L, int P, int E, i
     if (N == 0) return 0;
     p.packed = packed; p.P = P; p.E = E; p.B = 0; p.O = O; p.A = A; p.layout = layout; p.act = act; p.residual = residual; p.passes = 3;
     p.obs = obs; p.actn = actn; p.min_logvar = min_logvar; p.max_logvar = max_logvar; p.bounds_n = bounds_n;
-    p.perm = perm; p.row_off = offsets; p.noise = noise; p.pred = pred; p.D = head_dim;
+    p.perm = perm; p.row_off = offsets; p.noise = noise; p.pred = pred; p.pred_se = pred_member_stride; p.D = head_dim;
     // every member's rows round up to whole tile pairs: at most N / 256 + E pairs per sub-net
     return launch_fused(p, act, (long long)P * (N / (2 * TF_ROWS) + E), true, (cudaStream_t)stream);
 }

@@ -249,6 +249,13 @@ class VecFakeEnv(VecEnv):
             idx, noise = self._draw(mech, D)
         mask = model._kernel_mask()
         per_sample_mask = mask is not None and (mask.dim() == 4 or (mask.dim() == 3 and mask.shape[1] != model.ensemble_num))
+        if all_member_out is not None and not per_sample_mask:
+            means = self._all_member_means(model, obs, act)
+            if means is not None:
+                # MOPO penalty (fake_env.py:186-193) needs every member's mean: one pass of the fused tensor-core kernel over
+                # the all-member buckets (E x N rows), then the drawn member's sample through the selected-member pass
+                all_member_out["mean"] = means
+                return self.predict_selected(model, obs, act, idx, noise)
         if all_member_out is not None or per_sample_mask:
             with torch.no_grad():
                 mean, logvar = model.forward(obs.unsqueeze(0), act.unsqueeze(0))
@@ -257,8 +264,39 @@ class VecFakeEnv(VecEnv):
             return ops.select_sample(mean, logvar, idx, noise)
         return self.predict_selected(model, obs, act, idx, noise)
 
+    def _all_member_bufs(self, E, N, D, device):
+        key = (E, N, D, str(device))
+        cached = getattr(self, "_all_member_buckets", None)
+        if cached is None or cached[0] != key:
+            perm = torch.arange(N, device=device, dtype=torch.int32).repeat(E)
+            offsets = (torch.arange(E + 1, device=device, dtype=torch.int64) * N).to(torch.int32)
+            out = torch.empty((E, N, D), device=device, dtype=torch.float32)
+            cached = self._all_member_buckets = (key, perm, offsets, out)
+        return cached[1:]
+
+    def _all_member_means(self, model, obs, act):
+        """[E,N,D] means of EVERY member on the tensor-core tier of `self.precision`, or None when that tier does not take the
+        model (then the all-member CUDA-core forward runs).  The buckets are trivial: member e's rows are envs 0..N-1."""
+        if getattr(model, "repeat_times", None) is not None or model.deterministic:
+            return None
+        E, N, D = model.ensemble_num, obs.shape[0], model._head_dim
+        perm, offsets, out = self._all_member_bufs(E, N, D, obs.device)
+        mn, mx = model._bounds()
+        if self.precision == "f16":
+            return ops.mlp_rollout_f16(model.packed_f16(), model._parallel_num(), E, obs, act, perm, offsets, model.hid_size, D,
+                                       model._head_layout, True, model._act_kind, model._residual(), mn, mx, None, out=out,
+                                       all_members=True)  # fmt: skip
+        if self.precision == "fp32":
+            pack = model.packed_tf32()
+            if pack is not None and pack.ok:
+                return ops.mlp_rollout_tf32(pack, obs, act, perm, offsets, model._act_kind, model._residual(), mn, mx, None,
+                                            out=out, all_members=True)  # fmt: skip
+        return None
+
     def _prebuild_pack(self, model):
         """The packed operand copies of the active precision tier, built outside a graph capture (they allocate and launch)."""
+        if model is self.dynamics.transition and self.penalty_coeff and getattr(model, "repeat_times", None) is None:
+            self._all_member_bufs(model.ensemble_num, self.num_envs, model._head_dim, self.device)  # MOPO: all-member buckets
         model = getattr(model, "one_step_transition", model)  # ForwardEulerTransition rolls its one-step model out
         if self.precision == "f16":
             model.packed_f16()

@@ -457,7 +457,7 @@ TC_VARIANT = None
 
 
 def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, gaussian, act_kind, residual,
-                    min_logvar, max_logvar, noise, out=None):  # fmt: skip
+                    min_logvar, max_logvar, noise, out=None, all_members=False):  # fmt: skip
     import ctypes
 
     blob, layer_off, layer_k, layer_n = pack[:4]
@@ -471,12 +471,17 @@ def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, ga
     if pack[6]:
         assert act_kind == ACT_SILU, "this pack stores halved hidden layers: it belongs to a SiLU model"
         act_kind = ACT_SILU_HALF
-    pred = torch.empty((N, head_dim), device=obs.device, dtype=torch.float32) if out is None else out
+    # all_members: perm / offsets are the all-member buckets (E * N rows), the output is [E,N,D] (MOPO penalty: every member's mean)
+    rows = perm.numel()
+    if out is None:
+        out = torch.empty(((E, N, head_dim) if all_members else (N, head_dim)), device=obs.device, dtype=torch.float32)
+    pred = out
     bounds_n = 0 if min_logvar is None else min_logvar.numel()
     _lib.call("cmrl_mlp_rollout_f16", blob.data_ptr(), blob.shape[1], c_off, c_k, c_n, L,
-              P, E, N, O, A, H, head_dim, layout, 1 if gaussian else 0, act_kind, obs.data_ptr(), act.data_ptr(),
+              P, E, rows, O, A, H, head_dim, layout, 1 if gaussian else 0, act_kind, obs.data_ptr(), act.data_ptr(),
               perm.data_ptr(), offsets.data_ptr(), 1 if residual else 0, _ptr(min_logvar), _ptr(max_logvar),
-              bounds_n, _ptr(noise), pred.data_ptr(), 0 if TC_VARIANT is None else int(TC_VARIANT), _stream())  # fmt: skip
+              bounds_n, _ptr(noise), pred.data_ptr(), N * head_dim if all_members else 0,
+              0 if TC_VARIANT is None else int(TC_VARIANT), _stream())  # fmt: skip
     return pred
 
 
@@ -510,14 +515,17 @@ class Tf32RolloutPack:
                   self.in_size, self.hidden, head_outputs, _ptr(mask), m_str[0], m_str[1], self.packed.data_ptr(), _stream())
 
 
-def mlp_rollout_tf32(pack, obs, act, perm, offsets, act_kind, residual, min_logvar, max_logvar, noise, out=None):
-    """Fused selected-member rollout on tcgen05 kind::tf32 with hi/lo split operands (fp32-grade): see cmrl_mlp_rollout_tf32."""
+def mlp_rollout_tf32(pack, obs, act, perm, offsets, act_kind, residual, min_logvar, max_logvar, noise, out=None, all_members=False):
+    """Fused selected-member rollout on tcgen05 kind::tf32 with hi/lo split operands (fp32-grade): see cmrl_mlp_rollout_tf32.
+    all_members: perm / offsets are the all-member buckets (E * N rows) and the output is [E,N,D]."""
     N, O = obs.shape
-    pred = torch.empty((N, pack.head_dim), device=obs.device, dtype=torch.float32) if out is None else out
-    _lib.call("cmrl_mlp_rollout_tf32", pack.packed.data_ptr(), pack.L, pack.P, pack.E, N, O, act.shape[1], pack.hidden, pack.head_dim,
-              pack.layout, act_kind, 1 if residual else 0, obs.data_ptr(), act.data_ptr(), perm.data_ptr(), offsets.data_ptr(),
-              _ptr(min_logvar), _ptr(max_logvar), 0 if min_logvar is None else min_logvar.numel(), _ptr(noise), pred.data_ptr(), _stream())
-    return pred
+    if out is None:
+        out = torch.empty(((pack.E, N, pack.head_dim) if all_members else (N, pack.head_dim)), device=obs.device, dtype=torch.float32)
+    _lib.call("cmrl_mlp_rollout_tf32", pack.packed.data_ptr(), pack.L, pack.P, pack.E, perm.numel(), O, act.shape[1], pack.hidden,
+              pack.head_dim, pack.layout, act_kind, 1 if residual else 0, obs.data_ptr(), act.data_ptr(), perm.data_ptr(),
+              offsets.data_ptr(), _ptr(min_logvar), _ptr(max_logvar), 0 if min_logvar is None else min_logvar.numel(), _ptr(noise),
+              out.data_ptr(), N * pack.head_dim if all_members else 0, _stream())
+    return out
 
 
 # ----------------------------------------------------------------------------- fused tcgen05 training step

@@ -234,12 +234,14 @@ int cmrl_pack_layer_f16(const float* w, const float* b, const float* mask, long 
  * variant: 0 = chosen from the shape (the default of the Python host): 5 = weight-stationary CTA pairs (cta_group::2,
  * M=256) with two 256-row tiles in flight and part of the A operand in tensor memory, where two tiles' accumulators and heads
  * fit tensor memory; 3 = pairs with two 128-row tiles in flight (wider heads); 6 = pairs with the weights streamed in K chunks
- * (hidden layers too wide for shared memory, packed without widening: layer_n[0] == H). */
+ * (hidden layers too wide for shared memory, packed without widening: layer_n[0] == H).
+ * pred_member_stride: 0 for one [N,D] output; with ALL-MEMBER buckets (perm = 0..N-1 repeated E times, offsets[e] = e*N: every
+ * member evaluates every env -- what the MOPO penalty of fake_env.py:186-193 needs) pass N*D and a [E,N,D] output. */
 int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, const int* layer_off_halfs, const int* layer_k,
                          const int* layer_n, int num_layers, int P, int E, int N, int O, int A, int H, int head_dim,
                          int layout, int gaussian, int act, const float* obs, const float* actn, const int* perm,
                          const int* offsets, int residual, const float* min_logvar, const float* max_logvar,
-                         int bounds_n, const float* noise, float* pred, int variant, void* stream);
+                         int bounds_n, const float* noise, float* pred, long long pred_member_stride, int variant, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused training step (BaseDynamics.train, base_dynamics.py:181-186: `loss = get_nll_loss(...); loss.mean().backward()`
@@ -276,7 +278,7 @@ int cmrl_train_fused(const float* packed, int L, int P, int E, int B, int O, int
 int cmrl_mlp_rollout_tf32(const float* packed, int L, int P, int E, int N, int O, int A, int hidden, int head_dim, int layout,
                           int act, int residual, const float* obs, const float* actn, const int* perm, const int* offsets,
                           const float* min_logvar, const float* max_logvar, int bounds_n, const float* noise, float* pred,
-                          void* stream);
+                          long long pred_member_stride, void* stream);
 /* dw_host / db_host: HOST arrays of L+1 device pointers to the gradient tensors (overwritten, not accumulated).
  * mask as in cmrl_train_pack_tf32 (gradient rows of masked inputs are zero, as in the reference's masked forward).
  * workspace: optional device floats for deterministic batch-slice partial sums. */

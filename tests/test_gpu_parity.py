@@ -1405,3 +1405,43 @@ def test_small_training_kernels_round2(cm):
         assert err.value == 0
     finally:
         cm._lib.call("cmrl_dp_comm_destroy", comm)
+
+
+@pytest.mark.parametrize("kind", ["plain", "extmask"])
+def test_all_member_means_on_the_tensor_core_tiers(cm, kind):
+    """MOPO penalty path (fake_env.py:186-193): every member's mean for every env from ONE pass of the fused rollout kernels over
+    all-member buckets ([E,N,D] output through the member stride), against the all-member CUDA-core forward; the penalty and the
+    sampled next observation of a penalised step follow."""
+    torch.manual_seed(21)
+    rng = np.random.default_rng(21)
+    O, A, N = 5, 1, 3001
+    if kind == "plain":
+        tr = cm.PlainTransition(O, A, hid_size=200, activation_fn_cfg=SILU, device=DEV)
+    else:
+        tr = cm.ExternalMaskTransition(O, A, hid_size=200, activation_fn_cfg=SILU, device=DEV)
+        mask = (rng.uniform(size=(O, O + A)) < 0.6).astype(np.float32)
+        mask[np.arange(O), np.arange(O)] = 1
+        tr.set_input_mask(torch.from_numpy(mask))
+    rw = cm.PlainRewardMech(O, A, hid_size=200, activation_fn_cfg=SILU, device=DEV)
+    dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw)
+    env = cm.VecFakeEnv(N, None, None)
+    env.set_up(dyn, termination_fn=lambda n, o, a: np.zeros((n.shape[0], 1), bool), get_init_obs_fn=lambda n: rng.normal(size=(n, O)).astype(np.float32),
+               penalty_coeff=0.7)
+    env.reset()
+    obs = env._obs_dev.clone()
+    act = t(rng.uniform(-1, 1, size=(N, A)).astype(np.float32))
+    with torch.no_grad():
+        ref_mean, _ = tr.forward(obs.unsqueeze(0), act.unsqueeze(0))
+    ref_mean = ref_mean.cpu().numpy()
+    ref_pen = oc.mopo_penalty(ref_mean)
+    for precision, tol in (("fp32", TOL), ("f16", TOL_TC)):
+        env.precision = precision
+        means = env._all_member_means(tr, obs, act)
+        assert means is not None and tuple(means.shape) == (7, N, O)
+        assert record_max("all-member means %s %s" % (kind, precision), rel_err(means.cpu().numpy(), ref_mean)) < tol
+        pen = cm.ops.mopo_penalty(means).cpu().numpy()
+        assert record_max("MOPO penalty %s %s" % (kind, precision), rel_err(pen, ref_pen)) < (1e-4 if precision == "fp32" else 5e-2)
+    env.precision = "ffma"
+    assert env._all_member_means(tr, obs, act) is None  # the CUDA-core tier keeps the all-member forward
+    # (the penalised STEP through this path is pinned by the golden trajectory fake_env_penalty.npz of the real reference,
+    # which the default precision now runs through these kernels)
