@@ -731,6 +731,15 @@ def other_configs(cm, ctx, args, dyn_c2, act_host_c2):
     out["C2_ffma_tier"] = {"workload": WORKLOAD % N, "value": v, "ms_per_step": ms, "unit": "transitions/s",
                            "precision": "ffma (CUDA-core fp32 kernels, bit-identical to the all-member query path)"}  # fmt: skip
     del envff
+    # MOPO-penalised rollouts (penalty_coeff != 0: every member's mean is needed, fake_env.py:186-193): all-member pass + drawn
+    # member's sample on the tensor-core kernels; the CUDA-core tier runs the all-member forward of the per-layer kernels
+    for prec, steps_p in (("f16", 10), ("fp32", 5), ("ffma", 2)):
+        envp, _ = make_env(cm, ctx, dyn_c2, N, O, prec)
+        envp.penalty_coeff = 1.0
+        v, ms, _ = time_device_steps(cm, ctx, envp, torch.from_numpy(act_host_c2).to(dev), steps_p, 2)
+        out["C2_mopo_penalty_" + prec] = {"workload": WORKLOAD % N + ", penalty_coeff = 1 (MOPO: all 7 members evaluated per env)",
+                                          "value": v, "ms_per_step": ms, "unit": "transitions/s", "precision": prec}
+        del envp
     for prec in ("f16", "fp32"):
         envd, _ = make_env(cm, ctx, dyn_c2, N, O, prec, throughput_knobs=False)
         ev, ems = time_host_steps(ctx, envd, act_host_c2, 3, 2)
