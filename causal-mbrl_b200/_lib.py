@@ -29,6 +29,7 @@ PROTOTYPES = {
     "cmrl_nll_loss_fwd": [_P, _P, _P, _LL, _I, _LL, _F, _P, _P],
     "cmrl_nll_loss_bwd": [_P, _P, _P, _LL, _I, _LL, _P, _F, _P, _P, _P],
     "cmrl_mse_loss_fwd": [_P, _P, _LL, _I, _LL, _P, _P],
+    "cmrl_mse_loss_bwd": [_P, _P, _LL, _I, _LL, _P, _P, _P],
     "cmrl_mse_member_sums": [_P, _P, _LL, _I, _LL, _P, _P],
     "cmrl_adam_l2_step": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _I, _P],
     "cmrl_adam_l2_step_dev": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _P, _P],

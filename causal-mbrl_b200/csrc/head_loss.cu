@@ -117,6 +117,16 @@ __global__ void mse_loss_fwd_kernel(const float* __restrict__ mean, const float*
     }
 }
 
+// gradient of the un-reduced squared error: g_mean = 2 (mean - target) g_loss
+__global__ void mse_loss_bwd_kernel(const float* __restrict__ mean, const float* __restrict__ target, long long t_se, int E,
+                                    long long n, const float* __restrict__ g_loss, float* __restrict__ g_mean) {
+    const long long total = (long long)E * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long e = i / n, r = i - e * n;
+        g_mean[i] = 2.0f * (mean[i] - target[e * t_se + r]) * g_loss[i];
+    }
+}
+
 // grid = (blocks, E): per-member sum of squared errors, fp32 per thread -> fp64 warp/block -> one atomic per block
 __global__ void mse_member_sums_kernel(const float* __restrict__ mean, const float* __restrict__ target, long long t_se,
                                        long long n, double* __restrict__ sums) {
@@ -345,6 +355,17 @@ extern "C" int cmrl_mse_loss_fwd(const float* mean, const float* target, long lo
     mse_loss_fwd_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(mean, target, t_se, E, n_per_member,
                                                                                  loss);
     CMRL_CHECK_LAUNCH("mse_loss_fwd");
+    return 0;
+}
+
+extern "C" int cmrl_mse_loss_bwd(const float* mean, const float* target, long long t_se, int E, long long n_per_member,
+                                 const float* g_loss, float* g_mean, void* stream) {
+    CMRL_REQUIRE(mean && target && g_loss && g_mean, "mse_loss_bwd: null pointer");
+    long long total = (long long)E * n_per_member;
+    if (total == 0) return 0;
+    mse_loss_bwd_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(mean, target, t_se, E, n_per_member, g_loss,
+                                                                                 g_mean);
+    CMRL_CHECK_LAUNCH("mse_loss_bwd");
     return 0;
 }
 

@@ -66,7 +66,7 @@ class _MseLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss):
         mean, target = ctx.saved_tensors
-        return 2.0 * (mean - target) * g_loss, None
+        return ops.mse_loss_bwd(mean, target, g_loss), None
 
 
 class _NoGrad:

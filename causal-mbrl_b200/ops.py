@@ -281,6 +281,16 @@ def mse_loss_fwd(mean, target):
     return loss
 
 
+def mse_loss_bwd(mean, target, g_loss):
+    mean, g_loss = mean.contiguous(), g_loss.contiguous()
+    E = mean.shape[0]
+    n = mean[0].numel()
+    target, t_se = _target_stride(target, E)
+    g_mean = torch.empty_like(mean)
+    _lib.call("cmrl_mse_loss_bwd", mean.data_ptr(), target.data_ptr(), t_se, E, n, g_loss.data_ptr(), g_mean.data_ptr(), _stream())
+    return g_mean
+
+
 def mse_member_sums(mean, target, sums):
     """sums (float64 [E], caller-zeroed) += per-member sum of squared errors."""
     mean = mean.contiguous()

@@ -119,6 +119,9 @@ int cmrl_nll_loss_bwd(const float* mean, const float* logvar, const float* targe
                       float* g_logvar, void* stream);
 int cmrl_mse_loss_fwd(const float* mean, const float* target, long long t_se, int E, long long n_per_member,
                       float* loss, void* stream);
+/* Its gradient (autograd of `loss.mean().backward()` for deterministic mechanisms): g_mean = 2 (mean - target) g_loss. */
+int cmrl_mse_loss_bwd(const float* mean, const float* target, long long t_se, int E, long long n_per_member,
+                      const float* g_loss, float* g_mean, void* stream);
 /* Hold-out MSE for elite selection (plain_dynamics.py:74,82 `evaluate(...).mean(dim=(1,2))`):
  * sums[e] += sum_i (mean[e,i]-target[e,i])^2 in fp64 (caller zeroes `sums` [E] doubles, divides by n). */
 int cmrl_mse_member_sums(const float* mean, const float* target, long long t_se, int E, long long n_per_member,

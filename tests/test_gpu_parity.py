@@ -1445,3 +1445,28 @@ def test_all_member_means_on_the_tensor_core_tiers(cm, kind):
     assert env._all_member_means(tr, obs, act) is None  # the CUDA-core tier keeps the all-member forward
     # (the penalised STEP through this path is pinned by the golden trajectory fake_env_penalty.npz of the real reference,
     # which the default precision now runs through these kernels)
+
+
+def test_deterministic_mechanism_trains_through_the_mse_kernels(cm):
+    """Deterministic mechanisms train on `get_mse_loss` (mlp.py:68-70): the loss and its gradient kernel against the closed form
+    2 (mean - target) / numel applied by torch autograd to the same forward output, and one optimiser step of the dynamics."""
+    torch.manual_seed(8)
+    m = cm.PlainTransition(5, 1, hid_size=32, deterministic=True, activation_fn_cfg=SILU, device=DEV)
+    obs, act = torch.randn(7, 40, 5, device=DEV), torch.rand(7, 40, 1, device=DEV)
+    tgt = obs + 0.1 * torch.tanh(obs)
+    loss = m.get_mse_loss({"batch_obs": obs, "batch_action": act}, tgt)
+    mean, _ = m.forward(obs, act)
+    assert rel_err(loss.detach().cpu().numpy(), ((mean - tgt) ** 2).detach().cpu().numpy()) < 1e-6
+    g = torch.randn_like(loss)
+    got = cm.ops.mse_loss_bwd(mean.detach(), tgt, g)
+    assert rel_err(got.cpu().numpy(), (2.0 * (mean.detach() - tgt) * g).cpu().numpy()) < 1e-6
+    # shared (stride-0) targets, as `evaluate` passes them
+    tgt_shared = tgt[0].unsqueeze(0).expand(7, -1, -1)
+    got = cm.ops.mse_loss_bwd(mean.detach(), tgt_shared, g)
+    assert rel_err(got.cpu().numpy(), (2.0 * (mean.detach() - tgt_shared) * g).cpu().numpy()) < 1e-6
+    dyn = cm.PlainEnsembleDynamics(m, learned_reward=False, optim_lr=1e-3)
+    before = m.flat_parameters()[0].clone()
+    l0 = dyn.train_step("transition", obs, act, tgt).mean().item()
+    for _ in range(20):
+        l1 = dyn.train_step("transition", obs, act, tgt).mean().item()
+    assert l1 < l0 and not torch.equal(before, m.flat_parameters()[0])
