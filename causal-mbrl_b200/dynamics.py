@@ -328,7 +328,8 @@ class BaseDynamics:
         on_cuda = torch.device(self.device).type == "cuda"
         if sync == "auto" and os.environ.get("CMRL_DP_SYNC") in ("peer", "nccl"):  # operator override (A/B timing)
             sync = os.environ["CMRL_DP_SYNC"]
-        if sync == "auto":
+        auto = sync == "auto"
+        if auto:
             sync = "peer" if (on_cuda and self.dp_world > 1 and dist.get_backend(self.dp_group) == "nccl") else "nccl"
         if sync == "peer":
             from .peer_sync import PeerGradSync
@@ -339,7 +340,12 @@ class BaseDynamics:
                 model = getattr(self, mech)
                 model.flat_parameters()
                 largest = max(largest, int(model._n_trainable))
-            self._peer_sync = PeerGradSync(self.dp_group, largest, self.device)
+            try:
+                self._peer_sync = PeerGradSync(self.dp_group, largest, self.device)
+            except ops._lib.CmrlB200Error:
+                if not auto:
+                    raise
+                self._peer_sync = None  # consistent on all ranks (the set-up ends with an all-reduce of its outcome): NCCL path
 
     def enable_net_sharding(self, group=None):
         """The transition of this dynamics is one rank's NET SHARD of an ExternalMaskTransition (`subnet_range=`, see

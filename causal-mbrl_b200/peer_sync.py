@@ -28,10 +28,20 @@ class PeerGradSync:
             gathered = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(gathered, mine, group=group)
             blob = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
-            _lib.call("cmrl_dp_comm_connect", self._comm, blob)
-            # nobody pushes into a buffer whose owner has not finished set-up
-            dist.barrier(group=group)
+            err = None
+            try:
+                _lib.call("cmrl_dp_comm_connect", self._comm, blob)
+            except _lib.CmrlB200Error as e:  # e.g. a peer on another node: CUDA IPC only maps memory of the same node
+                err = e
+            # every rank learns whether EVERY rank connected (a rank that went on alone would wait for peers that never push);
+            # this all-reduce is also the barrier after which pushing into a peer's buffer is safe
+            ok = torch.tensor([0 if err is not None else 1], device=self.device, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
             torch.cuda.synchronize(self.device)
+            if int(ok.item()) == 0:
+                self.close()
+                raise _lib.CmrlB200Error("peer-memory gradient exchange: not every rank could map every peer's buffer%s"
+                                         % ("" if err is None else " (this rank: %s)" % err))
 
     def allreduce(self, flat_grad: torch.Tensor):
         """flat_grad <- sum over ranks (in rank order: bit-identical everywhere), one launch on the current stream."""
