@@ -198,13 +198,30 @@ class BaseDynamics:
         n, d = len(data), model._head_dim
         # data parallel: every rank evaluates its contiguous share of the hold-out rows, one [E] all-reduce at the end
         rows = dp_row_slice(n, self.dp_world, self.dp_rank) if self.dp_group is not None else slice(0, n)
+        # every member's mean of every hold-out row: one pass of the fused tcgen05 kernel (3xTF32, fp32-grade) over all-member
+        # buckets where it takes the model, else the all-member forward of the per-layer kernels
+        pack = model.packed_tf32() if (hasattr(model, "hidden_layers") and not model.deterministic
+                                       and torch.device(self.device).type == "cuda") else None  # (wrappers such as ForwardEuler: forward)
+        buckets = self.__dict__.setdefault("_eval_buckets", {})
         with torch.no_grad():
             for s in range(rows.start, rows.stop, chunk):
                 sl = slice(s, min(rows.stop, s + chunk))
                 obs = self.get_3d_tensor(data.batch_obs[sl], is_ensemble=False)
                 act = self.get_3d_tensor(data.batch_action[sl], is_ensemble=False)
                 target = self.get_3d_tensor(target_np[sl], is_ensemble=False)
-                mean, _ = model.forward(obs, act)
+                if pack is not None and pack.ok:
+                    E, nr = self.ensemble_num, obs.shape[1]
+                    if nr not in buckets:
+                        if len(buckets) >= 4:
+                            buckets.clear()
+                        buckets[nr] = (torch.arange(nr, device=obs.device, dtype=torch.int32).repeat(E),
+                                       (torch.arange(E + 1, device=obs.device, dtype=torch.int64) * nr).to(torch.int32))
+                    perm, offsets = buckets[nr]
+                    mn, mx = model._bounds()
+                    mean = ops.mlp_rollout_tf32(pack, obs[0].contiguous(), act[0].contiguous(), perm, offsets, model._act_kind,
+                                                model._residual(), mn, mx, None, all_members=True)  # fmt: skip
+                else:
+                    mean, _ = model.forward(obs, act)
                 d = mean.shape[-1]
                 ops.mse_member_sums(mean, target, sums)
         if self.dp_group is not None:
