@@ -89,23 +89,34 @@ TRAIN_GEMM_TIER = "auto"
 TRAIN_GEMM_TC_MIN_ROWS = 1024
 
 
-def _train_tier(kind, rows):
+def _train_tier(kind, rows, nets=1, k=0, n=0):
+    """GEMM tier of a per-layer training call: 3 = tcgen05 3xTF32, 0 = fp32 FFMA.  Few nets: from ~1k rows per member (below
+    that the launch is latency bound whichever pipe computes).  MANY nets (config C5: 1 600 nets of 512 x 512): the tensor-core
+    tiles fill the chip at any batch size -- what counts is tiles = nets x row tiles x column tiles, and layers wide enough
+    to fill a 128 x 256 tile."""
     if TRAIN_GEMM_TIER != "auto":
         return int(TRAIN_GEMM_TIER)
-    if kind == "dw":  # K of the dw GEMM is the batch: the tensor-core kernel pays once the batch is split over CTAs
-        return 3 if rows >= 2048 else 0
-    return 3 if rows >= TRAIN_GEMM_TC_MIN_ROWS else 0
+    wide = min(k, n) >= 128
+    if kind == "dw":  # K of the dw GEMM is the batch: the tensor-core kernel pays once the batch is split over CTAs ...
+        if rows >= 2048:
+            return 3
+        tiles = nets * -(-k // 128) * -(-n // 256)  # ... or there are enough (net, feature tile, column tile) items anyway
+        return 3 if (wide and rows >= 256 and tiles >= 296) else 0
+    if rows >= TRAIN_GEMM_TC_MIN_ROWS:
+        return 3
+    tiles = nets * -(-rows // 128) * -(-n // 256)
+    return 3 if (wide and rows >= 128 and tiles >= 296) else 0
 
 
 def ens_linear_fwd(x, w, b, act=ACT_IDENTITY, mask=None, mask_str=(0, 0, 0), want_z=False, row_offsets=None, tier=None):
     """y = act((x*mask) @ w + b).  w: [E,in,out] or [P,E,in,out]; x: [B,in] | [E,B,in] | [P,E,B,in]
     (broadcast dims allowed).  Ragged mode: x [N,in] flat + int32 row_offsets [E+1] -> y [N,out] / [P,N,out]."""
-    if tier is None:
-        tier = _train_tier("fwd", x.shape[-2]) if (want_z and row_offsets is None) else 0
     _req(x, "x"), _req(w, "weight")
     parallel = w.dim() == 4
     P = w.shape[0] if parallel else 1
     E, in_size, out_size = w.shape[-3], w.shape[-2], w.shape[-1]
+    if tier is None:
+        tier = _train_tier("fwd", x.shape[-2], P * E, in_size, out_size) if (want_z and row_offsets is None) else 0
     w = w.contiguous()
     if b is not None:
         b = _req(b, "bias").contiguous()
@@ -132,12 +143,12 @@ def ens_linear_fwd(x, w, b, act=ACT_IDENTITY, mask=None, mask_str=(0, 0, 0), wan
 
 def ens_linear_bwd_dx(dz, w, z_prev, act_prev, tier=None):
     """dx = (dz @ w^T) * act'(z_prev); dz [(P,)E,B,out] dense."""
-    tier = _train_tier("dx", dz.shape[-2]) if tier is None else tier
     dz = _req(dz, "dz").contiguous()
     w = w.contiguous()
     parallel = w.dim() == 4
     P = w.shape[0] if parallel else 1
     E, in_size, out_size = w.shape[-3], w.shape[-2], w.shape[-1]
+    tier = _train_tier("dx", dz.shape[-2], P * E, out_size, in_size) if tier is None else tier
     B = dz.shape[-2]
     dx = torch.empty(dz.shape[:-1] + (in_size,), device=dz.device, dtype=torch.float32)
     if z_prev is not None:
@@ -173,12 +184,12 @@ def splitk_workspace(device, floats):
 def ens_linear_bwd_dw(x, dz, w_shape, mask=None, mask_str=(0, 0, 0), dw=None, db=None, want_db=True, accumulate=False,
                       tier=None):
     """dw = (x*mask)^T @ dz, db = sum_b dz, written into dw/db when given (flat-arena views)."""
-    tier = _train_tier("dw", dz.shape[-2]) if tier is None else tier
     dz = _req(dz, "dz").contiguous()
     x = _rows_contig(_req(x, "x"), "x")
     parallel = len(w_shape) == 4
     P = w_shape[0] if parallel else 1
     E, in_size, out_size = w_shape[-3], w_shape[-2], w_shape[-1]
+    tier = _train_tier("dw", dz.shape[-2], P * E, in_size, out_size) if tier is None else tier
     B = dz.shape[-2]
     x_sp, x_se = _lead_strides(x)
     if dw is None:
