@@ -46,6 +46,7 @@ PROTOTYPES = {
     "cmrl_pack_layer_f16": [_P, _P, _P, _LL, _LL, _I, _I, _I, _I, _I, _I, _I, ctypes.c_float, _P, _LL, _P],
     "cmrl_mlp_rollout_f16": [_P, _LL, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P,
                              _I, _P, _P, _LL, _I, _P],
+    "cmrl_mlp_rollout_f16_groups": [_P, _I, _P],
     "cmrl_train_pack_tf32": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _LL, _LL, _P, _P],
     "cmrl_train_fused": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _P, _LL, _P, _LL, _I, _P, _P, _I, _F, _F,
                          _P, _P, _P],
@@ -59,6 +60,14 @@ PROTOTYPES = {
     "cmrl_allreduce_grads": [_P, _P, _LL, _P],
     "cmrl_allreduce_grads_adam": [_P, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _F, _P, _P],
 }
+
+class RolloutGroup(_c.Structure):
+    """struct cmrl_rollout_group (include/cmrl_b200.h): one mechanism of a grouped rollout launch."""
+
+    _fields_ = [("packed", _P), ("blob_halfs", _LL), ("layer_off_halfs", _P), ("layer_k", _P), ("layer_n", _P)] + \
+               [(n, _I) for n in ("num_layers", "P", "E", "N", "O", "A", "H", "head_dim", "layout", "gaussian", "act", "residual", "bounds_n")] + \
+               [(n, _P) for n in ("obs", "actn", "perm", "offsets", "min_logvar", "max_logvar", "noise", "pred")]
+
 
 _lib = None
 

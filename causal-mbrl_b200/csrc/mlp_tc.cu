@@ -62,6 +62,7 @@ namespace cmrl {
 namespace tc {
 int launch_rollout_v3(const RolloutP& p, cudaStream_t st);
 int launch_rollout_v5(const RolloutP& p, cudaStream_t st);
+int launch_rollout_v5_groups(const RolloutP* groups, int G, cudaStream_t st);
 int launch_rollout_v6(const RolloutP& p, cudaStream_t st);
 bool rollout_v5_supports(const RolloutP& p);
 }
@@ -87,18 +88,15 @@ extern "C" int cmrl_pack_layer_f16(const float* w, const float* b, const float* 
     return 0;
 }
 
-extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, const int* layer_off_halfs,
-                                    const int* layer_k, const int* layer_n, int num_layers, int P, int E, int N, int O,
-                                    int A, int H, int head_dim, int layout, int gaussian, int act, const float* obs,
-                                    const float* actn, const int* perm, const int* offsets, int residual,
-                                    const float* min_logvar, const float* max_logvar, int bounds_n, const float* noise,
-                                    float* pred, long long pred_member_stride, int variant, void* stream) {
+static int fill_rollout_p(tc::RolloutP& p, const void* packed, long long blob_halfs, const int* layer_off_halfs, const int* layer_k,
+                          const int* layer_n, int num_layers, int P, int E, int N, int O, int A, int H, int head_dim, int layout,
+                          int gaussian, int act, const float* obs, const float* actn, const int* perm, const int* offsets, int residual,
+                          const float* min_logvar, const float* max_logvar, int bounds_n, const float* noise, float* pred,
+                          long long pred_member_stride, int variant) {
     CMRL_REQUIRE(packed && obs && perm && offsets && pred, "mlp_rollout_f16: null pointer");
     CMRL_REQUIRE(num_layers >= 1 && num_layers <= 7, "mlp_rollout_f16: 1..7 hidden layers supported");
     CMRL_REQUIRE(E >= 1 && E <= 64, "mlp_rollout_f16: E must be <= 64");
     CMRL_REQUIRE(!gaussian || (min_logvar && max_logvar), "mlp_rollout_f16: gaussian head needs logvar bounds");
-    if (N == 0) return 0;
-    tc::RolloutP p{};
     p.packed = (const __half*)packed;
     p.blob_halfs = blob_halfs;
     const int HP = layer_n[0];
@@ -138,6 +136,21 @@ extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, co
     p.noise = noise;
     p.pred = pred;
     p.pred_se = pred_member_stride;
+    return 0;
+}
+
+extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, const int* layer_off_halfs,
+                                    const int* layer_k, const int* layer_n, int num_layers, int P, int E, int N, int O,
+                                    int A, int H, int head_dim, int layout, int gaussian, int act, const float* obs,
+                                    const float* actn, const int* perm, const int* offsets, int residual,
+                                    const float* min_logvar, const float* max_logvar, int bounds_n, const float* noise,
+                                    float* pred, long long pred_member_stride, int variant, void* stream) {
+    if (N == 0) return 0;
+    tc::RolloutP p{};
+    const int rc = fill_rollout_p(p, packed, blob_halfs, layer_off_halfs, layer_k, layer_n, num_layers, P, E, N, O, A, H, head_dim, layout,
+                                  gaussian, act, obs, actn, perm, offsets, residual, min_logvar, max_logvar, bounds_n, noise, pred,
+                                  pred_member_stride, variant);
+    if (rc != 0) return rc;
     // variant 0: chosen by shape -- un-widened packing (hidden layers too wide for the weight-stationary kernels) -> 6; two tiles'
     // accumulators and heads fit tensor memory and the operands fit shared memory -> 5; otherwise 3
     if (variant == 0) variant = layer_n[0] == H ? 6 : (tc::rollout_v5_supports(p) ? 5 : 3);
@@ -146,4 +159,26 @@ extern "C" int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, co
     CMRL_REQUIRE(variant == 3, "mlp_rollout_f16: variant must be 0 (by shape), 5 (CTA pairs, two 256-row tiles, A operand partly in TMEM), "
                                "3 (pairs, two 128-row tiles in flight) or 6 (pairs, streamed weights, wide hidden)");
     return tc::launch_rollout_v3(p, (cudaStream_t)stream);
+}
+
+/* Several mechanisms of one step (transition, reward mech, termination mech) in ONE launch of the weight-stationary pair kernel:
+ * see the header.  Returns -2 (and sets the error text) when the mechanisms cannot share a launch -- the caller then launches
+ * them one by one. */
+extern "C" int cmrl_mlp_rollout_f16_groups(const cmrl_rollout_group* groups, int n_groups, void* stream) {
+    CMRL_REQUIRE(groups && n_groups >= 1 && n_groups <= 3, "mlp_rollout_f16_groups: 1..3 groups");
+    tc::RolloutP ps[3];
+    for (int g = 0; g < n_groups; ++g) {
+        const cmrl_rollout_group& q = groups[g];
+        ps[g] = tc::RolloutP{};
+        CMRL_REQUIRE(q.N >= 1, "mlp_rollout_f16_groups: empty group");
+        const int rc = fill_rollout_p(ps[g], q.packed, q.blob_halfs, q.layer_off_halfs, q.layer_k, q.layer_n, q.num_layers, q.P, q.E, q.N, q.O,
+                                      q.A, q.H, q.head_dim, q.layout, q.gaussian, q.act, q.obs, q.actn, q.perm, q.offsets, q.residual,
+                                      q.min_logvar, q.max_logvar, q.bounds_n, q.noise, q.pred, 0, 5);
+        if (rc != 0) return rc;
+    }
+    if (!tc::rollout_v5_supports(ps[0])) {
+        set_error("mlp_rollout_f16_groups: the pair kernel with two 256-row tiles does not take this model shape");
+        return -2;
+    }
+    return tc::launch_rollout_v5_groups(ps, n_groups, (cudaStream_t)stream);
 }

@@ -50,57 +50,88 @@ enum {
     V5_BAR_COUNT = 15,
 };
 
-// The work list of a cluster is a contiguous range of 256-row tiles in (p, member, tile) order; consecutive tiles of
-// the same net are processed two at a time.  Every role walks the list with this iterator.
+// Several mechanisms (transition, reward mech, termination mech) can share ONE launch: the groups' layer tables, hidden
+// width and activation agree (checked on the host), everything else -- weights, buckets, noise, head layout, output -- is per
+// group.  The work list of the launch is group 0's tiles, then group 1's, ...
+constexpr int V5_MAX_GROUPS = 3;
+struct V5Groups {
+    int G;
+    RolloutP g[V5_MAX_GROUPS];
+};
+
+// The work list of a cluster is a contiguous range of 256-row tiles in (group, p, member, tile) order; consecutive tiles of
+// the same net are processed two at a time.  One thread per CTA cuts the cluster's range into SEGMENTS (a run of tiles of one
+// net) in shared memory when the kernel starts; every role then walks the segments with a cursor of two integers.  (The
+// general iterator -- groups, sub-nets, empty members -- inlined into seven roles doubled the kernel and cost 20 % through
+// the instruction caches; un-inlined it kept its state in local memory, which misses the L1 next to 220 KB of shared memory.)
+struct V5Seg {
+    int g, pp, netl, net;  // group, sub-net, net index inside the group, net index unique over the launch
+    int t0, t1;            // tiles [t0, t1) of the member's tiles belong to this cluster
+    int row_base, cnt;     // first bucketed row and number of rows of the member
+};
+constexpr int V5_MAX_SEGS = 40;
 struct V5Pair {
-    int net, pp, n;  // net index, sub-net index, tiles in this pair (1 or 2)
+    int g, net, netl, pp, n;  // n: tiles in this pair (1 or 2)
     int row0[2], nrows[2];
 };
-struct V5Iter {
-    int item, item_end, pp, e, t;
+struct V5Cur {
+    int i;
 };
 __device__ __forceinline__ int v5_tiles_of(const int* s_off, int e) { return (s_off[e + 1] - s_off[e] + V5_TILE - 1) / V5_TILE; }
-__device__ __forceinline__ void v5_iter_init(V5Iter& it, const RolloutP& p, int item_begin, int item_end, int tiles_total,
-                                             const int* s_off) {
-    it.item = item_begin;
-    it.item_end = item_end;
-    it.pp = tiles_total > 0 ? item_begin / tiles_total : 0;
-    int t = item_begin - it.pp * tiles_total;
-    it.e = 0;
-    while (it.e < p.E && t >= v5_tiles_of(s_off, it.e)) {
-        t -= v5_tiles_of(s_off, it.e);
-        ++it.e;
+// One thread per CTA lists the cluster's work when the kernel starts: SEGMENTS (a run of tiles of one net) and, per tile pair,
+// one word = segment << 24 | two-tile flag << 23 | first tile.  The roles only index these tables: the kernel's roles must
+// stay small -- the general iterator (groups, sub-nets, empty members) inlined into seven roles doubled the kernel and cost
+// 20 % through the instruction caches; un-inlined it kept its state in local memory, which misses the L1 next to 220 KB of
+// shared memory.
+constexpr int V5_MAX_PAIRS = 1024;
+__device__ __noinline__ int v5_build_work(const V5Groups* gs, const int (*s_off)[65], int item_begin, int item_end, V5Seg* segs,
+                                          uint32_t* pairs, int* n_pairs_out) {
+    int n = 0, np = 0, cur = 0, net_base = 0;
+    for (int g = 0; g < gs->G; ++g) {
+        const int P = gs->g[g].P, E = gs->g[g].E;
+        for (int pp = 0; pp < P; ++pp)
+            for (int e = 0; e < E; ++e) {
+                const int nt = v5_tiles_of(s_off[g], e);
+                const int lo = max(item_begin, cur), hi = min(item_end, cur + nt);
+                if (lo < hi) {
+                    if (n >= V5_MAX_SEGS) return -1;
+                    segs[n].g = g; segs[n].pp = pp; segs[n].netl = pp * E + e; segs[n].net = net_base + pp * E + e;
+                    segs[n].t0 = lo - cur; segs[n].t1 = hi - cur;
+                    segs[n].row_base = s_off[g][e]; segs[n].cnt = s_off[g][e + 1] - s_off[g][e];
+                    for (int t = lo - cur; t < hi - cur;) {
+                        const int two = t + 1 < hi - cur ? 1 : 0;
+                        if (np >= V5_MAX_PAIRS) return -1;
+                        pairs[np++] = ((uint32_t)n << 24) | ((uint32_t)two << 23) | (uint32_t)t;
+                        t += 1 + two;
+                    }
+                    ++n;
+                }
+                cur += nt;
+            }
+        net_base += P * E;
     }
-    it.t = t;
+    *n_pairs_out = np;
+    return n;
 }
-__device__ __forceinline__ bool v5_iter_next(V5Iter& it, const RolloutP& p, const int* s_off, V5Pair& pr) {
-    if (it.item >= it.item_end) return false;
-    while (it.t >= v5_tiles_of(s_off, it.e)) {  // skip exhausted / empty members
-        it.t = 0;
-        if (++it.e >= p.E) {
-            it.e = 0;
-            ++it.pp;
-        }
-    }
-    const int nt = v5_tiles_of(s_off, it.e);
-    const int cnt = s_off[it.e + 1] - s_off[it.e];
-    pr.pp = it.pp;
-    pr.net = it.pp * p.E + it.e;
-    pr.n = (it.t + 1 < nt && it.item + 1 < it.item_end) ? 2 : 1;
-    for (int s = 0; s < pr.n; ++s) {
-        pr.row0[s] = s_off[it.e] + (it.t + s) * V5_TILE;
-        pr.nrows[s] = min(V5_TILE, cnt - (it.t + s) * V5_TILE);
-    }
-    it.t += pr.n;
-    it.item += pr.n;
+__device__ __forceinline__ void v5_cur_init(V5Cur& c, const V5Seg*, int) { c.i = 0; }
+__device__ __forceinline__ bool v5_next(V5Cur& c, const V5Seg* segs, int n_pairs, V5Pair& pr, const uint32_t* pairs) {
+    if (c.i >= n_pairs) return false;
+    const uint32_t w = pairs[c.i++];
+    const V5Seg& sg = segs[w >> 24];
+    const int t = (int)(w & 0x7FFFFFu);
+    pr.g = sg.g; pr.pp = sg.pp; pr.netl = sg.netl; pr.net = sg.net;
+    pr.n = 1 + (int)((w >> 23) & 1u);
+    pr.row0[0] = sg.row_base + t * V5_TILE;
+    pr.row0[1] = pr.row0[0] + V5_TILE;
+    pr.nrows[0] = min(V5_TILE, sg.cnt - t * V5_TILE);
+    pr.nrows[1] = min(V5_TILE, sg.cnt - (t + 1) * V5_TILE);
     return true;
 }
 
 // MMA issuer of tile slot SLOT (compile-time slot: every descriptor is provably warp-uniform, see mlp_tc3.cu)
 template <int SLOT>
-__device__ __forceinline__ void v5_mma_role(const RolloutP& p, const V5Lay& lay, uint8_t* smem, uint64_t* bars, const int* s_off,
-                                            uint32_t tmem_base, uint32_t rank, int lane, int item_begin, int item_end,
-                                            int tiles_total) {
+__device__ __forceinline__ void v5_mma_role(const RolloutP& p, const V5Lay& lay, uint8_t* smem, uint64_t* bars, const V5Seg* segs, int nseg,
+                                            const uint32_t* pairs, int npairs, uint32_t tmem_base, uint32_t rank, int lane) {  // p: group 0 (all groups share the layer tables)
     constexpr int s = SLOT;
     if (rank != 0) return;
     const int L = p.num_layers;
@@ -117,9 +148,9 @@ __device__ __forceinline__ void v5_mma_role(const RolloutP& p, const V5Lay& lay,
     const uint32_t a_hi = (uint32_t)(ad_a >> 32);
     const uint32_t d_t = tmem_base + lay.d_col[s], dh_t = tmem_base + lay.dh_col[s], a_t = tmem_base + lay.at_col[s];
     V5Pair pr;
-    V5Iter it;
-    v5_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
-    while (v5_iter_next(it, p, s_off, pr)) {
+    V5Cur it;
+    v5_cur_init(it, segs, nseg);
+    while (v5_next(it, segs, npairs, pr, pairs)) {
         if (pr.net != cur_net) {
             if (cur_net != -1) v3_commit_uni(&bars[V5_W_EMPTY]);
             mbar_wait_sleep(&bars[V5_W_READY], n_w & 1, ns_mma);
@@ -170,10 +201,18 @@ __device__ __forceinline__ void v5_mma_role(const RolloutP& p, const V5Lay& lay,
 
 template <int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
-    mlp_rollout_f16_v5_kernel(const RolloutP p, const V5Lay lay) {
+    mlp_rollout_f16_v5_kernel(const V5Groups gs_param, const V5Lay lay) {
+    const RolloutP& p = gs_param.g[0];  // layer tables, hidden width and activation are the same in every group
+    // the per-group tables are read through shared memory by the (un-inlined) work-list iterator and the roles with slack: the
+    // kernel must stay small (instruction caches: inlining the grouped iterator into seven roles doubled it and cost 20 %)
+    __shared__ V5Groups s_gs;
+    for (int i = threadIdx.x; i < (int)(sizeof(V5Groups) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&s_gs)[i] = reinterpret_cast<const uint32_t*>(&gs_param)[i];
+    __syncthreads();
+    const V5Groups* gs = &s_gs;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_slot;
-    __shared__ int s_off[65];
+    __shared__ int s_off[V5_MAX_GROUPS][65];
     const int L = p.num_layers;
     const int HP = p.layer_n[0];
     const int K0 = p.layer_k[0];
@@ -184,7 +223,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
     const int lane = threadIdx.x & 31;
     const uint32_t ns_slack = 0u;  // poll interval of the roles with slack (head, weights, layer-0 loader)
 
-    for (int i = threadIdx.x; i <= p.E; i += blockDim.x) s_off[i] = p.offsets[i];
+    for (int g = 0; g < gs->G; ++g)
+        for (int i = threadIdx.x; i <= gs->g[g].E; i += blockDim.x) s_off[g][i] = gs->g[g].offsets[i];
     if (threadIdx.x == 0) {
         mbar_init(&bars[V5_W_FULL], 1);
         mbar_init(&bars[V5_W_READY], 2);
@@ -210,13 +250,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    int tiles_total = 0;
-    for (int e = 0; e < p.E; ++e) tiles_total += v5_tiles_of(s_off, e);
-    const int n_items = p.P * tiles_total;
-    const int n_clusters = gridDim.x / 2;
-    const int cid = blockIdx.x / 2;
-    const int item_begin = (int)((long long)cid * n_items / n_clusters);
-    const int item_end = (int)((long long)(cid + 1) * n_items / n_clusters);
+    // ---- this cluster's share of the work list, as segments in shared memory (built by one thread) -----------------------------
+    __shared__ V5Seg s_segs[V5_MAX_SEGS];
+    __shared__ uint32_t s_pairs[V5_MAX_PAIRS];
+    __shared__ int s_nseg, s_npairs;
+    if (threadIdx.x == 32) {  // (a lane of an epilogue warp: thread 0 is still busy with nothing, but keep warp 0's lane 0 free)
+        int n_items = 0;
+        for (int g = 0; g < gs->G; ++g) {
+            int tiles = 0;
+            for (int e = 0; e < gs->g[g].E; ++e) tiles += v5_tiles_of(s_off[g], e);
+            n_items += gs->g[g].P * tiles;
+        }
+        const int n_clusters = gridDim.x / 2;
+        const int cid = blockIdx.x / 2;
+        const int item_begin = (int)((long long)cid * n_items / n_clusters);
+        const int item_end = (int)((long long)(cid + 1) * n_items / n_clusters);
+        s_nseg = v5_build_work(gs, s_off, item_begin, item_end, s_segs, s_pairs, &s_npairs);
+    }
+    __syncthreads();
+    const V5Seg* segs = s_segs;
+    const uint32_t* pairs = s_pairs;
+    const int nseg = s_nseg, npairs = s_npairs;
+    if (nseg < 0) __trap();  // more nets per cluster than the segment table holds: never silently drop work
 
     if (warp == V5_WARP_W) {
         // ===================== weight producer: this CTA's half of every layer of the current net =====================
@@ -224,12 +279,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
             int cur_net = -1;
             uint32_t n_w = 0;
             V5Pair pr;
-            V5Iter it;
-            v5_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
-            while (v5_iter_next(it, p, s_off, pr)) {
+            V5Cur it;
+            v5_cur_init(it, segs, nseg);
+            while (v5_next(it, segs, npairs, pr, pairs)) {
                 if (pr.net == cur_net) continue;
                 if (cur_net != -1) mbar_wait_sleep(&bars[V5_W_EMPTY], (n_w - 1) & 1, ns_slack);
-                const __half* blob = p.packed + (long long)pr.net * p.blob_halfs;
+                const __half* blob = gs->g[pr.g].packed + (long long)pr.netl * gs->g[pr.g].blob_halfs;
                 uint32_t total = 0;
                 for (int l = 0; l <= L; ++l) total += (uint32_t)(p.layer_n[l] / 2) * p.layer_k[l] * 2;
                 mbar_expect_tx(&bars[V5_W_FULL], total);
@@ -245,17 +300,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
             }
         }
     } else if (warp == V5_WARP_MMA) {
-        v5_mma_role<0>(p, lay, smem, bars, s_off, tmem_base, rank, lane, item_begin, item_end, tiles_total);
+        v5_mma_role<0>(p, lay, smem, bars, segs, nseg, pairs, npairs, tmem_base, rank, lane);
     } else if (warp == V5_WARP_MMA + 1) {
-        v5_mma_role<1>(p, lay, smem, bars, s_off, tmem_base, rank, lane, item_begin, item_end, tiles_total);
+        v5_mma_role<1>(p, lay, smem, bars, segs, nseg, pairs, npairs, tmem_base, rank, lane);
     } else if (warp == V5_WARP_X) {
         // ===================== layer-0 operand loader: four rows per lane, one pair ahead ==============================
-        const int in = p.O + p.A;
         uint32_t n_x[2] = {0, 0};
         V5Pair pr;
-        V5Iter it;
-        v5_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
-        while (v5_iter_next(it, p, s_off, pr)) {
+        V5Cur it;
+        v5_cur_init(it, segs, nseg);
+        while (v5_next(it, segs, npairs, pr, pairs)) {
+            // this group's inputs, in registers (the group table lives in shared memory)
+            struct {
+                const float *obs, *actn;
+                const int* perm;
+                int O, A;
+            } p = {gs->g[pr.g].obs, gs->g[pr.g].actn, gs->g[pr.g].perm, gs->g[pr.g].O, gs->g[pr.g].A};
+            const int in = p.O + p.A;
             for (int s = 0; s < pr.n; ++s) {
                 mbar_wait_sleep(&bars[V5_X_EMPTY + s], (n_x[s] & 1) ^ 1, ns_slack);
                 ++n_x[s];
@@ -301,13 +362,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
         const int q = warp - V5_HEAD_WARP0;
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const int D = p.head_dim;
         const uint32_t dh0 = lay.dh_col[0], dh1 = lay.dh_col[1];
         uint32_t hph = 0;  // phase parity of DH_FULL[slot] in bit `slot`
         V5Pair pr;
-        V5Iter it;
-        v5_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
-        while (v5_iter_next(it, p, s_off, pr)) {
+        V5Cur it;
+        v5_cur_init(it, segs, nseg);
+        while (v5_next(it, segs, npairs, pr, pairs)) {
+            // this group's head description, in registers (the group table lives in shared memory)
+            const RolloutP& gq = gs->g[pr.g];
+            struct {
+                const float *obs, *noise, *min_logvar, *max_logvar;
+                const int* perm;
+                float* pred;
+                long long pred_se;
+                int O, E, head_dim, layout, gaussian, residual, bounds_n;
+            } p = {gq.obs, gq.noise, gq.min_logvar, gq.max_logvar, gq.perm, gq.pred, gq.pred_se,
+                   gq.O, gq.E, gq.head_dim, gq.layout, gq.gaussian, gq.residual, gq.bounds_n};
+            const int D = p.head_dim;
             for (int s = 0; s < pr.n; ++s) {
                 const int grow = (int)rank * V5_ROWS + row;
                 const bool valid = grow < pr.nrows[s];
@@ -343,7 +414,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
                             const float lv = soft_clamp_logvar(__uint_as_float(r1), p.min_logvar[bi], p.max_logvar[bi]);
                             m += sqrtf(expf(lv)) * (p.layout == CMRL_HEAD_PARALLEL ? nz0 : p.noise[env * D + d]);
                         }
-                        p.pred[(long long)(pr.net % p.E) * p.pred_se + env * D + od] = m;
+                        p.pred[(long long)(pr.netl % p.E) * p.pred_se + env * D + od] = m;
                     }
                 }
                 tc_fence_before();
@@ -379,9 +450,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
         uint32_t dph = 0;  // phase parity of D_FULL[slot] in bit `slot`
 
         V5Pair pr;
-        V5Iter it;
-        v5_iter_init(it, p, item_begin, item_end, tiles_total, s_off);
-        while (v5_iter_next(it, p, s_off, pr)) {
+        V5Cur it;
+        v5_cur_init(it, segs, nseg);
+        while (v5_next(it, segs, npairs, pr, pairs)) {
             const int n_steps = L * pr.n;  // tile-step ts -> layer ts / n, slot ts % n
 #pragma unroll 1
             for (int ts = 0; ts < n_steps; ++ts) {
@@ -462,7 +533,7 @@ static bool v5_layout(const RolloutP& p, V5Lay& lay) {
     lay.bar_off = off;
     off += V5_BAR_COUNT * 8;
     lay.total = off;
-    return lay.total <= 232448 - 1024;
+    return lay.total <= 232448 - 7424;  // (7 KB of static shared memory: group tables, bucket offsets, segment and pair tables)
 }
 
 bool rollout_v5_supports(const RolloutP& p) {
@@ -470,34 +541,52 @@ bool rollout_v5_supports(const RolloutP& p) {
     return v5_layout(p, lay);
 }
 
-int launch_rollout_v5(const RolloutP& p, cudaStream_t st) {
+// one launch for G mechanisms whose layer tables agree (G = 1: the plain rollout of one mechanism)
+int launch_rollout_v5_groups(const RolloutP* groups, int G, cudaStream_t st) {
+    CMRL_REQUIRE(G >= 1 && G <= V5_MAX_GROUPS, "mlp_rollout_f16 v5: 1..%d mechanisms per launch", V5_MAX_GROUPS);
+    const RolloutP& p = groups[0];
     V5Lay lay{};
     CMRL_REQUIRE(v5_layout(p, lay), "mlp_rollout_f16 v5: two 256-row tiles of this model (hidden %d, head %d columns) do not fit tensor / shared memory",
                  p.layer_n[0], p.layer_n[p.num_layers]);
+    V5Groups gs{};
+    gs.G = G;
+    long long max_items = 0;
+    for (int g = 0; g < G; ++g) {
+        const RolloutP& q = groups[g];
+        CMRL_REQUIRE(q.num_layers == p.num_layers && q.H == p.H && q.act == p.act, "mlp_rollout_f16 v5: grouped mechanisms must share depth, width and activation");
+        for (int l = 0; l <= p.num_layers; ++l)
+            CMRL_REQUIRE(q.layer_k[l] == p.layer_k[l] && q.layer_n[l] == p.layer_n[l] && q.layer_off[l] == p.layer_off[l],
+                         "mlp_rollout_f16 v5: grouped mechanisms must share the packed layer tables (layer %d differs)", l);
+        CMRL_REQUIRE(q.E >= 1 && q.E <= 64, "mlp_rollout_f16 v5: E must be <= 64");
+        gs.g[g] = q;
+        max_items += (long long)q.P * ((q.N + V5_TILE - 1) / V5_TILE + q.E);
+    }
     static cmrl::PerDeviceOnce attr_once;
     int attr_dev = 0;
     if (attr_once.pending(&attr_dev)) {
-        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7424));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7424));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7424));
+        CMRL_CUDA(cudaFuncSetAttribute(mlp_rollout_f16_v5_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 7424));
         attr_once.done(attr_dev);
     }
-    int max_items = p.P * ((p.N + V5_TILE - 1) / V5_TILE + p.E);
-    int clusters = num_sms() / 2;
+    long long clusters = num_sms() / 2;
     if (clusters > (max_items + 1) / 2) clusters = (max_items + 1) / 2;
     if (clusters < 1) clusters = 1;
+    const int grid = (int)clusters * 2;
     if (p.act == CMRL_ACT_SILU)
-        mlp_rollout_f16_v5_kernel<CMRL_ACT_SILU><<<clusters * 2, V5_THREADS, lay.total, st>>>(p, lay);
+        mlp_rollout_f16_v5_kernel<CMRL_ACT_SILU><<<grid, V5_THREADS, lay.total, st>>>(gs, lay);
     else if (p.act == CMRL_ACT_SILU_HALF)
-        mlp_rollout_f16_v5_kernel<CMRL_ACT_SILU_HALF><<<clusters * 2, V5_THREADS, lay.total, st>>>(p, lay);
+        mlp_rollout_f16_v5_kernel<CMRL_ACT_SILU_HALF><<<grid, V5_THREADS, lay.total, st>>>(gs, lay);
     else if (p.act == CMRL_ACT_RELU)
-        mlp_rollout_f16_v5_kernel<CMRL_ACT_RELU><<<clusters * 2, V5_THREADS, lay.total, st>>>(p, lay);
+        mlp_rollout_f16_v5_kernel<CMRL_ACT_RELU><<<grid, V5_THREADS, lay.total, st>>>(gs, lay);
     else
-        mlp_rollout_f16_v5_kernel<CMRL_ACT_IDENTITY><<<clusters * 2, V5_THREADS, lay.total, st>>>(p, lay);
+        mlp_rollout_f16_v5_kernel<CMRL_ACT_IDENTITY><<<grid, V5_THREADS, lay.total, st>>>(gs, lay);
     CMRL_CHECK_LAUNCH("mlp_rollout_f16_v5");
     return 0;
 }
+
+int launch_rollout_v5(const RolloutP& p, cudaStream_t st) { return launch_rollout_v5_groups(&p, 1, st); }
 
 }  // namespace tc
 }  // namespace cmrl

@@ -73,6 +73,10 @@ class VecFakeEnv(VecEnv):
         # B200-side knobs and state
         self.rng_mode = "numpy"
         self.infos_mode = "dicts"
+        # device-resident f16 steps: transition + reward (+ termination) mechs in ONE kernel launch.  "auto": where it was measured
+        # to pay -- three mechanisms, or few envs (launch bound); at 100 000 envs with two mechanisms one launch per mechanism
+        # is as fast (0.243 vs 0.247 ms), with three it is 6 % slower than the grouped launch, at 1 000 envs 5 % slower
+        self.group_mechs = "auto"
         self.precision = "fp32"  # "fp32" / "ffma": 1e-5 parity tiers (3xTF32 tensor cores / CUDA cores); "f16": tcgen05 tier (1e-3 parity)
         self.use_graph = True   # device rng_mode: replay the per-step launches from a CUDA graph
         self.return_views = False    # step(): hand out the pinned observation buffer itself instead of a copy (opt-in)
@@ -349,6 +353,16 @@ class VecFakeEnv(VecEnv):
         preps = self._prepare_all(need_all, ahead=ahead)
         if before_transition is not None:
             before_transition()
+        if after_transition is None and not need_all and self._group_on() and self.precision == "f16" and preps:
+            # device-resident steps: every learned mechanism in ONE launch of the fused kernel (the reward mech alone is a
+            # 60 us launch for a fifth of the transition's tiles: pipeline fill / drain and idle SMs at its tail)
+            self._join_prepare()
+            grouped = self._predict_grouped(obs, act, preps)
+            if grouped is not None:
+                if ahead is not None:
+                    self._prepare_next_transition(ahead)
+                    torch.cuda.current_stream().wait_stream(self._side_stream)
+                return grouped + (None,)
         next_obs = self._predict("transition", obs, act, all_out, prep=preps.get("transition"))
         if after_transition is not None:
             after_transition(next_obs)
@@ -363,16 +377,59 @@ class VecFakeEnv(VecEnv):
             torch.cuda.current_stream().wait_stream(self._side_stream)  # the next step's draws / buckets
         return next_obs, reward, terminal_f, penalty
 
+    def _group_on(self):
+        if self.group_mechs == "auto":
+            return (int(self.learned_reward) + int(self.learned_termination) >= 2) or self.num_envs <= 16384
+        return bool(self.group_mechs)
+
+    def _predict_grouped(self, obs, act, preps):
+        """(next_obs, reward, terminal) from one grouped launch, or None when the mechanisms cannot share one (a mechanism
+        without a selected-member bucket, a wrapper, different packed layer tables, a shape the pair kernel does not take)."""
+        mechs = ["transition"] + [m for m, on in (("reward_mech", self.learned_reward), ("termination_mech", self.learned_termination)) if on]
+        if len(mechs) < 2:
+            return None
+        groups = []
+        for mech in mechs:
+            model = getattr(self.dynamics, mech)
+            prep = preps.get(mech)
+            if prep is None or prep[2] is None or getattr(model, "repeat_times", None) is not None:
+                return None
+            idx, noise, (perm, offsets) = prep
+            mn, mx = model._bounds()
+            groups.append(dict(pack=model.packed_f16(), P=model._parallel_num(), E=model.ensemble_num, obs=obs, act=act, perm=perm,
+                               offsets=offsets, H=model.hid_size, head_dim=model._head_dim, layout=model._head_layout,
+                               gaussian=not model.deterministic, act_kind=model._act_kind, residual=model._residual(),
+                               min_logvar=mn, max_logvar=mx, noise=noise))  # fmt: skip
+        outs = ops.mlp_rollout_f16_groups(groups)
+        if outs is None:
+            return None
+        out = dict(zip(mechs, outs))
+        return out["transition"], out.get("reward_mech"), out.get("termination_mech")
+
     # ---- transition draws one step ahead (graph-replayed steps only) ---------------------------------------------
     def _ahead_ok(self, need_all):
         return (self.prep_ahead and self.overlap_prepare and self.rng_mode == "device"
                 and self._selected_path(self.dynamics.transition, need_all))
 
-    def _ahead_new(self, reset_source):
+    def _ahead_new(self, reset_source, grouped=False):
         """Capture-time description of a pipelined step graph: the transition kernel reads persistent draw / bucket
         buffers that the PREVIOUS replay filled (Philox stream id of this step's draw = t_id + device counter; the
-        draw for the next step uses t_id + n, n = draws per step, because the graph advances the counter by n)."""
+        draw for the next step uses t_id + n, n = draws per step, because the graph advances the counter by n).
+        grouped: the device-resident step launches all mechanisms in one kernel (`group_mechs`), so the reward /
+        termination mechs' draws and buckets are made a step ahead as well ("mechs"; their stream ids follow the
+        transition's in the fixed order of `_prepare_all`)."""
         tr = self.dynamics.transition
+        mechs = []
+        if grouped and self._group_on() and self.precision == "f16":
+            mechs = [m for m, on in (("reward_mech", self.learned_reward), ("termination_mech", self.learned_termination)) if on]
+        more = self.__dict__.setdefault("_ahead_more", {})
+        for m in mechs:
+            d = getattr(self.dynamics, m)._head_dim
+            cur = more.get(m)
+            if cur is None or cur[0].numel() != self.num_envs or (cur[1] is None) != bool(self.deterministic):
+                more[m] = (torch.empty(self.num_envs, device=self.device, dtype=torch.uint8),
+                           None if self.deterministic else torch.empty((self.num_envs, d), device=self.device))
+                self._ahead_family = None
         if self._ahead_bufs is None or self._ahead_bufs[0].numel() != self.num_envs or \
                 (self._ahead_bufs[1] is None) != bool(self.deterministic):
             idx = torch.empty(self.num_envs, device=self.device, dtype=torch.uint8)
@@ -380,15 +437,21 @@ class VecFakeEnv(VecEnv):
             self._ahead_bufs = (idx, noise)
             self._ahead_family = None
         n = 1 + int(self.learned_reward) + int(self.learned_termination) + int(bool(reset_source))
-        return {"t_id": self._draw_counter + 1, "n": n}
+        return {"t_id": self._draw_counter + 1, "n": n, "mechs": mechs}
 
-    def _ahead_draw(self, stream_id):
+    def _ahead_draw(self, stream_id, mechs=()):
         tr = self.dynamics.transition
         b = self._bufs
         ops.draw_member_noise(self._device_seed, stream_id, self.num_envs, self._elite_u8("transition"), tr._head_dim,
                               want_noise=not self.deterministic, stream_base=self._rng_base, out=self._ahead_bufs)
         ops.member_bucket(self._ahead_bufs[0], tr.ensemble_num, b["perm@transition"], b["offsets@transition"],
                           b["counters@transition"])
+        for k, m in enumerate(mechs):  # stream ids in the order of `_prepare_all`: transition, reward, termination
+            model = getattr(self.dynamics, m)
+            bufs = self._ahead_more[m]
+            ops.draw_member_noise(self._device_seed, stream_id + 1 + k, self.num_envs, self._elite_u8(m), model._head_dim,
+                                  want_noise=not self.deterministic, stream_base=self._rng_base, out=bufs)
+            ops.member_bucket(bufs[0], model.ensemble_num, b["perm@" + m], b["offsets@" + m], b["counters@" + m])
 
     def _prepare_next_transition(self, ahead):
         """(inside a capture) after the transition kernel consumed the buffers: refill them for the next replay, on the
@@ -396,7 +459,7 @@ class VecFakeEnv(VecEnv):
         side = self._side_stream
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            self._ahead_draw(ahead["t_id"] + ahead["n"])
+            self._ahead_draw(ahead["t_id"] + ahead["n"], ahead.get("mechs", ()))
 
     def _ahead_before_replay(self, ahead):
         """the buffers hold this step's draws only if the previous thing that advanced the device counter was a replay
@@ -405,7 +468,7 @@ class VecFakeEnv(VecEnv):
             self._ahead_family = None
             return
         if self._ahead_family != ahead["family"]:
-            self._ahead_draw(ahead["t_id"])
+            self._ahead_draw(ahead["t_id"], ahead.get("mechs", ()))
         self._ahead_family = ahead["family"]
 
     def _prepare_all(self, need_all, reset_source=False, ahead=None):
@@ -422,10 +485,14 @@ class VecFakeEnv(VecEnv):
             assert self._draw_counter == ahead["t_id"]
             b = self._bufs
             preps = {"transition": self._ahead_bufs + ((b["perm@transition"], b["offsets@transition"]),)}
+            for m in ahead.get("mechs", ()):  # drawn a step ahead too (grouped launch): consume their stream ids in order
+                self._draw_counter += 1
+                preps[m] = self._ahead_more[m] + ((b["perm@" + m], b["offsets@" + m]),)
         else:
             self._ahead_family = None  # the transition's bucket buffers are rewritten
             preps = {"transition": self._prepare("transition", need_all)}
-        others = [m for m, on in (("reward_mech", self.learned_reward), ("termination_mech", self.learned_termination)) if on]
+        others = [m for m, on in (("reward_mech", self.learned_reward), ("termination_mech", self.learned_termination))
+                  if on and m not in preps]
         if not self.overlap_prepare:
             for m in others:
                 preps[m] = self._prepare(m)
@@ -483,6 +550,7 @@ class VecFakeEnv(VecEnv):
             model = getattr(self.dynamics, m)
             parts.append((model.weights_token(), id(model._packed.get("f16")), id(model._packed.get("tf32")), id(model._elite_members),
                           model._flat.data_ptr() if model._flat is not None else 0, bool(model.deterministic)))
+        parts.append(self._group_on() if self.has_set_up else bool(self.group_mechs))
         return tuple(parts)
 
     def _predict_all_graphed_one(self, obs, act, need_all, host_next_buf, act_pin=None):
@@ -712,15 +780,29 @@ class VecFakeEnv(VecEnv):
         eager_base = self._rng_base is not None and not torch.cuda.is_current_stream_capturing()
         c_start = self._draw_counter
         preps = self._prepare_all(need_all, reset_source=True, ahead=_ahead)
-        next_obs = self._predict("transition", obs, actions, all_out, prep=preps.get("transition"))
-        if _ahead is not None:
-            self._prepare_next_transition(_ahead)
-        self._join_prepare()
-        reward = self._predict("reward_mech", obs, actions, prep=preps.get("reward_mech"))
+        grouped = None
+        if not need_all and self._group_on() and self.precision == "f16" and preps:
+            all_ahead = _ahead is not None and len(_ahead.get("mechs", ())) == int(self.learned_reward) + int(self.learned_termination)
+            if not all_ahead:  # the other mechs' draws / buckets of this step are on the side stream
+                self._join_prepare()
+            grouped = self._predict_grouped(obs, actions, preps)  # every learned mechanism in one launch of the fused kernel
+            if grouped is None and all_ahead:
+                pass  # (falls through to the per-mechanism launches below, which join before they read the side stream's work)
         terminal_f = terminal_u8 = None
-        if self.learned_termination:
-            terminal_f = self._predict("termination_mech", obs, actions, prep=preps.get("termination_mech"))
-        elif termination is not None:
+        if grouped is not None:
+            next_obs, reward, terminal_f = grouped
+            if _ahead is not None:
+                self._prepare_next_transition(_ahead)
+            self._join_prepare()  # the reset-row draw (side stream) before the tail reads it
+        else:
+            next_obs = self._predict("transition", obs, actions, all_out, prep=preps.get("transition"))
+            if _ahead is not None:
+                self._prepare_next_transition(_ahead)
+            self._join_prepare()
+            reward = self._predict("reward_mech", obs, actions, prep=preps.get("reward_mech"))
+            if self.learned_termination:
+                terminal_f = self._predict("termination_mech", obs, actions, prep=preps.get("termination_mech"))
+        if not self.learned_termination and termination is not None:
             terminal_u8 = termination(next_obs, obs, actions).to(torch.uint8).contiguous()
         penalty = ops.mopo_penalty(all_out["mean"]) if need_all else None
         reset_rows, reset_index = self._prep_reset
@@ -762,7 +844,7 @@ class VecFakeEnv(VecEnv):
             g = torch.cuda.CUDAGraph()
             c0 = self._draw_counter
             l0 = _lib.launch_count()
-            ahead = self._ahead_new(True) if self._ahead_ok(self.penalty_coeff != 0) else None
+            ahead = self._ahead_new(True, grouped=True) if self._ahead_ok(self.penalty_coeff != 0) else None
             with ops.graph_capture(g):
                 self._graph_out = self.step_device(b["act"], _ahead=ahead)
                 ops.counter_add(self._rng_base, self._draw_counter - c0)

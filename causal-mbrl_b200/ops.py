@@ -506,6 +506,56 @@ def mlp_rollout_f16(pack, P, E, obs, act, perm, offsets, H, head_dim, layout, ga
     return pred
 
 
+def mlp_rollout_f16_groups(groups):
+    """ONE launch of the fused f16 rollout kernel for several mechanisms of a step.  groups: list of dicts with the arguments of
+    `mlp_rollout_f16` (pack, P, E, obs, act, perm, offsets, H, head_dim, layout, gaussian, act_kind, residual, min_logvar,
+    max_logvar, noise, out).  Returns the outputs, or None when the mechanisms cannot share a launch (different packed layer
+    tables, a shape the pair kernel does not take): the caller then launches them one by one."""
+    import ctypes
+
+    first = groups[0]["pack"]
+    arr = (_lib.RolloutGroup * len(groups))()
+    keep, outs = [], []
+    for i, gd in enumerate(groups):
+        pack = gd["pack"]
+        blob, layer_off, layer_k, layer_n = pack[:4]
+        if (list(layer_off), list(layer_k), list(layer_n), bool(pack[6])) != (list(first[1]), list(first[2]), list(first[3]), bool(first[6])):
+            return None
+        L = len(layer_k) - 1
+        if pack[4] is None:
+            c_arr = ctypes.c_int * (L + 1)
+            pack[4] = (c_arr(*layer_off), c_arr(*layer_k), c_arr(*layer_n))
+        c_off, c_k, c_n = pack[4]
+        obs, act = gd["obs"], gd["act"]
+        N, O = obs.shape
+        act_kind = gd["act_kind"]
+        if pack[6]:
+            assert act_kind == ACT_SILU
+            act_kind = ACT_SILU_HALF
+        out = gd.get("out")
+        if out is None:
+            out = torch.empty((N, gd["head_dim"]), device=obs.device, dtype=torch.float32)
+        mn, mx, noise = gd["min_logvar"], gd["max_logvar"], gd["noise"]
+        g = arr[i]
+        g.packed, g.blob_halfs = blob.data_ptr(), blob.shape[1]
+        g.layer_off_halfs, g.layer_k, g.layer_n = (ctypes.cast(c_off, ctypes.c_void_p), ctypes.cast(c_k, ctypes.c_void_p),
+                                                   ctypes.cast(c_n, ctypes.c_void_p))
+        g.num_layers, g.P, g.E, g.N, g.O, g.A, g.H = L, gd["P"], gd["E"], gd["perm"].numel(), O, act.shape[1], gd["H"]
+        g.head_dim, g.layout, g.gaussian, g.act = gd["head_dim"], gd["layout"], 1 if gd["gaussian"] else 0, act_kind
+        g.residual, g.bounds_n = 1 if gd["residual"] else 0, 0 if mn is None else mn.numel()
+        g.obs, g.actn, g.perm, g.offsets = obs.data_ptr(), act.data_ptr(), gd["perm"].data_ptr(), gd["offsets"].data_ptr()
+        g.min_logvar, g.max_logvar, g.noise, g.pred = _ptr(mn), _ptr(mx), _ptr(noise), out.data_ptr()
+        keep.append((obs, act, mn, mx, noise))
+        outs.append(out)
+    lib = _lib.load()
+    rc = lib.cmrl_mlp_rollout_f16_groups(ctypes.byref(arr), len(groups), _stream())
+    if rc == -2:
+        return None
+    if rc != 0:
+        raise _lib.CmrlB200Error("cmrl_mlp_rollout_f16_groups failed (code %d): %s" % (rc, lib.cmrl_last_error().decode("utf-8", "replace")))
+    return outs
+
+
 class Tf32RolloutPack:
     """3xTF32 operand blob of a model for cmrl_mlp_rollout_tf32 (the layout cmrl_train_pack_tf32 writes), or ok == False
     when the fused tf32 kernel does not take the model (deterministic head, wide hidden layers, more than 16 head outputs)."""

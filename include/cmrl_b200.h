@@ -246,6 +246,22 @@ int cmrl_mlp_rollout_f16(const void* packed, long long blob_halfs, const int* la
                          const int* offsets, int residual, const float* min_logvar, const float* max_logvar,
                          int bounds_n, const float* noise, float* pred, long long pred_member_stride, int variant, void* stream);
 
+/* One launch for several mechanisms of a VecFakeEnv step (fake_env.py:97-115: transition, reward mech, termination mech are three
+ * independent get_dynamics_predict calls on the same observations and actions).  The groups must share depth, hidden width,
+ * activation and packed layer tables (checked); weights, buckets, noise, head layout and output are per group.  Fields as the
+ * arguments of cmrl_mlp_rollout_f16; the layer tables point at HOST arrays of num_layers + 1 ints. */
+typedef struct cmrl_rollout_group {
+    const void* packed;
+    long long blob_halfs;
+    const int *layer_off_halfs, *layer_k, *layer_n;
+    int num_layers, P, E, N, O, A, H, head_dim, layout, gaussian, act, residual, bounds_n;
+    const float *obs, *actn;
+    const int *perm, *offsets;
+    const float *min_logvar, *max_logvar, *noise;
+    float* pred;
+} cmrl_rollout_group;
+int cmrl_mlp_rollout_f16_groups(const cmrl_rollout_group* groups, int n_groups, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused training step (BaseDynamics.train, base_dynamics.py:181-186: `loss = get_nll_loss(...); loss.mean().backward()`
  * over PlainTransition / ExternalMaskTransition / PlainRewardMech / PlainTerminationMech) on tcgen05 kind::tf32 tensor

@@ -1470,3 +1470,48 @@ def test_deterministic_mechanism_trains_through_the_mse_kernels(cm):
     for _ in range(20):
         l1 = dyn.train_step("transition", obs, act, tgt).mean().item()
     assert l1 < l0 and not torch.equal(before, m.flat_parameters()[0])
+
+
+@pytest.mark.parametrize("learned_termination", [False, True])
+def test_grouped_mechanism_launch_equals_separate_launches(cm, learned_termination):
+    """Device-resident f16 steps run transition + reward (+ termination) mechs in ONE launch of the fused kernel
+    (cmrl_mlp_rollout_f16_groups): same tiles, same arithmetic -- trajectories are bit-identical to one launch per mechanism,
+    kernel by kernel and graph-replayed, for the causal-mask (parallel head) and plain transitions."""
+    for kind in ("extmask", "plain"):
+        torch.manual_seed(31)
+        rng = np.random.default_rng(31)
+        O, A, N = 5, 1, 20_011
+        if kind == "extmask":
+            tr = cm.ExternalMaskTransition(O, A, hid_size=200, activation_fn_cfg=SILU, device=DEV)
+            mask = (rng.uniform(size=(O, O + A)) < 0.6).astype(np.float32)
+            mask[np.arange(O), np.arange(O)] = 1
+            tr.set_input_mask(torch.from_numpy(mask))
+        else:
+            tr = cm.PlainTransition(O, A, hid_size=200, activation_fn_cfg=SILU, device=DEV)
+        rw = cm.PlainRewardMech(O, A, hid_size=200, activation_fn_cfg=SILU, device=DEV)
+        tm = cm.PlainTerminationMech(O, A, hid_size=200, activation_fn_cfg=SILU, device=DEV) if learned_termination else None
+        dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw, learned_termination=learned_termination, termination_mech=tm)
+        init = rng.normal(size=(N, O)).astype(np.float32)
+        act = t(rng.uniform(-1, 1, size=(N, A)).astype(np.float32))
+        runs = {}
+        for grouped in (True, False):
+            for graphed in (False, True):
+                env = cm.VecFakeEnv(N, None, None)
+                env.set_up(dyn, termination_fn=None if learned_termination else (lambda n, o, a: np.zeros((n.shape[0], 1), bool)),
+                           get_init_obs_fn=lambda n: init[:n].copy(), max_episode_steps=3)
+                env.rng_mode, env.precision, env.group_mechs = "device", "f16", grouped
+                env.seed(5)
+                env.reset()
+                rec = []
+                for _ in range(4):
+                    out = env.step_device_graphed(act) if graphed else env.step_device(act)
+                    rec.append([x.clone() for x in out])
+                runs[(grouped, graphed)] = rec
+        ref = runs[(False, False)]
+        for key, rec in runs.items():
+            for a_step, b_step in zip(rec, ref):
+                for x, y in zip(a_step, b_step):
+                    assert torch.equal(x, y), (kind, key)
+        assert float(ref[-1][0].abs().sum()) > 0
+        if not learned_termination:  # (a learned termination mech ends every episode at once: "non-zero => done", reference quirk 2)
+            assert bool(ref[2][3].any())  # the step limit truncated episodes

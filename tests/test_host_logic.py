@@ -272,7 +272,7 @@ def test_draw_ahead_buffers_are_trusted_only_after_a_replay_of_the_same_graph_fa
     counter-advancing event was a replay of the same graph family; anything else draws them before the replay."""
     env = cm.VecFakeEnv(4, None, None)
     drawn = []
-    env._ahead_draw = drawn.append  # the kernels are not under test here
+    env._ahead_draw = lambda stream_id, mechs=(): drawn.append(stream_id)  # the kernels are not under test here
     predict = {"t_id": 5, "n": 3, "family": ("predict", "key", 5, 3)}
     step = {"t_id": 5, "n": 4, "family": ("step", 1234, 5, 4)}
     env._ahead_before_replay(predict)  # first replay: nothing prepared yet
