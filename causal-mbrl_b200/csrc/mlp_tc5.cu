@@ -91,22 +91,26 @@ __device__ __noinline__ int v5_build_work(const V5Groups* gs, const int (*s_off)
         const int P = gs->g[g].P, E = gs->g[g].E;
         for (int pp = 0; pp < P; ++pp)
             for (int e = 0; e < E; ++e) {
-                const int nt = v5_tiles_of(s_off[g], e);
-                const int lo = max(item_begin, cur), hi = min(item_end, cur + nt);
+                // the range is counted in PAIR units (tiles 2k, 2k+1 of a net): a cluster boundary never splits a pair, so the
+                // only single tiles are the last ones of nets with an odd tile count (a single tile runs without a partner to
+                // overlap with; boundaries at tile granularity added about one per cluster)
+                const int nt = v5_tiles_of(s_off[g], e), nu = (nt + 1) / 2;
+                const int lo = max(item_begin, cur), hi = min(item_end, cur + nu);
                 if (lo < hi) {
                     if (n >= V5_MAX_SEGS) return -1;
+                    const int t0 = 2 * (lo - cur), t1 = min(nt, 2 * (hi - cur));
                     segs[n].g = g; segs[n].pp = pp; segs[n].netl = pp * E + e; segs[n].net = net_base + pp * E + e;
-                    segs[n].t0 = lo - cur; segs[n].t1 = hi - cur;
+                    segs[n].t0 = t0; segs[n].t1 = t1;
                     segs[n].row_base = s_off[g][e]; segs[n].cnt = s_off[g][e + 1] - s_off[g][e];
-                    for (int t = lo - cur; t < hi - cur;) {
-                        const int two = t + 1 < hi - cur ? 1 : 0;
+                    for (int t = t0; t < t1;) {
+                        const int two = t + 1 < t1 ? 1 : 0;
                         if (np >= V5_MAX_PAIRS) return -1;
                         pairs[np++] = ((uint32_t)n << 24) | ((uint32_t)two << 23) | (uint32_t)t;
                         t += 1 + two;
                     }
                     ++n;
                 }
-                cur += nt;
+                cur += nu;
             }
         net_base += P * E;
     }
@@ -258,7 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
         int n_items = 0;
         for (int g = 0; g < gs->G; ++g) {
             int tiles = 0;
-            for (int e = 0; e < gs->g[g].E; ++e) tiles += v5_tiles_of(s_off[g], e);
+            for (int e = 0; e < gs->g[g].E; ++e) tiles += (v5_tiles_of(s_off[g], e) + 1) / 2;  // pair units
             n_items += gs->g[g].P * tiles;
         }
         const int n_clusters = gridDim.x / 2;
