@@ -84,38 +84,83 @@ __device__ __forceinline__ int v5_tiles_of(const int* s_off, int e) { return (s_
 // 20 % through the instruction caches; un-inlined it kept its state in local memory, which misses the L1 next to 220 KB of
 // shared memory.
 constexpr int V5_MAX_PAIRS = 1024;
-__device__ __noinline__ int v5_build_work(const V5Groups* gs, const int (*s_off)[65], int item_begin, int item_end, V5Seg* segs,
-                                          uint32_t* pairs, int* n_pairs_out) {
-    int n = 0, np = 0, cur = 0, net_base = 0;
-    for (int g = 0; g < gs->G; ++g) {
-        const int P = gs->g[g].P, E = gs->g[g].E;
-        for (int pp = 0; pp < P; ++pp)
-            for (int e = 0; e < E; ++e) {
-                // the range is counted in PAIR units (tiles 2k, 2k+1 of a net): a cluster boundary never splits a pair, so the
-                // only single tiles are the last ones of nets with an odd tile count (a single tile runs without a partner to
-                // overlap with; boundaries at tile granularity added about one per cluster)
-                const int nt = v5_tiles_of(s_off[g], e), nu = (nt + 1) / 2;
-                const int lo = max(item_begin, cur), hi = min(item_end, cur + nu);
-                if (lo < hi) {
-                    if (n >= V5_MAX_SEGS) return -1;
-                    const int t0 = 2 * (lo - cur), t1 = min(nt, 2 * (hi - cur));
-                    segs[n].g = g; segs[n].pp = pp; segs[n].netl = pp * E + e; segs[n].net = net_base + pp * E + e;
-                    segs[n].t0 = t0; segs[n].t1 = t1;
-                    segs[n].row_base = s_off[g][e]; segs[n].cnt = s_off[g][e + 1] - s_off[g][e];
-                    for (int t = t0; t < t1;) {
-                        const int two = t + 1 < t1 ? 1 : 0;
-                        if (np >= V5_MAX_PAIRS) return -1;
-                        pairs[np++] = ((uint32_t)n << 24) | ((uint32_t)two << 23) | (uint32_t)t;
-                        t += 1 + two;
-                    }
-                    ++n;
-                }
-                cur += nu;
-            }
-        net_base += P * E;
+// Executed by ONE WARP when the kernel starts (a single thread walking 35 nets cost ~2 us of a 180 us launch): lane i takes
+// nets i, i + 32, ...; warp scans give every net its first pair unit, its segment slot and its first pair slot.  The range
+// is counted in PAIR units (tiles 2k, 2k+1 of a net): a cluster boundary never splits a pair, so the only single tiles are
+// the last ones of nets with an odd tile count.
+__device__ __noinline__ void v5_build_work(const V5Groups* gs, const int (*s_off)[65], int n_clusters, int cid, V5Seg* segs,
+                                           uint32_t* pairs, int* n_segs_out, int* n_pairs_out, int lane) {
+    int total_nets = 0;
+    for (int g = 0; g < gs->G; ++g) total_nets += gs->g[g].P * gs->g[g].E;
+    auto decode = [&](int id, int& g, int& pp, int& e) {
+        g = 0;
+        while (id >= gs->g[g].P * gs->g[g].E) {
+            id -= gs->g[g].P * gs->g[g].E;
+            ++g;
+        }
+        pp = id / gs->g[g].E;
+        e = id - pp * gs->g[g].E;
+    };
+    // pass 1: pair units of the whole launch
+    int mine = 0;
+    for (int id = lane; id < total_nets; id += 32) {
+        int g, pp, e;
+        decode(id, g, pp, e);
+        mine += (v5_tiles_of(s_off[g], e) + 1) / 2;
     }
-    *n_pairs_out = np;
-    return n;
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    const int u_begin = (int)((long long)cid * mine / n_clusters), u_end = (int)((long long)(cid + 1) * mine / n_clusters);
+    // pass 2: nets in order, 32 at a time
+    int cur_base = 0, seg_base = 0, pair_base = 0;
+    bool overflow = false;
+    for (int id0 = 0; id0 < total_nets; id0 += 32) {
+        const int id = id0 + lane;
+        int g = 0, pp = 0, e = 0, nt = 0;
+        if (id < total_nets) {
+            decode(id, g, pp, e);
+            nt = v5_tiles_of(s_off[g], e);
+        }
+        const int nu = (nt + 1) / 2;
+        int incl = nu;  // inclusive scan of the units
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int cur = cur_base + incl - nu;
+        const int lo = max(u_begin, cur), hi = min(u_end, cur + nu);
+        const bool hit = lo < hi;
+        const int t0 = hit ? 2 * (lo - cur) : 0, t1 = hit ? min(nt, 2 * (hi - cur)) : 0;
+        const int np = (t1 - t0 + 1) / 2;
+        const unsigned ball = __ballot_sync(0xffffffffu, hit);
+        const int seg = seg_base + __popc(ball & ((1u << lane) - 1u));
+        int pincl = np;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, pincl, o);
+            if (lane >= o) pincl += v;
+        }
+        const int pfirst = pair_base + pincl - np;
+        if (hit) {
+            if (seg >= V5_MAX_SEGS || pfirst + np > V5_MAX_PAIRS) {
+                overflow = true;
+            } else {
+                int net_base = 0;
+                for (int h = 0; h < g; ++h) net_base += gs->g[h].P * gs->g[h].E;
+                segs[seg].g = g; segs[seg].pp = pp; segs[seg].netl = pp * gs->g[g].E + e; segs[seg].net = net_base + pp * gs->g[g].E + e;
+                segs[seg].t0 = t0; segs[seg].t1 = t1;
+                segs[seg].row_base = s_off[g][e]; segs[seg].cnt = s_off[g][e + 1] - s_off[g][e];
+                int k = pfirst;
+                for (int t = t0; t < t1; t += 2) pairs[k++] = ((uint32_t)seg << 24) | ((uint32_t)(t + 1 < t1 ? 1 : 0) << 23) | (uint32_t)t;
+            }
+        }
+        cur_base += __shfl_sync(0xffffffffu, incl, 31);
+        seg_base += __popc(ball);
+        pair_base += __shfl_sync(0xffffffffu, pincl, 31);
+    }
+    overflow = __any_sync(0xffffffffu, overflow);
+    if (lane == 0) {
+        *n_segs_out = overflow ? -1 : seg_base;
+        *n_pairs_out = pair_base;
+    }
 }
 __device__ __forceinline__ void v5_cur_init(V5Cur& c, const V5Seg*, int) { c.i = 0; }
 __device__ __forceinline__ bool v5_next(V5Cur& c, const V5Seg* segs, int n_pairs, V5Pair& pr, const uint32_t* pairs) {
@@ -258,19 +303,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V5_THREADS, 1)
     __shared__ V5Seg s_segs[V5_MAX_SEGS];
     __shared__ uint32_t s_pairs[V5_MAX_PAIRS];
     __shared__ int s_nseg, s_npairs;
-    if (threadIdx.x == 32) {  // (a lane of an epilogue warp: thread 0 is still busy with nothing, but keep warp 0's lane 0 free)
-        int n_items = 0;
-        for (int g = 0; g < gs->G; ++g) {
-            int tiles = 0;
-            for (int e = 0; e < gs->g[g].E; ++e) tiles += (v5_tiles_of(s_off[g], e) + 1) / 2;  // pair units
-            n_items += gs->g[g].P * tiles;
-        }
-        const int n_clusters = gridDim.x / 2;
-        const int cid = blockIdx.x / 2;
-        const int item_begin = (int)((long long)cid * n_items / n_clusters);
-        const int item_end = (int)((long long)(cid + 1) * n_items / n_clusters);
-        s_nseg = v5_build_work(gs, s_off, item_begin, item_end, s_segs, s_pairs, &s_npairs);
-    }
+    if (warp == 1) v5_build_work(gs, s_off, gridDim.x / 2, blockIdx.x / 2, s_segs, s_pairs, &s_nseg, &s_npairs, lane);
     __syncthreads();
     const V5Seg* segs = s_segs;
     const uint32_t* pairs = s_pairs;
