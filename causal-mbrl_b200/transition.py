@@ -194,7 +194,7 @@ class ExternalMaskTransition(BaseTransition):
         return self._input_mask
 
     def _parallel_num(self):
-        return self.obs_size
+        return self._sub1 - self._sub0  # obs_size unless this is a net shard
 
     def _residual(self):
         return self.residual

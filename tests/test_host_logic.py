@@ -364,3 +364,56 @@ def test_weights_token_sees_torch_writes_and_fused_optimiser_steps(monkeypatch):
     tr.set_elite_members([0, 1, 2, 3, 4])
     assert env._graph_state_key(False) != k1
     assert env._graph_state_key(True) != env._graph_state_key(False)
+
+
+def test_round2_host_rules():
+    """Small host-side rules added in round 2: net shard ranges cover the sub-networks exactly once in contiguous near-equal
+    shares; the per-layer training GEMMs pick the tensor-core tier by tile count as well as by rows; mechanisms are grouped
+    into one rollout launch only where that was measured to pay."""
+    for P in (1, 5, 100):
+        for world in (1, 2, 3, 8):
+            if world > P:
+                continue
+            ranges = [cm.net_shard_range(P, world, r) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == P
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 1
+    tier = cm.ops._train_tier
+    assert tier("fwd", 256, 7, 200, 200) == 0 and tier("fwd", 4096, 7, 200, 200) == 3          # few nets: by rows
+    assert tier("fwd", 256, 1600, 512, 512) == 3 and tier("dx", 256, 1600, 512, 512) == 3        # many nets: by tiles
+    assert tier("fwd", 256, 1600, 512, 2) == 0 and tier("fwd", 256, 1600, 120, 512) == 0         # narrow layers stay on FFMA
+    assert tier("dw", 256, 7, 200, 200) == 0 and tier("dw", 2048, 7, 200, 200) == 3 and tier("dw", 256, 1600, 512, 512) == 3
+    keep = cm.ops.TRAIN_GEMM_TIER
+    try:
+        cm.ops.TRAIN_GEMM_TIER = 0
+        assert tier("fwd", 1 << 20, 1600, 512, 512) == 0  # an explicit tier overrides the rule
+    finally:
+        cm.ops.TRAIN_GEMM_TIER = keep
+    env = cm.VecFakeEnv(100_000, None, None)
+    env.learned_reward, env.learned_termination = True, False
+    assert env.group_mechs == "auto" and not env._group_on()      # two mechanisms, many envs: one launch per mechanism
+    env.learned_termination = True
+    assert env._group_on()                                          # three mechanisms
+    small = cm.VecFakeEnv(1000, None, None)
+    small.learned_reward, small.learned_termination = True, False
+    assert small._group_on()                                        # few envs: launch bound
+    small.group_mechs = False
+    assert not small._group_on()
+
+
+def test_external_mask_shard_is_the_full_models_slice_on_the_host():
+    """A net shard built with subnet_range has the full model's interface restricted to its dimensions (no kernels involved)."""
+    sh = cm.ExternalMaskTransition(6, 2, hid_size=8, subnet_range=(2, 5))
+    assert sh.is_net_shard and sh.subnet_range == (2, 5) and sh._head_dim == 3 and sh._parallel_num() == 3 and sh._grad_dims() == 6
+    assert [tuple(p.shape) for p in sh.parameters()][-2:] == [(3, 7, 8, 2), (3, 7, 1, 2)]  # head weight / bias of three sub-networks
+    mask = np.arange(6 * 8, dtype=np.float32).reshape(6, 8)
+    sh.set_input_mask(torch.from_numpy(mask))
+    assert np.array_equal(sh._kernel_mask().numpy(), mask[2:5]) and np.array_equal(sh.input_mask.numpy(), mask)
+    tgt = torch.arange(24.0).view(2, 2, 6)
+    assert torch.equal(sh.target_columns(tgt), tgt[..., 2:5])
+    full = cm.ExternalMaskTransition(6, 2, hid_size=8)
+    assert not full.is_net_shard and full.target_columns(tgt) is tgt and full._nll_reg() == pytest.approx(0.01 * 6 * 10.5)
+    assert sh._nll_reg() == pytest.approx(full._nll_reg())  # the loss constant of the FULL model
+    with pytest.raises(AssertionError):
+        cm.ExternalMaskTransition(6, 2, hid_size=8, subnet_range=(2, 5), learn_logvar_bounds=True)
