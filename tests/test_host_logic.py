@@ -417,3 +417,31 @@ def test_external_mask_shard_is_the_full_models_slice_on_the_host():
     assert sh._nll_reg() == pytest.approx(full._nll_reg())  # the loss constant of the FULL model
     with pytest.raises(AssertionError):
         cm.ExternalMaskTransition(6, 2, hid_size=8, subnet_range=(2, 5), learn_logvar_bounds=True)
+
+
+def test_peer_exchange_partition_covers_every_gradient_once():
+    """csrc/dp_sync.cu cuts an arena of n floats into W slices of S floats and every slice into 148 CTA sub-ranges of T floats
+    (both multiples of 4, the last ones clipped to n).  Restated here: every float belongs to exactly one (slice, CTA), every
+    16-byte vector lies inside one sub-range, and the buffers sized for the communicator's capacity hold any smaller arena."""
+    ctas = 148
+    for world in (1, 2, 3, 8, 16):
+        for n in (1, 3, 4, 5, 1000, 868072, 868075, 12_345_679):
+            S = ((n + world - 1) // world + 3) // 4 * 4
+            T = ((S + ctas - 1) // ctas + 3) // 4 * 4
+            assert S % 4 == 0 and T % 4 == 0 and S * world >= n and T * ctas >= S
+            covered = 0
+            prev_end = 0
+            for q in range(world):
+                for b in range(ctas):
+                    lo, hi = b * T, min((b + 1) * T, S)
+                    if hi <= lo:
+                        continue
+                    g_lo, g_hi = min(n, q * S + lo), min(n, q * S + hi)
+                    assert g_lo == prev_end or g_lo == n  # contiguous, in order, no overlap
+                    covered += g_hi - g_lo
+                    prev_end = max(prev_end, g_hi)
+                    assert lo % 4 == 0  # vectors never straddle two CTAs
+            assert covered == n and prev_end == n
+            cap = n + 12345
+            slice_cap = ((cap + world - 1) // world + 3) // 4 * 4
+            assert S <= slice_cap
