@@ -534,6 +534,7 @@ class _DeviceEpochRunner:
         self.sum_ws = torch.zeros(66, device=dev, dtype=torch.float64)
         self.side = torch.cuda.Stream(device=dev)
         self.graph = None
+        self._graph_key = None
         self._order_pinned = [torch.empty(self.N, dtype=torch.int32).pin_memory() for _ in range(2)]
         self._order_flip = 0
         self._staged_order = None  # (the int64 permutation object, its int32 copy in pinned memory)
@@ -589,16 +590,29 @@ class _DeviceEpochRunner:
         self.loss_sum.zero_()
         model = getattr(self.dyn, self.mech)
         model._nll_reg()  # host-side constant, cached before any capture
-        model.flat_parameters()
+        flat, flat_grad = model.flat_parameters()
+        plan = None
         if self.Bl > 0:
             plan = ops.fused_train_plan(model, self.E, self.Bl)  # buffers of the fused tcgen05 step: allocated before the capture
             if plan is not None:
                 plan.pinned = True  # the captured graph bakes their addresses
-        getattr(self.dyn, "{}_optimizer".format(self.mech)).prepare_graphable()
+        optim = getattr(self.dyn, "{}_optimizer".format(self.mech))
+        optim.prepare_graphable()
         n_full = self.N // self.B
+        ws = None
         if self.Bl >= 2048:  # split-K dw workspace (ops.ens_linear_bwd_dw) must exist before the step is captured
             worst = max((p.numel() // p.shape[-2]) * (p.shape[-2] + 1) for p in model.parameters() if p.dim() >= 3 and p.shape[-2] > 1)
-            ops.splitk_workspace(self.obs.device, min(32 * worst, (256 << 20) // 4))
+            ws = ops.splitk_workspace(self.obs.device, min(32 * worst, (256 << 20) // 4))
+        # a captured step bakes the addresses of the arena, the Adam moments, the plan's buffers, the mask and the workspace:
+        # when one of them was replaced since the capture (model.to(), set_input_mask, an optimiser state loaded from a
+        # checkpoint, a larger workspace) the step is captured again
+        mask = model._kernel_mask()
+        graph_key = (flat.data_ptr(), flat_grad.data_ptr(), None if plan is None else (plan.packed.data_ptr(), plan.scratch.data_ptr()),
+                     None if mask is None else (mask.data_ptr(), mask._version),
+                     None if ws is None else ws.data_ptr(), optim._exp_avg.data_ptr(), optim._exp_avg_sq.data_ptr())  # fmt: skip
+        if self.graph is not None and graph_key != self._graph_key:
+            self.graph = None
+        self._graph_key = graph_key
         if self.use_graph and self.graph is None and n_full > 0:
             if self.dyn.dp_group is not None and getattr(self.dyn, "_peer_sync", None) is None:
                 self._step()  # one eager step first: NCCL sets its communicator up outside the capture

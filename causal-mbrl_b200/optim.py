@@ -99,7 +99,11 @@ class FusedAdamL2(torch.optim.Optimizer):
         self._step = state["step"]
         if self._step_dev is not None:
             self._step_dev[:1].fill_(self._step)
-        self._exp_avg = None if state["exp_avg"] is None else state["exp_avg"].clone()
-        self._exp_avg_sq = None if state["exp_avg_sq"] is None else state["exp_avg_sq"].clone()
+        for name in ("exp_avg", "exp_avg_sq"):
+            new, cur = state[name], getattr(self, "_" + name)
+            if new is not None and cur is not None and cur.shape == new.shape and cur.device == new.device:
+                cur.copy_(new)  # in place: captured step graphs hold the moment buffers' addresses
+            else:
+                setattr(self, "_" + name, None if new is None else new.clone())
         for g, s in zip(self.param_groups, state["param_groups"]):
             g.update(s)

@@ -631,6 +631,38 @@ def test_device_epoch_matches_host_iterator_path(cm, use_graph):
         assert rel_err(w1[k], w0[k]) < 1e-5, k
 
 
+def test_device_epoch_recaptures_after_the_arena_moved(cm):
+    """The captured training step bakes the addresses of the parameter arena and of the fused plan's buffers.  When the
+    arena is re-homed between two epochs over the SAME data set (here: `_flatten_parameters()`, what `model.to()` leads to)
+    the runner has to capture the step again: the second epoch must update the live parameters exactly like a dynamics
+    that never used a graph."""
+    g = load_golden("learn_small.npz")
+    from oracle.refshim import DuckReplayBuffer
+
+    buf = DuckReplayBuffer(g["obs"], g["act"], g["next_obs"], g["rew"], g["done"])
+    results = []
+    for use_graph in (False, True):
+        tr = cm.PlainTransition(5, 1, hid_size=32, activation_fn_cfg=SILU, device=DEV)
+        load_sd(tr, params_of(g, "tr0."))
+        dyn = cm.PlainEnsembleDynamics(tr, learned_reward=False, optim_lr=1e-3)
+        seeds = iter(range(50, 60))
+        real = np.random.default_rng
+        with mock.patch("numpy.random.default_rng", lambda seed=None: real(next(seeds) if seed is None else seed)):
+            train_it, _ = dyn.dataset_split(buf, 0.2, 100)
+        losses = [dyn.train_epoch_device(train_it, "transition", use_graph=use_graph)]
+        old_ptr = tr.flat_parameters()[0].data_ptr()
+        keep = tr.flat_parameters()  # the old arena stays allocated, so that the new one cannot reuse its address
+        tr._flatten_parameters()
+        assert tr.flat_parameters()[0].data_ptr() != old_ptr
+        losses.append(dyn.train_epoch_device(train_it, "transition", use_graph=use_graph))
+        del keep
+        results.append((losses, {k: v.cpu().numpy() for k, v in tr.state_dict().items()}))
+    (l0, w0), (l1, w1) = results
+    assert rel_err(np.asarray(l1), np.asarray(l0)) < 1e-5
+    for k in w0:
+        assert rel_err(w1[k], w0[k]) < 1e-5, k
+
+
 def test_step_device_graphed(cm):
     """CUDA-graph replay of the device-resident step: episode bookkeeping advances, every replay draws fresh noise."""
     g = load_golden("fake_env_truncate.npz")
