@@ -23,16 +23,22 @@ class PeerGradSync:
         self._comm = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
         with torch.cuda.device(self.device):
-            _lib.call("cmrl_dp_comm_create", self.rank, self.world, self.max_floats, ctypes.byref(self._comm), handle)
+            # a rank whose set-up fails at any stage still takes part in both collectives below (with an all-zero handle):
+            # leaving early would hang the peers in the all-gather
+            err = None
+            try:
+                _lib.call("cmrl_dp_comm_create", self.rank, self.world, self.max_floats, ctypes.byref(self._comm), handle)
+            except _lib.CmrlB200Error as e:  # e.g. no memory for the exchange buffer, CUDA IPC not available in this process
+                err = e
             mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(self.device)
             gathered = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(gathered, mine, group=group)
             blob = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
-            err = None
-            try:
-                _lib.call("cmrl_dp_comm_connect", self._comm, blob)
-            except _lib.CmrlB200Error as e:  # e.g. a peer on another node: CUDA IPC only maps memory of the same node
-                err = e
+            if err is None:
+                try:
+                    _lib.call("cmrl_dp_comm_connect", self._comm, blob)
+                except _lib.CmrlB200Error as e:  # e.g. a peer on another node: CUDA IPC only maps memory of the same node
+                    err = e
             # every rank learns whether EVERY rank connected (a rank that went on alone would wait for peers that never push);
             # this all-reduce is also the barrier after which pushing into a peer's buffer is safe
             ok = torch.tensor([0 if err is not None else 1], device=self.device, dtype=torch.int32)
