@@ -742,7 +742,7 @@ class VecFakeEnv(VecEnv):
         if done_idx.size:
             if device_rng:  # rows the fused tail wrote into the done envs
                 if done_idx.size * 4 < N:
-                    rows = obs.index_select(0, torch.from_numpy(done_idx).to(self.device)).cpu().numpy()
+                    rows = ops.gather_rows(obs, torch.from_numpy(done_idx.astype(np.int32)).to(self.device)).cpu().numpy()
                 else:
                     b["h_term_obs"].copy_(obs, non_blocking=True)
                     stream.synchronize()

@@ -388,6 +388,14 @@ def gather_inputs(obs, act, perm):
     return x
 
 
+def gather_rows(x, rows):
+    """x[rows] for a dense [N,C] float32 tensor and int32 row numbers on the device (cmrl_gather_inputs without an action part)."""
+    assert x.dim() == 2 and x.is_contiguous() and rows.dtype == torch.int32
+    out = torch.empty((rows.numel(), x.shape[1]), device=x.device, dtype=torch.float32)
+    _lib.call("cmrl_gather_inputs", x.data_ptr(), None, rows.data_ptr(), rows.numel(), x.shape[1], 0, out.data_ptr(), _stream())
+    return out
+
+
 def sample_scatter(raw_sorted, layout, perm, N, D, obs, min_logvar, max_logvar, noise, out=None):
     pred = torch.empty((N, D), device=raw_sorted.device, dtype=torch.float32) if out is None else out
     bounds_n = 0 if min_logvar is None else min_logvar.numel()

@@ -1025,6 +1025,9 @@ def test_step_return_views_equals_copies(cm, make):
         oa, ra, da, ia = env_a.step(act)
         ob, rb, db, ib = env_b.step(act)
         assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and np.array_equal(da, db)
+        # the host mirror (next_obs read back before the tail, patched at the done rows fetched through `ops.gather_rows` or the
+        # full copy) is the observation state in HBM, reset rows included; both fetch paths occur (few / many done envs)
+        assert np.array_equal(oa, env_a._obs_dev.cpu().numpy()) and np.array_equal(ob, env_b._obs_dev.cpu().numpy())
         for i in np.nonzero(da)[0][:20]:
             assert np.array_equal(ia[i]["terminal_observation"], ib[i]["terminal_observation"])
         if prev is not None:
