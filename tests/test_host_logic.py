@@ -32,6 +32,97 @@ def test_abi_exports_every_declared_symbol():
     assert rc < 0 and b"null pointer" in lib.cmrl_last_error()
 
 
+def _header_declarations():
+    """[(name, [parameter categories])] of every function include/cmrl_b200.h declares (comments stripped)."""
+    text = open(os.path.join(ROOT, "include", "cmrl_b200.h")).read()
+    text = re.sub(r"//[^\n]*", "", re.sub(r"/\*.*?\*/", "", text, flags=re.S))
+    scalar = {"int": "int", "long long": "ll", "unsigned long long": "ull", "float": "float"}
+    out = []
+    for name, params in re.findall(r"\b(?:int|long long|const char\*)\s+(cmrl_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        cats = []
+        for p_ in params.split(","):
+            p_ = " ".join(p_.split())
+            if p_ == "void":
+                continue
+            if "*" in p_:
+                cats.append("ptr")
+            else:
+                cats.append(scalar[re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*$", "", p_).replace("const ", "").strip()])
+        out.append((name, cats))
+    return out
+
+
+def test_ctypes_prototypes_match_the_header_parameter_by_parameter():
+    """A parameter bound as `int` that the header declares `long long` (or a float bound as a pointer) would corrupt a call
+    silently: every ctypes prototype of _lib.py is compared with the C declaration, type class by type class."""
+    ctype_cat = {ctypes.c_int: "int", ctypes.c_longlong: "ll", ctypes.c_ulonglong: "ull", ctypes.c_float: "float",
+                 ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr"}
+    decls = _header_declarations()
+    assert len(decls) >= 40
+    checked = 0
+    for name, cats in decls:
+        proto = cm._lib.PROTOTYPES.get(name)
+        if proto is None:
+            continue
+        bound = [ctype_cat.get(t, "ptr" if issubclass(t, ctypes._Pointer) else None) for t in proto]
+        assert bound == cats, (name, cats, bound)
+        checked += 1
+    assert checked == len(cm._lib.PROTOTYPES)
+    # struct cmrl_rollout_group: same field order and types as the ctypes Structure
+    text = open(os.path.join(ROOT, "include", "cmrl_b200.h")).read()
+    body = re.search(r"typedef struct cmrl_rollout_group\s*\{(.*?)\}\s*cmrl_rollout_group;", text, flags=re.S).group(1)
+    body = re.sub(r"//[^\n]*", "", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    fields = []
+    for stmt in body.split(";"):
+        stmt = " ".join(stmt.split())
+        if not stmt:
+            continue
+        ptr = "*" in stmt
+        base = "ptr" if ptr else ("ll" if stmt.startswith("long long") else "int")
+        names = re.sub(r"^(const\s+)?(unsigned\s+)?(long long|int|float|void|uint8_t)\s*\**", "", stmt)
+        for n_ in names.split(","):
+            fields.append((n_.replace("*", "").strip(), base))
+    got = [(n_, ctype_cat[t]) for n_, t in cm._lib.RolloutGroup._fields_]
+    assert got == fields, (got, fields)
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library():
+    """The boundary is a C ABI: include/cmrl_b200.h compiles as C99 and as C++17, and a C program (no Python, no torch) links
+    against libcmrl_b200.so, reads the ABI version and gets the documented error code / message for an invalid call."""
+    import shutil
+    import subprocess
+
+    gcc, gxx = shutil.which("gcc"), shutil.which("g++")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    hdr = os.path.join(ROOT, "include", "cmrl_b200.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    if gxx is not None:
+        subprocess.run([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
+    libdir = os.path.dirname(cm._lib.LIB_PATH)
+    prog = r"""
+#include <stdio.h>
+#include <string.h>
+#include "cmrl_b200.h"
+int main(void) {
+    if (cmrl_abi_version() != 1) return 1;
+    int rc = cmrl_gather_inputs(NULL, NULL, NULL, 4, 5, 1, NULL, NULL);   /* argument validation precedes any CUDA call */
+    if (rc >= 0) return 2;
+    if (strstr(cmrl_last_error(), "null pointer") == NULL) return 3;
+    printf("abi %d, launches %lld\\n", cmrl_abi_version(), cmrl_launch_count());
+    return 0;
+}
+"""
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "consumer.c"), os.path.join(d, "consumer")
+        open(src, "w").write(prog)
+        subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                        "-L", libdir, "-l:libcmrl_b200.so", "-Wl,-rpath," + libdir], check=True)
+        res = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
+        assert res.stdout.startswith("abi 1, launches ")
+
+
 def test_no_cpu_fallback():
     m = cm.PlainTransition(5, 1, hid_size=8)
     with pytest.raises(cm._lib.CmrlB200Error):
