@@ -122,6 +122,7 @@ def load_reference():
     from cmrl.models.termination_mech.plain_termination_mech import PlainTerminationMech
     from cmrl.models.dynamics.base_dynamics import BaseDynamics
     from cmrl.models.dynamics.plain_dynamics import PlainEnsembleDynamics
+    from cmrl.models.dynamics.constraint_based_dynamics import ConstraintBasedDynamics
     from cmrl.models.fake_env import VecFakeEnv
     from cmrl.util.transition_iterator import BootstrapIterator, TransitionIterator
     from cmrl.types import InteractionBatch

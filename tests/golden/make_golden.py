@@ -168,6 +168,10 @@ def euler_fixtures():
     out["fe_elite"] = np.asarray(fe.elite_members, dtype=np.int64)
     out["tr_elite"] = np.asarray(one.elite_members, dtype=np.int64)
     out["rw_elite"] = np.asarray(rw.elite_members, dtype=np.int64)
+    if reset_by_buffer:
+        out["pool_obs"] = pool
+        out["pool_pos"] = np.int64(33)
+        np.random.seed(123)  # the tests seed the global generator the same way right before reset()
     out["reset_obs"] = env.reset()
     actions = rng.uniform(-1, 1, size=(T, N, A)).astype(np.float32)
     out["actions"] = actions
@@ -238,7 +242,8 @@ def learn_fixture(name):
     print(name, "elites", tr.elite_members, rw.elite_members, "epochs", dyn.total_epoch)
 
 
-def fake_env_fixture(name, learned_termination, penalty_coeff, deterministic, max_episode_steps, transition_kind="plain"):
+def fake_env_fixture(name, learned_termination, penalty_coeff, deterministic, max_episode_steps, transition_kind="plain",
+                     reset_by_buffer=False):
     torch.manual_seed(5)
     np.random.seed(5)
     rng = np.random.default_rng(5)
@@ -267,12 +272,19 @@ def fake_env_fixture(name, learned_termination, penalty_coeff, deterministic, ma
     def termination_fn(next_obs, obs, act):
         return np.abs(next_obs[:, 0:1]) > 1.5
 
+    pool = None
+    if reset_by_buffer:
+        # resets draw rows of a (partly filled) real replay buffer with the GLOBAL numpy RNG (fake_env.py:152-155,175-178)
+        pool = init_rng.normal(size=(40, O)).astype(np.float32)
+        buf = refshim.DuckReplayBuffer(pool, np.zeros((40, A), np.float32), pool, np.zeros(40, np.float32), np.zeros(40, bool))
+        buf.full, buf.pos = False, 33
     env = ref.VecFakeEnv(N, None, None)
     env.set_up(
         dyn,
         reward_fn=None,
         termination_fn=None if learned_termination else termination_fn,
-        get_init_obs_fn=get_init_obs_fn,
+        get_init_obs_fn=None if reset_by_buffer else get_init_obs_fn,
+        real_replay_buffer=buf if reset_by_buffer else None,
         penalty_coeff=penalty_coeff,
         deterministic=deterministic,
         max_episode_steps=max_episode_steps,
@@ -287,6 +299,10 @@ def fake_env_fixture(name, learned_termination, penalty_coeff, deterministic, ma
     out["tr_elite"] = np.asarray(tr.elite_members, dtype=np.int64)
     out["rw_elite"] = np.asarray(rw.elite_members, dtype=np.int64)
     out["tm_elite"] = np.asarray(tm.elite_members, dtype=np.int64)
+    if reset_by_buffer:
+        out["pool_obs"] = pool
+        out["pool_pos"] = np.int64(33)
+        np.random.seed(123)  # the tests seed the global generator the same way right before reset()
     out["reset_obs"] = env.reset()
     actions = rng.uniform(-1, 1, size=(T, N, A)).astype(np.float32)
     out["actions"] = actions
@@ -367,8 +383,59 @@ def main():
     fake_env_fixture("fake_env_extmask.npz", False, 0.0, False, 1000, transition_kind="extmask")
 
 
+def constraint_fixtures():
+    """ConstraintBasedDynamics.learn (constraint_based_dynamics.py:83-183): the oracle causal mask is set on the transition
+    before training, bootstrap PERMUTATIONS per member, a ragged last batch, checkpoint written at the end."""
+    import tempfile
+
+    torch.manual_seed(7)
+    np.random.seed(7)
+    rng = np.random.default_rng(7)
+    O, A, E, H, N = 5, 1, 7, 24, 650
+    tr = ref.ExternalMaskTransition(O, A, ensemble_num=E, elite_num=5, hid_size=H, activation_fn_cfg=SILU)
+    rw = ref.PlainRewardMech(O, A, ensemble_num=E, elite_num=5, hid_size=H, activation_fn_cfg=SILU)
+    dyn = ref.ConstraintBasedDynamics(tr, learned_reward=True, reward_mech=rw, optim_lr=1e-3)
+    assert dyn.transition_oracle_mask is None and tuple(dyn.transition_history_mask.shape) == (O, O + A)
+    assert not hasattr(dyn, "reward_mech_oracle_mask")
+    mask = (rng.uniform(size=(O, O + A)) < 0.5).astype(np.float32)
+    mask[np.arange(O), np.arange(O)] = 1.0
+    dyn.set_oracle_mask("transition", mask)
+    out = sd_np(tr, "tr0.")
+    out.update(sd_np(rw, "rw0."))
+    obs, act, nxt, rew, done = synth_dataset(rng, N, O, A)
+    buf = refshim.DuckReplayBuffer(obs, act, nxt, rew, done)
+    seeds = iter(range(3000, 4000))
+    real_default_rng = np.random.default_rng
+
+    def seeded_default_rng(seed=None):
+        return real_default_rng(next(seeds) if seed is None else seed)
+
+    with tempfile.TemporaryDirectory() as d, mock.patch("numpy.random.default_rng", seeded_default_rng):
+        dyn.learn(buf, validation_ratio=0.2, batch_size=64, bootstrap_permutes=True, longest_epoch=3,
+                  improvement_threshold=0.01, patience=2, work_dir=d)
+        files = sorted(os.listdir(d))
+        saved = torch.load(os.path.join(d, "external_mask_transition.pth"), weights_only=False)
+    assert torch.equal(tr.input_mask, torch.from_numpy(mask))
+    out.update(sd_np(tr, "tr1."))
+    out.update(sd_np(rw, "rw1."))
+    out.update(obs=obs, act=act, next_obs=nxt, rew=rew, done=done, oracle_mask=mask,
+               saved_input_mask=saved["input_mask"].numpy(), saved_keys=np.asarray(sorted(saved.keys())),
+               files=np.asarray(files),
+               tr_elite=np.asarray(tr.elite_members, dtype=np.int64), rw_elite=np.asarray(rw.elite_members, dtype=np.int64),
+               total_epoch_tr=np.int64(dyn.total_epoch["transition"]), total_epoch_rw=np.int64(dyn.total_epoch["reward_mech"]))
+    _, val_it = dyn.dataset_split(buf, 0.2, 64)
+    out["tr_val_mse"] = dyn.evaluate(val_it, "transition").mean(dim=(1, 2)).numpy()
+    out["rw_val_mse"] = dyn.evaluate(val_it, "reward_mech").mean(dim=(1, 2)).numpy()
+    np.savez_compressed(os.path.join(HERE, "constraint_learn.npz"), **out)
+    print("constraint_learn.npz", "elites", tr.elite_members, rw.elite_members, "epochs", dyn.total_epoch, files)
+    # VecFakeEnv whose resets come from the real replay buffer (global numpy RNG), many resets: short episodes + termination_fn
+    fake_env_fixture("fake_env_bufreset.npz", False, 0.0, False, 2, reset_by_buffer=True)
+
+
 if __name__ == "__main__":
-    if "--only-cmi" in sys.argv:
+    if "--only-constraint" in sys.argv:
+        constraint_fixtures()
+    elif "--only-cmi" in sys.argv:
         cmi_fixtures()
     elif "--only-euler" in sys.argv:
         euler_fixtures()
@@ -376,3 +443,4 @@ if __name__ == "__main__":
         main()
         cmi_fixtures()
         euler_fixtures()
+        constraint_fixtures()

@@ -298,6 +298,54 @@ def test_learn_golden(cm):
         dyn.load(d)
 
 
+def test_constraint_based_dynamics_learn_golden(cm):
+    """ConstraintBasedDynamics.learn against the reference run (constraint_based_dynamics.py:83-183): the oracle causal mask
+    is put on the masked transition before training, every member iterates its own PERMUTATION of the data
+    (`bootstrap_permutes=True`), ragged last batch, checkpoint (with the mask) written at the end.  Epoch counts and elite
+    indices bit-exact, weights and hold-out scores within 1e-4 after three epochs of Adam steps."""
+    g = load_golden("constraint_learn.npz")
+    from oracle.refshim import DuckReplayBuffer
+
+    tr = cm.ExternalMaskTransition(5, 1, hid_size=24, activation_fn_cfg=SILU, device=DEV)
+    rw = cm.PlainRewardMech(5, 1, hid_size=24, activation_fn_cfg=SILU, device=DEV)
+    load_sd(tr, params_of(g, "tr0."))
+    load_sd(rw, params_of(g, "rw0."))
+    dyn = cm.ConstraintBasedDynamics(tr, learned_reward=True, reward_mech=rw, optim_lr=1e-3)
+    assert dyn.transition_oracle_mask is None and tuple(dyn.transition_history_mask.shape) == (5, 6)
+    assert not hasattr(dyn, "reward_mech_oracle_mask")  # only mechanisms with an input mask get one
+    buf = DuckReplayBuffer(g["obs"], g["act"], g["next_obs"], g["rew"], g["done"])
+    with pytest.raises(ValueError):  # no oracle mask yet: `set_input_mask(None)` fails as in the reference (util.py:64-69)
+        dyn.learn(buf, longest_epoch=1, work_dir=None)
+    dyn.set_oracle_mask("transition", g["oracle_mask"])
+    seeds = iter(range(3000, 4000))
+    real_default_rng = np.random.default_rng
+
+    def seeded_default_rng(seed=None):
+        return real_default_rng(next(seeds) if seed is None else seed)
+
+    with tempfile.TemporaryDirectory() as d, mock.patch("numpy.random.default_rng", seeded_default_rng):
+        dyn.learn(buf, validation_ratio=0.2, batch_size=64, bootstrap_permutes=True, longest_epoch=3,
+                  improvement_threshold=0.01, patience=2, work_dir=d)
+        assert sorted(os.listdir(d)) == list(g["files"])
+        saved = torch.load(os.path.join(d, "external_mask_transition.pth"), weights_only=False)
+    assert sorted(saved.keys()) == list(g["saved_keys"])
+    assert np.array_equal(saved["input_mask"].cpu().numpy(), g["saved_input_mask"])
+    assert np.array_equal(tr.input_mask.cpu().numpy(), g["oracle_mask"])
+    assert dyn.total_epoch == {"transition": int(g["total_epoch_tr"]), "reward_mech": int(g["total_epoch_rw"])}
+    assert list(map(int, tr.elite_members)) == list(map(int, g["tr_elite"]))
+    assert list(map(int, rw.elite_members)) == list(map(int, g["rw_elite"]))
+    for pre, m in (("tr1.", tr), ("rw1.", rw)):
+        ref = params_of(g, pre)
+        sd = m.state_dict()
+        for k in ref:
+            if k.endswith("weight"):
+                assert record_max("constraint learn " + pre + k, rel_err(sd[k].cpu().numpy(), ref[k])) < 1e-4, k
+    _, val_it = dyn.dataset_split(buf, 0.2, 64)
+    assert rel_err(dyn.evaluate_member_mse(val_it, "transition").numpy(), g["tr_val_mse"]) < 1e-4
+    assert rel_err(dyn.evaluate(val_it, "transition").mean(dim=(1, 2)).numpy(), g["tr_val_mse"]) < 1e-4
+    assert rel_err(dyn.evaluate_member_mse(val_it, "reward_mech").numpy(), g["rw_val_mse"]) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ VecFakeEnv
 def _build_env(cm, g, rng_mode="numpy"):
     learned_term, penalty_coeff, deterministic, max_steps = g["cfg"]
@@ -319,11 +367,19 @@ def _build_env(cm, g, rng_mode="numpy"):
         tm.set_elite_members(list(g["tm_elite"]))
     dyn = cm.PlainEnsembleDynamics(tr, learned_reward=True, reward_mech=rw, learned_termination=learned_term, termination_mech=tm)
     init_rng = np.random.default_rng(77)
+    buf = None
+    if "pool_obs" in g:  # resets draw rows of a partly filled real replay buffer with the global numpy RNG
+        from oracle.refshim import DuckReplayBuffer
+
+        pool = g["pool_obs"]
+        buf = DuckReplayBuffer(pool, np.zeros((len(pool), A), np.float32), pool, np.zeros(len(pool), np.float32), np.zeros(len(pool), bool))
+        buf.full, buf.pos = False, int(g["pool_pos"])
     env = cm.VecFakeEnv(N, None, None)
     env.set_up(
         dyn,
         termination_fn=None if learned_term else (lambda next_obs, obs, act: np.abs(next_obs[:, 0:1]) > 1.5),
-        get_init_obs_fn=lambda n: init_rng.normal(size=(n, O)).astype(np.float32),
+        get_init_obs_fn=None if buf is not None else (lambda n: init_rng.normal(size=(n, O)).astype(np.float32)),
+        real_replay_buffer=buf,
         penalty_coeff=penalty_coeff,
         deterministic=deterministic,
         max_episode_steps=max_steps,
@@ -334,7 +390,8 @@ def _build_env(cm, g, rng_mode="numpy"):
 
 
 @pytest.mark.parametrize(
-    "name", ["fake_env_termfn.npz", "fake_env_truncate.npz", "fake_env_learned_term.npz", "fake_env_penalty.npz", "fake_env_deterministic.npz", "fake_env_extmask.npz"]
+    "name", ["fake_env_termfn.npz", "fake_env_truncate.npz", "fake_env_learned_term.npz", "fake_env_penalty.npz", "fake_env_deterministic.npz", "fake_env_extmask.npz",
+             "fake_env_bufreset.npz"]
 )
 @pytest.mark.parametrize("infos_mode", ["dicts", "shared"])
 def test_fake_env_step_golden(cm, name, infos_mode):
@@ -343,6 +400,8 @@ def test_fake_env_step_golden(cm, name, infos_mode):
     g = load_golden(name)
     env = _build_env(cm, g)
     env.infos_mode = infos_mode
+    if "pool_obs" in g:
+        np.random.seed(123)  # buffer resets use the global generator (fake_env.py:154,177): seeded like the fixture's run
     obs0 = env.reset()
     assert np.array_equal(obs0, g["reset_obs"])
     N = obs0.shape[0]

@@ -328,6 +328,41 @@ def test_dynamics_host_logic_without_gpu():
     assert tuple(dyn.get_3d_tensor(np.ones((7, 4), np.float32), is_ensemble=True).shape) == (7, 4, 1)
 
 
+def test_constraint_based_dynamics_host_logic_matches_the_reference():
+    """ConstraintBasedDynamics (constraint_based_dynamics.py:22-111): oracle / history mask attributes only for mechanisms that
+    have an input mask, `set_oracle_mask`, and `learn` without an oracle mask failing in `set_input_mask(None)` exactly like the
+    reference -- compared with the unmodified class where the reference tree is mounted."""
+    def build(ns, extra):
+        tr = ns.ExternalMaskTransition(4, 2, hid_size=8, **extra)
+        rw = ns.PlainRewardMech(4, 2, hid_size=8, **extra)
+        return ns.ConstraintBasedDynamics(tr, learned_reward=True, reward_mech=rw)
+
+    rng = np.random.default_rng(0)
+    n = 40
+    buf = refshim.DuckReplayBuffer(rng.normal(size=(n, 4)).astype(np.float32), rng.normal(size=(n, 2)).astype(np.float32),
+                                   rng.normal(size=(n, 4)).astype(np.float32), rng.normal(size=n).astype(np.float32), np.zeros(n, bool))
+    mask = (rng.uniform(size=(4, 6)) < 0.5).astype(np.float32)
+    variants = [(cm, {})]
+    if refshim.mounted():
+        variants.append((refshim.load_reference(), {}))
+    seen = []
+    for ns, extra in variants:
+        dyn = build(ns, extra)
+        attrs = sorted(a for a in vars(dyn) if a.endswith("_oracle_mask") or a.endswith("_history_mask"))
+        assert attrs == ["transition_history_mask", "transition_oracle_mask"]
+        assert dyn.transition_oracle_mask is None
+        assert torch.equal(dyn.transition_history_mask, torch.ones(4, 6))
+        with pytest.raises(AssertionError):
+            dyn.set_oracle_mask("reward_mech", mask)  # the reward mech has no input mask
+        with pytest.raises(ValueError):
+            dyn.learn(buf, batch_size=16, longest_epoch=1, work_dir=None)  # to_tensor(None) (util.py:64-69)
+        dyn.set_oracle_mask("transition", mask)
+        assert torch.equal(dyn.transition_oracle_mask, torch.from_numpy(mask))
+        assert torch.equal(dyn.transition.input_mask, torch.ones(4, 6))  # applied by learn(), not by set_oracle_mask
+        seen.append((dyn.learn_mech, dict(dyn.total_epoch)))
+    assert all(x == seen[0] for x in seen)
+
+
 def test_fake_env_host_side_contract():
     env = cm.VecFakeEnv(8, None, None)
     assert env.num_envs == 8 and not env.has_set_up and env.reset() is None
