@@ -100,22 +100,9 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library():
     if gxx is not None:
         subprocess.run([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
     libdir = os.path.dirname(cm._lib.LIB_PATH)
-    prog = r"""
-#include <stdio.h>
-#include <string.h>
-#include "cmrl_b200.h"
-int main(void) {
-    if (cmrl_abi_version() != 1) return 1;
-    int rc = cmrl_gather_inputs(NULL, NULL, NULL, 4, 5, 1, NULL, NULL);   /* argument validation precedes any CUDA call */
-    if (rc >= 0) return 2;
-    if (strstr(cmrl_last_error(), "null pointer") == NULL) return 3;
-    printf("abi %d, launches %lld\\n", cmrl_abi_version(), cmrl_launch_count());
-    return 0;
-}
-"""
+    src = os.path.join(ROOT, "examples", "abi_consumer.c")
     with tempfile.TemporaryDirectory() as d:
-        src, exe = os.path.join(d, "consumer.c"), os.path.join(d, "consumer")
-        open(src, "w").write(prog)
+        exe = os.path.join(d, "consumer")
         subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
                         "-L", libdir, "-l:libcmrl_b200.so", "-Wl,-rpath," + libdir], check=True)
         res = subprocess.run([exe], capture_output=True, text=True, timeout=60)
