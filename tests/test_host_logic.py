@@ -168,6 +168,37 @@ def test_state_dict_layout_and_checkpoint_roundtrip(cls, kw, fname):
             assert torch.equal(m2.input_mask, m.input_mask) and "input_mask" in m.save_attr
 
 
+@pytest.mark.skipif(not refshim.mounted(), reason="needs the reference tree (build container)")
+@pytest.mark.parametrize("cls", ["PlainTransition", "ExternalMaskTransition", "PlainRewardMech", "PlainTerminationMech"])
+def test_checkpoints_cross_load_with_the_reference(cls):
+    """`.pth` files are part of the boundary (mlp.py:46-63): a checkpoint written by the unmodified reference loads into the
+    drop-in class and one written here loads into the reference -- same file name, same keys, weights, elite set and (for the
+    masked transition) input mask."""
+    ref = refshim.load_reference()
+    rng = np.random.default_rng(4)
+    for writer, reader in ((ref, cm), (cm, ref)):
+        torch.manual_seed(11)
+        src = getattr(writer, cls)(5, 1, hid_size=16, activation_fn_cfg=SILU)
+        dst = getattr(reader, cls)(5, 1, hid_size=16, activation_fn_cfg=SILU)
+        src.set_elite_members([6, 1, 3, 0, 4])
+        if cls == "ExternalMaskTransition":
+            src.set_input_mask(torch.from_numpy((rng.uniform(size=(5, 6)) < 0.5).astype(np.float32)))
+        assert src.model_file_name == dst.model_file_name
+        with tempfile.TemporaryDirectory() as d:
+            src.save(d)
+            assert os.listdir(d) == [dst.model_file_name]
+            blob = torch.load(os.path.join(d, dst.model_file_name), weights_only=False)
+            assert sorted(blob) == sorted(dst.save_attr)
+            dst.load(d)
+        a, b = src.state_dict(), dst.state_dict()
+        assert list(a) == list(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+        assert list(map(int, dst.elite_members)) == [6, 1, 3, 0, 4]
+        if cls == "ExternalMaskTransition":
+            assert torch.equal(dst.input_mask, src.input_mask)
+
+
 def test_elite_bookkeeping_and_random_index():
     m = cm.PlainTransition(5, 1, hid_size=8)
     assert len(m.elite_members) == 5
