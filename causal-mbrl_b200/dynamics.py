@@ -758,13 +758,40 @@ class ConstraintBasedDynamics(PlainEnsembleDynamics):
     """PlainEnsembleDynamics whose masked mechanisms get an oracle causal mask before training
     (constraint_based_dynamics.py:22-183; its CMI-test network is commented out in the reference)."""
 
-    def __init__(self, *args, **kwargs):
-        super().__init__(*args, **kwargs)
+    def __init__(
+        self,
+        transition: BaseTransition,
+        learned_reward: bool = True,
+        reward_mech: Optional[BaseRewardMech] = None,
+        learned_termination: bool = False,
+        termination_mech: Optional[BaseTerminationMech] = None,
+        # trainer
+        optim_lr: float = 1e-4,
+        weight_decay: float = 1e-5,
+        optim_eps: float = 1e-8,
+        logger=None,
+    ):
+        super().__init__(
+            transition=transition, learned_reward=learned_reward, reward_mech=reward_mech,
+            learned_termination=learned_termination, termination_mech=termination_mech, optim_lr=optim_lr,
+            weight_decay=weight_decay, optim_eps=optim_eps, logger=logger,
+        )  # fmt: skip
         for mech in self.learn_mech:
             if hasattr(getattr(self, mech), "input_mask"):
                 setattr(self, "{}_oracle_mask".format(mech), None)
                 setattr(self, "{}_history_mask".format(mech),
                         torch.ones(getattr(self, mech).input_mask.shape).to(self.device))  # fmt: skip
+
+    def build_cmi_test(self):
+        """The conditional-mutual-information test network of the transition's shape (constraint_based_dynamics.py:66-78; the
+        reference constructor has the call commented out, so nothing trains it by default)."""
+        from .cmi_test import TransitionConditionalMutualInformationTest
+
+        self.cmi_test = TransitionConditionalMutualInformationTest(
+            obs_size=self.transition.obs_size, action_size=self.transition.action_size, ensemble_num=1, elite_num=1,
+            residual=self.transition.residual, learn_logvar_bounds=self.transition.learn_logvar_bounds, num_layers=4,
+            hid_size=200, activation_fn_cfg=self.transition.activation_fn_cfg, device=self.transition.device,
+        )  # fmt: skip
 
     def set_oracle_mask(self, mech: str, mask):
         assert hasattr(self, "{}_oracle_mask".format(mech))

@@ -16,7 +16,7 @@ def gaussian_nll(pred_mean, pred_logvar, target, reduce=True):
     return losses
 
 
-def truncated_normal_(tensor, mean=0.0, std=1.0):
+def truncated_normal_(tensor, mean=0, std=1):
     """In-place N(mean, std^2) truncated to +-2 std by resampling the violators until none is left.
     Same RNG call sequence as the reference (normal_ on the slice, then torch.normal(size=(n,)) per
     round), so a given torch seed yields the reference's initial weights."""

@@ -199,6 +199,40 @@ def test_checkpoints_cross_load_with_the_reference(cls):
             assert torch.equal(dst.input_mask, src.input_mask)
 
 
+@pytest.mark.skipif(not refshim.mounted(), reason="needs the reference tree (build container)")
+def test_public_signatures_are_the_references():
+    """The drop-in boundary is the Python class API: every public method (and `__init__`) of the reference's classes
+    on the path exists here with the same parameter names, kinds, order and defaults; every property exists.  Additions are
+    allowed only as trailing parameters WITH defaults (e.g. `subnet_range=None`)."""
+    import inspect
+
+    ref = refshim.load_reference()
+    classes = ["PlainTransition", "ExternalMaskTransition", "ForwardEulerTransition", "PlainRewardMech", "PlainTerminationMech",
+               "BaseDynamics", "PlainEnsembleDynamics", "ConstraintBasedDynamics", "VecFakeEnv", "TransitionIterator",
+               "BootstrapIterator", "InteractionBatch", "EnsembleLinearLayer", "ParallelEnsembleLinearLayer", "EnsembleMLP",
+               "TransitionConditionalMutualInformationTest"]
+
+    def params(f):
+        return [(n, p_.kind.name, None if p_.default is inspect.Parameter.empty else repr(p_.default))
+                for n, p_ in inspect.signature(f).parameters.items()]
+
+    checked = 0
+    for name in classes:
+        theirs, ours = getattr(ref, name), getattr(cm, name)
+        for meth, fn in inspect.getmembers(theirs, predicate=inspect.isfunction):
+            if meth.startswith("_") and meth != "__init__":
+                continue
+            mine = getattr(ours, meth, None)
+            assert mine is not None, "%s.%s is missing" % (name, meth)
+            a, b = params(fn), params(mine)
+            assert b[:len(a)] == a, "%s.%s: %s != %s" % (name, meth, b, a)
+            assert all(d is not None for _, _, d in b[len(a):]), "%s.%s: extra parameters need defaults" % (name, meth)
+            checked += 1
+        for prop, _ in inspect.getmembers(theirs, predicate=lambda x: isinstance(x, property)):
+            assert hasattr(ours, prop), "%s.%s (property) is missing" % (name, prop)
+    assert checked > 120
+
+
 def test_elite_bookkeeping_and_random_index():
     m = cm.PlainTransition(5, 1, hid_size=8)
     assert len(m.elite_members) == 5
