@@ -231,6 +231,23 @@ def test_public_signatures_are_the_references():
         for prop, _ in inspect.getmembers(theirs, predicate=lambda x: isinstance(x, property)):
             assert hasattr(ours, prop), "%s.%s (property) is missing" % (name, prop)
     assert checked > 120
+    # instance attributes, parameters and sub-modules the callers read (SURVEY 8b's attribute list)
+    def public(o):
+        names = set(n for n in vars(o) if not n.startswith("_"))
+        if isinstance(o, torch.nn.Module):
+            names |= set(o._parameters) | set(o._modules)
+        return names
+
+    for name in ("PlainTransition", "ExternalMaskTransition", "PlainRewardMech", "PlainTerminationMech",
+                 "TransitionConditionalMutualInformationTest"):
+        theirs, ours = (getattr(ns, name)(5, 1, hid_size=8, activation_fn_cfg=SILU) for ns in (ref, cm))
+        assert public(theirs) <= public(ours), (name, public(theirs) - public(ours))
+    t_ref, t_our = ref.PlainTransition(5, 1, hid_size=8), cm.PlainTransition(5, 1, hid_size=8)
+    assert public(ref.ForwardEulerTransition(t_ref, 3)) <= public(cm.ForwardEulerTransition(t_our, 3))
+    d_ref, d_our = ref.PlainEnsembleDynamics(t_ref, learned_reward=False), cm.PlainEnsembleDynamics(t_our, learned_reward=False)
+    assert public(d_ref) <= public(d_our), public(d_ref) - public(d_our)
+    e_ref, e_our = ref.VecFakeEnv(4, None, None), cm.VecFakeEnv(4, None, None)
+    assert all(hasattr(e_our, n) for n in vars(e_ref)), [n for n in vars(e_ref) if not hasattr(e_our, n)]
 
 
 def test_elite_bookkeeping_and_random_index():
